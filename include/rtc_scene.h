@@ -42,7 +42,8 @@ enum {
     SG_TRIANGLE = 5,
     SG_SMOOTH_TRIANGLE = 6,
     SG_GROUP = 7,
-    SG_CSG = 8
+    SG_CSG = 8,
+    SG_TEST_SHAPE = 9 /* shape/test_shape.rs — the reference's test double; accepted by the oracle only */
 };
 
 /* CSG operators (lib/src/shape/csg.rs:10-15) */

@@ -160,6 +160,7 @@ int sg_shape_new(sg_ctx* c, int kind) {
         case SG_CYLINDER: return c->add_shape(std::make_unique<Cylinder>());
         case SG_CONE: return c->add_shape(std::make_unique<Cone>());
         case SG_GROUP: return c->add_shape(std::make_unique<GroupShape>());
+        case SG_TEST_SHAPE: return c->add_shape(std::make_unique<TestShape>());
     }
     return fail("sg_shape_new: bad kind");
 }
@@ -574,6 +575,12 @@ int orc_shape_normal_to_world(sg_ctx* c, int h, const float n[3], float out[3]) 
     Shape* s = c->shape(h);
     if (!s) return fail("bad shape handle");
     put3(out, s->normal_to_world(vec(n)));
+    return 0;
+}
+int orc_test_shape_saved_ray(sg_ctx* c, int h, float out[6]) {
+    auto* s = dynamic_cast<TestShape*>(c->shape(h));
+    if (!s || !s->has_saved_ray) return fail("no saved ray");
+    put3(out, s->saved_ray.origin), put3(out + 3, s->saved_ray.direction);
     return 0;
 }
 int orc_shape_includes(sg_ctx* c, int a, int b) {

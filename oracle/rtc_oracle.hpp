@@ -584,6 +584,30 @@ struct Cube : Shape {
     }
 };
 
+// shape/test_shape.rs:11-57 — the reference's own test double (records the object-space ray; normal is
+// (2x, 3y, 4z)); only the transcribed unit tests use it.
+struct TestShape : Shape {
+    mutable Ray saved_ray;
+    mutable bool has_saved_ray = false;
+    TestShape() : Shape(9) {}
+    std::unique_ptr<Shape> clone() const override {
+        auto s = std::make_unique<TestShape>(*this);
+        s->id = g_next_id++;
+        return s;
+    }
+    void local_intersect(const Ray& r, std::vector<Intersection>&, Counters*) const override {
+        saved_ray = r;
+        has_saved_ray = true;
+    }
+    Tuple local_norm_at(Tuple p, const Intersection&) const override { return vector(2.0f * p.x, 3.0f * p.y, 4.0f * p.z); }
+    BoundingBox bounding_box() const override {
+        BoundingBox b;
+        b.min = point(-1, -1, -1);
+        b.max = point(1, 1, 1);
+        return b;
+    }
+};
+
 constexpr float kCloseToZero = 0.000001f;  // cylinder.rs:82, cone.rs:87
 
 struct Cylinder : Shape {

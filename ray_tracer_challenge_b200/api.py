@@ -25,7 +25,7 @@ FP = C.POINTER(C.c_float)
 IP = C.POINTER(C.c_int)
 U8P = C.POINTER(C.c_uint8)
 
-SG_SPHERE, SG_PLANE, SG_CUBE, SG_CYLINDER, SG_CONE, SG_TRIANGLE, SG_SMOOTH_TRIANGLE, SG_GROUP, SG_CSG = range(9)
+SG_SPHERE, SG_PLANE, SG_CUBE, SG_CYLINDER, SG_CONE, SG_TRIANGLE, SG_SMOOTH_TRIANGLE, SG_GROUP, SG_CSG, SG_TEST_SHAPE = range(10)
 SG_PAT_STRIPES, SG_PAT_GRADIENT, SG_PAT_RINGS, SG_PAT_CHECKERS, SG_PAT_SINE2D, SG_PAT_TEST = range(6)
 SG_UV_CHECKERS, SG_UV_ALIGN_CHECK = 0, 1
 SG_MAP_SPHERICAL, SG_MAP_PLANAR, SG_MAP_CYLINDRICAL = 0, 1, 2
@@ -472,11 +472,12 @@ class Api:
         self.Cube = type("Cube", (Shape,), {"_kind": SG_CUBE})
         self.Cylinder = type("Cylinder", (_Bounded,), {"_kind": SG_CYLINDER})
         self.Cone = type("Cone", (_Bounded,), {"_kind": SG_CONE})
+        self.TestShape = type("TestShape", (Shape,), {"_kind": SG_TEST_SHAPE})
         self.Triangle, self.SmoothTriangle, self.GroupShape, self.CSG = Triangle, SmoothTriangle, GroupShape, CSG
         self._by_kind = {
             SG_SPHERE: self.Sphere, SG_PLANE: self.Plane, SG_CUBE: self.Cube, SG_CYLINDER: self.Cylinder,
             SG_CONE: self.Cone, SG_TRIANGLE: Triangle, SG_SMOOTH_TRIANGLE: SmoothTriangle, SG_GROUP: GroupShape,
-            SG_CSG: CSG,
+            SG_CSG: CSG, SG_TEST_SHAPE: self.TestShape,
         }
 
         # ---------------------------------------------------------------- world / camera

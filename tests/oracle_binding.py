@@ -27,6 +27,7 @@ _PROBES = {
     "orc_shape_world_to_object": (I, [V, I, FP, FP]),
     "orc_shape_normal_to_world": (I, [V, I, FP, FP]),
     "orc_shape_includes": (I, [V, I, I]),
+    "orc_test_shape_saved_ray": (I, [V, I, FP]),
     "orc_world_intersect": (I, [V, I, FP, FP, FP, IP, I]),
     "orc_hit_index": (I, [FP, I]),
     "orc_color_at": (I, [V, I, FP, FP, I, FP]),
@@ -98,6 +99,11 @@ class Probes:
         nn, out = f32(n), np.zeros(3, np.float32)
         self._ck(self.lib.orc_shape_normal_to_world(self.ctx, shape.handle, fptr(nn), fptr(out)))
         return out
+
+    def saved_ray(self, test_shape):
+        out = np.zeros(6, np.float32)
+        self._ck(self.lib.orc_test_shape_saved_ray(self.ctx, test_shape.handle, fptr(out)))
+        return out[:3], out[3:]
 
     def includes(self, a, b):
         return bool(self._ck(self.lib.orc_shape_includes(self.ctx, a.handle, b.handle)))
