@@ -1,0 +1,190 @@
+/* rtc_b200.h — the drop-in boundary: a C ABI over the B200 (sm_100a) implementation of the reference's
+ * `Camera::render` hot path.
+ *
+ * The reference (garfieldnate/ray_tracer_challenge, Rust) has no FFI of its own; its boundary for this path
+ * is the method `Camera::render(&self, world: World, depth: i16) -> Canvas` (lib/src/camera.rs:76-91).
+ * A Rust host would add the sibling `Camera::render_b200` which flattens `World` (lib/src/world.rs:18-21)
+ * into the POD arrays below and calls this library through a `-sys` crate (see INTEGRATION.md for the
+ * binding).  In this repo the same calls are made by the C++ host mirror
+ * (ray_tracer_challenge_b200/csrc/host/, Camera::render_b200) and, for tests, by Python/ctypes.
+ *
+ * Conventions: every function returns 0 on success or a negative RtcStatus; nothing panics or throws
+ * across the ABI; rtc_last_error() returns the thread-local message of the last failure.  All pointers
+ * are caller-owned and copied before the call returns.  Matrices are 16 f32, row-major.  A scene handle
+ * may be used by one host thread at a time.  There is NO CPU fallback: without a CUDA device
+ * rtc_scene_commit / rtc_render fail with RTC_ERR_NO_DEVICE.
+ */
+#ifndef RTC_B200_H
+#define RTC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct RtcScene RtcScene;
+
+typedef enum RtcStatus {
+    RTC_OK = 0,
+    RTC_ERR_INVALID = -1,   /* bad argument / inconsistent scene */
+    RTC_ERR_NO_DEVICE = -2, /* no CUDA device, or CUDA call failed */
+    RTC_ERR_CAPACITY = -3,  /* a documented device-side capacity was exceeded (depth, CSG size) */
+    RTC_ERR_STATE = -4      /* call sequence error (render before commit, ...) */
+} RtcStatus;
+
+/* Leaf primitive kinds — lib/src/shape/{sphere,plane,cube,cylinder,cone,triangle}.rs.  SmoothTriangle
+ * (smooth_triangle.rs:39-41) delegates its intersection to the inner flat Triangle, so it is lowered to
+ * RTC_TRIANGLE. */
+enum { RTC_SPHERE = 0, RTC_PLANE = 1, RTC_CUBE = 2, RTC_CYLINDER = 3, RTC_CONE = 4, RTC_TRIANGLE = 5 };
+
+/* One leaf of the shape tree, in depth-first order of World::objects / GroupShape::children / CSG s1,s2.
+ * That order is the reference's tie-break between equal distances (world.rs:58 stable sort +
+ * intersection.rs:30-35 first minimum). */
+typedef struct RtcPrim {
+    int32_t type;
+    int32_t material;     /* index into the material table */
+    int32_t casts_shadow; /* BaseShape::casts_shadow, base_shape.rs:14 */
+    int32_t parent;       /* index into the node table (enclosing GroupShape / CSG) or -1 */
+    float inv[16];        /* Shape::transformation_inverse(), base_shape.rs:56-60; the inverse-transpose used
+                             by normal_to_world (shape.rs:130) is its transpose */
+    float params[12];     /* cylinder / cone: {minimum_y, maximum_y, closed}; triangle: p1, e1, e2, normal
+                             (triangle.rs:20-33) */
+    float bbox_min[3];    /* Shape::parent_space_bounding_box(), shape.rs:162-164 */
+    float bbox_max[3];
+} RtcPrim;
+
+/* Interior node of the shape tree.  Groups have already pushed their transform into their leaves
+ * (group.rs:39-44,101-114) and act only as bounding-box culls (group.rs:119-133); CSG nodes keep their own
+ * transform (csg.rs:78) and filter their children's sorted hits (csg.rs:37-58,87-104). */
+enum { RTC_NODE_GROUP = 0, RTC_NODE_CSG = 1 };
+enum { RTC_CSG_UNION = 0, RTC_CSG_INTERSECTION = 1, RTC_CSG_DIFFERENCE = 2 };
+typedef struct RtcNode {
+    int32_t kind;
+    int32_t parent;      /* node index or -1 */
+    int32_t op;          /* CSG operator */
+    int32_t child_begin; /* into the child reference array */
+    int32_t child_count; /* CSG: exactly 2 (s1, s2) */
+    float inv[16];       /* CSG: its own transformation_inverse(); groups: identity */
+    float bbox_min[3];   /* the node's own bounding_box() as the reference caches it (group.rs:138-150,
+                            csg.rs:119-130), in the space its cull test runs in */
+    float bbox_max[3];
+    float world_bbox_min[3]; /* parent_space_bounding_box() (csg: bounding_box().transform(t)) */
+    float world_bbox_max[3];
+} RtcNode;
+/* child reference: >= 0 is a primitive index, < 0 is ~node_index */
+
+typedef struct RtcMaterial { /* material.rs:19-51 */
+    float color[3];
+    float ambient, diffuse, specular, shininess, reflective, transparency, refractive_index;
+    int32_t pattern; /* index into the pattern table or -1 */
+} RtcMaterial;
+
+/* pattern/{stripes,gradient,rings,checkers,sine_2d,pattern,uv}.rs */
+enum {
+    RTC_PAT_STRIPES = 0,
+    RTC_PAT_GRADIENT = 1,
+    RTC_PAT_RINGS = 2,
+    RTC_PAT_CHECKERS = 3,
+    RTC_PAT_SINE2D = 4,
+    RTC_PAT_TEST = 5,
+    RTC_PAT_TEXTURE_MAP = 6,
+    RTC_PAT_CUBIC_MAP = 7
+};
+enum { RTC_UV_CHECKERS = 0, RTC_UV_ALIGN_CHECK = 1 };
+enum { RTC_MAP_SPHERICAL = 0, RTC_MAP_PLANAR = 1, RTC_MAP_CYLINDRICAL = 2 };
+typedef struct RtcPattern {
+    int32_t kind;
+    int32_t mapping; /* TextureMap */
+    int32_t uv[6];   /* TextureMap: uv[0]; CubicMap: Front, Back, Left, Right, Up, Down (uv.rs:229-249) */
+    float inv[16];   /* BasePattern::t_inverse, pattern.rs:53-55 */
+    float a[3];      /* first colour */
+    float b[3];      /* second colour; for Gradient / Sine2D the precomputed `distance = b - a`
+                        (gradient.rs:23, sine_2d.rs:22) */
+} RtcPattern;
+typedef struct RtcUvPattern {
+    int32_t kind;
+    float params[15]; /* UVCheckers: width, height, a.rgb, b.rgb; AlignCheck: main, ul, ur, bl, br */
+} RtcUvPattern;
+
+typedef struct RtcStats {
+    uint64_t primary_rays;   /* color_at calls from render (camera.rs:83) */
+    uint64_t secondary_rays; /* color_at calls from reflected_color / refracted_color (world.rs:129,159) */
+    uint64_t shadow_rays;    /* is_shadowed calls (world.rs:104) */
+    uint64_t shades;         /* shade_hit calls */
+    uint64_t node_visits;    /* BVH boxes tested (detailed pass only) */
+    uint64_t prim_tests[8];  /* local_intersect calls by RTC_* type; [6] = CSG evaluations (detailed pass only) */
+    uint64_t xforms;         /* ray -> object transforms actually performed (detailed pass only) */
+    uint64_t patterns, cells, schlicks, refr_dirs;
+    uint64_t capacity_overflows; /* CSG hit-buffer overflows: must be 0 for a valid frame */
+    double flops;            /* algorithmic FP32 flops; detailed pass only */
+    double kernel_ms;        /* CUDA-event time of the render kernel(s), max over devices */
+    double total_ms;         /* host wall time of the call including D2H copies */
+    int32_t n_devices;
+    int32_t detailed;
+} RtcStats;
+
+const char* rtc_last_error(void);
+int rtc_device_count(void); /* >= 0, or a negative RtcStatus */
+
+int rtc_scene_create(RtcScene** out);
+void rtc_scene_destroy(RtcScene*);
+
+/* Camera::new's derived fields exactly as the reference computes them (camera.rs:23-56). */
+int rtc_set_camera(RtcScene*, uint32_t width, uint32_t height, float half_width, float half_height, float pixel_size,
+                   const float transform_inverse[16]);
+int rtc_set_primitives(RtcScene*, uint32_t n, const RtcPrim* prims);
+int rtc_set_nodes(RtcScene*, uint32_t n_nodes, const RtcNode* nodes, uint32_t n_refs, const int32_t* child_refs);
+int rtc_set_materials(RtcScene*, uint32_t n, const RtcMaterial* materials);
+int rtc_set_patterns(RtcScene*, uint32_t n, const RtcPattern* patterns, uint32_t n_uv, const RtcUvPattern* uv);
+/* PointLight (point_light.rs:7-18) */
+int rtc_set_point_light(RtcScene*, const float position[3], const float intensity[3]);
+/* RectangleLight after construction (rectangle_light.rs:48-58): u_cell / v_cell are the per-cell edges,
+ * `position` the rectangle centre used by phong_lighting (phong_lighting.rs:36).  Jitter: a cyclic table
+ * consumed `for v { for u { j_u, j_v } }` from index 0 at every intensity_at (rectangle_light.rs:60-88), or,
+ * with table_len == 0, the counter-based generator seeded by `seed` (stand-in for thread_rng,
+ * rectangle_light.rs:46). */
+int rtc_set_rect_light(RtcScene*, const float intensity[3], const float corner[3], const float u_cell[3],
+                       int32_t u_steps, const float v_cell[3], int32_t v_steps, const float position[3],
+                       const float* jitter_table, uint32_t table_len, uint64_t seed);
+
+/* Options (set before commit).  RTC_OPT_STRICT_FP = 1 selects the build of the kernels compiled without
+ * FMA contraction (bit-for-bit the Rust evaluation order; slower); default 0. */
+enum { RTC_OPT_STRICT_FP = 1, RTC_OPT_BVH_LEAF_SIZE = 2, RTC_OPT_BVH_MIN_PRIMS = 3 };
+int rtc_set_option(RtcScene*, int32_t option, int64_t value);
+
+/* Validate, build the BVH over the primitives' bounding boxes and upload one scene replica per device.
+ * device_ids == NULL selects devices 0..n_devices-1; n_devices == 0 selects every visible device. */
+int rtc_scene_commit(RtcScene*, int32_t n_devices, const int32_t* device_ids);
+
+/* Camera::render.  rgb_f32: width*height*3 (row-major, the Canvas layout, canvas.rs:6-25), rgb_u8: the same
+ * pixels through Canvas::scale_color (canvas.rs:39-43); either may be NULL (NULL, NULL = render and leave the
+ * frame on the device: kernel timing).  Rows are split in interleaved bands over the committed devices. */
+int rtc_render(RtcScene*, int32_t depth, float* rgb_f32, uint8_t* rgb_u8, RtcStats* stats);
+/* Same, for one shard of a frame shared by several processes (one process per GPU): only the bands
+ * b with b % n_shards == shard are rendered and written; the other rows of the buffers are not touched. */
+int rtc_render_shard(RtcScene*, int32_t depth, int32_t shard, int32_t n_shards, float* rgb_f32, uint8_t* rgb_u8,
+                     RtcStats* stats);
+/* As rtc_render but with the detailed work counters (node visits, primitive tests, flops). */
+int rtc_render_detailed(RtcScene*, int32_t depth, float* rgb_f32, uint8_t* rgb_u8, RtcStats* stats);
+/* World::color_at (world.rs:88-101) for caller-supplied rays: origins / directions are n*3 f32; out_rgb n*3;
+ * out_t (optional) the hit distance or -1; out_prim (optional) the hit primitive index or -1. */
+int rtc_trace_rays(RtcScene*, uint32_t n, const float* origins, const float* directions, int32_t depth,
+                   float* out_rgb, float* out_t, int32_t* out_prim);
+
+/* Pinned host memory for canvases (page-locked so the device-to-host copy runs at PCIe speed). */
+void* rtc_host_alloc(size_t bytes);
+void rtc_host_free(void*);
+int rtc_host_register(void* ptr, size_t bytes);
+int rtc_host_unregister(void* ptr);
+/* Evict the L2 between timed iterations (writes a buffer larger than the 126 MB L2). */
+int rtc_flush_l2(RtcScene*);
+/* Sustained FP32 FMA throughput of device `device` in TFLOP/s (micro-benchmark; the roofline's measured
+ * denominator). */
+int rtc_measure_fp32_peak(int32_t device, double* tflops, double* sm_clock_mhz);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -551,7 +551,13 @@ class Api:
 
     def material_handle(self, m: Material) -> int:
         p = m.params()
-        return self.check(self.lib.sg_material_new(self.ctx, fptr(p), m.pattern.handle if m.pattern is not None else -1))
+        ph = m.pattern.handle if m.pattern is not None else -1
+        key = (p.tobytes(), ph)
+        cache = self.__dict__.setdefault("_material_cache", {})
+        h = cache.get(key)
+        if h is None:
+            h = cache[key] = self.check(self.lib.sg_material_new(self.ctx, fptr(p), ph))
+        return h
 
     def wrap_shape(self, handle: int):
         kind = self.check(self.lib.sg_shape_kind(self.ctx, handle))

@@ -1,0 +1,917 @@
+// rtc_api.cu — the C ABI of include/rtc_b200.h: scene intake, commit (validation, transform
+// de-duplication, binned-SAH BVH over the book's bounding boxes, CSG flattening, upload of one replica per
+// device) and the render entry points that drive the kernels of rtc_kernels.cu.
+//
+// There is no CPU rendering path in this library: every pixel comes from the sm_100a kernels, and every
+// entry point that needs a device fails with RTC_ERR_NO_DEVICE when there is none.
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/rtc_b200.h"
+#include "rtc_launch.h"
+#include "rtc_types.h"
+
+using namespace rtc;
+
+namespace {
+
+thread_local std::string g_error;
+int fail(int code, const std::string& msg) {
+    g_error = msg;
+    return code;
+}
+#define CUDA_TRY(expr)                                                                                          \
+    do {                                                                                                        \
+        cudaError_t _e = (expr);                                                                                \
+        if (_e != cudaSuccess)                                                                                  \
+            return fail(RTC_ERR_NO_DEVICE, std::string(#expr) + ": " + cudaGetErrorString(_e));                  \
+    } while (0)
+
+struct Box {
+    float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    void grow(const Box& o) {
+        for (int a = 0; a < 3; a++) lo[a] = std::min(lo[a], o.lo[a]), hi[a] = std::max(hi[a], o.hi[a]);
+    }
+    float area() const {
+        float dx = hi[0] - lo[0], dy = hi[1] - lo[1], dz = hi[2] - lo[2];
+        if (dx < 0 || dy < 0 || dz < 0) return 0.f;
+        return 2.f * (dx * dy + dy * dz + dz * dx);
+    }
+    bool finite() const {
+        for (int a = 0; a < 3; a++)
+            if (!std::isfinite(lo[a]) || !std::isfinite(hi[a]) || lo[a] > hi[a]) return false;
+        return true;
+    }
+};
+
+// One committed replica of the scene on one device.
+struct Replica {
+    int device = -1;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::vector<void*> allocs;
+    DevScene scene{};
+    float* d_rgb = nullptr;
+    unsigned char* d_u8 = nullptr;
+    DevCounters* d_counters = nullptr;
+    void* d_flush = nullptr;
+    size_t flush_bytes = 0;
+};
+
+}  // namespace
+
+struct RtcScene {
+    bool have_camera = false, have_light = false, committed = false;
+    uint32_t width = 0, height = 0;
+    float half_w = 0, half_h = 0, pixel_size = 0;
+    float cam_inv[16];
+    std::vector<RtcPrim> prims;
+    std::vector<RtcNode> nodes;
+    std::vector<int32_t> refs;
+    std::vector<RtcMaterial> materials;
+    std::vector<RtcPattern> patterns;
+    std::vector<RtcUvPattern> uvs;
+    bool light_is_rect = false;
+    float light_pos[3], light_rgb[3], corner[3], u_cell[3], v_cell[3];
+    int u_steps = 1, v_steps = 1;
+    std::vector<float> jitter;
+    uint64_t seed = 0;
+    int strict_fp = 0, leaf_size = 4, bvh_min_prims = 8;
+    std::vector<Replica> replicas;
+    std::vector<int> pos_to_prim;  // device position -> API primitive index (-1 for CSG pseudo-primitives)
+    // commit statistics
+    int n_bvh_nodes = 0, n_linear = 0, n_xforms = 0;
+};
+
+namespace {
+
+void release(RtcScene* s) {
+    for (Replica& r : s->replicas) {
+        cudaSetDevice(r.device);
+        for (void* p : r.allocs) cudaFree(p);
+        if (r.d_flush) cudaFree(r.d_flush);
+        if (r.ev0) cudaEventDestroy(r.ev0);
+        if (r.ev1) cudaEventDestroy(r.ev1);
+        if (r.stream) cudaStreamDestroy(r.stream);
+    }
+    s->replicas.clear();
+    s->committed = false;
+}
+
+template <class T>
+int upload(Replica& r, const std::vector<T>& v, const T** out) {
+    *out = nullptr;
+    if (v.empty()) return 0;
+    void* p = nullptr;
+    CUDA_TRY(cudaMalloc(&p, v.size() * sizeof(T)));
+    r.allocs.push_back(p);
+    CUDA_TRY(cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    *out = reinterpret_cast<const T*>(p);
+    return 0;
+}
+
+void rows3(const float m[16], float4 out[3]) {
+    for (int r = 0; r < 3; r++) out[r] = make_float4(m[r * 4], m[r * 4 + 1], m[r * 4 + 2], m[r * 4 + 3]);
+}
+
+// ---- binned-SAH BVH over the top-level items -----------------------------------------------------------
+struct BuildItem {
+    Box box;
+    float centroid[3];
+    int item;  // index into the bounded item list
+};
+struct Builder {
+    std::vector<BuildItem>& items;
+    std::vector<DevBvhNode>& nodes;
+    int leaf_size;
+    // returns the link for the range [b, e): >= 0 inner node, < 0 leaf code
+    int build(int b, int e, int depth) {
+        int n = e - b;
+        if (n <= leaf_size || depth > 40) {
+            if (n <= 16) return ~((b << 4) | (n - 1));
+            // forced leaf too large for the 4-bit count: split in the middle regardless of cost
+            return make_inner(b, (b + e) / 2, e, depth);
+        }
+        Box cb;
+        for (int i = b; i < e; i++)
+            for (int a = 0; a < 3; a++)
+                cb.lo[a] = std::min(cb.lo[a], items[i].centroid[a]), cb.hi[a] = std::max(cb.hi[a], items[i].centroid[a]);
+        int axis = 0;
+        float ext = cb.hi[0] - cb.lo[0];
+        for (int a = 1; a < 3; a++)
+            if (cb.hi[a] - cb.lo[a] > ext) axis = a, ext = cb.hi[a] - cb.lo[a];
+        int mid = -1;
+        if (ext > 0.f) {
+            constexpr int kBins = 16;
+            Box bins[kBins];
+            int counts[kBins] = {0};
+            float scale = kBins / ext;
+            auto bin_of = [&](const BuildItem& it) {
+                int k = (int)((it.centroid[axis] - cb.lo[axis]) * scale);
+                return std::min(std::max(k, 0), kBins - 1);
+            };
+            for (int i = b; i < e; i++) {
+                int k = bin_of(items[i]);
+                bins[k].grow(items[i].box);
+                counts[k]++;
+            }
+            float right_area[kBins];
+            int right_count[kBins];
+            Box acc;
+            int cnt = 0;
+            for (int k = kBins - 1; k > 0; k--) {
+                acc.grow(bins[k]);
+                cnt += counts[k];
+                right_area[k] = acc.area();
+                right_count[k] = cnt;
+            }
+            Box left;
+            int lcnt = 0, best_k = -1;
+            float best_cost = INFINITY;
+            for (int k = 0; k < kBins - 1; k++) {
+                left.grow(bins[k]);
+                lcnt += counts[k];
+                if (lcnt == 0 || right_count[k + 1] == 0) continue;
+                float cost = left.area() * lcnt + right_area[k + 1] * right_count[k + 1];
+                if (cost < best_cost) best_cost = cost, best_k = k;
+            }
+            if (best_k >= 0) {
+                auto it = std::partition(items.begin() + b, items.begin() + e,
+                                         [&](const BuildItem& x) { return bin_of(x) <= best_k; });
+                mid = (int)(it - items.begin());
+            }
+        }
+        if (mid <= b || mid >= e) {  // degenerate: equal centroids — split by count
+            mid = (b + e) / 2;
+            std::nth_element(items.begin() + b, items.begin() + mid, items.begin() + e,
+                             [&](const BuildItem& x, const BuildItem& y) { return x.centroid[axis] < y.centroid[axis]; });
+        }
+        return make_inner(b, mid, e, depth);
+    }
+    int make_inner(int b, int mid, int e, int depth) {
+        int idx = (int)nodes.size();
+        nodes.emplace_back();
+        Box b0, b1;
+        for (int i = b; i < mid; i++) b0.grow(items[i].box);
+        for (int i = mid; i < e; i++) b1.grow(items[i].box);
+        int c0 = build(b, mid, depth + 1);
+        int c1 = build(mid, e, depth + 1);
+        DevBvhNode& n = nodes[idx];
+        n.a = make_float4(b0.lo[0], b0.lo[1], b0.lo[2], b0.hi[0]);
+        n.b = make_float4(b0.hi[1], b0.hi[2], b1.lo[0], b1.lo[1]);
+        n.c = make_float4(b1.lo[2], b1.hi[0], b1.hi[1], b1.hi[2]);
+        n.d = make_int4(c0, c1, 0, 0);
+        return idx;
+    }
+};
+
+// worst-case number of intersections a leaf kind can emit (cone: 2 walls + 2 caps)
+int max_hits(int type) {
+    switch (type) {
+        case RTC_SPHERE: return 2;
+        case RTC_PLANE: return 1;
+        case RTC_CUBE: return 2;
+        case RTC_CYLINDER: return 3;
+        case RTC_CONE: return 4;
+        default: return 1;
+    }
+}
+
+struct Flattened {
+    std::vector<int4> head;  // 2 * n_pos entries: [pos] main, [n_pos + pos] {cull-chain parent node, api prim, 0, 0}
+    std::vector<float4> xform, tri, bound;
+    std::vector<DevBvhNode> bvh;
+    std::vector<int> linear;
+    std::vector<DevNode> nodes;
+    std::vector<DevCsgOp> ops;
+    std::vector<DevMaterial> materials;
+    std::vector<DevPattern> patterns;
+    std::vector<DevUvPattern> uvs;
+    std::vector<float4> samples;
+    int bvh_root = -1;
+    int n_pos = 0;
+    int all_cast_shadow = 1;
+};
+
+int flatten(RtcScene* s, Flattened& f) {
+    const int np = (int)s->prims.size(), nn = (int)s->nodes.size();
+    // ---- validate references
+    for (int i = 0; i < np; i++) {
+        const RtcPrim& p = s->prims[i];
+        if (p.type < RTC_SPHERE || p.type > RTC_TRIANGLE) return fail(RTC_ERR_INVALID, "primitive " + std::to_string(i) + ": bad type");
+        if (p.material < 0 || p.material >= (int)s->materials.size())
+            return fail(RTC_ERR_INVALID, "primitive " + std::to_string(i) + ": bad material index");
+        if (p.parent < -1 || p.parent >= nn) return fail(RTC_ERR_INVALID, "primitive " + std::to_string(i) + ": bad parent");
+    }
+    for (int i = 0; i < nn; i++) {
+        const RtcNode& n = s->nodes[i];
+        if (n.kind != RTC_NODE_GROUP && n.kind != RTC_NODE_CSG) return fail(RTC_ERR_INVALID, "node: bad kind");
+        if (n.parent < -1 || n.parent >= nn || n.parent == i) return fail(RTC_ERR_INVALID, "node: bad parent");
+        if (n.child_begin < 0 || n.child_count < 0 || n.child_begin + n.child_count > (int)s->refs.size())
+            return fail(RTC_ERR_INVALID, "node: bad child range");
+        if (n.kind == RTC_NODE_CSG && (n.child_count != 2 || n.op < 0 || n.op > 2)) return fail(RTC_ERR_INVALID, "csg node: needs 2 children and a valid operator");
+        for (int c = 0; c < n.child_count; c++) {
+            int r = s->refs[n.child_begin + c];
+            if (r >= np || (r < 0 && ~r >= nn)) return fail(RTC_ERR_INVALID, "node: bad child reference");
+        }
+    }
+    for (const RtcMaterial& m : s->materials)
+        if (m.pattern < -1 || m.pattern >= (int)s->patterns.size()) return fail(RTC_ERR_INVALID, "material: bad pattern index");
+    for (const RtcPattern& p : s->patterns) {
+        if (p.kind < RTC_PAT_STRIPES || p.kind > RTC_PAT_CUBIC_MAP) return fail(RTC_ERR_INVALID, "pattern: bad kind");
+        int need = p.kind == RTC_PAT_TEXTURE_MAP ? 1 : (p.kind == RTC_PAT_CUBIC_MAP ? 6 : 0);
+        for (int i = 0; i < need; i++)
+            if (p.uv[i] < 0 || p.uv[i] >= (int)s->uvs.size()) return fail(RTC_ERR_INVALID, "pattern: bad uv pattern index");
+    }
+
+    // ---- which CSG (if any) is the outermost CSG ancestor of each node / primitive
+    std::vector<int> top_csg_of_node(nn, -1);
+    auto resolve = [&](int node) {
+        int top = -1, guard = 0;
+        for (int a = node; a >= 0; a = s->nodes[a].parent) {
+            if (s->nodes[a].kind == RTC_NODE_CSG) top = a;
+            if (++guard > nn) return -2;
+        }
+        return top;
+    };
+    for (int i = 0; i < nn; i++) {
+        top_csg_of_node[i] = resolve(i);
+        if (top_csg_of_node[i] == -2) return fail(RTC_ERR_INVALID, "node parents form a cycle");
+    }
+    std::vector<int> prim_top_csg(np, -1);
+    for (int i = 0; i < np; i++) prim_top_csg[i] = s->prims[i].parent >= 0 ? top_csg_of_node[s->prims[i].parent] : -1;
+
+    // ---- top-level items: free primitives and outermost CSG nodes
+    struct Item {
+        int prim;  // >= 0 primitive, else ~csg node
+        Box box;
+    };
+    std::vector<Item> bounded, unbounded;
+    auto add_item = [&](int ref, const float* lo, const float* hi) {
+        Item it;
+        it.prim = ref;
+        for (int a = 0; a < 3; a++) it.box.lo[a] = lo[a], it.box.hi[a] = hi[a];
+        (it.box.finite() ? bounded : unbounded).push_back(it);
+    };
+    for (int i = 0; i < np; i++)
+        if (prim_top_csg[i] < 0) add_item(i, s->prims[i].bbox_min, s->prims[i].bbox_max);
+    for (int i = 0; i < nn; i++)
+        if (s->nodes[i].kind == RTC_NODE_CSG && top_csg_of_node[i] == i) add_item(~i, s->nodes[i].world_bbox_min, s->nodes[i].world_bbox_max);
+    if ((int)bounded.size() < s->bvh_min_prims) {  // tiny scene: test everything for every ray, no tree
+        unbounded.insert(unbounded.end(), bounded.begin(), bounded.end());
+        bounded.clear();
+        // keep depth-first order in the linear list (purely cosmetic: ties are broken by the order field)
+        std::sort(unbounded.begin(), unbounded.end(), [&](const Item& a, const Item& b) {
+            auto key = [&](const Item& it) { return it.prim >= 0 ? it.prim : np + ~it.prim; };
+            return key(a) < key(b);
+        });
+    }
+
+    // ---- BVH
+    std::vector<BuildItem> build_items(bounded.size());
+    for (size_t i = 0; i < bounded.size(); i++) {
+        BuildItem& b = build_items[i];
+        b.box = bounded[i].box;
+        b.item = (int)i;
+        for (int a = 0; a < 3; a++) {
+            // pad: the tree must never reject a hit the reference would report (it is only an accelerator)
+            float ext = b.box.hi[a] - b.box.lo[a];
+            float pad = 1e-4f * ext + 1e-5f * std::max(std::fabs(b.box.lo[a]), std::fabs(b.box.hi[a])) + 1e-6f;
+            b.box.lo[a] -= pad;
+            b.box.hi[a] += pad;
+            b.centroid[a] = 0.5f * (b.box.lo[a] + b.box.hi[a]);
+        }
+    }
+    if (!build_items.empty()) {
+        Builder builder{build_items, f.bvh, std::min(std::max(s->leaf_size, 1), 16)};
+        f.bvh.reserve(build_items.size());
+        int root = builder.build(0, (int)build_items.size(), 0);
+        if (root < 0) {  // a single leaf: wrap it so the traversal always starts at an inner node
+            DevBvhNode n;
+            Box b;
+            for (auto& it : build_items) b.grow(it.box);
+            n.a = make_float4(b.lo[0], b.lo[1], b.lo[2], b.hi[0]);
+            n.b = make_float4(b.hi[1], b.hi[2], NAN, NAN);  // second child: a NaN box never passes the slab test
+            n.c = make_float4(NAN, NAN, NAN, NAN);
+            n.d = make_int4(root, root, 0, 0);
+            f.bvh.push_back(n);
+            root = (int)f.bvh.size() - 1;
+        }
+        f.bvh_root = root;
+    }
+
+    // ---- device positions: BVH order, then the linear list, then CSG-internal primitives
+    std::vector<int> item_refs;
+    for (const BuildItem& b : build_items) item_refs.push_back(bounded[b.item].prim);
+    const int n_tree = (int)item_refs.size();
+    for (const Item& it : unbounded) item_refs.push_back(it.prim);
+    const int n_items = (int)item_refs.size();
+    std::vector<int> prim_pos(np, -1), csg_pos(nn, -1);
+    for (int i = 0; i < n_items; i++) {
+        if (item_refs[i] >= 0)
+            prim_pos[item_refs[i]] = i;
+        else
+            csg_pos[~item_refs[i]] = i;
+    }
+    int next = n_items;
+    for (int i = 0; i < np; i++)
+        if (prim_top_csg[i] >= 0) prim_pos[i] = next++;
+    f.n_pos = next;
+    for (int i = n_tree; i < n_items; i++) f.linear.push_back(i);
+
+    // ---- transforms (deduplicated bitwise), triangle and bound tables, heads
+    std::map<std::vector<uint32_t>, int> xf_ids;
+    auto xform_id = [&](const float m[16]) {
+        std::vector<uint32_t> key(12);
+        memcpy(key.data(), m, 12 * sizeof(float));
+        auto it = xf_ids.find(key);
+        if (it != xf_ids.end()) return it->second;
+        int id = (int)f.xform.size() / 3;
+        float4 r[3];
+        rows3(m, r);
+        f.xform.insert(f.xform.end(), r, r + 3);
+        xf_ids.emplace(std::move(key), id);
+        return id;
+    };
+    f.head.assign(2 * (size_t)f.n_pos, make_int4(0, 0, 0, 0));
+    s->pos_to_prim.assign(f.n_pos, -1);
+    for (int i = 0; i < np; i++) {
+        const RtcPrim& p = s->prims[i];
+        int pos = prim_pos[i];
+        int aux = 0;
+        if (p.type == RTC_TRIANGLE) {
+            aux = (int)f.tri.size() / 3;
+            const float* q = p.params;  // p1, e1, e2, normal
+            f.tri.push_back(make_float4(q[0], q[1], q[2], q[3]));
+            f.tri.push_back(make_float4(q[4], q[5], q[6], q[7]));
+            f.tri.push_back(make_float4(q[8], q[9], q[10], q[11]));
+        } else if (p.type == RTC_CYLINDER || p.type == RTC_CONE) {
+            aux = (int)f.bound.size();
+            f.bound.push_back(make_float4(p.params[0], p.params[1], p.params[2] != 0.f ? 1.f : 0.f, 0.f));
+        }
+        int flags = p.casts_shadow ? kFlagCastsShadow : 0;
+        if (!p.casts_shadow) f.all_cast_shadow = 0;
+        bool in_linear = pos >= n_tree && pos < n_items;
+        if (in_linear && p.parent >= 0) flags |= kFlagHasParent;
+        f.head[pos] = make_int4(p.type | (flags << 4) | (p.material << 8), xform_id(p.inv), aux, i);
+        f.head[f.n_pos + pos] = make_int4(prim_top_csg[i] < 0 ? p.parent : -1, i, 0, 0);
+        s->pos_to_prim[pos] = i;
+    }
+
+    // ---- reference shape-tree nodes
+    f.nodes.resize(nn);
+    for (int i = 0; i < nn; i++) {
+        const RtcNode& n = s->nodes[i];
+        DevNode& d = f.nodes[i];
+        rows3(n.inv, d.inv);
+        for (int a = 0; a < 3; a++) d.bmin[a] = n.bbox_min[a], d.bmax[a] = n.bbox_max[a];
+        d.kind = n.kind;
+        d.parent = n.parent;
+        d.op = n.op;
+        d.pad = 0;
+    }
+
+    // ---- CSG programs
+    struct Emit {
+        RtcScene* s;
+        Flattened& f;
+        std::vector<int>& prim_pos;
+        int worst_hits = 0, max_depth = 0;
+        int emit(int ref, int csg_depth) {  // returns worst-case hit count of the subtree
+            if (ref >= 0) {
+                f.ops.push_back(DevCsgOp{OP_PRIM, prim_pos[ref], 0, 0});
+                return max_hits(s->prims[ref].type);
+            }
+            int node = ~ref;
+            const RtcNode& n = s->nodes[node];
+            int total = 0;
+            if (n.kind == RTC_NODE_GROUP) {
+                size_t idx = f.ops.size();
+                f.ops.push_back(DevCsgOp{OP_GROUP, node, 0, 0});
+                for (int c = 0; c < n.child_count; c++) total += emit(s->refs[n.child_begin + c], csg_depth);
+                f.ops[idx].skip = (int)f.ops.size();
+            } else {
+                max_depth = std::max(max_depth, csg_depth + 1);
+                size_t idx = f.ops.size();
+                f.ops.push_back(DevCsgOp{OP_CSG_ENTER, node, 0, 0});
+                total += emit(s->refs[n.child_begin], csg_depth + 1);
+                f.ops.push_back(DevCsgOp{OP_CSG_MID, node, 0, 0});
+                total += emit(s->refs[n.child_begin + 1], csg_depth + 1);
+                f.ops.push_back(DevCsgOp{OP_CSG_EXIT, node, 0, 0});
+                f.ops[idx].skip = (int)f.ops.size();
+            }
+            worst_hits = std::max(worst_hits, total);
+            return total;
+        }
+    } emitter{s, f, prim_pos};
+    for (int i = 0; i < nn; i++) {
+        if (csg_pos[i] < 0) continue;
+        int start = (int)f.ops.size();
+        emitter.emit(~i, 0);
+        int pos = csg_pos[i];
+        // order: depth-first index of the CSG's first leaf (ties are resolved with the leaves' own orders)
+        f.head[pos] = make_int4(T_CSG | (kFlagCastsShadow << 4), 0, start, 0);
+        f.head[f.n_pos + pos] = make_int4(s->nodes[i].parent, -1, 0, 0);
+    }
+    if (emitter.worst_hits > kCsgHitCap)
+        return fail(RTC_ERR_CAPACITY, "a CSG subtree can produce " + std::to_string(emitter.worst_hits) +
+                                          " intersections on one ray; the device hit buffer holds " + std::to_string(kCsgHitCap));
+    if (emitter.max_depth > kCsgRayDepth - 1)
+        return fail(RTC_ERR_CAPACITY, "CSG nesting depth " + std::to_string(emitter.max_depth) + " exceeds " + std::to_string(kCsgRayDepth - 1));
+
+    // ---- shading tables
+    for (const RtcMaterial& m : s->materials) {
+        DevMaterial d{};
+        memcpy(d.color, m.color, sizeof(d.color));
+        d.ambient = m.ambient, d.diffuse = m.diffuse, d.specular = m.specular, d.shininess = m.shininess;
+        d.reflective = m.reflective, d.transparency = m.transparency, d.refractive_index = m.refractive_index;
+        d.pattern = m.pattern;
+        f.materials.push_back(d);
+    }
+    for (const RtcPattern& p : s->patterns) {
+        DevPattern d{};
+        rows3(p.inv, d.inv);
+        memcpy(d.a, p.a, sizeof(d.a));
+        memcpy(d.b, p.b, sizeof(d.b));
+        d.kind = p.kind, d.mapping = p.mapping;
+        memcpy(d.uv, p.uv, sizeof(d.uv));
+        f.patterns.push_back(d);
+    }
+    for (const RtcUvPattern& u : s->uvs) {
+        DevUvPattern d{};
+        d.kind = u.kind;
+        memcpy(d.p, u.params, sizeof(d.p));
+        f.uvs.push_back(d);
+    }
+    // ---- table-mode light samples: point_on_light (rectangle_light.rs:60-66) is the same for every shade
+    if (s->light_is_rect && !s->jitter.empty()) {
+        size_t cursor = 0, L = s->jitter.size();
+        for (int v = 0; v < s->v_steps; v++)
+            for (int u = 0; u < s->u_steps; u++) {
+                float j1 = s->jitter[cursor % L], j2 = s->jitter[(cursor + 1) % L];
+                cursor += 2;
+                float su = (float)u + j1, sv = (float)v + j2;
+                float p[3];
+                for (int a = 0; a < 3; a++) {
+                    volatile float t1 = s->u_cell[a] * su;  // volatile: no host-side contraction / reassociation
+                    volatile float t2 = s->corner[a] + t1;
+                    volatile float t3 = s->v_cell[a] * sv;
+                    p[a] = t2 + t3;
+                }
+                f.samples.push_back(make_float4(p[0], p[1], p[2], 0.f));
+            }
+    }
+    s->n_bvh_nodes = (int)f.bvh.size();
+    s->n_linear = (int)f.linear.size();
+    s->n_xforms = (int)f.xform.size() / 3;
+    return 0;
+}
+
+int upload_replica(RtcScene* s, const Flattened& f, Replica& r) {
+    CUDA_TRY(cudaSetDevice(r.device));
+    CUDA_TRY(cudaStreamCreateWithFlags(&r.stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreate(&r.ev0));
+    CUDA_TRY(cudaEventCreate(&r.ev1));
+    DevScene& d = r.scene;
+    memset(&d, 0, sizeof(d));
+    rows3(s->cam_inv, d.cam_inv);
+    d.half_w = s->half_w, d.half_h = s->half_h, d.pixel_size = s->pixel_size;
+    d.width = (int)s->width, d.height = (int)s->height;
+    d.light_is_rect = s->light_is_rect;
+    memcpy(d.light_pos, s->light_pos, 12);
+    memcpy(d.light_rgb, s->light_rgb, 12);
+    memcpy(d.corner, s->corner, 12);
+    memcpy(d.u_vec, s->u_cell, 12);
+    memcpy(d.v_vec, s->v_cell, 12);
+    d.u_steps = s->u_steps, d.v_steps = s->v_steps, d.cells = s->u_steps * s->v_steps;
+    d.jitter_len = (int)s->jitter.size();
+    d.seed = s->seed;
+    int rc;
+    if ((rc = upload(r, s->jitter, &d.jitter))) return rc;
+    if ((rc = upload(r, f.samples, &d.samples))) return rc;
+    if ((rc = upload(r, f.head, &d.head))) return rc;
+    if ((rc = upload(r, f.xform, &d.xform))) return rc;
+    if ((rc = upload(r, f.tri, &d.tri))) return rc;
+    if ((rc = upload(r, f.bound, &d.bound))) return rc;
+    if ((rc = upload(r, f.bvh, &d.bvh))) return rc;
+    if ((rc = upload(r, f.linear, &d.linear))) return rc;
+    if ((rc = upload(r, f.nodes, &d.nodes))) return rc;
+    if ((rc = upload(r, f.ops, &d.csg_ops))) return rc;
+    if ((rc = upload(r, f.materials, &d.materials))) return rc;
+    if ((rc = upload(r, f.patterns, &d.patterns))) return rc;
+    if ((rc = upload(r, f.uvs, &d.uvs))) return rc;
+    d.n_linear = (int)f.linear.size();
+    d.bvh_root = f.bvh_root;
+    d.n_prims = f.n_pos;
+    d.all_cast_shadow = f.all_cast_shadow;
+    size_t px = (size_t)s->width * s->height;
+    void* p = nullptr;
+    CUDA_TRY(cudaMalloc(&p, std::max<size_t>(px * 3 * sizeof(float), 16)));
+    r.allocs.push_back(p);
+    r.d_rgb = (float*)p;
+    CUDA_TRY(cudaMalloc(&p, std::max<size_t>(px * 3, 16)));
+    r.allocs.push_back(p);
+    r.d_u8 = (unsigned char*)p;
+    CUDA_TRY(cudaMalloc(&p, sizeof(DevCounters)));
+    r.allocs.push_back(p);
+    r.d_counters = (DevCounters*)p;
+    // the kernels keep their bounce and traversal stacks in local memory
+    size_t want = 8192;
+    size_t have = 0;
+    cudaDeviceGetLimit(&have, cudaLimitStackSize);
+    if (have < want) CUDA_TRY(cudaDeviceSetLimit(cudaLimitStackSize, want));
+    return 0;
+}
+
+double flops_of(const RtcStats& st, uint64_t pixels) {
+    const double pf[8] = {30, 2, 29, 45, 50, 46, 0, 0};
+    double f = 33.0 * st.xforms + 26.0 * st.node_visits;
+    for (int i = 0; i < 8; i++) f += pf[i] * st.prim_tests[i];
+    f += 36.0 * st.primary_rays + (85.0 + 75.0 + 9.0) * st.shades + 41.0 * st.patterns;
+    f += 13.0 * st.shadow_rays + 14.0 * st.cells + 20.0 * st.schlicks + 25.0 * st.refr_dirs + 3.0 * pixels;
+    return f;
+}
+
+void add_counters(RtcStats& st, const DevCounters& c) {
+    st.primary_rays += c.primary, st.secondary_rays += c.secondary, st.shadow_rays += c.shadow, st.shades += c.shades;
+    st.node_visits += c.node_visits;
+    for (int i = 0; i < 8; i++) st.prim_tests[i] += c.prim_tests[i];
+    st.xforms += c.xforms, st.patterns += c.patterns, st.cells += c.cells, st.schlicks += c.schlicks;
+    st.refr_dirs += c.refr_dirs, st.capacity_overflows += c.overflows;
+}
+
+// Copy the rows of this shard's bands from the device frame into the caller's full-size canvas.
+int copy_bands(Replica& r, const RtcScene* s, int shard, int n_shards, int n_bands, const void* src, void* dst, size_t px_bytes) {
+    const size_t row = (size_t)s->width * px_bytes;
+    const size_t band = row * kBandRows;
+    if (n_bands <= 0) return 0;
+    if (n_shards == 1) {
+        CUDA_TRY(cudaMemcpyAsync(dst, src, row * s->height, cudaMemcpyDeviceToHost, r.stream));
+        return 0;
+    }
+    // every band but possibly the last one is full height
+    int last_band = shard + (n_bands - 1) * n_shards;
+    int last_rows = std::min<int>(kBandRows, (int)s->height - last_band * kBandRows);
+    int full = (last_rows == kBandRows) ? n_bands : n_bands - 1;
+    size_t off = (size_t)shard * band;
+    if (full > 0)
+        CUDA_TRY(cudaMemcpy2DAsync((char*)dst + off, band * n_shards, (const char*)src + off, band * n_shards, band, full,
+                                   cudaMemcpyDeviceToHost, r.stream));
+    if (full < n_bands) {
+        size_t o2 = (size_t)last_band * band;
+        CUDA_TRY(cudaMemcpyAsync((char*)dst + o2, (const char*)src + o2, row * last_rows, cudaMemcpyDeviceToHost, r.stream));
+    }
+    return 0;
+}
+
+int render_impl(RtcScene* s, int depth, int shard0, int n_shards_ext, float* rgb, uint8_t* u8, RtcStats* stats, bool detailed) {
+    if (!s) return fail(RTC_ERR_INVALID, "null scene");
+    if (!s->committed) return fail(RTC_ERR_STATE, "rtc_render before rtc_scene_commit");
+    if (depth < 0 || depth > kMaxFrames - 1)
+        return fail(RTC_ERR_CAPACITY, "reflection_recursion_depth must be in [0, " + std::to_string(kMaxFrames - 1) + "]");
+    auto t0 = std::chrono::steady_clock::now();
+    const int ndev = (int)s->replicas.size();
+    const bool external = n_shards_ext > 0;
+    if (external && ndev != 1) return fail(RTC_ERR_STATE, "rtc_render_shard needs a scene committed on exactly one device");
+    if (external && (shard0 < 0 || shard0 >= n_shards_ext)) return fail(RTC_ERR_INVALID, "bad shard index");
+    const int n_shards = external ? n_shards_ext : ndev;
+    const int total_bands = ((int)s->height + kBandRows - 1) / kBandRows;
+    RtcStats st;
+    memset(&st, 0, sizeof(st));
+    st.n_devices = ndev;
+    st.detailed = detailed;
+    std::vector<int> bands(ndev, 0);
+    for (int i = 0; i < ndev; i++) {
+        Replica& r = s->replicas[i];
+        int shard = external ? shard0 : i;
+        int nb = shard < total_bands ? (total_bands - shard + n_shards - 1) / n_shards : 0;
+        bands[i] = nb;
+        CUDA_TRY(cudaSetDevice(r.device));
+        CUDA_TRY(cudaMemsetAsync(r.d_counters, 0, sizeof(DevCounters), r.stream));
+        DevFrame F{r.d_rgb, r.d_u8, shard, n_shards, depth, nb};
+        CUDA_TRY(cudaEventRecord(r.ev0, r.stream));
+        if (s->strict_fp)
+            strict::launch_render(r.scene, F, r.d_counters, detailed, r.stream);
+        else
+            fast::launch_render(r.scene, F, r.d_counters, detailed, r.stream);
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaEventRecord(r.ev1, r.stream));
+        int rc;
+        if (rgb && (rc = copy_bands(r, s, shard, n_shards, nb, r.d_rgb, rgb, 3 * sizeof(float)))) return rc;
+        if (u8 && (rc = copy_bands(r, s, shard, n_shards, nb, r.d_u8, u8, 3))) return rc;
+    }
+    for (int i = 0; i < ndev; i++) {
+        Replica& r = s->replicas[i];
+        CUDA_TRY(cudaSetDevice(r.device));
+        CUDA_TRY(cudaStreamSynchronize(r.stream));
+        float ms = 0.f;
+        CUDA_TRY(cudaEventElapsedTime(&ms, r.ev0, r.ev1));
+        st.kernel_ms = std::max(st.kernel_ms, (double)ms);
+        DevCounters c;
+        CUDA_TRY(cudaMemcpy(&c, r.d_counters, sizeof(c), cudaMemcpyDeviceToHost));
+        add_counters(st, c);
+    }
+    st.flops = detailed ? flops_of(st, st.primary_rays) : 0.0;
+    st.total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    if (stats) *stats = st;
+    if (st.capacity_overflows)
+        return fail(RTC_ERR_CAPACITY, "CSG hit buffer overflowed " + std::to_string(st.capacity_overflows) + " times");
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* rtc_last_error(void) { return g_error.c_str(); }
+
+int rtc_device_count(void) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) return fail(RTC_ERR_NO_DEVICE, std::string("cudaGetDeviceCount: ") + cudaGetErrorString(e));
+    return n;
+}
+
+int rtc_scene_create(RtcScene** out) {
+    if (!out) return fail(RTC_ERR_INVALID, "null out pointer");
+    *out = new RtcScene();
+    return 0;
+}
+void rtc_scene_destroy(RtcScene* s) {
+    if (!s) return;
+    release(s);
+    delete s;
+}
+
+int rtc_set_camera(RtcScene* s, uint32_t w, uint32_t h, float half_w, float half_h, float pixel_size, const float inv[16]) {
+    if (!s || !inv) return fail(RTC_ERR_INVALID, "null argument");
+    if (w == 0 || h == 0 || (uint64_t)w * h > (1ull << 31) / 3) return fail(RTC_ERR_INVALID, "bad canvas size");
+    s->width = w, s->height = h, s->half_w = half_w, s->half_h = half_h, s->pixel_size = pixel_size;
+    memcpy(s->cam_inv, inv, sizeof(s->cam_inv));
+    s->have_camera = true;
+    s->committed = false;
+    return 0;
+}
+int rtc_set_primitives(RtcScene* s, uint32_t n, const RtcPrim* prims) {
+    if (!s || (n && !prims)) return fail(RTC_ERR_INVALID, "null argument");
+    if (n >= (1u << 27)) return fail(RTC_ERR_CAPACITY, "too many primitives");
+    s->prims.assign(prims, prims + n);
+    s->committed = false;
+    return 0;
+}
+int rtc_set_nodes(RtcScene* s, uint32_t n_nodes, const RtcNode* nodes, uint32_t n_refs, const int32_t* refs) {
+    if (!s || (n_nodes && !nodes) || (n_refs && !refs)) return fail(RTC_ERR_INVALID, "null argument");
+    s->nodes.assign(nodes, nodes + n_nodes);
+    s->refs.assign(refs, refs + n_refs);
+    s->committed = false;
+    return 0;
+}
+int rtc_set_materials(RtcScene* s, uint32_t n, const RtcMaterial* m) {
+    if (!s || (n && !m)) return fail(RTC_ERR_INVALID, "null argument");
+    if (n >= (1u << 23)) return fail(RTC_ERR_CAPACITY, "too many materials");
+    s->materials.assign(m, m + n);
+    s->committed = false;
+    return 0;
+}
+int rtc_set_patterns(RtcScene* s, uint32_t n, const RtcPattern* p, uint32_t n_uv, const RtcUvPattern* uv) {
+    if (!s || (n && !p) || (n_uv && !uv)) return fail(RTC_ERR_INVALID, "null argument");
+    s->patterns.assign(p, p + n);
+    s->uvs.assign(uv, uv + n_uv);
+    s->committed = false;
+    return 0;
+}
+int rtc_set_point_light(RtcScene* s, const float position[3], const float intensity[3]) {
+    if (!s || !position || !intensity) return fail(RTC_ERR_INVALID, "null argument");
+    s->light_is_rect = false;
+    memcpy(s->light_pos, position, 12);
+    memcpy(s->light_rgb, intensity, 12);
+    memset(s->corner, 0, 12), memset(s->u_cell, 0, 12), memset(s->v_cell, 0, 12);
+    s->u_steps = s->v_steps = 1;
+    s->jitter.clear();
+    s->have_light = true;
+    s->committed = false;
+    return 0;
+}
+int rtc_set_rect_light(RtcScene* s, const float intensity[3], const float corner[3], const float u_cell[3], int32_t u_steps,
+                       const float v_cell[3], int32_t v_steps, const float position[3], const float* table, uint32_t table_len,
+                       uint64_t seed) {
+    if (!s || !intensity || !corner || !u_cell || !v_cell || !position || (table_len && !table))
+        return fail(RTC_ERR_INVALID, "null argument");
+    if (u_steps < 1 || v_steps < 1 || (int64_t)u_steps * v_steps > (1 << 20)) return fail(RTC_ERR_INVALID, "bad light steps");
+    s->light_is_rect = true;
+    memcpy(s->light_rgb, intensity, 12);
+    memcpy(s->corner, corner, 12);
+    memcpy(s->u_cell, u_cell, 12);
+    memcpy(s->v_cell, v_cell, 12);
+    memcpy(s->light_pos, position, 12);
+    s->u_steps = u_steps, s->v_steps = v_steps;
+    s->jitter.assign(table, table + table_len);
+    s->seed = seed;
+    s->have_light = true;
+    s->committed = false;
+    return 0;
+}
+int rtc_set_option(RtcScene* s, int32_t option, int64_t value) {
+    if (!s) return fail(RTC_ERR_INVALID, "null scene");
+    switch (option) {
+        case RTC_OPT_STRICT_FP: s->strict_fp = value != 0; return 0;  // may change between renders
+        case RTC_OPT_BVH_LEAF_SIZE:
+            if (value < 1 || value > 16) return fail(RTC_ERR_INVALID, "leaf size must be in [1,16]");
+            s->leaf_size = (int)value;
+            s->committed = false;
+            return 0;
+        case RTC_OPT_BVH_MIN_PRIMS:
+            s->bvh_min_prims = (int)std::max<int64_t>(0, value);
+            s->committed = false;
+            return 0;
+    }
+    return fail(RTC_ERR_INVALID, "unknown option");
+}
+
+int rtc_scene_commit(RtcScene* s, int32_t n_devices, const int32_t* device_ids) {
+    if (!s) return fail(RTC_ERR_INVALID, "null scene");
+    if (!s->have_camera) return fail(RTC_ERR_STATE, "camera not set");
+    if (!s->have_light) return fail(RTC_ERR_STATE, "World light should be set");  // world.rs:66
+    int visible = rtc_device_count();
+    if (visible < 0) return visible;
+    if (visible == 0) return fail(RTC_ERR_NO_DEVICE, "no CUDA device is visible; this library has no CPU fallback");
+    if (n_devices == 0) n_devices = visible;
+    if (n_devices < 0 || n_devices > visible) return fail(RTC_ERR_INVALID, "bad device count");
+    release(s);
+    Flattened f;
+    int rc = flatten(s, f);
+    if (rc) return rc;
+    s->replicas.resize(n_devices);
+    for (int i = 0; i < n_devices; i++) {
+        s->replicas[i].device = device_ids ? device_ids[i] : i;
+        if (s->replicas[i].device < 0 || s->replicas[i].device >= visible) {
+            release(s);
+            return fail(RTC_ERR_INVALID, "bad device id");
+        }
+        if ((rc = upload_replica(s, f, s->replicas[i]))) {
+            release(s);
+            return rc;
+        }
+    }
+    s->committed = true;
+    return 0;
+}
+
+int rtc_render(RtcScene* s, int32_t depth, float* rgb, uint8_t* u8, RtcStats* stats) {
+    return render_impl(s, depth, 0, 0, rgb, u8, stats, false);
+}
+int rtc_render_shard(RtcScene* s, int32_t depth, int32_t shard, int32_t n_shards, float* rgb, uint8_t* u8, RtcStats* stats) {
+    if (n_shards < 1) return fail(RTC_ERR_INVALID, "n_shards must be >= 1");
+    return render_impl(s, depth, shard, n_shards, rgb, u8, stats, false);
+}
+int rtc_render_detailed(RtcScene* s, int32_t depth, float* rgb, uint8_t* u8, RtcStats* stats) {
+    return render_impl(s, depth, 0, 0, rgb, u8, stats, true);
+}
+
+int rtc_trace_rays(RtcScene* s, uint32_t n, const float* origins, const float* directions, int32_t depth, float* out_rgb,
+                   float* out_t, int32_t* out_prim) {
+    if (!s || !origins || !directions || !out_rgb) return fail(RTC_ERR_INVALID, "null argument");
+    if (!s->committed) return fail(RTC_ERR_STATE, "rtc_trace_rays before rtc_scene_commit");
+    if (depth < 0 || depth > kMaxFrames - 1) return fail(RTC_ERR_CAPACITY, "depth out of range");
+    if (n == 0) return 0;
+    Replica& r = s->replicas[0];
+    CUDA_TRY(cudaSetDevice(r.device));
+    float *d_o = nullptr, *d_d = nullptr, *d_rgb = nullptr, *d_t = nullptr;
+    int* d_pos = nullptr;
+    size_t b3 = (size_t)n * 3 * sizeof(float);
+    CUDA_TRY(cudaMalloc(&d_o, b3));
+    CUDA_TRY(cudaMalloc(&d_d, b3));
+    CUDA_TRY(cudaMalloc(&d_rgb, b3));
+    CUDA_TRY(cudaMalloc(&d_t, (size_t)n * sizeof(float)));
+    CUDA_TRY(cudaMalloc(&d_pos, (size_t)n * sizeof(int)));
+    CUDA_TRY(cudaMemcpyAsync(d_o, origins, b3, cudaMemcpyHostToDevice, r.stream));
+    CUDA_TRY(cudaMemcpyAsync(d_d, directions, b3, cudaMemcpyHostToDevice, r.stream));
+    CUDA_TRY(cudaMemsetAsync(r.d_counters, 0, sizeof(DevCounters), r.stream));
+    if (s->strict_fp)
+        strict::launch_trace(r.scene, (int)n, d_o, d_d, depth, d_rgb, d_t, d_pos, r.d_counters, r.stream);
+    else
+        fast::launch_trace(r.scene, (int)n, d_o, d_d, depth, d_rgb, d_t, d_pos, r.d_counters, r.stream);
+    CUDA_TRY(cudaGetLastError());
+    std::vector<int> pos(n);
+    CUDA_TRY(cudaMemcpyAsync(out_rgb, d_rgb, b3, cudaMemcpyDeviceToHost, r.stream));
+    if (out_t) CUDA_TRY(cudaMemcpyAsync(out_t, d_t, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, r.stream));
+    CUDA_TRY(cudaMemcpyAsync(pos.data(), d_pos, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, r.stream));
+    CUDA_TRY(cudaStreamSynchronize(r.stream));
+    if (out_prim)
+        for (uint32_t i = 0; i < n; i++) out_prim[i] = pos[i] >= 0 ? s->pos_to_prim[pos[i]] : -1;
+    cudaFree(d_o), cudaFree(d_d), cudaFree(d_rgb), cudaFree(d_t), cudaFree(d_pos);
+    return 0;
+}
+
+void* rtc_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) {
+        g_error = "cudaHostAlloc failed";
+        return nullptr;
+    }
+    return p;
+}
+void rtc_host_free(void* p) {
+    if (p) cudaFreeHost(p);
+}
+int rtc_host_register(void* ptr, size_t bytes) {
+    CUDA_TRY(cudaHostRegister(ptr, bytes, cudaHostRegisterPortable));
+    return 0;
+}
+int rtc_host_unregister(void* ptr) {
+    CUDA_TRY(cudaHostUnregister(ptr));
+    return 0;
+}
+
+int rtc_flush_l2(RtcScene* s) {
+    if (!s || !s->committed) return fail(RTC_ERR_STATE, "scene not committed");
+    for (Replica& r : s->replicas) {
+        CUDA_TRY(cudaSetDevice(r.device));
+        if (!r.d_flush) {
+            r.flush_bytes = 256u << 20;  // > 126 MB L2
+            CUDA_TRY(cudaMalloc(&r.d_flush, r.flush_bytes));
+        }
+        CUDA_TRY(cudaMemsetAsync(r.d_flush, 0x5a, r.flush_bytes, r.stream));
+        CUDA_TRY(cudaStreamSynchronize(r.stream));
+    }
+    return 0;
+}
+
+int rtc_measure_fp32_peak(int32_t device, double* tflops, double* sm_clock_mhz) {
+    if (!tflops) return fail(RTC_ERR_INVALID, "null argument");
+    CUDA_TRY(cudaSetDevice(device));
+    int sms = 0, khz = 0;
+    CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    CUDA_TRY(cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, device));
+    if (sm_clock_mhz) *sm_clock_mhz = khz / 1000.0;
+    float* d = nullptr;
+    CUDA_TRY(cudaMalloc(&d, 64));
+    cudaEvent_t e0, e1;
+    CUDA_TRY(cudaEventCreate(&e0));
+    CUDA_TRY(cudaEventCreate(&e1));
+    const int blocks = sms * 16, iters = 32768;
+    double best = 0;
+    for (int rep = 0; rep < 4; rep++) {
+        CUDA_TRY(cudaEventRecord(e0, 0));
+        fast::launch_fma_peak(d, blocks, iters, 0);
+        CUDA_TRY(cudaEventRecord(e1, 0));
+        CUDA_TRY(cudaEventSynchronize(e1));
+        float ms = 0;
+        CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+        double fl = (double)blocks * 256 * 8 * 2 * iters;
+        if (rep > 0) best = std::max(best, fl / (ms * 1e-3) / 1e12);
+    }
+    *tflops = best;
+    cudaEventDestroy(e0), cudaEventDestroy(e1), cudaFree(d);
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,1016 @@
+// rtc_device.cuh — device functions of the B200 path for the reference's Camera::render hot loop.
+//
+// One thread owns one pixel sample end to end: ray generation (camera.rs:60-74), world intersection
+// (world.rs:52-60 — here a BVH walk with a short per-thread stack instead of the reference's linear scan
+// and sort), the hit record (world.rs:212-283), Phong + patterns (phong_lighting.rs:12-63), shadow rays
+// and the area-light cell loop (world.rs:104-119, rectangle_light.rs:76-88), and the reflect / refract
+// recursion (world.rs:121-162) unrolled into an explicit bounded stack that keeps the reference's
+// post-order arithmetic, so every colour is combined in exactly the order the Rust code combines it.
+//
+// Arithmetic is spelled left to right exactly as the reference spells it.  This file is compiled twice
+// (rtc_kernels.cu): once with FMA contraction (the fast build) and once with -fmad=false (RTC_STRICT), the
+// latter reproducing the Rust/IEEE evaluation bit for bit apart from libm (powf, cosf, atan2f, acosf).
+#pragma once
+#include <cuda_runtime.h>
+#include <math_constants.h>
+
+#include "rtc_types.h"
+
+#ifndef RTC_NS
+#error "define RTC_NS (fast | strict) before including rtc_device.cuh"
+#endif
+
+namespace rtc {
+namespace RTC_NS {
+
+struct V3 {
+    float x, y, z;
+};
+__device__ __forceinline__ V3 mk(float x, float y, float z) { return V3{x, y, z}; }
+__device__ __forceinline__ V3 operator+(V3 a, V3 b) { return mk(a.x + b.x, a.y + b.y, a.z + b.z); }
+__device__ __forceinline__ V3 operator-(V3 a, V3 b) { return mk(a.x - b.x, a.y - b.y, a.z - b.z); }
+__device__ __forceinline__ V3 operator*(V3 a, float s) { return mk(a.x * s, a.y * s, a.z * s); }
+__device__ __forceinline__ V3 operator*(V3 a, V3 b) { return mk(a.x * b.x, a.y * b.y, a.z * b.z); }
+__device__ __forceinline__ V3 operator/(V3 a, float s) { return mk(a.x / s, a.y / s, a.z / s); }
+__device__ __forceinline__ V3 operator-(V3 a) { return mk(-a.x, -a.y, -a.z); }
+// tuple.rs:44-46 (the w lanes are 0 for every hot-path call)
+__device__ __forceinline__ float dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+// tuple.rs:29-43
+__device__ __forceinline__ float magnitude(V3 a) { return sqrtf(a.x * a.x + a.y * a.y + a.z * a.z); }
+__device__ __forceinline__ V3 norm(V3 a) {
+    float m = magnitude(a);
+    return mk(a.x / m, a.y / m, a.z / m);
+}
+__device__ __forceinline__ V3 ld3(const float* p) { return mk(p[0], p[1], p[2]); }
+// ray.rs:42-44
+__device__ __forceinline__ V3 reflect(V3 in, V3 n) { return -(n * 2.0f * dot(in, n) - in); }
+
+struct Xf {
+    float4 r0, r1, r2;
+};
+__device__ __forceinline__ Xf load_xf(const float4* p) { return Xf{__ldg(p), __ldg(p + 1), __ldg(p + 2)}; }
+// matrix.rs:73-84 with w = 1 / w = 0 (the products with an exact 0 or 1 are exact)
+__device__ __forceinline__ V3 xf_point(const Xf& m, V3 p) {
+    return mk(m.r0.x * p.x + m.r0.y * p.y + m.r0.z * p.z + m.r0.w, m.r1.x * p.x + m.r1.y * p.y + m.r1.z * p.z + m.r1.w,
+              m.r2.x * p.x + m.r2.y * p.y + m.r2.z * p.z + m.r2.w);
+}
+__device__ __forceinline__ V3 xf_vec(const Xf& m, V3 v) {
+    return mk(m.r0.x * v.x + m.r0.y * v.y + m.r0.z * v.z, m.r1.x * v.x + m.r1.y * v.y + m.r1.z * v.z,
+              m.r2.x * v.x + m.r2.y * v.y + m.r2.z * v.z);
+}
+// shape.rs:130 — inverse-transpose times the object normal = transpose of the stored inverse
+__device__ __forceinline__ V3 xf_normal(const Xf& m, V3 n) {
+    return mk(m.r0.x * n.x + m.r1.x * n.y + m.r2.x * n.z, m.r0.y * n.x + m.r1.y * n.y + m.r2.y * n.z,
+              m.r0.z * n.x + m.r1.z * n.y + m.r2.z * n.z);
+}
+
+constexpr float kInfF = __builtin_huge_valf();
+constexpr float kAcne = 1.1920929e-7f * 10000.0f;  // world.rs:210
+constexpr float kCloseToZero = 0.000001f;           // cylinder.rs:82, cone.rs:87
+
+// Work counters.  The plain build keeps only the four ray/shade counts (one register each); the detailed
+// build (STATS) also counts every unit of Appendix E.
+template <bool STATS>
+struct Ctr;
+template <>
+struct Ctr<false> {
+    unsigned primary = 0, secondary = 0, shadow = 0, shades = 0;
+    __device__ __forceinline__ void node() {}
+    __device__ __forceinline__ void prim(int) {}
+    __device__ __forceinline__ void xform() {}
+    __device__ __forceinline__ void pattern() {}
+    __device__ __forceinline__ void cell() {}
+    __device__ __forceinline__ void schlick() {}
+    __device__ __forceinline__ void refr_dir() {}
+    __device__ __forceinline__ void overflow() {}
+};
+template <>
+struct Ctr<true> {
+    unsigned primary = 0, secondary = 0, shadow = 0, shades = 0;
+    unsigned nodes = 0, prims[8] = {0, 0, 0, 0, 0, 0, 0, 0}, xforms = 0, patterns = 0, cells = 0, schlicks = 0, refr_dirs = 0,
+             overflows = 0;
+    __device__ __forceinline__ void node() { nodes++; }
+    __device__ __forceinline__ void prim(int t) { prims[t]++; }
+    __device__ __forceinline__ void xform() { xforms++; }
+    __device__ __forceinline__ void pattern() { patterns++; }
+    __device__ __forceinline__ void cell() { cells++; }
+    __device__ __forceinline__ void schlick() { schlicks++; }
+    __device__ __forceinline__ void refr_dir() { refr_dirs++; }
+    __device__ __forceinline__ void overflow() { overflows++; }
+};
+
+// ---------------------------------------------------------------------------------------------------
+// cube.rs:90-129 — the reference's slab test, used for Cube::local_intersect and for every group / CSG
+// bounding-box cull that has to be reproduced exactly.  fminf/fmaxf return the non-NaN operand like Rust's
+// f32::min/max.
+__device__ __forceinline__ bool aabb_ref(V3 o, V3 d, V3 mn, V3 mx, float& lo, float& hi) {
+    V3 inv = mk(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);  // ray.rs:16
+    float a = (mn.x - o.x) * inv.x, b = (mx.x - o.x) * inv.x;
+    lo = fminf(a, b);
+    hi = fmaxf(a, b);
+    a = (mn.y - o.y) * inv.y, b = (mx.y - o.y) * inv.y;
+    lo = fmaxf(lo, fminf(a, b));
+    hi = fminf(hi, fmaxf(a, b));
+    a = (mn.z - o.z) * inv.z, b = (mx.z - o.z) * inv.z;
+    lo = fmaxf(lo, fminf(a, b));
+    hi = fminf(hi, fmaxf(a, b));
+    return hi >= fmaxf(0.0f, lo);
+}
+
+// Shape::local_intersect of every leaf kind.  Writes the distances in the reference's emission order and
+// returns how many there are (0..4).
+__device__ __forceinline__ int local_intersect(const DevScene& S, int type, int aux, V3 o, V3 d, float t[4]) {
+    switch (type) {
+        case T_SPHERE: {  // sphere.rs:47-70 (centre is the origin)
+            float a = dot(d, d);
+            float b = 2.0f * dot(d, o);
+            float c = dot(o, o) - 1.0f;
+            float disc = b * b - 4.0f * a * c;
+            if (disc < 0.0f) return 0;
+            float two_a = 2.0f * a;
+            float ds = sqrtf(disc);
+            t[0] = (-b - ds) / two_a;
+            t[1] = (-b + ds) / two_a;
+            return 2;
+        }
+        case T_PLANE: {  // plane.rs:45-56
+            if (fabsf(d.y) < kAcne) return 0;
+            t[0] = -o.y / d.y;
+            return 1;
+        }
+        case T_CUBE: {  // cube.rs:55-63
+            float lo, hi;
+            if (!aabb_ref(o, d, mk(-1.f, -1.f, -1.f), mk(1.f, 1.f, 1.f), lo, hi)) return 0;
+            t[0] = lo;
+            t[1] = hi;
+            return 2;
+        }
+        case T_CYLINDER: {  // cylinder.rs:52-59, 84-151
+            float4 bd = __ldg(&S.bound[aux]);
+            int n = 0;
+            float two_a = 2.0f * (d.x * d.x + d.z * d.z);
+            if (!(fabsf(two_a) < kCloseToZero)) {
+                float b = 2.0f * (o.x * d.x + o.z * d.z);
+                float c = o.x * o.x + o.z * o.z - 1.0f;
+                float disc = b * b - 2.0f * two_a * c;
+                if (!(disc < 0.0f)) {
+                    float ds = sqrtf(disc);
+                    float d1 = (-b - ds) / two_a;
+                    float d2 = (-b + ds) / two_a;
+                    if (d1 > d2) {
+                        float tmp = d1;
+                        d1 = d2;
+                        d2 = tmp;
+                    }
+                    float y1 = o.y + d1 * d.y;
+                    if (bd.x < y1 && y1 < bd.y) t[n++] = d1;
+                    float y2 = o.y + d2 * d.y;
+                    if (bd.x < y2 && y2 < bd.y) t[n++] = d2;
+                }
+            }
+            if (n < 2 && bd.z != 0.0f) {  // caps only when the walls gave fewer than two hits
+                float tc = (bd.x - o.y) / d.y;
+                float x = o.x + tc * d.x, z = o.z + tc * d.z;
+                if ((x * x + z * z) <= 1.0f + kCloseToZero) t[n++] = tc;
+                tc = (bd.y - o.y) / d.y;
+                x = o.x + tc * d.x, z = o.z + tc * d.z;
+                if ((x * x + z * z) <= 1.0f + kCloseToZero) t[n++] = tc;
+            }
+            return n;
+        }
+        case T_CONE: {  // cone.rs:52-57, 89-174
+            float4 bd = __ldg(&S.bound[aux]);
+            int n = 0;
+            float two_a = 2.0f * (d.x * d.x - d.y * d.y + d.z * d.z);
+            float b = 2.0f * (o.x * d.x - o.y * d.y + o.z * d.z);
+            if (fabsf(two_a) < kCloseToZero) {
+                if (!(fabsf(b) < kCloseToZero)) {
+                    float c = o.x * o.x - o.y * o.y + o.z * o.z;
+                    t[n++] = -c / (2.0f * b);
+                }
+            } else {
+                float c = o.x * o.x - o.y * o.y + o.z * o.z;
+                float disc = b * b - 2.0f * two_a * c;
+                if (!(disc < 0.0f)) {
+                    float ds = sqrtf(disc);
+                    float d1 = (-b - ds) / two_a;
+                    float d2 = (-b + ds) / two_a;
+                    if (d1 > d2) {
+                        float tmp = d1;
+                        d1 = d2;
+                        d2 = tmp;
+                    }
+                    float y1 = o.y + d1 * d.y;
+                    if (bd.x < y1 && y1 < bd.y) t[n++] = d1;
+                    float y2 = o.y + d2 * d.y;
+                    if (bd.x < y2 && y2 < bd.y) t[n++] = d2;
+                }
+            }
+            if (bd.z != 0.0f) {  // caps are always tested; the radius is |y|, not y^2
+                float tc = (bd.x - o.y) / d.y;
+                float x = o.x + tc * d.x, z = o.z + tc * d.z;
+                if ((x * x + z * z) <= fabsf(bd.x) + kCloseToZero) t[n++] = tc;
+                tc = (bd.y - o.y) / d.y;
+                x = o.x + tc * d.x, z = o.z + tc * d.z;
+                if ((x * x + z * z) <= fabsf(bd.y) + kCloseToZero) t[n++] = tc;
+            }
+            return n;
+        }
+        default: {  // T_TRIANGLE — triangle.rs:45-76
+            const float4* tp = S.tri + 3 * (size_t)aux;
+            float4 q0 = __ldg(tp), q1 = __ldg(tp + 1), q2 = __ldg(tp + 2);
+            V3 p1 = mk(q0.x, q0.y, q0.z), e1 = mk(q0.w, q1.x, q1.y), e2 = mk(q1.z, q1.w, q2.x);
+            V3 dce2 = mk(d.y * e2.z - d.z * e2.y, d.z * e2.x - d.x * e2.z, d.x * e2.y - d.y * e2.x);
+            float det = dot(e1, dce2);
+            if (fabsf(det) < 0.0000001f) return 0;
+            float f = 1.0f / det;
+            V3 p1o = o - p1;
+            float u = f * dot(p1o, dce2);
+            if (u < 0.0f || u > 1.0f) return 0;
+            V3 oce1 = mk(p1o.y * e1.z - p1o.z * e1.y, p1o.z * e1.x - p1o.x * e1.z, p1o.x * e1.y - p1o.y * e1.x);
+            float v = f * dot(d, oce1);
+            if (v < 0.0f || (u + v) > 1.0f) return 0;
+            t[0] = f * dot(e2, oce1);
+            return 1;
+        }
+    }
+}
+
+// Shape::local_norm_at of every leaf kind.
+__device__ __forceinline__ V3 local_normal(const DevScene& S, int type, int aux, V3 p) {
+    switch (type) {
+        case T_SPHERE: return p;                      // sphere.rs:71-73
+        case T_PLANE: return mk(0.f, 1.f, 0.f);       // plane.rs:57-59
+        case T_CUBE: {                                // cube.rs:66-80
+            float xa = fabsf(p.x), ya = fabsf(p.y), za = fabsf(p.z);
+            float mc = fmaxf(xa, fmaxf(ya, za));
+            if (xa == mc) return mk(p.x, 0.f, 0.f);
+            if (ya == mc) return mk(0.f, p.y, 0.f);
+            return mk(0.f, 0.f, p.z);
+        }
+        case T_CYLINDER: {  // cylinder.rs:62-72
+            float4 bd = __ldg(&S.bound[aux]);
+            float dist2 = p.x * p.x + p.z * p.z;
+            if (dist2 < 1.0f) {
+                if (p.y >= bd.y - kCloseToZero) return mk(0.f, 1.f, 0.f);
+                if (p.y <= bd.x + kCloseToZero) return mk(0.f, -1.f, 0.f);
+            }
+            return mk(p.x, 0.f, p.z);
+        }
+        case T_CONE: {  // cone.rs:60-73
+            float4 bd = __ldg(&S.bound[aux]);
+            float dist2 = p.x * p.x + p.z * p.z;
+            if (dist2 < 1.0f) {
+                if (p.y >= bd.y - kCloseToZero) return mk(0.f, 1.f, 0.f);
+                if (p.y <= bd.x + kCloseToZero) return mk(0.f, -1.f, 0.f);
+            }
+            float y = sqrtf(p.x * p.x + p.z * p.z);
+            y = (p.y > 0.0f) ? -y : y;
+            return mk(p.x, y, p.z);
+        }
+        default: {  // triangle.rs:78-81 — the flat normal precomputed at construction (also for smooth triangles, Q5)
+            float4 q2 = __ldg(S.tri + 3 * (size_t)aux + 2);
+            return mk(q2.y, q2.z, q2.w);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Nearest hit so far.  `order` is the primitive's depth-first index: the reference's tie-break (Q8).
+struct Hit {
+    float t;
+    int pos;
+    int order;
+};
+__device__ __forceinline__ void consider(Hit& best, float t, int pos, int order) {
+    if (t >= 0.0f && (t < best.t || (t == best.t && order < best.order))) {
+        best.t = t;
+        best.pos = pos;
+        best.order = order;
+    }
+}
+
+// The world ray as seen by the primitive being tested; cached by transform id so that a mesh whose
+// triangles share one transform pays for one ray transform per traversal, not one per triangle.
+struct ObjRay {
+    int xf_id = -1;
+    V3 o, d;
+};
+
+// Every enclosing GroupShape culls with the forward ray (group.rs:119-125); the walk stops at a CSG because
+// CSG subtrees are evaluated whole by csg_eval.
+__device__ __forceinline__ bool ancestors_pass(const DevScene& S, int node, V3 o, V3 d) {
+    while (node >= 0) {
+        const DevNode& n = S.nodes[node];
+        float lo, hi;
+        if (!aabb_ref(o, d, ld3(n.bmin), ld3(n.bmax), lo, hi)) return false;
+        node = n.parent;
+    }
+    return true;
+}
+
+// CSG::local_intersect (csg.rs:87-104) for a whole CSG subtree, flattened at commit time into a post-order
+// instruction list.  ht/hp receive the filtered hits (distance, primitive position) in the reference's
+// sorted order; returns their count.
+template <bool STATS>
+__device__ __noinline__ int csg_eval(const DevScene& S, int pc, V3 wo, V3 wd, float* ht, int* hp, Ctr<STATS>& k) {
+    V3 ro[kCsgRayDepth], rd[kCsgRayDepth];
+    int s_mark[kCsgRayDepth], m_mark[kCsgRayDepth];
+    int rsp = 0, n = 0;
+    ro[0] = wo;
+    rd[0] = wd;
+    k.prim(T_CSG);
+    const int end = S.csg_ops[pc].skip;  // the root's ENTER skips to one past its EXIT
+    while (pc < end) {
+        DevCsgOp op = S.csg_ops[pc];
+        switch (op.op) {
+            case OP_CSG_ENTER: {
+                const DevNode& nd = S.nodes[op.arg];
+                Xf m{nd.inv[0], nd.inv[1], nd.inv[2]};
+                V3 o2 = xf_point(m, ro[rsp]), d2 = xf_vec(m, rd[rsp]);  // shape.rs:60-70 on the CSG itself
+                k.xform();
+                float lo, hi;
+                k.node();
+                if (!aabb_ref(o2, d2, ld3(nd.bmin), ld3(nd.bmax), lo, hi)) {  // csg.rs:90-93
+                    pc = op.skip;
+                    break;
+                }
+                rsp++;
+                ro[rsp] = o2;
+                rd[rsp] = d2;
+                s_mark[rsp] = n;
+                pc++;
+                break;
+            }
+            case OP_CSG_MID:
+                m_mark[rsp] = n;
+                pc++;
+                break;
+            case OP_CSG_EXIT: {
+                const int s = s_mark[rsp], m = m_mark[rsp], e = n;
+                const int csg_op = S.nodes[op.arg].op;
+                for (int i = s; i < m; i++) hp[i] |= 0x40000000;  // came from s1 (csg.rs:46 `s1.includes`)
+                for (int i = s + 1; i < e; i++) {                 // stable insertion sort by distance (csg.rs:101)
+                    float ti = ht[i];
+                    int pi = hp[i];
+                    int j = i - 1;
+                    while (j >= s && ht[j] > ti) {
+                        ht[j + 1] = ht[j];
+                        hp[j + 1] = hp[j];
+                        j--;
+                    }
+                    ht[j + 1] = ti;
+                    hp[j + 1] = pi;
+                }
+                bool in1 = false, in2 = false;  // csg.rs:37-58
+                int w = s;
+                for (int i = s; i < e; i++) {
+                    bool hit1 = (hp[i] & 0x40000000) != 0;
+                    bool allowed;
+                    if (csg_op == 0)
+                        allowed = (hit1 && !in2) || (!hit1 && !in1);
+                    else if (csg_op == 1)
+                        allowed = (hit1 && in2) || (!hit1 && in1);
+                    else
+                        allowed = (hit1 && !in2) || (!hit1 && in1);
+                    if (allowed) {
+                        ht[w] = ht[i];
+                        hp[w] = hp[i] & 0x3fffffff;
+                        w++;
+                    }
+                    if (hit1)
+                        in1 = !in1;
+                    else
+                        in2 = !in2;
+                }
+                n = w;
+                rsp--;
+                pc++;
+                break;
+            }
+            case OP_GROUP: {
+                const DevNode& nd = S.nodes[op.arg];
+                float lo, hi;
+                k.node();
+                if (!aabb_ref(ro[rsp], rd[rsp], ld3(nd.bmin), ld3(nd.bmax), lo, hi))  // group.rs:122-125
+                    pc = op.skip;
+                else
+                    pc++;
+                break;
+            }
+            default: {  // OP_PRIM
+                int4 h = __ldg(&S.head[op.arg]);
+                Xf m = load_xf(S.xform + 3 * (size_t)h.y);
+                V3 o2 = xf_point(m, ro[rsp]), d2 = xf_vec(m, rd[rsp]);
+                k.xform();
+                float t[4];
+                int type = h.x & 15;
+                k.prim(type);
+                int c = local_intersect(S, type, h.z, o2, d2, t);
+                for (int i = 0; i < c; i++) {
+                    if (n < kCsgHitCap) {
+                        ht[n] = t[i];
+                        hp[n] = op.arg;
+                        n++;
+                    } else {
+                        k.overflow();
+                    }
+                }
+                pc++;
+                break;
+            }
+        }
+    }
+    return n;
+}
+
+// Test one stored primitive against the world ray for the nearest-hit search.
+template <bool STATS>
+__device__ __forceinline__ void test_prim(const DevScene& S, int pos, V3 o, V3 d, ObjRay& cache, Hit& best, Ctr<STATS>& k) {
+    int4 h = __ldg(&S.head[pos]);
+    int type = h.x & 15;
+    if (type == T_CSG) {
+        float ht[kCsgHitCap];
+        int hp[kCsgHitCap];
+        int n = csg_eval<STATS>(S, h.z, o, d, ht, hp, k);
+        for (int i = 0; i < n; i++) {
+            if (ht[i] >= 0.0f) {
+                consider(best, ht[i], hp[i], __ldg(&S.head[hp[i]]).w);
+                break;  // the list is sorted: the first non-negative entry is this CSG's nearest
+            }
+        }
+        return;
+    }
+    if (h.y != cache.xf_id) {  // shape.rs:60-70 / ray.rs:26-31
+        Xf m = load_xf(S.xform + 3 * (size_t)h.y);
+        cache.o = xf_point(m, o);
+        cache.d = xf_vec(m, d);
+        cache.xf_id = h.y;
+        k.xform();
+    }
+    float t[4];
+    k.prim(type);
+    int n = local_intersect(S, type, h.z, cache.o, cache.d, t);
+    float tn = kInfF;
+    bool any = false;
+    for (int i = 0; i < n; i++) {
+        if (t[i] >= 0.0f && t[i] <= tn) {
+            tn = fminf(tn, t[i]);
+            any = true;
+        }
+    }
+    if (!any) return;
+    if (((h.x >> 4) & kFlagHasParent) && !ancestors_pass(S, __ldg(&S.head[pos + S.n_prims]).x, o, d)) return;
+    consider(best, tn, pos, h.w);
+}
+
+// Conservative slab test for the acceleration structure (boxes are padded at build time, so this never
+// rejects a primitive the reference would have hit; it is not part of the reference's semantics).
+__device__ __forceinline__ bool slab(V3 o, V3 inv, float lx, float ly, float lz, float hx, float hy, float hz, float tmax,
+                                     float& tnear) {
+    float a = (lx - o.x) * inv.x, b = (hx - o.x) * inv.x;
+    float lo = fminf(a, b), hi = fmaxf(a, b);
+    a = (ly - o.y) * inv.y, b = (hy - o.y) * inv.y;
+    lo = fmaxf(lo, fminf(a, b));
+    hi = fminf(hi, fmaxf(a, b));
+    a = (lz - o.z) * inv.z, b = (hz - o.z) * inv.z;
+    lo = fmaxf(lo, fminf(a, b));
+    hi = fminf(hi, fmaxf(a, b));
+    tnear = lo;
+    return hi >= fmaxf(lo, 0.0f) && lo <= tmax;
+}
+
+// World::intersect + Intersection::hit (world.rs:52-60, intersection.rs:30-35): nearest t >= 0 with the
+// depth-first tie-break, searched through the BVH.  `best.t` on entry is the search limit (exclusive).
+// ANY: stop at the first hit (shadow rays when every primitive casts a shadow).
+template <bool STATS, bool ANY>
+__device__ __forceinline__ void nearest_hit(const DevScene& S, V3 o, V3 d, Hit& best, Ctr<STATS>& k) {
+    ObjRay cache;
+    for (int i = 0; i < S.n_linear; i++) {
+        test_prim<STATS>(S, __ldg(&S.linear[i]), o, d, cache, best, k);
+        if (ANY && best.pos >= 0) return;
+    }
+    if (S.bvh_root < 0) return;
+    V3 inv = mk(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+    int stack[kBvhStack];
+    int sp = 0;
+    int node = S.bvh_root;
+    for (;;) {
+        if (node >= 0) {
+            const float4* np = reinterpret_cast<const float4*>(S.bvh + node);
+            float4 a = __ldg(np), b = __ldg(np + 1), c = __ldg(np + 2);
+            int4 link = __ldg(reinterpret_cast<const int4*>(np + 3));
+            float t0, t1;
+            k.node();
+            k.node();
+            bool h0 = slab(o, inv, a.x, a.y, a.z, a.w, b.x, b.y, best.t, t0);
+            bool h1 = slab(o, inv, b.z, b.w, c.x, c.y, c.z, c.w, best.t, t1);
+            if (h0 && h1) {
+                int near = link.x, far = link.y;
+                if (t1 < t0) {
+                    near = link.y;
+                    far = link.x;
+                }
+                if (sp < kBvhStack) stack[sp++] = far;
+                node = near;
+                continue;
+            }
+            if (h0) {
+                node = link.x;
+                continue;
+            }
+            if (h1) {
+                node = link.y;
+                continue;
+            }
+        } else {
+            int code = ~node;
+            int first = code >> 4, count = (code & 15) + 1;
+            for (int i = 0; i < count; i++) {
+                test_prim<STATS>(S, first + i, o, d, cache, best, k);
+                if (ANY && best.pos >= 0) return;
+            }
+        }
+        if (sp == 0) return;
+        node = stack[--sp];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// n1 / n2 (world.rs:235-263) without materialising the sorted list.  In the render
+// path the hit is the first t >= 0 entry, so the containers are decided by the NEGATIVE-t intersections:
+// an object is open when it has an odd number of them, and the open object whose last negative hit is
+// latest in the sorted order (t, then depth-first order) is the innermost one.
+struct Containers {
+    float best_t = -kInfF;  // innermost open object other than the hit object
+    int best_order = -1;
+    int best_pos = -1;
+    bool hit_open = false;  // the hit object itself is open (we are leaving it)
+    float hit_t = -kInfF;
+    int hit_order = -1;
+};
+__device__ __forceinline__ void container_add(Containers& c, int hit_pos, float t_last, int pos, int order) {
+    if (pos == hit_pos) {
+        c.hit_open = true;
+        c.hit_t = t_last;
+        c.hit_order = order;
+    } else if (t_last > c.best_t || (t_last == c.best_t && order > c.best_order)) {
+        c.best_t = t_last;
+        c.best_order = order;
+        c.best_pos = pos;
+    }
+}
+template <bool STATS>
+__device__ __forceinline__ void container_prim(const DevScene& S, int pos, V3 o, V3 d, ObjRay& cache, int hit_pos, Containers& c,
+                                               Ctr<STATS>& k) {
+    int4 h = __ldg(&S.head[pos]);
+    int type = h.x & 15;
+    if (type == T_CSG) {
+        float ht[kCsgHitCap];
+        int hp[kCsgHitCap];
+        int n = csg_eval<STATS>(S, h.z, o, d, ht, hp, k);
+        // per leaf: parity and last negative hit among the filtered hits
+        for (int i = 0; i < n; i++) {
+            if (!(ht[i] < 0.0f)) break;
+            int p = hp[i];
+            bool seen = false;
+            for (int j = 0; j < i; j++) seen |= (hp[j] == p);
+            if (seen) continue;
+            int cnt = 0;
+            float last = 0.f;
+            for (int j = i; j < n && ht[j] < 0.0f; j++)
+                if (hp[j] == p) {
+                    cnt++;
+                    last = ht[j];
+                }
+            if (cnt & 1) container_add(c, hit_pos, last, p, __ldg(&S.head[p]).w);
+        }
+        return;
+    }
+    if (h.y != cache.xf_id) {
+        Xf m = load_xf(S.xform + 3 * (size_t)h.y);
+        cache.o = xf_point(m, o);
+        cache.d = xf_vec(m, d);
+        cache.xf_id = h.y;
+        k.xform();
+    }
+    float t[4];
+    k.prim(type);
+    int n = local_intersect(S, type, h.z, cache.o, cache.d, t);
+    int cnt = 0;
+    float last = -kInfF;
+    for (int i = 0; i < n; i++)
+        if (t[i] < 0.0f) {
+            cnt++;
+            last = fmaxf(last, t[i]);
+        }
+    if (!(cnt & 1)) return;
+    // a grouped primitive only reports hits when every enclosing group's box passes the forward ray (Q6)
+    int parent = __ldg(&S.head[pos + S.n_prims]).x;
+    if (parent >= 0 && !ancestors_pass(S, parent, o, d)) return;
+    container_add(c, hit_pos, last, pos, h.w);
+}
+template <bool STATS>
+__device__ __noinline__ void find_containers(const DevScene& S, V3 o, V3 d, int hit_pos, float& n1, float& n2, Ctr<STATS>& k) {
+    Containers c;
+    ObjRay cache;
+    for (int i = 0; i < S.n_linear; i++) container_prim<STATS>(S, __ldg(&S.linear[i]), o, d, cache, hit_pos, c, k);
+    if (S.bvh_root >= 0) {
+        // walk the backward half-line: the forward half-line of the reversed ray
+        V3 inv = mk(-1.0f / d.x, -1.0f / d.y, -1.0f / d.z);
+        int stack[kBvhStack];
+        int sp = 0;
+        int node = S.bvh_root;
+        for (;;) {
+            if (node >= 0) {
+                const float4* np = reinterpret_cast<const float4*>(S.bvh + node);
+                float4 a = __ldg(np), b = __ldg(np + 1), cc = __ldg(np + 2);
+                int4 link = __ldg(reinterpret_cast<const int4*>(np + 3));
+                float t0, t1;
+                k.node();
+                k.node();
+                bool h0 = slab(o, inv, a.x, a.y, a.z, a.w, b.x, b.y, kInfF, t0);
+                bool h1 = slab(o, inv, b.z, b.w, cc.x, cc.y, cc.z, cc.w, kInfF, t1);
+                if (h0 && h1) {
+                    if (sp < kBvhStack) stack[sp++] = link.y;
+                    node = link.x;
+                    continue;
+                }
+                if (h0) {
+                    node = link.x;
+                    continue;
+                }
+                if (h1) {
+                    node = link.y;
+                    continue;
+                }
+            } else {
+                int code = ~node;
+                int first = code >> 4, count = (code & 15) + 1;
+                for (int i = 0; i < count; i++) container_prim<STATS>(S, first + i, o, d, cache, hit_pos, c, k);
+            }
+            if (sp == 0) break;
+            node = stack[--sp];
+        }
+    }
+    auto index_of = [&](int pos) { return S.materials[(__ldg(&S.head[pos]).x >> 8)].refractive_index; };
+    float other = (c.best_pos >= 0) ? index_of(c.best_pos) : 1.0f;  // REFRACTION_VACCUM, world.rs:242
+    if (c.hit_open) {
+        // leaving the hit object: n1 is the innermost open object (possibly the hit object itself)
+        bool hit_is_inner = c.best_pos < 0 || c.hit_t > c.best_t || (c.hit_t == c.best_t && c.hit_order > c.best_order);
+        n1 = hit_is_inner ? index_of(hit_pos) : other;
+        n2 = other;
+    } else {
+        n1 = other;
+        n2 = index_of(hit_pos);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Patterns (pattern/*.rs).  floor(..) as i32 % 2 with Rust semantics: the cast saturates and NaN maps to 0
+// (__float2int_rz does both), and % keeps the dividend's sign so negative odd numbers give -1 != 0 (Q16).
+__device__ __forceinline__ bool even_floor(float v) { return (__float2int_rz(floorf(v)) % 2) == 0; }
+__device__ __forceinline__ float rem_euclid(float a, float b) {
+    float r = fmodf(a, b);
+    return (r < 0.0f) ? r + fabsf(b) : r;
+}
+__device__ __forceinline__ V3 uv_color(const DevScene& S, int id, float u, float v) {
+    const DevUvPattern& p = S.uvs[id];
+    if (p.kind == 0) {  // UVCheckers, uv.rs:45-56
+        int u2 = __float2int_rz(floorf(u * p.p[0]));
+        int v2 = __float2int_rz(floorf(v * p.p[1]));
+        int s = (int)((unsigned)u2 + (unsigned)v2);
+        return (s % 2 == 0) ? ld3(p.p + 2) : ld3(p.p + 5);
+    }
+    // AlignCheck, uv.rs:155-176
+    if (v > 0.8f) {
+        if (u < 0.2f) return ld3(p.p + 3);
+        if (u > 0.8f) return ld3(p.p + 6);
+    } else if (v < 0.2f) {
+        if (u < 0.2f) return ld3(p.p + 9);
+        if (u > 0.8f) return ld3(p.p + 12);
+    }
+    return ld3(p.p);
+}
+__device__ __forceinline__ float u_from_azimuth(V3 p) {  // uv.rs:117-132
+    const float frac_1_2pi = 1.0f / (2.0f * 3.14159265358979323846f);
+    float theta = atan2f(p.x, p.z);
+    float raw_u = theta * frac_1_2pi;
+    return 1.f - (raw_u + 0.5f);
+}
+__device__ __noinline__ V3 pattern_color(const DevScene& S, int pid, V3 object_point) {
+    const DevPattern& P = S.patterns[pid];
+    Xf m{P.inv[0], P.inv[1], P.inv[2]};
+    V3 p = xf_point(m, object_point);  // pattern.rs:17
+    V3 a = ld3(P.a), b = ld3(P.b);
+    switch (P.kind) {
+        case 0: return even_floor(p.x) ? a : b;                                       // stripes.rs:39-45
+        case 1: return a + (b * (p.x - floorf(p.x)));                                 // gradient.rs:33-36 (b holds `distance`)
+        case 2: return even_floor(sqrtf(p.x * p.x + p.z * p.z)) ? a : b;              // rings.rs:38-50
+        case 3: return even_floor(fabsf(p.x) + fabsf(p.y) + fabsf(p.z)) ? a : b;      // checkers.rs:38-46
+        case 4: {                                                                     // sine_2d.rs:39-44
+            float cosine = cosf(p.x + p.z);
+            float fraction = (-cosine + 1.0f) / 2.0f;
+            return a + (b * fraction);
+        }
+        case 5: return p;  // TestPattern, pattern.rs:84-86
+        case 6: {          // TextureMap, uv.rs:89-132,196-212
+            const float pi = 3.14159265358979323846f;
+            float u, v;
+            if (P.mapping == 0) {
+                u = u_from_azimuth(p);
+                float radius = magnitude(p);
+                float phi = acosf(p.y / radius);
+                v = 1.f - phi * 0.318309886183790671538f;
+            } else if (P.mapping == 1) {
+                u = rem_euclid(p.x, 1.f);
+                v = rem_euclid(p.z, 1.f);
+            } else {
+                u = u_from_azimuth(p);
+                v = rem_euclid(p.y, 2.f * pi) * (1.0f / (2.0f * pi));
+            }
+            return uv_color(S, P.uv[0], u, v);
+        }
+        default: {  // CubicMap, uv.rs:256-326 (Face: Front 0, Back 1, Left 2, Right 3, Up 4, Down 5)
+            float coord = fmaxf(fmaxf(fabsf(p.x), fabsf(p.y)), fabsf(p.z));
+            int face;
+            if (coord == p.x)
+                face = 3;
+            else if (coord == -p.x)
+                face = 2;
+            else if (coord == p.y)
+                face = 4;
+            else if (coord == -p.y)
+                face = 5;
+            else if (coord == p.z)
+                face = 0;
+            else
+                face = 1;
+            float u, v;
+            switch (face) {
+                case 0: u = fmodf(p.x + 1.f, 2.f) / 2.f, v = fmodf(p.y + 1.f, 2.f) / 2.f; break;
+                case 1: u = fmodf(1.f - p.x, 2.f) / 2.f, v = fmodf(p.y + 1.f, 2.f) / 2.f; break;
+                case 2: u = fmodf(p.z + 1.f, 2.f) / 2.f, v = fmodf(p.y + 1.f, 2.f) / 2.f; break;
+                case 3: u = fmodf(1.f - p.z, 2.f) / 2.f, v = fmodf(p.y + 1.f, 2.f) / 2.f; break;
+                case 4: u = fmodf(p.x + 1.f, 2.f) / 2.f, v = fmodf(1.f - p.z, 2.f) / 2.f; break;
+                default: u = fmodf(p.x + 1.f, 2.f) / 2.f, v = fmodf(p.z + 1.f, 2.f) / 2.f; break;
+            }
+            return uv_color(S, P.uv[face], u, v);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Counter-based stand-in for thread_rng().sample(OpenClosed01) (rectangle_light.rs:46): identical to the
+// oracle's jitter_hash / jitter_open_closed01.
+__device__ __forceinline__ float jitter_value(unsigned long long seed, unsigned pixel, unsigned path, unsigned index) {
+    unsigned long long z = seed + 0x9E3779B97F4A7C15ull * (unsigned long long)(pixel + 1u);
+    z ^= ((unsigned long long)path << 32) | index;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z = z ^ (z >> 31);
+    unsigned bits = (unsigned)(z >> 32);
+    return (float)((bits >> 8) + 1u) * 5.9604644775390625e-08f;
+}
+
+// World::is_shadowed (world.rs:104-119): nearest hit on the point->light ray; shadowed iff that object
+// casts a shadow and is nearer than the light (Q9).
+template <bool STATS>
+__device__ __forceinline__ bool is_shadowed(const DevScene& S, V3 light_position, V3 p, Ctr<STATS>& k) {
+    k.shadow++;
+    V3 v = light_position - p;
+    float distance = magnitude(v);
+    V3 direction = mk(v.x / distance, v.y / distance, v.z / distance);
+    Hit best{distance, -1, -1};  // order -1: a hit AT the light distance is never accepted (`<`, world.rs:116)
+    if (S.all_cast_shadow) {
+        nearest_hit<STATS, true>(S, p, direction, best, k);
+        return best.pos >= 0;
+    }
+    nearest_hit<STATS, false>(S, p, direction, best, k);
+    return best.pos >= 0 && ((__ldg(&S.head[best.pos]).x >> 4) & kFlagCastsShadow);
+}
+
+// Light::intensity_at (point_light.rs:28-34, rectangle_light.rs:76-88)
+template <bool STATS>
+__device__ __forceinline__ float intensity_at(const DevScene& S, V3 p, unsigned pixel, unsigned path, Ctr<STATS>& k) {
+    if (!S.light_is_rect) return is_shadowed<STATS>(S, ld3(S.light_pos), p, k) ? 0.f : 1.f;
+    float total = 0.f;
+    int cell = 0;
+    for (int v = 0; v < S.v_steps; v++) {
+        for (int u = 0; u < S.u_steps; u++, cell++) {
+            V3 lp;
+            k.cell();
+            if (S.jitter_len > 0) {
+                float4 s = __ldg(&S.samples[cell]);  // table mode: point_on_light is the same for every shade
+                lp = mk(s.x, s.y, s.z);
+            } else {
+                float j1 = jitter_value(S.seed, pixel, path, 2u * cell);
+                float j2 = jitter_value(S.seed, pixel, path, 2u * cell + 1u);
+                // rectangle_light.rs:60-66
+                lp = ld3(S.corner) + ld3(S.u_vec) * ((float)u + j1) + ld3(S.v_vec) * ((float)v + j2);
+            }
+            if (!is_shadowed<STATS>(S, lp, p, k)) total += 1.0f;
+        }
+    }
+    return total / (float)S.cells;
+}
+
+__device__ __forceinline__ float powi5(float x) {  // llvm.powi with a constant 5: x * (x^2)^2
+    float x2 = x * x;
+    return x * (x2 * x2);
+}
+
+// One pending shade_hit whose children are still being traced (world.rs:62-86).
+struct Frame {
+    V3 surface;
+    V3 refl;          // reflected_color once known
+    V3 refr_o, refr_d;
+    float reflective, transparency;
+    float reflectance;  // Schlick R, or < 0 when the plain sum applies (world.rs:80-85)
+    int remaining;
+    unsigned path;
+    int stage;  // 1: waiting for the reflection subtree, 2: waiting for the refraction subtree
+    int has_refr;
+};
+
+__device__ __forceinline__ V3 combine(V3 surface, V3 reflected, V3 refracted, float reflectance) {
+    if (reflectance >= 0.0f) return surface + reflected * reflectance + refracted * (1.0f - reflectance);
+    return surface + reflected + refracted;
+}
+
+// World::color_at (world.rs:88-101) with the recursion of reflected_color / refracted_color replaced by an
+// explicit stack of at most depth+1 frames, evaluated in the reference's order (surface, then the whole
+// reflection subtree, then the whole refraction subtree) and combined bottom-up with the same arithmetic.
+// out_t / out_pos (optional) receive the primary hit.
+template <bool STATS>
+__device__ __forceinline__ V3 color_at(const DevScene& S, V3 ro, V3 rd, int depth, unsigned pixel, Ctr<STATS>& k, float* out_t,
+                                       int* out_pos) {
+    Frame stack[kMaxFrames];
+    int sp = 0;
+    int remaining = depth;
+    unsigned path = 1u;
+    bool primary = true;
+    for (;;) {
+        Hit best{kInfF, -1, 0x7fffffff};
+        nearest_hit<STATS, false>(S, ro, rd, best, k);
+        if (primary) {
+            if (out_t) *out_t = best.pos >= 0 ? best.t : -1.0f;
+            if (out_pos) *out_pos = best.pos;
+            primary = false;
+        }
+        V3 c = mk(0.f, 0.f, 0.f);
+        if (best.pos >= 0) {
+            // ---- precompute_values (world.rs:212-283)
+            k.shades++;
+            int4 h = __ldg(&S.head[best.pos]);
+            int type = h.x & 15;
+            const DevMaterial& mat = S.materials[h.x >> 8];
+            Xf m = load_xf(S.xform + 3 * (size_t)h.y);
+            V3 point = ro + rd * best.t;
+            V3 object_point = xf_point(m, point);
+            V3 n = norm(xf_normal(m, local_normal(S, type, h.z, object_point)));  // shape.rs:148-154,130-145
+            V3 eye = -rd;
+            V3 reflectv = reflect(rd, n);
+            if (dot(n, eye) < 0.0f) n = -n;
+            V3 over_point = point + n * kAcne;
+            // ---- shade_hit (world.rs:62-86): light intensity first, then Phong (phong_lighting.rs:12-63)
+            float li = intensity_at<STATS>(S, over_point, pixel, path, k);
+            V3 material_color = ld3(mat.color);
+            if (mat.pattern >= 0) {
+                k.pattern();
+                material_color = pattern_color(S, mat.pattern, xf_point(m, over_point));  // pattern.rs:15-19 at over_point (Q4)
+            }
+            V3 light_rgb = ld3(S.light_rgb);
+            V3 effective = material_color * light_rgb;
+            V3 ambient = effective * mat.ambient;
+            V3 surface = ambient;
+            if (li != 0.f) {
+                V3 to_light = norm(ld3(S.light_pos) - over_point);
+                float lnc = dot(to_light, n);
+                V3 diffuse = mk(0.f, 0.f, 0.f), specular = mk(0.f, 0.f, 0.f);
+                if (!(lnc < 0.0f)) {
+                    diffuse = effective * mat.diffuse * lnc;
+                    V3 sr = reflect(-to_light, n);
+                    float rec = dot(sr, eye);
+                    if (!(rec <= 0.0f)) {
+                        float factor = powf(rec, mat.shininess);
+                        specular = light_rgb * mat.specular * factor;
+                    }
+                }
+                surface = ambient + (diffuse + specular) * li;
+            }
+            // ---- children (world.rs:121-162) with the reference's asymmetric guards (Q11)
+            bool want_refl = mat.reflective != 0.0f && remaining >= 1;
+            bool want_refr = false;
+            float reflectance = -1.0f;
+            V3 refr_d = mk(0.f, 0.f, 0.f);
+            if (mat.transparency != 0.0f) {
+                float n1, n2;
+                find_containers<STATS>(S, ro, rd, best.pos, n1, n2, k);
+                float cos_i = dot(eye, n);
+                if (remaining != 0) {
+                    float n_ratio = n1 / n2;  // world.rs:196-207
+                    float sin2 = (n_ratio * n_ratio) * (1.0f - cos_i * cos_i);
+                    if (!(sin2 > 1.0f)) {
+                        k.refr_dir();
+                        float cos_t = sqrtf(1.0f - sin2);
+                        refr_d = n * (n_ratio * cos_i - cos_t) - (eye * n_ratio);
+                        want_refr = true;
+                    }
+                }
+                if (mat.reflective > 0.0f && mat.transparency > 0.0f) {  // schlick_reflectance, world.rs:285-303
+                    k.schlick();
+                    float cosine = cos_i;
+                    reflectance = 2.0f;  // sentinel, replaced below
+                    bool tir = false;
+                    if (n1 > n2) {
+                        float nn = n1 / n2;
+                        float sin2_t = (nn * nn) * (1.0f - cosine * cosine);
+                        if (sin2_t > 1.0f)
+                            tir = true;
+                        else
+                            cosine = sqrtf(1.0f - sin2_t);
+                    }
+                    if (tir) {
+                        reflectance = 1.0f;
+                    } else {
+                        float q = (n1 - n2) / (n1 + n2);
+                        float r0 = q * q;
+                        reflectance = r0 + (1.0f - r0) * powi5(1.0f - cosine);
+                    }
+                }
+            }
+            if ((want_refl || want_refr) && sp < kMaxFrames) {
+                Frame& f = stack[sp++];
+                f.surface = surface;
+                f.refl = mk(0.f, 0.f, 0.f);
+                f.refr_o = point - n * kAcne;  // under_point
+                f.refr_d = refr_d;
+                f.reflective = mat.reflective;
+                f.transparency = mat.transparency;
+                f.reflectance = reflectance;
+                f.remaining = remaining;
+                f.path = path;
+                f.has_refr = want_refr;
+                k.secondary++;
+                remaining = remaining - 1;
+                if (want_refl) {
+                    f.stage = 1;
+                    ro = over_point;
+                    rd = reflectv;
+                    path = path * 3u + 1u;
+                } else {
+                    f.stage = 2;
+                    ro = f.refr_o;
+                    rd = refr_d;
+                    path = path * 3u + 2u;
+                }
+                continue;
+            }
+            c = combine(surface, mk(0.f, 0.f, 0.f), mk(0.f, 0.f, 0.f), reflectance);
+        }
+        // ---- hand the colour to the waiting frames
+        for (;;) {
+            if (sp == 0) return c;
+            Frame& f = stack[sp - 1];
+            if (f.stage == 1) {
+                f.refl = c * f.reflective;  // world.rs:131
+                if (f.has_refr) {
+                    f.stage = 2;
+                    ro = f.refr_o;
+                    rd = f.refr_d;
+                    remaining = f.remaining - 1;
+                    path = f.path * 3u + 2u;
+                    k.secondary++;
+                    break;
+                }
+                c = combine(f.surface, f.refl, mk(0.f, 0.f, 0.f), f.reflectance);
+            } else {
+                c = combine(f.surface, f.refl, c * f.transparency, f.reflectance);  // world.rs:159-160
+            }
+            sp--;
+        }
+    }
+}
+
+// Camera::ray_for_pixel (camera.rs:60-74)
+__device__ __forceinline__ void ray_for_pixel(const DevScene& S, int x, int y, V3& o, V3& d) {
+    float x_offset = ((float)x + 0.5f) * S.pixel_size;
+    float y_offset = ((float)y + 0.5f) * S.pixel_size;
+    float world_x = S.half_w - x_offset;
+    float world_y = S.half_h - y_offset;
+    Xf m{S.cam_inv[0], S.cam_inv[1], S.cam_inv[2]};
+    V3 pixel = xf_point(m, mk(world_x, world_y, -1.0f));
+    o = xf_point(m, mk(0.f, 0.f, 0.f));
+    d = norm(pixel - o);
+}
+
+// Canvas::scale_color (canvas.rs:39-43): clamp, then truncate; NaN -> 255 because f32::min returns the
+// non-NaN operand (fminf does the same) and `as u8` saturates.
+__device__ __forceinline__ unsigned char scale_color(float c) {
+    float s = fmaxf(fminf(c * 255.0f, 255.0f), 0.0f);
+    return (unsigned char)__float2uint_rz(s);
+}
+
+}  // namespace RTC_NS
+}  // namespace rtc

@@ -1,0 +1,141 @@
+// rtc_kernels.cu — the sm_100a kernels.  Compiled twice into the library: as namespace `fast` (FMA
+// contraction on) and, with -DRTC_STRICT -fmad=false, as namespace `strict` (the Rust / IEEE evaluation
+// order bit for bit).  rtc_api.cu picks one per scene (RTC_OPT_STRICT_FP).
+//
+// K1 render_tiles : Camera::render (camera.rs:76-91) — one thread per pixel, 128-thread blocks covering a
+//                   16x8 pixel tile as four 8x4 warps so that a warp's rays stay coherent; writes the f32
+//                   RGB canvas and the 8-bit canvas (canvas.rs:39-43) in the same pass.
+// K4 trace_rays   : World::color_at for caller-supplied rays (the unit-test probe).
+// K5 fma_peak     : dependent-FMA micro-benchmark for the measured FP32 roofline denominator.
+#ifdef RTC_STRICT
+#define RTC_NS strict
+#else
+#define RTC_NS fast
+#endif
+
+#include "rtc_device.cuh"
+#include "rtc_launch.h"
+
+namespace rtc {
+namespace RTC_NS {
+
+template <bool STATS>
+__device__ __forceinline__ void flush_counters(const Ctr<STATS>& k, DevCounters* out);
+
+__device__ __forceinline__ void warp_add(unsigned long long* dst, unsigned v) {
+    unsigned s = __reduce_add_sync(0xffffffffu, v);
+    if ((threadIdx.x & 31) == 0 && s) atomicAdd(dst, (unsigned long long)s);
+}
+template <>
+__device__ __forceinline__ void flush_counters<false>(const Ctr<false>& k, DevCounters* out) {
+    warp_add(&out->primary, k.primary);
+    warp_add(&out->secondary, k.secondary);
+    warp_add(&out->shadow, k.shadow);
+    warp_add(&out->shades, k.shades);
+}
+template <>
+__device__ __forceinline__ void flush_counters<true>(const Ctr<true>& k, DevCounters* out) {
+    warp_add(&out->primary, k.primary);
+    warp_add(&out->secondary, k.secondary);
+    warp_add(&out->shadow, k.shadow);
+    warp_add(&out->shades, k.shades);
+    warp_add(&out->node_visits, k.nodes);
+    for (int i = 0; i < 8; i++) warp_add(&out->prim_tests[i], k.prims[i]);
+    warp_add(&out->xforms, k.xforms);
+    warp_add(&out->patterns, k.patterns);
+    warp_add(&out->cells, k.cells);
+    warp_add(&out->schlicks, k.schlicks);
+    warp_add(&out->refr_dirs, k.refr_dirs);
+    warp_add(&out->overflows, k.overflows);
+}
+
+template <bool STATS>
+__global__ void __launch_bounds__(128) render_tiles(const DevScene S, const DevFrame F, DevCounters* counters) {
+    // block (bx, by) -> tile of 16x8 pixels in band `shard + by * n_shards`; warp w -> 8x4 sub-tile
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int band = F.shard + blockIdx.y * F.n_shards;
+    const int x = blockIdx.x * kTileW + (warp & 1) * 8 + (lane & 7);
+    const int y = band * kBandRows + (warp >> 1) * 4 + (lane >> 3);
+    Ctr<STATS> k;
+    V3 c = mk(0.f, 0.f, 0.f);
+    const bool inside = x < S.width && y < S.height;
+    // camera.rs:80-81 — the last row and the last column are never rendered and stay black (canvas.rs:23)
+    if (inside && x < S.width - 1 && y < S.height - 1) {
+        V3 o, d;
+        ray_for_pixel(S, x, y, o, d);
+        k.primary++;
+        c = color_at<STATS>(S, o, d, F.depth, (unsigned)(y * S.width + x), k, nullptr, nullptr);
+    }
+    if (inside) {
+        size_t idx = ((size_t)y * S.width + x) * 3;
+        if (F.rgb) {
+            F.rgb[idx] = c.x;
+            F.rgb[idx + 1] = c.y;
+            F.rgb[idx + 2] = c.z;
+        }
+        if (F.u8) {
+            F.u8[idx] = scale_color(c.x);
+            F.u8[idx + 1] = scale_color(c.y);
+            F.u8[idx + 2] = scale_color(c.z);
+        }
+    }
+    flush_counters<STATS>(k, counters);
+}
+
+__global__ void __launch_bounds__(128) trace_rays(const DevScene S, int n, const float* origins, const float* directions, int depth,
+                                                  float* out_rgb, float* out_t, int* out_pos, DevCounters* counters) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    Ctr<false> k;
+    if (i < n) {
+        V3 o = ld3(origins + 3 * (size_t)i), d = ld3(directions + 3 * (size_t)i);
+        float t;
+        int pos;
+        V3 c = color_at<false>(S, o, d, depth, (unsigned)i, k, &t, &pos);
+        out_rgb[3 * (size_t)i] = c.x;
+        out_rgb[3 * (size_t)i + 1] = c.y;
+        out_rgb[3 * (size_t)i + 2] = c.z;
+        if (out_t) out_t[i] = t;
+        if (out_pos) out_pos[i] = pos;
+    }
+    flush_counters<false>(k, counters);
+}
+
+void launch_render(const DevScene& S, const DevFrame& F, DevCounters* counters, bool detailed, cudaStream_t stream) {
+    dim3 grid((S.width + kTileW - 1) / kTileW, F.n_bands);
+    if (grid.x == 0 || grid.y == 0) return;
+    if (detailed)
+        render_tiles<true><<<grid, 128, 0, stream>>>(S, F, counters);
+    else
+        render_tiles<false><<<grid, 128, 0, stream>>>(S, F, counters);
+}
+
+void launch_trace(const DevScene& S, int n, const float* origins, const float* directions, int depth, float* out_rgb,
+                  float* out_t, int* out_pos, DevCounters* counters, cudaStream_t stream) {
+    if (n <= 0) return;
+    trace_rays<<<(n + 127) / 128, 128, 0, stream>>>(S, n, origins, directions, depth, out_rgb, out_t, out_pos, counters);
+}
+
+#ifndef RTC_STRICT
+// K5: 8 independent FMA chains per thread, 4096 iterations: 2 * 8 * 4096 flops per thread.
+__global__ void __launch_bounds__(256) fma_peak(float* out, float a, float b, int iters) {
+    float x0 = threadIdx.x, x1 = x0 + 1.f, x2 = x0 + 2.f, x3 = x0 + 3.f, x4 = x0 + 4.f, x5 = x0 + 5.f, x6 = x0 + 6.f, x7 = x0 + 7.f;
+    for (int i = 0; i < iters; i++) {
+        x0 = fmaf(x0, a, b);
+        x1 = fmaf(x1, a, b);
+        x2 = fmaf(x2, a, b);
+        x3 = fmaf(x3, a, b);
+        x4 = fmaf(x4, a, b);
+        x5 = fmaf(x5, a, b);
+        x6 = fmaf(x6, a, b);
+        x7 = fmaf(x7, a, b);
+    }
+    float s = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+    if (s == 12345.678f) out[0] = s;  // keep the chains alive
+}
+void launch_fma_peak(float* out, int blocks, int iters, cudaStream_t stream) {
+    fma_peak<<<blocks, 256, 0, stream>>>(out, 0.999f, 0.001f, iters);
+}
+#endif
+
+}  // namespace RTC_NS
+}  // namespace rtc

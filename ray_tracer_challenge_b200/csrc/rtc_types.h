@@ -1,0 +1,125 @@
+// rtc_types.h — device-resident scene layout shared by the host (rtc_api.cu) and the kernels.
+//
+// Everything a ray touches lives in a handful of flat arrays in HBM (L2-resident for every BASELINE config:
+// 100 k primitives ~ 8 MB):
+//   head[i]   int4   {type | flags<<4 | material<<8, xform id, aux, dfs order}         16 B / primitive
+//   xform[k]  3xfloat4 rows of the primitive's inverse transform (deduplicated)        48 B / transform
+//   tri[a]    3xfloat4 {p1.xyz e1.x | e1.yz e2.xy | e2.z n.xyz}                        48 B / triangle
+//   bound[a]  float4 {minimum_y, maximum_y, closed, 0}                                 16 B / cylinder, cone
+//   bvh[n]    4xfloat4 two child boxes + two child links                               64 B / node
+// Primitives are stored in BVH leaf order; `dfs order` keeps the reference's depth-first emission order,
+// which is the tie-break between equal hit distances (world.rs:58, intersection.rs:30-35).
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#include <cuda_runtime.h>
+#else
+#include <vector_types.h>
+#endif
+
+namespace rtc {
+
+enum : int { T_SPHERE = 0, T_PLANE = 1, T_CUBE = 2, T_CYLINDER = 3, T_CONE = 4, T_TRIANGLE = 5, T_CSG = 6 };
+
+constexpr int kFlagCastsShadow = 1;   // BaseShape::casts_shadow
+constexpr int kFlagHasParent = 2;     // has an enclosing group / CSG whose cull must be honoured exactly
+constexpr int kMaxFrames = 24;        // explicit reflect/refract stack: depth + 1 frames (depth <= 23)
+constexpr int kCsgHitCap = 32;        // hits a CSG evaluation may hold at once
+constexpr int kCsgRayDepth = 6;       // nested CSG transforms
+constexpr int kBvhStack = 48;
+
+struct DevMaterial {  // 48 B
+    float color[3];
+    float ambient, diffuse, specular, shininess, reflective, transparency, refractive_index;
+    int pattern;
+    int pad;
+};
+
+struct DevPattern {  // 112 B
+    float4 inv[3];
+    float a[3];
+    float b[3];
+    int kind, mapping;
+    int uv[6];
+};
+
+struct DevUvPattern {  // 64 B
+    int kind;
+    float p[15];
+};
+
+struct DevNode {  // group / CSG node of the reference shape tree (cull chain + CSG evaluation)
+    float4 inv[3];
+    float bmin[3];
+    float bmax[3];
+    int kind, parent, op, pad;
+};
+
+// One instruction of a flattened CSG tree (post-order), see csg_eval in rtc_device.cuh.
+enum : int { OP_CSG_ENTER = 0, OP_CSG_MID = 1, OP_CSG_EXIT = 2, OP_GROUP = 3, OP_PRIM = 4 };
+struct DevCsgOp {
+    int op;    // OP_*
+    int arg;   // node index (ENTER/MID/EXIT/GROUP) or primitive position (PRIM)
+    int skip;  // ENTER/GROUP: instruction to jump to when the bounding-box cull rejects the ray
+    int pad;
+};
+
+struct DevBvhNode {  // 64 B
+    float4 a;  // lo0.xyz, hi0.x
+    float4 b;  // hi0.yz, lo1.xy
+    float4 c;  // lo1.z, hi1.xyz
+    int4 d;    // child0, child1 (>= 0 inner node; < 0 leaf: ~((first << 4) | (count - 1))), unused, unused
+};
+
+struct DevScene {
+    // camera (camera.rs:8-20)
+    float4 cam_inv[3];
+    float half_w, half_h, pixel_size;
+    int width, height;
+    // light
+    int light_is_rect;
+    float light_pos[3];  // PointLight::position or the rectangle centre
+    float light_rgb[3];
+    float corner[3], u_vec[3], v_vec[3];  // per-cell edges
+    int u_steps, v_steps, cells;
+    int jitter_len;            // > 0: table mode
+    const float* jitter;       // table
+    const float4* samples;     // table mode: the `cells` precomputed point_on_light positions
+    unsigned long long seed;   // counter mode
+    // geometry
+    const int4* head;
+    const float4* xform;
+    const float4* tri;
+    const float4* bound;
+    const DevBvhNode* bvh;
+    const int* linear;  // primitive positions tested for every ray (unbounded shapes, or every shape of a tiny scene)
+    int n_linear;
+    int bvh_root;       // -1: no BVH
+    int n_prims;
+    const DevNode* nodes;
+    const DevCsgOp* csg_ops;
+    // shading
+    const DevMaterial* materials;
+    const DevPattern* patterns;
+    const DevUvPattern* uvs;
+    int all_cast_shadow;  // every primitive casts a shadow: shadow rays may stop at the first hit
+};
+
+struct DevFrame {  // where a render writes
+    float* rgb;            // width*height*3 f32 or null
+    unsigned char* u8;     // width*height*3 or null
+    int shard, n_shards;   // interleaved bands of kBandRows rows
+    int depth;
+    int n_bands;           // bands this launch renders
+};
+
+constexpr int kTileW = 16, kTileH = 8;  // pixels per 128-thread block: 4 warps of 8x4
+constexpr int kBandRows = kTileH;
+
+struct DevCounters {  // accumulated with one atomic per warp
+    unsigned long long primary, secondary, shadow, shades;
+    unsigned long long node_visits, prim_tests[8], xforms, patterns, cells, schlicks, refr_dirs, overflows;
+};
+
+}  // namespace rtc
