@@ -149,9 +149,13 @@ int rtc_set_rect_light(RtcScene*, const float intensity[3], const float corner[3
                        int32_t u_steps, const float v_cell[3], int32_t v_steps, const float position[3],
                        const float* jitter_table, uint32_t table_len, uint64_t seed);
 
-/* Options (set before commit).  RTC_OPT_STRICT_FP = 1 selects the build of the kernels compiled without
- * FMA contraction (bit-for-bit the Rust evaluation order; slower); default 0. */
-enum { RTC_OPT_STRICT_FP = 1, RTC_OPT_BVH_LEAF_SIZE = 2, RTC_OPT_BVH_MIN_PRIMS = 3 };
+/* Options.  RTC_OPT_FMA_CONTRACTION (default 0): the kernels exist in two builds of the same source.  The
+ * default one is compiled with -fmad=false and evaluates every expression in the Rust / IEEE order, so frames
+ * are bit-for-bit the reference's apart from libm (powf, cosf, atan2f, acosf).  1 selects the FMA-contracted
+ * build: a few percent faster, but its last-place differences flip ill-conditioned threshold tests (the
+ * discriminant of a distant sphere cancels catastrophically in f32), so it meets the <= 1 LSB bar only on
+ * well-conditioned scenes.  It may be changed between renders; the BVH options only before commit. */
+enum { RTC_OPT_FMA_CONTRACTION = 1, RTC_OPT_BVH_LEAF_SIZE = 2, RTC_OPT_BVH_MIN_PRIMS = 3 };
 int rtc_set_option(RtcScene*, int32_t option, int64_t value);
 
 /* Validate, build the BVH over the primitives' bounding boxes and upload one scene replica per device.

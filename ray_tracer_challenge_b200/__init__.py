@@ -86,7 +86,7 @@ class PreparedScene:
         self.last_stats = None
 
     def render(self, depth=DEFAULT_RAY_RECURSION_DEPTH, out_rgb=None, out_u8=None, want_rgb=True, want_u8=True,
-               shard=0, n_shards=0, detailed=False, strict_fp=False):
+               shard=0, n_shards=0, detailed=False, fma=False):
         """rtc_render / rtc_render_shard.  Buffers may be caller-supplied (e.g. pinned); want_* = False leaves the
         frame on the device (kernel timing)."""
         w, h = self.camera.width_pixels, self.camera.height_pixels
@@ -97,19 +97,19 @@ class PreparedScene:
         stats = SgStats()
         api = self.api
         api.check(api.lib.sg_render_prepared(
-            api.ctx, self.handle, int(depth), int(shard), int(n_shards), int(detailed), int(strict_fp),
+            api.ctx, self.handle, int(depth), int(shard), int(n_shards), int(detailed), int(fma),
             _api.fptr(out_rgb) if want_rgb else None, out_u8.ctypes.data_as(_U8P) if want_u8 else None,
             C.byref(stats)))
         self.last_stats = api.last_rtc_stats()
         return Canvas(w, h, out_rgb if want_rgb else None, out_u8 if want_u8 else None)
 
-    def trace_rays(self, origins, directions, depth=DEFAULT_RAY_RECURSION_DEPTH, strict_fp=False):
+    def trace_rays(self, origins, directions, depth=DEFAULT_RAY_RECURSION_DEPTH, fma=False):
         """World::color_at (world.rs:88-101) for arbitrary rays: returns (rgb[n,3], t[n], shape_handle[n])."""
         o, d = _api.f32(origins).reshape(-1, 3), _api.f32(directions).reshape(-1, 3)
         n = o.shape[0]
         rgb, t, shape = np.zeros((n, 3), np.float32), np.zeros(n, np.float32), np.zeros(n, np.int32)
         api = self.api
-        api.check(api.lib.sg_trace_rays(api.ctx, self.handle, n, _api.fptr(o), _api.fptr(d), int(depth), int(strict_fp),
+        api.check(api.lib.sg_trace_rays(api.ctx, self.handle, n, _api.fptr(o), _api.fptr(d), int(depth), int(fma),
                                         _api.fptr(rgb), _api.fptr(t), shape.ctypes.data_as(_IP)))
         return rgb, t, shape
 
@@ -144,12 +144,12 @@ class HostApi(_api.Api):
         self.Camera.render = render_b200
         self.Camera.prepare = lambda camera, world: PreparedScene(api, camera, world)
 
-    def set_render_options(self, n_devices=1, device_ids=None, strict_fp=False, detailed=False):
+    def set_render_options(self, n_devices=1, device_ids=None, fma=False, detailed=False):
         ids = None
         if device_ids is not None:
             ids = (C.c_int * len(device_ids))(*device_ids)
             n_devices = len(device_ids)
-        self.check(self.lib.sg_set_render_options(self.ctx, int(n_devices), ids, int(strict_fp), int(detailed)))
+        self.check(self.lib.sg_set_render_options(self.ctx, int(n_devices), ids, int(fma), int(detailed)))
 
     def last_rtc_stats(self) -> RtcStats:
         st = RtcStats()

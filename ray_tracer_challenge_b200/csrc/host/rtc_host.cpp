@@ -165,7 +165,7 @@ static void to_sg_stats(const RtcStats& r, sg_stats* s) {
 
 static int commit(sg_ctx* c, RtcScene* scene) {
     const RenderOptions& o = c->options;
-    if (rtc_set_option(scene, RTC_OPT_STRICT_FP, o.strict_fp ? 1 : 0)) return fail(rtc_last_error());
+    if (rtc_set_option(scene, RTC_OPT_FMA_CONTRACTION, o.fma ? 1 : 0)) return fail(rtc_last_error());
     const int32_t* ids = o.device_ids.empty() ? nullptr : o.device_ids.data();
     int n = o.device_ids.empty() ? o.n_devices : (int)o.device_ids.size();
     if (rtc_scene_commit(scene, n, ids)) return fail(rtc_last_error());
@@ -344,13 +344,13 @@ int sg_camera_new(sg_ctx* c, uint32_t w, uint32_t h, float fov, const float m[16
 }
 
 // ---- host-library extensions (not exported by the oracle) ------------------------------------------------
-// devices the next render / prepare commits to (device_ids may be NULL: 0..n_devices-1); strict_fp selects the
-// kernels built without FMA contraction; detailed adds the Appendix-E work counters to the stats.
-int sg_set_render_options(sg_ctx* c, int n_devices, const int* device_ids, int strict_fp, int detailed) {
+// devices the next render / prepare commits to (device_ids may be NULL: 0..n_devices-1); fma selects the
+// FMA-contracted kernel build (RTC_OPT_FMA_CONTRACTION); detailed adds the Appendix-E work counters to the stats.
+int sg_set_render_options(sg_ctx* c, int n_devices, const int* device_ids, int fma, int detailed) {
     c->options.n_devices = n_devices;
     c->options.device_ids.clear();
     if (device_ids) c->options.device_ids.assign(device_ids, device_ids + n_devices);
-    c->options.strict_fp = strict_fp != 0;
+    c->options.fma = fma != 0;
     c->options.detailed = detailed != 0;
     return 0;
 }
@@ -411,11 +411,11 @@ int sg_release_prepared(sg_ctx* c, int h) {
     return 0;
 }
 // n_shards == 0: the committed devices split the frame; n_shards >= 1: this process renders only `shard`.
-int sg_render_prepared(sg_ctx* c, int h, int depth, int shard, int n_shards, int detailed, int strict_fp, float* out_rgb,
+int sg_render_prepared(sg_ctx* c, int h, int depth, int shard, int n_shards, int detailed, int fma, float* out_rgb,
                        uint8_t* out_u8, sg_stats* stats) {
     if (h < 0 || h >= (int)c->prepared.size() || !c->prepared[h]) return fail("bad prepared handle");
     RtcScene* scene = c->prepared[h]->scene;
-    if (rtc_set_option(scene, RTC_OPT_STRICT_FP, strict_fp ? 1 : 0)) return fail(rtc_last_error());
+    if (rtc_set_option(scene, RTC_OPT_FMA_CONTRACTION, fma ? 1 : 0)) return fail(rtc_last_error());
     int rc;
     if (n_shards >= 1)
         rc = rtc_render_shard(scene, depth, shard, n_shards, out_rgb, out_u8, &c->last_stats);
@@ -431,11 +431,11 @@ int sg_flush_l2(sg_ctx* c, int h) {
     return rtc_flush_l2(c->prepared[h]->scene) ? fail(rtc_last_error()) : 0;
 }
 // World::color_at for caller-supplied rays on a prepared scene; out_shape receives the hit SHAPE handle.
-int sg_trace_rays(sg_ctx* c, int h, uint32_t n, const float* origins, const float* directions, int depth, int strict_fp,
+int sg_trace_rays(sg_ctx* c, int h, uint32_t n, const float* origins, const float* directions, int depth, int fma,
                   float* out_rgb, float* out_t, int* out_shape) {
     if (h < 0 || h >= (int)c->prepared.size() || !c->prepared[h]) return fail("bad prepared handle");
     Prepared& p = *c->prepared[h];
-    if (rtc_set_option(p.scene, RTC_OPT_STRICT_FP, strict_fp ? 1 : 0)) return fail(rtc_last_error());
+    if (rtc_set_option(p.scene, RTC_OPT_FMA_CONTRACTION, fma ? 1 : 0)) return fail(rtc_last_error());
     std::vector<int32_t> prim(n);
     if (rtc_trace_rays(p.scene, n, origins, directions, depth, out_rgb, out_t, prim.data())) return fail(rtc_last_error());
     if (out_shape)

@@ -583,7 +583,7 @@ class Flattener {
 struct RenderOptions {
     int n_devices = 1;
     std::vector<int> device_ids;
-    bool strict_fp = false;
+    bool fma = false;  // RTC_OPT_FMA_CONTRACTION
     bool detailed = false;
 };
 

@@ -84,7 +84,7 @@ struct RtcScene {
     int u_steps = 1, v_steps = 1;
     std::vector<float> jitter;
     uint64_t seed = 0;
-    int strict_fp = 0, leaf_size = 4, bvh_min_prims = 8;
+    int strict_fp = 1, leaf_size = 4, bvh_min_prims = 8;
     std::vector<Replica> replicas;
     std::vector<int> pos_to_prim;  // device position -> API primitive index (-1 for CSG pseudo-primitives)
     // commit statistics
@@ -762,7 +762,7 @@ int rtc_set_rect_light(RtcScene* s, const float intensity[3], const float corner
 int rtc_set_option(RtcScene* s, int32_t option, int64_t value) {
     if (!s) return fail(RTC_ERR_INVALID, "null scene");
     switch (option) {
-        case RTC_OPT_STRICT_FP: s->strict_fp = value != 0; return 0;  // may change between renders
+        case RTC_OPT_FMA_CONTRACTION: s->strict_fp = value == 0; return 0;  // may change between renders
         case RTC_OPT_BVH_LEAF_SIZE:
             if (value < 1 || value > 16) return fail(RTC_ERR_INVALID, "leaf size must be in [1,16]");
             s->leaf_size = (int)value;

@@ -30,7 +30,7 @@ def trace(gpu, world, origin, direction, depth=5, camera=None):
     try:
         out = {}
         for strict in (True, False):
-            rgb, t, shape = p.trace_rays([origin], [direction], depth, strict_fp=strict)
+            rgb, t, shape = p.trace_rays([origin], [direction], depth, fma=not strict)
             out[strict] = (rgb[0], float(t[0]), int(shape[0]))
         return out
     finally:
@@ -69,7 +69,7 @@ def test_render_pixel_5_5(gpu):  # camera.rs:155-167 through the full render ker
     w = gpu.World.default()
     p = cam.prepare(w)
     for strict, eps in ((True, EPS_STRICT), (False, EPS_FAST)):
-        img = p.render(5, strict_fp=strict)
+        img = p.render(5, fma=not strict)
         assert_abs_diff_eq(img.pixel_at(5, 5), (0.38063288, 0.47579104, 0.28547466), epsilon=eps)
         assert not img.data[10].any() and not img.data[:, 10].any()
     p.release()
@@ -140,7 +140,7 @@ def test_refraction_through_nested_spheres_matches_oracle(gpu, oracle):
     dirs = [(0.02, 0.01, 1.0)] * len(origins)
     dirs = [tuple(np.asarray(d, np.float32) / np.float32(np.linalg.norm(np.asarray(d, np.float32)))) for d in dirs]
     for strict, eps in ((True, 2e-6), (False, 2e-5)):
-        rgb, t, shape = p.trace_rays(origins, dirs, 5, strict_fp=strict)
+        rgb, t, shape = p.trace_rays(origins, dirs, 5, fma=not strict)
         for i, (o, d) in enumerate(zip(origins, dirs)):
             want = oracle.probe.color_at(ow, o, d, 5)
             assert_abs_diff_eq(rgb[i], want, epsilon=eps, msg=f"origin {o} strict={strict}")
