@@ -59,6 +59,7 @@ struct Replica {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::vector<void*> allocs;
     DevScene scene{};
+    SmallScene small{};
     float* d_rgb = nullptr;
     unsigned char* d_u8 = nullptr;
     DevCounters* d_counters = nullptr;
@@ -84,7 +85,7 @@ struct RtcScene {
     int u_steps = 1, v_steps = 1;
     std::vector<float> jitter;
     uint64_t seed = 0;
-    int strict_fp = 1, leaf_size = 4, bvh_min_prims = 8;
+    int strict_fp = 1, leaf_size = 4, bvh_min_prims = kSmallCap + 1;
     std::vector<Replica> replicas;
     std::vector<int> pos_to_prim;  // device position -> API primitive index (-1 for CSG pseudo-primitives)
     // commit statistics
@@ -236,6 +237,7 @@ struct Flattened {
     std::vector<DevPattern> patterns;
     std::vector<DevUvPattern> uvs;
     std::vector<float4> samples;
+    SmallScene small{};
     int bvh_root = -1;
     int n_pos = 0;
     int all_cast_shadow = 1;
@@ -509,6 +511,25 @@ int flatten(RtcScene* s, Flattened& f) {
                 f.samples.push_back(make_float4(p[0], p[1], p[2], 0.f));
             }
     }
+    // ---- small-scene table (kernel parameter block): no tree, every item in the linear list, few enough of them
+    memset(&f.small, 0, sizeof(f.small));
+    if (f.bvh_root < 0 && n_items > 0 && n_items <= kSmallCap) {
+        f.small.n = n_items;
+        f.small.two_pass_shadows = 1;
+        for (int i = 0; i < n_items; i++) {
+            SmallPrim& sp = f.small.p[i];
+            int4 h = f.head[i];
+            sp.head = make_int4(h.x, f.head[f.n_pos + i].x, h.z, h.w);
+            int type = h.x & 15;
+            if (type == T_CSG) {
+                f.small.two_pass_shadows = 0;
+                sp.r0 = sp.r1 = sp.r2 = sp.bound = make_float4(0.f, 0.f, 0.f, 0.f);
+                continue;
+            }
+            sp.r0 = f.xform[3 * (size_t)h.y], sp.r1 = f.xform[3 * (size_t)h.y + 1], sp.r2 = f.xform[3 * (size_t)h.y + 2];
+            sp.bound = (type == T_CYLINDER || type == T_CONE) ? f.bound[h.z] : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
     s->n_bvh_nodes = (int)f.bvh.size();
     s->n_linear = (int)f.linear.size();
     s->n_xforms = (int)f.xform.size() / 3;
@@ -552,6 +573,7 @@ int upload_replica(RtcScene* s, const Flattened& f, Replica& r) {
     d.bvh_root = f.bvh_root;
     d.n_prims = f.n_pos;
     d.all_cast_shadow = f.all_cast_shadow;
+    r.small = f.small;
     size_t px = (size_t)s->width * s->height;
     void* p = nullptr;
     CUDA_TRY(cudaMalloc(&p, std::max<size_t>(px * 3 * sizeof(float), 16)));
@@ -639,9 +661,9 @@ int render_impl(RtcScene* s, int depth, int shard0, int n_shards_ext, float* rgb
         DevFrame F{r.d_rgb, r.d_u8, shard, n_shards, depth, nb};
         CUDA_TRY(cudaEventRecord(r.ev0, r.stream));
         if (s->strict_fp)
-            strict::launch_render(r.scene, F, r.d_counters, detailed, r.stream);
+            strict::launch_render(r.scene, r.small, F, r.d_counters, detailed, r.stream);
         else
-            fast::launch_render(r.scene, F, r.d_counters, detailed, r.stream);
+            fast::launch_render(r.scene, r.small, F, r.d_counters, detailed, r.stream);
         CUDA_TRY(cudaGetLastError());
         CUDA_TRY(cudaEventRecord(r.ev1, r.stream));
         int rc;
@@ -836,9 +858,9 @@ int rtc_trace_rays(RtcScene* s, uint32_t n, const float* origins, const float* d
     CUDA_TRY(cudaMemcpyAsync(d_d, directions, b3, cudaMemcpyHostToDevice, r.stream));
     CUDA_TRY(cudaMemsetAsync(r.d_counters, 0, sizeof(DevCounters), r.stream));
     if (s->strict_fp)
-        strict::launch_trace(r.scene, (int)n, d_o, d_d, depth, d_rgb, d_t, d_pos, r.d_counters, r.stream);
+        strict::launch_trace(r.scene, r.small, (int)n, d_o, d_d, depth, d_rgb, d_t, d_pos, r.d_counters, r.stream);
     else
-        fast::launch_trace(r.scene, (int)n, d_o, d_d, depth, d_rgb, d_t, d_pos, r.d_counters, r.stream);
+        fast::launch_trace(r.scene, r.small, (int)n, d_o, d_d, depth, d_rgb, d_t, d_pos, r.d_counters, r.stream);
     CUDA_TRY(cudaGetLastError());
     std::vector<int> pos(n);
     CUDA_TRY(cudaMemcpyAsync(out_rgb, d_rgb, b3, cudaMemcpyDeviceToHost, r.stream));

@@ -119,7 +119,7 @@ __device__ __forceinline__ bool aabb_ref(V3 o, V3 d, V3 mn, V3 mx, float& lo, fl
 
 // Shape::local_intersect of every leaf kind.  Writes the distances in the reference's emission order and
 // returns how many there are (0..4).
-__device__ __forceinline__ int local_intersect(const DevScene& S, int type, int aux, V3 o, V3 d, float t[4]) {
+__device__ __forceinline__ int local_intersect(const DevScene& S, int type, int aux, float4 bd, V3 o, V3 d, float t[4]) {
     switch (type) {
         case T_SPHERE: {  // sphere.rs:47-70 (centre is the origin)
             float a = dot(d, d);
@@ -146,7 +146,6 @@ __device__ __forceinline__ int local_intersect(const DevScene& S, int type, int 
             return 2;
         }
         case T_CYLINDER: {  // cylinder.rs:52-59, 84-151
-            float4 bd = __ldg(&S.bound[aux]);
             int n = 0;
             float two_a = 2.0f * (d.x * d.x + d.z * d.z);
             if (!(fabsf(two_a) < kCloseToZero)) {
@@ -179,7 +178,6 @@ __device__ __forceinline__ int local_intersect(const DevScene& S, int type, int 
             return n;
         }
         case T_CONE: {  // cone.rs:52-57, 89-174
-            float4 bd = __ldg(&S.bound[aux]);
             int n = 0;
             float two_a = 2.0f * (d.x * d.x - d.y * d.y + d.z * d.z);
             float b = 2.0f * (o.x * d.x - o.y * d.y + o.z * d.z);
@@ -232,6 +230,55 @@ __device__ __forceinline__ int local_intersect(const DevScene& S, int type, int 
             if (v < 0.0f || (u + v) > 1.0f) return 0;
             t[0] = f * dot(e2, oce1);
             return 1;
+        }
+    }
+}
+
+__device__ __forceinline__ float4 load_bound(const DevScene& S, int type, int aux) {
+    return (type == T_CYLINDER || type == T_CONE) ? __ldg(&S.bound[aux]) : make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+// The smallest non-negative distance the primitive reports for this object-space ray (what
+// Intersection::hit would pick among its intersections), or a negative / NaN value when there is none.
+// Same arithmetic as local_intersect, minus the work whose result cannot be the answer: for a sphere the
+// far root is only divided out when the near root is negative (the sign of a quotient by 2a > 0 is the sign
+// of its numerator).
+__device__ __forceinline__ float nearest_t(const DevScene& S, int type, int aux, float4 bd, V3 o, V3 d) {
+    switch (type) {
+        case T_SPHERE: {  // sphere.rs:47-70
+            float a = dot(d, d);
+            float b = 2.0f * dot(d, o);
+            float c = dot(o, o) - 1.0f;
+            float disc = b * b - 4.0f * a * c;
+            if (disc < 0.0f) return -1.0f;
+            float two_a = 2.0f * a;
+            float ds = sqrtf(disc);
+            float n0 = -b - ds, n1 = -b + ds;
+            if (two_a > 0.0f) {
+                if (n0 >= 0.0f) return n0 / two_a;
+                if (n1 >= 0.0f) return n1 / two_a;
+                return -1.0f;
+            }
+            float t0 = n0 / two_a, t1 = n1 / two_a;
+            if (t0 >= 0.0f && !(t1 < t0)) return t0;
+            return t1 >= 0.0f ? t1 : t0;
+        }
+        case T_PLANE: {  // plane.rs:45-56
+            if (fabsf(d.y) < kAcne) return -1.0f;
+            return -o.y / d.y;
+        }
+        case T_CUBE: {  // cube.rs:55-63
+            float lo, hi;
+            if (!aabb_ref(o, d, mk(-1.f, -1.f, -1.f), mk(1.f, 1.f, 1.f), lo, hi)) return -1.0f;
+            return lo >= 0.0f ? lo : hi;
+        }
+        default: {
+            float t[4];
+            int n = local_intersect(S, type, aux, bd, o, d, t);
+            float tn = -1.0f;
+            for (int i = 0; i < n; i++)
+                if (t[i] >= 0.0f && (!(tn >= 0.0f) || t[i] < tn)) tn = t[i];
+            return tn;
         }
     }
 }
@@ -406,7 +453,7 @@ __device__ __noinline__ int csg_eval(const DevScene& S, int pc, V3 wo, V3 wd, fl
                 float t[4];
                 int type = h.x & 15;
                 k.prim(type);
-                int c = local_intersect(S, type, h.z, o2, d2, t);
+                int c = local_intersect(S, type, h.z, load_bound(S, type, h.z), o2, d2, t);
                 for (int i = 0; i < c; i++) {
                     if (n < kCsgHitCap) {
                         ht[n] = t[i];
@@ -448,18 +495,9 @@ __device__ __forceinline__ void test_prim(const DevScene& S, int pos, V3 o, V3 d
         cache.xf_id = h.y;
         k.xform();
     }
-    float t[4];
     k.prim(type);
-    int n = local_intersect(S, type, h.z, cache.o, cache.d, t);
-    float tn = kInfF;
-    bool any = false;
-    for (int i = 0; i < n; i++) {
-        if (t[i] >= 0.0f && t[i] <= tn) {
-            tn = fminf(tn, t[i]);
-            any = true;
-        }
-    }
-    if (!any) return;
+    float tn = nearest_t(S, type, h.z, load_bound(S, type, h.z), cache.o, cache.d);
+    if (!(tn >= 0.0f)) return;
     if (((h.x >> 4) & kFlagHasParent) && !ancestors_pass(S, __ldg(&S.head[pos + S.n_prims]).x, o, d)) return;
     consider(best, tn, pos, h.w);
 }
@@ -596,7 +634,7 @@ __device__ __forceinline__ void container_prim(const DevScene& S, int pos, V3 o,
     }
     float t[4];
     k.prim(type);
-    int n = local_intersect(S, type, h.z, cache.o, cache.d, t);
+    int n = local_intersect(S, type, h.z, load_bound(S, type, h.z), cache.o, cache.d, t);
     int cnt = 0;
     float last = -kInfF;
     for (int i = 0; i < n; i++)
@@ -773,15 +811,107 @@ __device__ __forceinline__ float jitter_value(unsigned long long seed, unsigned 
     return (float)((bits >> 8) + 1u) * 5.9604644775390625e-08f;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// What a thread needs to trace: the scene, the small-scene table (kernel parameter block) and, for small
+// scenes, its private slice of the shared-memory origin cache (element (i, c) at org[(i * 3 + c) * 128]).
+struct Env {
+    const DevScene& S;
+    const SmallScene& SS;
+    float* org;
+};
+
+// One primitive of a small scene against the world ray.  CACHED: the object-space origin of this ray was
+// stored by cache_origins (all shadow rays of one shade share their origin, so `inverse * origin`,
+// shape.rs:60-70, is evaluated once per primitive instead of once per light cell — same arithmetic, hoisted).
+template <bool STATS, bool CACHED>
+__device__ __forceinline__ void test_small(const Env& E, int i, V3 o, V3 d, Hit& best, Ctr<STATS>& k) {
+    const SmallPrim& P = E.SS.p[i];
+    const int type = P.head.x & 15;
+    if (type == T_CSG) {
+        float ht[kCsgHitCap];
+        int hp[kCsgHitCap];
+        int n = csg_eval<STATS>(E.S, P.head.z, o, d, ht, hp, k);
+        for (int j = 0; j < n; j++) {
+            if (ht[j] >= 0.0f) {
+                consider(best, ht[j], hp[j], __ldg(&E.S.head[hp[j]]).w);
+                break;
+            }
+        }
+        return;
+    }
+    Xf m{P.r0, P.r1, P.r2};
+    V3 o2;
+    if (CACHED && i < kOrgCache) {
+        o2 = mk(E.org[(i * 3 + 0) * 128], E.org[(i * 3 + 1) * 128], E.org[(i * 3 + 2) * 128]);
+    } else {
+        o2 = xf_point(m, o);
+    }
+    V3 d2 = xf_vec(m, d);
+    k.xform();
+    k.prim(type);
+    float tn = nearest_t(E.S, type, P.head.z, P.bound, o2, d2);
+    if (!(tn >= 0.0f)) return;
+    if (((P.head.x >> 4) & kFlagHasParent) && !ancestors_pass(E.S, P.head.y, o, d)) return;
+    consider(best, tn, i, P.head.w);
+}
+
+__device__ __forceinline__ void cache_origins(const Env& E, V3 o) {
+    const int n = E.SS.n < kOrgCache ? E.SS.n : kOrgCache;
+    for (int i = 0; i < n; i++) {
+        const SmallPrim& P = E.SS.p[i];
+        Xf m{P.r0, P.r1, P.r2};
+        V3 o2 = xf_point(m, o);
+        E.org[(i * 3 + 0) * 128] = o2.x;
+        E.org[(i * 3 + 1) * 128] = o2.y;
+        E.org[(i * 3 + 2) * 128] = o2.z;
+    }
+}
+
+// World::intersect + Intersection::hit for the nearest hit, general (BVH) or small-scene (uniform loop) form.
+template <bool STATS, bool SMALL>
+__device__ __forceinline__ void find_hit(const Env& E, V3 o, V3 d, Hit& best, Ctr<STATS>& k) {
+    if (SMALL) {
+        for (int i = 0; i < E.SS.n; i++) test_small<STATS, false>(E, i, o, d, best, k);
+    } else {
+        nearest_hit<STATS, false>(E.S, o, d, best, k);
+    }
+}
+
 // World::is_shadowed (world.rs:104-119): nearest hit on the point->light ray; shadowed iff that object
 // casts a shadow and is nearer than the light (Q9).
-template <bool STATS>
-__device__ __forceinline__ bool is_shadowed(const DevScene& S, V3 light_position, V3 p, Ctr<STATS>& k) {
+//
+// Small scenes test the shadow casters first: with no caster in [0, distance) the answer is "lit" whatever
+// the non-casting objects do, and otherwise only a non-casting object NEARER than the nearest caster (same
+// (t, depth-first order) comparison as Intersection::hit) can un-shadow the point.  Same predicate as the
+// reference's, evaluated with fewer intersection tests.
+template <bool STATS, bool SMALL, bool CACHED>
+__device__ __forceinline__ bool is_shadowed(const Env& E, V3 light_position, V3 p, Ctr<STATS>& k) {
+    const DevScene& S = E.S;
     k.shadow++;
     V3 v = light_position - p;
     float distance = magnitude(v);
     V3 direction = mk(v.x / distance, v.y / distance, v.z / distance);
     Hit best{distance, -1, -1};  // order -1: a hit AT the light distance is never accepted (`<`, world.rs:116)
+    if (SMALL) {
+        const SmallScene& SS = E.SS;
+        if (!SS.two_pass_shadows) {
+            for (int i = 0; i < SS.n; i++) test_small<STATS, CACHED>(E, i, p, direction, best, k);
+            return best.pos >= 0 && ((__ldg(&S.head[best.pos]).x >> 4) & kFlagCastsShadow);
+        }
+        for (int i = 0; i < SS.n; i++) {
+            if (!((SS.p[i].head.x >> 4) & kFlagCastsShadow)) continue;
+            test_small<STATS, CACHED>(E, i, p, direction, best, k);
+            if (S.all_cast_shadow && best.pos >= 0) return true;
+        }
+        if (best.pos < 0) return false;
+        if (S.all_cast_shadow) return true;
+        const int caster = best.pos;
+        for (int i = 0; i < SS.n; i++) {
+            if ((SS.p[i].head.x >> 4) & kFlagCastsShadow) continue;
+            test_small<STATS, CACHED>(E, i, p, direction, best, k);
+        }
+        return best.pos == caster;
+    }
     if (S.all_cast_shadow) {
         nearest_hit<STATS, true>(S, p, direction, best, k);
         return best.pos >= 0;
@@ -791,9 +921,11 @@ __device__ __forceinline__ bool is_shadowed(const DevScene& S, V3 light_position
 }
 
 // Light::intensity_at (point_light.rs:28-34, rectangle_light.rs:76-88)
-template <bool STATS>
-__device__ __forceinline__ float intensity_at(const DevScene& S, V3 p, unsigned pixel, unsigned path, Ctr<STATS>& k) {
-    if (!S.light_is_rect) return is_shadowed<STATS>(S, ld3(S.light_pos), p, k) ? 0.f : 1.f;
+template <bool STATS, bool SMALL>
+__device__ __forceinline__ float intensity_at(const Env& E, V3 p, unsigned pixel, unsigned path, Ctr<STATS>& k) {
+    const DevScene& S = E.S;
+    if (!S.light_is_rect) return is_shadowed<STATS, SMALL, false>(E, ld3(S.light_pos), p, k) ? 0.f : 1.f;
+    if (SMALL) cache_origins(E, p);
     float total = 0.f;
     int cell = 0;
     for (int v = 0; v < S.v_steps; v++) {
@@ -809,7 +941,7 @@ __device__ __forceinline__ float intensity_at(const DevScene& S, V3 p, unsigned 
                 // rectangle_light.rs:60-66
                 lp = ld3(S.corner) + ld3(S.u_vec) * ((float)u + j1) + ld3(S.v_vec) * ((float)v + j2);
             }
-            if (!is_shadowed<STATS>(S, lp, p, k)) total += 1.0f;
+            if (!is_shadowed<STATS, SMALL, SMALL>(E, lp, p, k)) total += 1.0f;
         }
     }
     return total / (float)S.cells;
@@ -842,9 +974,10 @@ __device__ __forceinline__ V3 combine(V3 surface, V3 reflected, V3 refracted, fl
 // explicit stack of at most depth+1 frames, evaluated in the reference's order (surface, then the whole
 // reflection subtree, then the whole refraction subtree) and combined bottom-up with the same arithmetic.
 // out_t / out_pos (optional) receive the primary hit.
-template <bool STATS>
-__device__ __forceinline__ V3 color_at(const DevScene& S, V3 ro, V3 rd, int depth, unsigned pixel, Ctr<STATS>& k, float* out_t,
+template <bool STATS, bool SMALL>
+__device__ __forceinline__ V3 color_at(const Env& E, V3 ro, V3 rd, int depth, unsigned pixel, Ctr<STATS>& k, float* out_t,
                                        int* out_pos) {
+    const DevScene& S = E.S;
     Frame stack[kMaxFrames];
     int sp = 0;
     int remaining = depth;
@@ -852,7 +985,7 @@ __device__ __forceinline__ V3 color_at(const DevScene& S, V3 ro, V3 rd, int dept
     bool primary = true;
     for (;;) {
         Hit best{kInfF, -1, 0x7fffffff};
-        nearest_hit<STATS, false>(S, ro, rd, best, k);
+        find_hit<STATS, SMALL>(E, ro, rd, best, k);
         if (primary) {
             if (out_t) *out_t = best.pos >= 0 ? best.t : -1.0f;
             if (out_pos) *out_pos = best.pos;
@@ -874,7 +1007,7 @@ __device__ __forceinline__ V3 color_at(const DevScene& S, V3 ro, V3 rd, int dept
             if (dot(n, eye) < 0.0f) n = -n;
             V3 over_point = point + n * kAcne;
             // ---- shade_hit (world.rs:62-86): light intensity first, then Phong (phong_lighting.rs:12-63)
-            float li = intensity_at<STATS>(S, over_point, pixel, path, k);
+            float li = intensity_at<STATS, SMALL>(E, over_point, pixel, path, k);
             V3 material_color = ld3(mat.color);
             if (mat.pattern >= 0) {
                 k.pattern();
@@ -893,7 +1026,9 @@ __device__ __forceinline__ V3 color_at(const DevScene& S, V3 ro, V3 rd, int dept
                     V3 sr = reflect(-to_light, n);
                     float rec = dot(sr, eye);
                     if (!(rec <= 0.0f)) {
-                        float factor = powf(rec, mat.shininess);
+                        // `intensity * specular * factor` (phong_lighting.rs:56-57): with specular == 0 the product
+                        // is 0 for every finite factor, so powf is only evaluated when it can matter
+                        float factor = (mat.specular == 0.0f && mat.shininess <= 1.0e4f) ? 1.0f : powf(rec, mat.shininess);
                         specular = light_rgb * mat.specular * factor;
                     }
                 }
@@ -921,7 +1056,6 @@ __device__ __forceinline__ V3 color_at(const DevScene& S, V3 ro, V3 rd, int dept
                 if (mat.reflective > 0.0f && mat.transparency > 0.0f) {  // schlick_reflectance, world.rs:285-303
                     k.schlick();
                     float cosine = cos_i;
-                    reflectance = 2.0f;  // sentinel, replaced below
                     bool tir = false;
                     if (n1 > n2) {
                         float nn = n1 / n2;

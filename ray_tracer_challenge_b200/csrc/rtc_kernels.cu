@@ -49,8 +49,12 @@ __device__ __forceinline__ void flush_counters<true>(const Ctr<true>& k, DevCoun
     warp_add(&out->overflows, k.overflows);
 }
 
-template <bool STATS>
-__global__ void __launch_bounds__(128) render_tiles(const DevScene S, const DevFrame F, DevCounters* counters) {
+template <bool STATS, bool SMALL>
+__global__ void __launch_bounds__(128) render_tiles(const __grid_constant__ DevScene S, const __grid_constant__ SmallScene SS,
+                                                    const DevFrame F, DevCounters* counters) {
+    // small scenes: per-thread cache of the object-space shadow-ray origins (see test_small)
+    __shared__ float s_org[SMALL ? kOrgCache * 3 * 128 : 1];
+    const Env E{S, SS, s_org + threadIdx.x};
     // block (bx, by) -> tile of 16x8 pixels in band `shard + by * n_shards`; warp w -> 8x4 sub-tile
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int band = F.shard + blockIdx.y * F.n_shards;
@@ -64,7 +68,7 @@ __global__ void __launch_bounds__(128) render_tiles(const DevScene S, const DevF
         V3 o, d;
         ray_for_pixel(S, x, y, o, d);
         k.primary++;
-        c = color_at<STATS>(S, o, d, F.depth, (unsigned)(y * S.width + x), k, nullptr, nullptr);
+        c = color_at<STATS, SMALL>(E, o, d, F.depth, (unsigned)(y * S.width + x), k, nullptr, nullptr);
     }
     if (inside) {
         size_t idx = ((size_t)y * S.width + x) * 3;
@@ -82,15 +86,19 @@ __global__ void __launch_bounds__(128) render_tiles(const DevScene S, const DevF
     flush_counters<STATS>(k, counters);
 }
 
-__global__ void __launch_bounds__(128) trace_rays(const DevScene S, int n, const float* origins, const float* directions, int depth,
-                                                  float* out_rgb, float* out_t, int* out_pos, DevCounters* counters) {
+template <bool SMALL>
+__global__ void __launch_bounds__(128) trace_rays(const __grid_constant__ DevScene S, const __grid_constant__ SmallScene SS, int n,
+                                                  const float* origins, const float* directions, int depth, float* out_rgb,
+                                                  float* out_t, int* out_pos, DevCounters* counters) {
+    __shared__ float s_org[SMALL ? kOrgCache * 3 * 128 : 1];
+    const Env E{S, SS, s_org + threadIdx.x};
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     Ctr<false> k;
     if (i < n) {
         V3 o = ld3(origins + 3 * (size_t)i), d = ld3(directions + 3 * (size_t)i);
         float t;
         int pos;
-        V3 c = color_at<false>(S, o, d, depth, (unsigned)i, k, &t, &pos);
+        V3 c = color_at<false, SMALL>(E, o, d, depth, (unsigned)i, k, &t, &pos);
         out_rgb[3 * (size_t)i] = c.x;
         out_rgb[3 * (size_t)i + 1] = c.y;
         out_rgb[3 * (size_t)i + 2] = c.z;
@@ -100,19 +108,31 @@ __global__ void __launch_bounds__(128) trace_rays(const DevScene S, int n, const
     flush_counters<false>(k, counters);
 }
 
-void launch_render(const DevScene& S, const DevFrame& F, DevCounters* counters, bool detailed, cudaStream_t stream) {
+void launch_render(const DevScene& S, const SmallScene& SS, const DevFrame& F, DevCounters* counters, bool detailed,
+                   cudaStream_t stream) {
     dim3 grid((S.width + kTileW - 1) / kTileW, F.n_bands);
     if (grid.x == 0 || grid.y == 0) return;
-    if (detailed)
-        render_tiles<true><<<grid, 128, 0, stream>>>(S, F, counters);
-    else
-        render_tiles<false><<<grid, 128, 0, stream>>>(S, F, counters);
+    const bool small = SS.n > 0;
+    if (detailed) {
+        if (small)
+            render_tiles<true, true><<<grid, 128, 0, stream>>>(S, SS, F, counters);
+        else
+            render_tiles<true, false><<<grid, 128, 0, stream>>>(S, SS, F, counters);
+    } else {
+        if (small)
+            render_tiles<false, true><<<grid, 128, 0, stream>>>(S, SS, F, counters);
+        else
+            render_tiles<false, false><<<grid, 128, 0, stream>>>(S, SS, F, counters);
+    }
 }
 
-void launch_trace(const DevScene& S, int n, const float* origins, const float* directions, int depth, float* out_rgb,
-                  float* out_t, int* out_pos, DevCounters* counters, cudaStream_t stream) {
+void launch_trace(const DevScene& S, const SmallScene& SS, int n, const float* origins, const float* directions, int depth,
+                  float* out_rgb, float* out_t, int* out_pos, DevCounters* counters, cudaStream_t stream) {
     if (n <= 0) return;
-    trace_rays<<<(n + 127) / 128, 128, 0, stream>>>(S, n, origins, directions, depth, out_rgb, out_t, out_pos, counters);
+    if (SS.n > 0)
+        trace_rays<true><<<(n + 127) / 128, 128, 0, stream>>>(S, SS, n, origins, directions, depth, out_rgb, out_t, out_pos, counters);
+    else
+        trace_rays<false><<<(n + 127) / 128, 128, 0, stream>>>(S, SS, n, origins, directions, depth, out_rgb, out_t, out_pos, counters);
 }
 
 #ifndef RTC_STRICT

@@ -6,14 +6,16 @@
 
 namespace rtc {
 namespace fast {
-void launch_render(const DevScene& S, const DevFrame& F, DevCounters* counters, bool detailed, cudaStream_t stream);
-void launch_trace(const DevScene& S, int n, const float* origins, const float* directions, int depth, float* out_rgb,
-                  float* out_t, int* out_pos, DevCounters* counters, cudaStream_t stream);
+void launch_render(const DevScene& S, const SmallScene& SS, const DevFrame& F, DevCounters* counters, bool detailed,
+                   cudaStream_t stream);
+void launch_trace(const DevScene& S, const SmallScene& SS, int n, const float* origins, const float* directions, int depth,
+                  float* out_rgb, float* out_t, int* out_pos, DevCounters* counters, cudaStream_t stream);
 void launch_fma_peak(float* out, int blocks, int iters, cudaStream_t stream);
 }  // namespace fast
 namespace strict {
-void launch_render(const DevScene& S, const DevFrame& F, DevCounters* counters, bool detailed, cudaStream_t stream);
-void launch_trace(const DevScene& S, int n, const float* origins, const float* directions, int depth, float* out_rgb,
-                  float* out_t, int* out_pos, DevCounters* counters, cudaStream_t stream);
+void launch_render(const DevScene& S, const SmallScene& SS, const DevFrame& F, DevCounters* counters, bool detailed,
+                   cudaStream_t stream);
+void launch_trace(const DevScene& S, const SmallScene& SS, int n, const float* origins, const float* directions, int depth,
+                  float* out_rgb, float* out_t, int* out_pos, DevCounters* counters, cudaStream_t stream);
 }  // namespace strict
 }  // namespace rtc

@@ -106,6 +106,23 @@ struct DevScene {
     int all_cast_shadow;  // every primitive casts a shadow: shadow rays may stop at the first hit
 };
 
+// Small scenes (every BASELINE demo scene: 4..13 primitives) skip the tree: their primitives travel in the
+// kernel's parameter block (constant bank), so the per-ray loop over them is warp-uniform — matrix rows come
+// through the uniform datapath, no global loads, no address arithmetic, no divergence on the type switch.
+constexpr int kSmallCap = 16;   // primitives (or CSG roots) held in the parameter block
+constexpr int kOrgCache = 8;    // object-space shadow-ray origins cached per thread in shared memory
+struct SmallPrim {              // 80 B
+    int4 head;                  // type | flags << 4 | material << 8, cull-chain parent node, aux, dfs order
+    float4 r0, r1, r2;          // rows of the inverse transform
+    float4 bound;               // cylinder / cone: minimum_y, maximum_y, closed
+};
+struct SmallScene {
+    int n;                      // 0: the scene does not qualify, use the general path
+    int two_pass_shadows;       // no CSG roots among them: shadow rays may test casters first (see shadowed_small)
+    int pad[2];
+    SmallPrim p[kSmallCap];
+};
+
 struct DevFrame {  // where a render writes
     float* rgb;            // width*height*3 f32 or null
     unsigned char* u8;     // width*height*3 or null
