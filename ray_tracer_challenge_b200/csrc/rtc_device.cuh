@@ -244,8 +244,8 @@ __device__ __forceinline__ float4 load_bound(const DevScene& S, int type, int au
 // far root is only divided out when the near root is negative (the sign of a quotient by 2a > 0 is the sign
 // of its numerator).
 __device__ __forceinline__ float nearest_t(const DevScene& S, int type, int aux, float4 bd, V3 o, V3 d) {
-    switch (type) {
-        case T_SPHERE: {  // sphere.rs:47-70
+    {
+        if (type == T_SPHERE) {  // sphere.rs:47-70
             float a = dot(d, d);
             float b = 2.0f * dot(d, o);
             float c = dot(o, o) - 1.0f;
@@ -263,16 +263,16 @@ __device__ __forceinline__ float nearest_t(const DevScene& S, int type, int aux,
             if (t0 >= 0.0f && !(t1 < t0)) return t0;
             return t1 >= 0.0f ? t1 : t0;
         }
-        case T_PLANE: {  // plane.rs:45-56
+        if (type == T_PLANE) {  // plane.rs:45-56
             if (fabsf(d.y) < kAcne) return -1.0f;
             return -o.y / d.y;
         }
-        case T_CUBE: {  // cube.rs:55-63
+        if (type == T_CUBE) {  // cube.rs:55-63
             float lo, hi;
             if (!aabb_ref(o, d, mk(-1.f, -1.f, -1.f), mk(1.f, 1.f, 1.f), lo, hi)) return -1.0f;
             return lo >= 0.0f ? lo : hi;
         }
-        default: {
+        {
             float t[4];
             int n = local_intersect(S, type, aux, bd, o, d, t);
             float tn = -1.0f;
@@ -330,11 +330,10 @@ struct Hit {
     int order;
 };
 __device__ __forceinline__ void consider(Hit& best, float t, int pos, int order) {
-    if (t >= 0.0f && (t < best.t || (t == best.t && order < best.order))) {
-        best.t = t;
-        best.pos = pos;
-        best.order = order;
-    }
+    const bool better = t >= 0.0f && (t < best.t || (t == best.t && order < best.order));
+    best.t = better ? t : best.t;
+    best.pos = better ? pos : best.pos;
+    best.order = better ? order : best.order;
 }
 
 // The world ray as seen by the primitive being tested; cached by transform id so that a mesh whose
@@ -346,7 +345,7 @@ struct ObjRay {
 
 // Every enclosing GroupShape culls with the forward ray (group.rs:119-125); the walk stops at a CSG because
 // CSG subtrees are evaluated whole by csg_eval.
-__device__ __forceinline__ bool ancestors_pass(const DevScene& S, int node, V3 o, V3 d) {
+__device__ __noinline__ bool ancestors_pass(const DevScene& S, int node, V3 o, V3 d) {
     while (node >= 0) {
         const DevNode& n = S.nodes[node];
         float lo, hi;
@@ -812,25 +811,53 @@ __device__ __forceinline__ float jitter_value(unsigned long long seed, unsigned 
 }
 
 // ---------------------------------------------------------------------------------------------------
-// What a thread needs to trace: the scene, the small-scene table (kernel parameter block) and, for small
-// scenes, its private slice of the shared-memory origin cache (element (i, c) at org[(i * 3 + c) * 128]).
+// What a thread needs to trace: the scene, the small-scene table and, for small scenes, its private slice of
+// the shared-memory origin cache (element (i, c) at org[(i * 3 + c) * 128]).
 struct Env {
     const DevScene& S;
     const SmallScene& SS;
+    const float4* tab;  // small scenes: the primitive table staged in shared memory (5 x 16 B per primitive)
     float* org;
 };
 
-// One primitive of a small scene against the world ray.  CACHED: the object-space origin of this ray was
-// stored by cache_origins (all shadow rays of one shade share their origin, so `inverse * origin`,
-// shape.rs:60-70, is evaluated once per primitive instead of once per light cell — same arithmetic, hoisted).
+// Small scenes keep their primitive table in shared memory (copied from the kernel parameter block by
+// stage_small_scene): every thread of a warp reads the same entry, so each row is one broadcast LDS.128.
+__device__ __forceinline__ void stage_small_scene(const SmallScene& SS, float4* s_tab) {
+    const float4* src = reinterpret_cast<const float4*>(SS.p);
+    for (int i = threadIdx.x; i < SS.n * 5; i += blockDim.x) s_tab[i] = src[i];
+    __syncthreads();
+}
+
+// Object-space ray of small-scene primitive i and its nearest non-negative distance (negative / NaN: none).
+// CACHED: the object-space origin was stored by cache_origins — all shadow rays of one shade share their
+// origin, so `inverse * origin` (shape.rs:60-70) is evaluated once per primitive instead of once per light
+// cell: the same arithmetic, hoisted.  Not for CSG roots (see test_small).
+template <bool STATS, bool CACHED>
+__device__ __forceinline__ float small_t(const Env& E, int i, int head_x, int aux, V3 o, V3 d, Ctr<STATS>& k) {
+    const float4* row = E.tab + i * 5;
+    Xf m{row[1], row[2], row[3]};
+    V3 o2;
+    if (CACHED && i < kOrgCache) {
+        o2 = mk(E.org[(i * 3 + 0) * 128], E.org[(i * 3 + 1) * 128], E.org[(i * 3 + 2) * 128]);
+    } else {
+        o2 = xf_point(m, o);
+    }
+    V3 d2 = xf_vec(m, d);
+    const int type = head_x & 15;
+    k.xform();
+    k.prim(type);
+    float4 bd = (type == T_CYLINDER || type == T_CONE) ? row[4] : make_float4(0.f, 0.f, 0.f, 0.f);
+    return nearest_t(E.S, type, aux, bd, o2, d2);
+}
+
+// One item of a small scene (primitive or CSG root) for the nearest-hit search.
 template <bool STATS, bool CACHED>
 __device__ __forceinline__ void test_small(const Env& E, int i, V3 o, V3 d, Hit& best, Ctr<STATS>& k) {
-    const SmallPrim& P = E.SS.p[i];
-    const int type = P.head.x & 15;
-    if (type == T_CSG) {
+    const int4 head = *reinterpret_cast<const int4*>(E.tab + i * 5);
+    if ((head.x & 15) == T_CSG) {
         float ht[kCsgHitCap];
         int hp[kCsgHitCap];
-        int n = csg_eval<STATS>(E.S, P.head.z, o, d, ht, hp, k);
+        int n = csg_eval<STATS>(E.S, head.z, o, d, ht, hp, k);
         for (int j = 0; j < n; j++) {
             if (ht[j] >= 0.0f) {
                 consider(best, ht[j], hp[j], __ldg(&E.S.head[hp[j]]).w);
@@ -839,27 +866,16 @@ __device__ __forceinline__ void test_small(const Env& E, int i, V3 o, V3 d, Hit&
         }
         return;
     }
-    Xf m{P.r0, P.r1, P.r2};
-    V3 o2;
-    if (CACHED && i < kOrgCache) {
-        o2 = mk(E.org[(i * 3 + 0) * 128], E.org[(i * 3 + 1) * 128], E.org[(i * 3 + 2) * 128]);
-    } else {
-        o2 = xf_point(m, o);
-    }
-    V3 d2 = xf_vec(m, d);
-    k.xform();
-    k.prim(type);
-    float tn = nearest_t(E.S, type, P.head.z, P.bound, o2, d2);
-    if (!(tn >= 0.0f)) return;
-    if (((P.head.x >> 4) & kFlagHasParent) && !ancestors_pass(E.S, P.head.y, o, d)) return;
-    consider(best, tn, i, P.head.w);
+    float tn = small_t<STATS, CACHED>(E, i, head.x, head.z, o, d, k);
+    if (((head.x >> 4) & kFlagHasParent) && tn >= 0.0f && !ancestors_pass(E.S, head.y, o, d)) return;
+    consider(best, tn, i, head.w);
 }
 
 __device__ __forceinline__ void cache_origins(const Env& E, V3 o) {
     const int n = E.SS.n < kOrgCache ? E.SS.n : kOrgCache;
     for (int i = 0; i < n; i++) {
-        const SmallPrim& P = E.SS.p[i];
-        Xf m{P.r0, P.r1, P.r2};
+        const float4* row = E.tab + i * 5;
+        Xf m{row[1], row[2], row[3]};
         V3 o2 = xf_point(m, o);
         E.org[(i * 3 + 0) * 128] = o2.x;
         E.org[(i * 3 + 1) * 128] = o2.y;
@@ -871,7 +887,8 @@ __device__ __forceinline__ void cache_origins(const Env& E, V3 o) {
 template <bool STATS, bool SMALL>
 __device__ __forceinline__ void find_hit(const Env& E, V3 o, V3 d, Hit& best, Ctr<STATS>& k) {
     if (SMALL) {
-        for (int i = 0; i < E.SS.n; i++) test_small<STATS, false>(E, i, o, d, best, k);
+        const int n = E.SS.n;
+        for (int i = 0; i < n; i++) test_small<STATS, false>(E, i, o, d, best, k);
     } else {
         nearest_hit<STATS, false>(E.S, o, d, best, k);
     }
@@ -891,27 +908,45 @@ __device__ __forceinline__ bool is_shadowed(const Env& E, V3 light_position, V3 
     V3 v = light_position - p;
     float distance = magnitude(v);
     V3 direction = mk(v.x / distance, v.y / distance, v.z / distance);
-    Hit best{distance, -1, -1};  // order -1: a hit AT the light distance is never accepted (`<`, world.rs:116)
     if (SMALL) {
         const SmallScene& SS = E.SS;
-        if (!SS.two_pass_shadows) {
-            for (int i = 0; i < SS.n; i++) test_small<STATS, CACHED>(E, i, p, direction, best, k);
+        const int n = SS.n;
+        if (!SS.two_pass_shadows) {  // a CSG root is present: plain nearest-hit search
+            Hit best{distance, -1, -1};
+            for (int i = 0; i < n; i++) test_small<STATS, CACHED>(E, i, p, direction, best, k);
             return best.pos >= 0 && ((__ldg(&S.head[best.pos]).x >> 4) & kFlagCastsShadow);
         }
-        for (int i = 0; i < SS.n; i++) {
-            if (!((SS.p[i].head.x >> 4) & kFlagCastsShadow)) continue;
-            test_small<STATS, CACHED>(E, i, p, direction, best, k);
-            if (S.all_cast_shadow && best.pos >= 0) return true;
+        if (S.all_cast_shadow) {  // any hit in [0, distance) shadows the point
+            for (int i = 0; i < n; i++) {
+                const int4 head = *reinterpret_cast<const int4*>(E.tab + i * 5);
+                float t = small_t<STATS, CACHED>(E, i, head.x, head.z, p, direction, k);
+                if (t >= 0.0f && t < distance) {
+                    if (!((head.x >> 4) & kFlagHasParent) || ancestors_pass(S, head.y, p, direction)) return true;
+                }
+            }
+            return false;
+        }
+        // order -1: a hit AT the light distance is never accepted (`<`, world.rs:116)
+        Hit best{distance, -1, -1};
+        for (int i = 0; i < n; i++) {
+            const int4 head = *reinterpret_cast<const int4*>(E.tab + i * 5);
+            if (!((head.x >> 4) & kFlagCastsShadow)) continue;
+            float t = small_t<STATS, CACHED>(E, i, head.x, head.z, p, direction, k);
+            if (((head.x >> 4) & kFlagHasParent) && t >= 0.0f && !ancestors_pass(S, head.y, p, direction)) continue;
+            consider(best, t, i, head.w);
         }
         if (best.pos < 0) return false;
-        if (S.all_cast_shadow) return true;
         const int caster = best.pos;
-        for (int i = 0; i < SS.n; i++) {
-            if ((SS.p[i].head.x >> 4) & kFlagCastsShadow) continue;
-            test_small<STATS, CACHED>(E, i, p, direction, best, k);
+        for (int i = 0; i < n; i++) {
+            const int4 head = *reinterpret_cast<const int4*>(E.tab + i * 5);
+            if ((head.x >> 4) & kFlagCastsShadow) continue;
+            float t = small_t<STATS, CACHED>(E, i, head.x, head.z, p, direction, k);
+            if (((head.x >> 4) & kFlagHasParent) && t >= 0.0f && !ancestors_pass(S, head.y, p, direction)) continue;
+            consider(best, t, i, head.w);
         }
         return best.pos == caster;
     }
+    Hit best{distance, -1, -1};
     if (S.all_cast_shadow) {
         nearest_hit<STATS, true>(S, p, direction, best, k);
         return best.pos >= 0;

@@ -54,7 +54,9 @@ __global__ void __launch_bounds__(128) render_tiles(const __grid_constant__ DevS
                                                     const DevFrame F, DevCounters* counters) {
     // small scenes: per-thread cache of the object-space shadow-ray origins (see test_small)
     __shared__ float s_org[SMALL ? kOrgCache * 3 * 128 : 1];
-    const Env E{S, SS, s_org + threadIdx.x};
+    __shared__ float4 s_tab[SMALL ? kSmallCap * 5 : 1];
+    if (SMALL) stage_small_scene(SS, s_tab);
+    const Env E{S, SS, s_tab, s_org + threadIdx.x};
     // block (bx, by) -> tile of 16x8 pixels in band `shard + by * n_shards`; warp w -> 8x4 sub-tile
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int band = F.shard + blockIdx.y * F.n_shards;
@@ -91,7 +93,9 @@ __global__ void __launch_bounds__(128) trace_rays(const __grid_constant__ DevSce
                                                   const float* origins, const float* directions, int depth, float* out_rgb,
                                                   float* out_t, int* out_pos, DevCounters* counters) {
     __shared__ float s_org[SMALL ? kOrgCache * 3 * 128 : 1];
-    const Env E{S, SS, s_org + threadIdx.x};
+    __shared__ float4 s_tab[SMALL ? kSmallCap * 5 : 1];
+    if (SMALL) stage_small_scene(SS, s_tab);
+    const Env E{S, SS, s_tab, s_org + threadIdx.x};
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     Ctr<false> k;
     if (i < n) {
