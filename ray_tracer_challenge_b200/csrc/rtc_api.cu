@@ -11,6 +11,7 @@
 #include <cstring>
 #include <map>
 #include <string>
+#include <tuple>
 #include <vector>
 
 #include <cuda_runtime.h>
@@ -310,9 +311,16 @@ int flatten(RtcScene* s, Flattened& f) {
     if ((int)bounded.size() < s->bvh_min_prims) {  // tiny scene: test everything for every ray, no tree
         unbounded.insert(unbounded.end(), bounded.begin(), bounded.end());
         bounded.clear();
-        // keep depth-first order in the linear list (purely cosmetic: ties are broken by the order field)
-        std::sort(unbounded.begin(), unbounded.end(), [&](const Item& a, const Item& b) {
-            auto key = [&](const Item& it) { return it.prim >= 0 ? it.prim : np + ~it.prim; };
+        // group the linear list by (shadow casters first, kind) — the small-scene kernels loop over runs of one
+        // kind; depth-first order inside a run (ties are broken by the stored order field, not by position)
+        std::stable_sort(unbounded.begin(), unbounded.end(), [&](const Item& a, const Item& b) {
+            auto key = [&](const Item& it) {
+                int dfs = it.prim >= 0 ? it.prim : np + ~it.prim;
+                int caster = it.prim >= 0 ? (s->prims[it.prim].casts_shadow ? 0 : 1) : 0;
+                int type = it.prim >= 0 ? s->prims[it.prim].type : 99;
+                int bucket = type == RTC_SPHERE ? 0 : type == RTC_PLANE ? 1 : type == RTC_CUBE ? 2 : 3;
+                return std::make_tuple(caster, bucket, dfs);
+            };
             return key(a) < key(b);
         });
     }
@@ -516,11 +524,16 @@ int flatten(RtcScene* s, Flattened& f) {
     if (f.bvh_root < 0 && n_items > 0 && n_items <= kSmallCap) {
         f.small.n = n_items;
         f.small.two_pass_shadows = 1;
+        int ends[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         for (int i = 0; i < n_items; i++) {
             SmallPrim& sp = f.small.p[i];
             int4 h = f.head[i];
             sp.head = make_int4(h.x, f.head[f.n_pos + i].x, h.z, h.w);
             int type = h.x & 15;
+            bool caster = type == T_CSG || ((h.x >> 4) & kFlagCastsShadow);
+            int bucket = (caster ? 0 : 4) + (type == T_SPHERE ? 0 : type == T_PLANE ? 1 : type == T_CUBE ? 2 : 3);
+            for (int b = bucket; b < 8; b++) ends[b] = i + 1;
+            if ((h.x >> 4) & kFlagHasParent) f.small.has_cull_chain = 1;
             if (type == T_CSG) {
                 f.small.two_pass_shadows = 0;
                 sp.r0 = sp.r1 = sp.r2 = sp.bound = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -529,6 +542,8 @@ int flatten(RtcScene* s, Flattened& f) {
             sp.r0 = f.xform[3 * (size_t)h.y], sp.r1 = f.xform[3 * (size_t)h.y + 1], sp.r2 = f.xform[3 * (size_t)h.y + 2];
             sp.bound = (type == T_CYLINDER || type == T_CONE) ? f.bound[h.z] : make_float4(0.f, 0.f, 0.f, 0.f);
         }
+        f.small.caster_end = make_int4(ends[0], ends[1], ends[2], ends[3]);
+        f.small.other_end = make_int4(ends[4], ends[5], ends[6], ends[7]);
     }
     s->n_bvh_nodes = (int)f.bvh.size();
     s->n_linear = (int)f.linear.size();

@@ -811,50 +811,65 @@ __device__ __forceinline__ float jitter_value(unsigned long long seed, unsigned 
 }
 
 // ---------------------------------------------------------------------------------------------------
-// What a thread needs to trace: the scene, the small-scene table and, for small scenes, its private slice of
-// the shared-memory origin cache (element (i, c) at org[(i * 3 + c) * 128]).
+// What a thread needs to trace: the scene and the small-scene table (both in the kernel parameter block).
 struct Env {
     const DevScene& S;
     const SmallScene& SS;
-    const float4* tab;  // small scenes: the primitive table staged in shared memory (5 x 16 B per primitive)
-    float* org;
 };
 
-// Small scenes keep their primitive table in shared memory (copied from the kernel parameter block by
-// stage_small_scene): every thread of a warp reads the same entry, so each row is one broadcast LDS.128.
-__device__ __forceinline__ void stage_small_scene(const SmallScene& SS, float4* s_tab) {
+// Small scenes keep two things in (dynamic) shared memory:
+//   tab : the primitive table, 5 x float4 per primitive {head, row0, row1, row2, bound}, copied from the
+//         parameter block by stage_small_scene — every thread of a warp reads the same entry, so a row is one
+//         broadcast LDS.128 with an immediate offset;
+//   org : per thread, the object-space origin of the current shade's shadow rays for the first kOrgCache
+//         primitives (element (i, c) of thread t at org[(i * 3 + c) * 128 + t]).
+__device__ __forceinline__ const float4* small_tab() {
+    extern __shared__ float4 rtc_smem[];
+    return rtc_smem;
+}
+__device__ __forceinline__ float* small_org() {
+    extern __shared__ float4 rtc_smem[];
+    return reinterpret_cast<float*>(rtc_smem + kSmallCap * 5) + threadIdx.x;
+}
+__device__ __forceinline__ void stage_small_scene(const SmallScene& SS) {
+    extern __shared__ float4 rtc_smem[];
     const float4* src = reinterpret_cast<const float4*>(SS.p);
-    for (int i = threadIdx.x; i < SS.n * 5; i += blockDim.x) s_tab[i] = src[i];
+    for (int i = threadIdx.x; i < SS.n * 5; i += blockDim.x) rtc_smem[i] = src[i];
     __syncthreads();
 }
 
-// Object-space ray of small-scene primitive i and its nearest non-negative distance (negative / NaN: none).
-// CACHED: the object-space origin was stored by cache_origins — all shadow rays of one shade share their
-// origin, so `inverse * origin` (shape.rs:60-70) is evaluated once per primitive instead of once per light
-// cell: the same arithmetic, hoisted.  Not for CSG roots (see test_small).
-template <bool STATS, bool CACHED>
-__device__ __forceinline__ float small_t(const Env& E, int i, int head_x, int aux, V3 o, V3 d, Ctr<STATS>& k) {
-    const float4* row = E.tab + i * 5;
-    Xf m{row[1], row[2], row[3]};
-    V3 o2;
+// Object-space origin of primitive i: from the per-shade cache (all shadow rays of one shade share their
+// origin, so `inverse * origin`, shape.rs:60-70, is evaluated once per primitive instead of once per light
+// cell — the same arithmetic, hoisted) or computed.
+template <bool CACHED>
+__device__ __forceinline__ V3 small_origin(int i, const Xf& m, V3 o) {
     if (CACHED && i < kOrgCache) {
-        o2 = mk(E.org[(i * 3 + 0) * 128], E.org[(i * 3 + 1) * 128], E.org[(i * 3 + 2) * 128]);
-    } else {
-        o2 = xf_point(m, o);
+        const float* org = small_org();
+        return mk(org[(i * 3 + 0) * 128], org[(i * 3 + 1) * 128], org[(i * 3 + 2) * 128]);
     }
-    V3 d2 = xf_vec(m, d);
-    const int type = head_x & 15;
-    k.xform();
-    k.prim(type);
-    float4 bd = (type == T_CYLINDER || type == T_CONE) ? row[4] : make_float4(0.f, 0.f, 0.f, 0.f);
-    return nearest_t(E.S, type, aux, bd, o2, d2);
+    return xf_point(m, o);
 }
 
-// One item of a small scene (primitive or CSG root) for the nearest-hit search.
+__device__ __forceinline__ void cache_origins(const Env& E, V3 o) {
+    const int n = E.SS.n < kOrgCache ? E.SS.n : kOrgCache;
+    const float4* tab = small_tab();
+    float* org = small_org();
+    for (int i = 0; i < n; i++) {
+        Xf m{tab[i * 5 + 1], tab[i * 5 + 2], tab[i * 5 + 3]};
+        V3 o2 = xf_point(m, o);
+        org[(i * 3 + 0) * 128] = o2.x;
+        org[(i * 3 + 1) * 128] = o2.y;
+        org[(i * 3 + 2) * 128] = o2.z;
+    }
+}
+
+// One item of a small scene of any kind (primitive or CSG root), honouring the cull chain: the general form.
 template <bool STATS, bool CACHED>
 __device__ __forceinline__ void test_small(const Env& E, int i, V3 o, V3 d, Hit& best, Ctr<STATS>& k) {
-    const int4 head = *reinterpret_cast<const int4*>(E.tab + i * 5);
-    if ((head.x & 15) == T_CSG) {
+    const float4* tab = small_tab();
+    const int4 head = *reinterpret_cast<const int4*>(tab + i * 5);
+    const int type = head.x & 15;
+    if (type == T_CSG) {
         float ht[kCsgHitCap];
         int hp[kCsgHitCap];
         int n = csg_eval<STATS>(E.S, head.z, o, d, ht, hp, k);
@@ -866,29 +881,89 @@ __device__ __forceinline__ void test_small(const Env& E, int i, V3 o, V3 d, Hit&
         }
         return;
     }
-    float tn = small_t<STATS, CACHED>(E, i, head.x, head.z, o, d, k);
+    Xf m{tab[i * 5 + 1], tab[i * 5 + 2], tab[i * 5 + 3]};
+    V3 o2 = small_origin<CACHED>(i, m, o);
+    V3 d2 = xf_vec(m, d);
+    k.xform();
+    k.prim(type);
+    float tn = nearest_t(E.S, type, head.z, tab[i * 5 + 4], o2, d2);
     if (((head.x >> 4) & kFlagHasParent) && tn >= 0.0f && !ancestors_pass(E.S, head.y, o, d)) return;
     consider(best, tn, i, head.w);
 }
 
-__device__ __forceinline__ void cache_origins(const Env& E, V3 o) {
-    const int n = E.SS.n < kOrgCache ? E.SS.n : kOrgCache;
-    for (int i = 0; i < n; i++) {
-        const float4* row = E.tab + i * 5;
-        Xf m{row[1], row[2], row[3]};
-        V3 o2 = xf_point(m, o);
-        E.org[(i * 3 + 0) * 128] = o2.x;
-        E.org[(i * 3 + 1) * 128] = o2.y;
-        E.org[(i * 3 + 2) * 128] = o2.z;
+// Nearest hit among the items [begin, ends.w) of a small scene, which are runs of spheres, planes, cubes and
+// "everything else" ending at ends.x / .y / .z / .w: one tight loop per kind, no per-item dispatch.
+// ANY: return true as soon as some item is hit in [0, best.t) (shadow rays when every object casts a shadow).
+template <bool STATS, bool CACHED, bool ANY>
+__device__ __forceinline__ bool scan_small(const Env& E, int begin, int4 ends, V3 o, V3 d, Hit& best, Ctr<STATS>& k) {
+    const float4* tab = small_tab();
+    int i = begin;
+    for (; i < ends.x; i++) {  // spheres — sphere.rs:47-70
+        Xf m{tab[i * 5 + 1], tab[i * 5 + 2], tab[i * 5 + 3]};
+        V3 o2 = small_origin<CACHED>(i, m, o);
+        V3 d2 = xf_vec(m, d);
+        k.xform();
+        k.prim(T_SPHERE);
+        float t = nearest_t(E.S, T_SPHERE, 0, make_float4(0.f, 0.f, 0.f, 0.f), o2, d2);
+        if (ANY) {
+            if (t >= 0.0f && t < best.t) return true;
+        } else {
+            consider(best, t, i, __float_as_int(tab[i * 5].w));
+        }
     }
+    for (; i < ends.y; i++) {  // planes — plane.rs:45-56 only reads the y components of the object-space ray
+        float4 r1 = tab[i * 5 + 2];
+        float oy;
+        if (CACHED && i < kOrgCache)
+            oy = small_org()[(i * 3 + 1) * 128];
+        else
+            oy = r1.x * o.x + r1.y * o.y + r1.z * o.z + r1.w;
+        float dy = r1.x * d.x + r1.y * d.y + r1.z * d.z;
+        k.xform();
+        k.prim(T_PLANE);
+        float t = (fabsf(dy) < kAcne) ? -1.0f : -oy / dy;
+        if (ANY) {
+            if (t >= 0.0f && t < best.t) return true;
+        } else {
+            consider(best, t, i, __float_as_int(tab[i * 5].w));
+        }
+    }
+    for (; i < ends.z; i++) {  // cubes — cube.rs:55-63
+        Xf m{tab[i * 5 + 1], tab[i * 5 + 2], tab[i * 5 + 3]};
+        V3 o2 = small_origin<CACHED>(i, m, o);
+        V3 d2 = xf_vec(m, d);
+        k.xform();
+        k.prim(T_CUBE);
+        float t = nearest_t(E.S, T_CUBE, 0, make_float4(0.f, 0.f, 0.f, 0.f), o2, d2);
+        if (ANY) {
+            if (t >= 0.0f && t < best.t) return true;
+        } else {
+            consider(best, t, i, __float_as_int(tab[i * 5].w));
+        }
+    }
+    for (; i < ends.w; i++) {  // cylinders, cones, triangles, CSG roots
+        if (ANY) {
+            Hit h{best.t, -1, -1};
+            test_small<STATS, CACHED>(E, i, o, d, h, k);
+            if (h.pos >= 0) return true;
+        } else {
+            test_small<STATS, CACHED>(E, i, o, d, best, k);
+        }
+    }
+    return false;
 }
 
-// World::intersect + Intersection::hit for the nearest hit, general (BVH) or small-scene (uniform loop) form.
+// World::intersect + Intersection::hit for the nearest hit, general (BVH) or small-scene form.
 template <bool STATS, bool SMALL>
 __device__ __forceinline__ void find_hit(const Env& E, V3 o, V3 d, Hit& best, Ctr<STATS>& k) {
     if (SMALL) {
-        const int n = E.SS.n;
-        for (int i = 0; i < n; i++) test_small<STATS, false>(E, i, o, d, best, k);
+        const SmallScene& SS = E.SS;
+        if (SS.has_cull_chain) {
+            for (int i = 0; i < SS.n; i++) test_small<STATS, false>(E, i, o, d, best, k);
+        } else {
+            scan_small<STATS, false, false>(E, 0, SS.caster_end, o, d, best, k);
+            scan_small<STATS, false, false>(E, SS.caster_end.w, SS.other_end, o, d, best, k);
+        }
     } else {
         nearest_hit<STATS, false>(E.S, o, d, best, k);
     }
@@ -908,45 +983,22 @@ __device__ __forceinline__ bool is_shadowed(const Env& E, V3 light_position, V3 
     V3 v = light_position - p;
     float distance = magnitude(v);
     V3 direction = mk(v.x / distance, v.y / distance, v.z / distance);
+    // order -1: a hit AT the light distance is never accepted (`<`, world.rs:116)
+    Hit best{distance, -1, -1};
     if (SMALL) {
         const SmallScene& SS = E.SS;
-        const int n = SS.n;
-        if (!SS.two_pass_shadows) {  // a CSG root is present: plain nearest-hit search
-            Hit best{distance, -1, -1};
-            for (int i = 0; i < n; i++) test_small<STATS, CACHED>(E, i, p, direction, best, k);
+        if (!SS.two_pass_shadows || SS.has_cull_chain) {  // a CSG root or a cull chain: plain nearest-hit search
+            for (int i = 0; i < SS.n; i++) test_small<STATS, CACHED>(E, i, p, direction, best, k);
             return best.pos >= 0 && ((__ldg(&S.head[best.pos]).x >> 4) & kFlagCastsShadow);
         }
-        if (S.all_cast_shadow) {  // any hit in [0, distance) shadows the point
-            for (int i = 0; i < n; i++) {
-                const int4 head = *reinterpret_cast<const int4*>(E.tab + i * 5);
-                float t = small_t<STATS, CACHED>(E, i, head.x, head.z, p, direction, k);
-                if (t >= 0.0f && t < distance) {
-                    if (!((head.x >> 4) & kFlagHasParent) || ancestors_pass(S, head.y, p, direction)) return true;
-                }
-            }
-            return false;
-        }
-        // order -1: a hit AT the light distance is never accepted (`<`, world.rs:116)
-        Hit best{distance, -1, -1};
-        for (int i = 0; i < n; i++) {
-            const int4 head = *reinterpret_cast<const int4*>(E.tab + i * 5);
-            if (!((head.x >> 4) & kFlagCastsShadow)) continue;
-            float t = small_t<STATS, CACHED>(E, i, head.x, head.z, p, direction, k);
-            if (((head.x >> 4) & kFlagHasParent) && t >= 0.0f && !ancestors_pass(S, head.y, p, direction)) continue;
-            consider(best, t, i, head.w);
-        }
+        if (S.all_cast_shadow)  // any hit in [0, distance) shadows the point
+            return scan_small<STATS, CACHED, true>(E, 0, SS.caster_end, p, direction, best, k);
+        scan_small<STATS, CACHED, false>(E, 0, SS.caster_end, p, direction, best, k);
         if (best.pos < 0) return false;
         const int caster = best.pos;
-        for (int i = 0; i < n; i++) {
-            const int4 head = *reinterpret_cast<const int4*>(E.tab + i * 5);
-            if ((head.x >> 4) & kFlagCastsShadow) continue;
-            float t = small_t<STATS, CACHED>(E, i, head.x, head.z, p, direction, k);
-            if (((head.x >> 4) & kFlagHasParent) && t >= 0.0f && !ancestors_pass(S, head.y, p, direction)) continue;
-            consider(best, t, i, head.w);
-        }
+        scan_small<STATS, CACHED, false>(E, SS.caster_end.w, SS.other_end, p, direction, best, k);
         return best.pos == caster;
     }
-    Hit best{distance, -1, -1};
     if (S.all_cast_shadow) {
         nearest_hit<STATS, true>(S, p, direction, best, k);
         return best.pos >= 0;

@@ -52,11 +52,9 @@ __device__ __forceinline__ void flush_counters<true>(const Ctr<true>& k, DevCoun
 template <bool STATS, bool SMALL>
 __global__ void __launch_bounds__(128) render_tiles(const __grid_constant__ DevScene S, const __grid_constant__ SmallScene SS,
                                                     const DevFrame F, DevCounters* counters) {
-    // small scenes: per-thread cache of the object-space shadow-ray origins (see test_small)
-    __shared__ float s_org[SMALL ? kOrgCache * 3 * 128 : 1];
-    __shared__ float4 s_tab[SMALL ? kSmallCap * 5 : 1];
-    if (SMALL) stage_small_scene(SS, s_tab);
-    const Env E{S, SS, s_tab, s_org + threadIdx.x};
+    // small scenes: primitive table + per-thread shadow-origin cache in dynamic shared memory (kSmallSmemBytes)
+    if (SMALL) stage_small_scene(SS);
+    const Env E{S, SS};
     // block (bx, by) -> tile of 16x8 pixels in band `shard + by * n_shards`; warp w -> 8x4 sub-tile
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int band = F.shard + blockIdx.y * F.n_shards;
@@ -92,10 +90,8 @@ template <bool SMALL>
 __global__ void __launch_bounds__(128) trace_rays(const __grid_constant__ DevScene S, const __grid_constant__ SmallScene SS, int n,
                                                   const float* origins, const float* directions, int depth, float* out_rgb,
                                                   float* out_t, int* out_pos, DevCounters* counters) {
-    __shared__ float s_org[SMALL ? kOrgCache * 3 * 128 : 1];
-    __shared__ float4 s_tab[SMALL ? kSmallCap * 5 : 1];
-    if (SMALL) stage_small_scene(SS, s_tab);
-    const Env E{S, SS, s_tab, s_org + threadIdx.x};
+    if (SMALL) stage_small_scene(SS);
+    const Env E{S, SS};
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     Ctr<false> k;
     if (i < n) {
@@ -119,12 +115,12 @@ void launch_render(const DevScene& S, const SmallScene& SS, const DevFrame& F, D
     const bool small = SS.n > 0;
     if (detailed) {
         if (small)
-            render_tiles<true, true><<<grid, 128, 0, stream>>>(S, SS, F, counters);
+            render_tiles<true, true><<<grid, 128, kSmallSmemBytes, stream>>>(S, SS, F, counters);
         else
             render_tiles<true, false><<<grid, 128, 0, stream>>>(S, SS, F, counters);
     } else {
         if (small)
-            render_tiles<false, true><<<grid, 128, 0, stream>>>(S, SS, F, counters);
+            render_tiles<false, true><<<grid, 128, kSmallSmemBytes, stream>>>(S, SS, F, counters);
         else
             render_tiles<false, false><<<grid, 128, 0, stream>>>(S, SS, F, counters);
     }
@@ -134,7 +130,7 @@ void launch_trace(const DevScene& S, const SmallScene& SS, int n, const float* o
                   float* out_rgb, float* out_t, int* out_pos, DevCounters* counters, cudaStream_t stream) {
     if (n <= 0) return;
     if (SS.n > 0)
-        trace_rays<true><<<(n + 127) / 128, 128, 0, stream>>>(S, SS, n, origins, directions, depth, out_rgb, out_t, out_pos, counters);
+        trace_rays<true><<<(n + 127) / 128, 128, kSmallSmemBytes, stream>>>(S, SS, n, origins, directions, depth, out_rgb, out_t, out_pos, counters);
     else
         trace_rays<false><<<(n + 127) / 128, 128, 0, stream>>>(S, SS, n, origins, directions, depth, out_rgb, out_t, out_pos, counters);
 }

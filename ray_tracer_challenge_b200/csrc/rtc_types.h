@@ -116,12 +116,19 @@ struct SmallPrim {              // 80 B
     float4 r0, r1, r2;          // rows of the inverse transform
     float4 bound;               // cylinder / cone: minimum_y, maximum_y, closed
 };
+// The table is sorted by (casts shadow first, then kind) so every loop over it is a run of ONE kind:
+//   casters:     spheres [0, c.x) planes [c.x, c.y) cubes [c.y, c.z) everything else [c.z, c.w)
+//   non-casters: spheres [c.w, o.x) planes [o.x, o.y) cubes [o.y, o.z) everything else [o.z, o.w = n)
+// (hit ties are broken by the stored depth-first order, so the storage order is free).
 struct SmallScene {
     int n;                      // 0: the scene does not qualify, use the general path
-    int two_pass_shadows;       // no CSG roots among them: shadow rays may test casters first (see shadowed_small)
-    int pad[2];
+    int two_pass_shadows;       // no CSG roots among them: shadow rays may test casters first (see is_shadowed)
+    int has_cull_chain;         // some unbounded primitive sits inside a group whose cull must be honoured (Q6)
+    int pad;
+    int4 caster_end, other_end;
     SmallPrim p[kSmallCap];
 };
+constexpr int kSmallSmemBytes = kSmallCap * 80 + kOrgCache * 3 * 128 * 4;
 
 struct DevFrame {  // where a render writes
     float* rgb;            // width*height*3 f32 or null
