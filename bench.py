@@ -50,18 +50,26 @@ WORKLOADS = {
 
 
 def sample_clocks(stop: threading.Event, out: list, gpu_index: int) -> None:
+    """One streaming nvidia-smi (-lms 50) for the whole timed region; every line is one sample."""
     q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
-    while not stop.is_set():
-        try:
-            r = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(gpu_index)],
-                               capture_output=True, text=True, timeout=5)
-            parts = [p.strip() for p in r.stdout.strip().split(",")]
+    try:
+        proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(gpu_index),
+                                 "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+    except Exception:
+        return
+
+    def reader():
+        for line in proc.stdout:
+            parts = [p.strip() for p in line.strip().split(",")]
             if len(parts) >= 6:
                 out.append(parts)
-        except Exception:
-            pass
-        stop.wait(0.15)
+
+    t = threading.Thread(target=reader, daemon=True)
+    t.start()
+    stop.wait()
+    proc.terminate()
+    t.join(timeout=2)
 
 
 def clocks_summary(samples: list) -> dict:
@@ -209,6 +217,10 @@ def main() -> None:
     stop = threading.Event()
     sampler = threading.Thread(target=sample_clocks, args=(stop, clock_samples, local_rank), daemon=True)
     sampler.start()
+    # keep the GPU under the same load while the sampler spins up (nvidia-smi needs ~100 ms for its first line)
+    t_spin = time.perf_counter()
+    while time.perf_counter() - t_spin < 0.4:
+        prepared.render(depth, want_rgb=False, want_u8=False, shard=rank, n_shards=n_shards, fma=args.fma)
     barrier()
     kernel_ms, rays = 0.0, 0
     wall0 = time.perf_counter()
@@ -222,12 +234,10 @@ def main() -> None:
     stop.set()
     sampler.join(timeout=2)
 
-    t = torch.tensor([kernel_ms], dtype=torch.float64, device="cuda")
-    r = torch.tensor([float(rays)], dtype=torch.float64, device="cuda")
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dist.all_reduce(r, op=dist.ReduceOp.SUM)
-    kernel_ms_max, rays_total = float(t.item()), float(r.item())
+    from ray_tracer_challenge_b200 import multi
+
+    kernel_ms_max = multi.reduce_scalar(dist, kernel_ms, "max", "cuda")
+    rays_total = multi.reduce_scalar(dist, rays, "sum", "cuda")
     value = rays_total / (kernel_ms_max * 1e-3) / 1e6
 
     # ---- end to end through Camera::render_b200 into pinned host canvases
@@ -275,25 +285,11 @@ def main() -> None:
     else:
         # every rank copies its bands straight into one shared host canvas (POSIX shared memory, page-locked by
         # each rank): the "simple host gather" of SURVEY.md §8e with no extra copy
-        from multiprocessing import shared_memory
-
-        name = f"rtc_bench_{os.environ.get('MASTER_PORT', '0')}"
-        size = w * h * 15
-        if rank == 0:
-            try:
-                shared_memory.SharedMemory(name=name).unlink()
-            except FileNotFoundError:
-                pass
-            shm = shared_memory.SharedMemory(name=name, create=True, size=size)
-        dist.barrier()
-        if rank != 0:
-            shm = shared_memory.SharedMemory(name=name)
-        buf = np.ndarray((size,), np.uint8, buffer=shm.buf)
-        rgb = buf[: w * h * 12].view(np.float32).reshape(h, w, 3)
-        u8 = buf[w * h * 12:].reshape(h, w, 3)
+        canvas = multi.open_shared_canvas(dist, rank, f"rtc_bench_{os.environ.get('MASTER_PORT', '0')}", w, h)
+        rgb, u8 = canvas.rgb, canvas.u8
         lib.rtc_host_register.argtypes = [C.c_void_p, C.c_size_t]
         lib.rtc_host_unregister.argtypes = [C.c_void_p]
-        registered = lib.rtc_host_register(buf.ctypes.data, size) == 0
+        registered = lib.rtc_host_register(canvas.address, canvas.nbytes) == 0
         for _ in range(2):
             prepared.render(depth, out_rgb=rgb, out_u8=u8, shard=rank, n_shards=n_shards, fma=args.fma)
         barrier()
@@ -302,20 +298,17 @@ def main() -> None:
         for _ in range(e_steps):
             prepared.render(depth, out_rgb=rgb, out_u8=u8, shard=rank, n_shards=n_shards, fma=args.fma)
         barrier()
-        e_dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
-        dist.all_reduce(e_dt, op=dist.ReduceOp.MAX)
-        e2e = {"value": round(rays_total / args.steps * e_steps / float(e_dt.item()) / 1e6, 3), "unit": "Mrays/s",
-               "ms_per_frame": round(float(e_dt.item()) / e_steps * 1e3, 3), "h2d_bytes_per_step": 0,
+        e_dt = multi.reduce_scalar(dist, time.perf_counter() - t0, "max", "cuda")
+        e2e = {"value": round(rays_total / args.steps * e_steps / e_dt / 1e6, 3), "unit": "Mrays/s",
+               "ms_per_frame": round(e_dt / e_steps * 1e3, 3), "h2d_bytes_per_step": 0,
                "d2h_bytes_per_step": int(d2h),
                "path": "resident scene, each rank renders its bands and copies them into one shared pinned host canvas"
                        + ("" if registered else " (cudaHostRegister failed: pageable copy)")}
         if registered:
-            lib.rtc_host_unregister(buf.ctypes.data)
-        del rgb, u8, buf
+            lib.rtc_host_unregister(canvas.address)
+        del rgb, u8
         dist.barrier()
-        shm.close()
-        if rank == 0:
-            shm.unlink()
+        canvas.close()
 
     # ---- roofline + CPU baseline (rank 0, N = 1 only)
     roofline, cpu = None, None

@@ -170,6 +170,12 @@ int rtc_render(RtcScene*, int32_t depth, float* rgb_f32, uint8_t* rgb_u8, RtcSta
  * b with b % n_shards == shard are rendered and written; the other rows of the buffers are not touched. */
 int rtc_render_shard(RtcScene*, int32_t depth, int32_t shard, int32_t n_shards, float* rgb_f32, uint8_t* rgb_u8,
                      RtcStats* stats);
+/* The sharding rule of rtc_render / rtc_render_shard, exposed for hosts that place the shards themselves
+ * (pure host arithmetic, no device needed): the frame is cut into bands of RTC_BAND_ROWS rows; band b belongs
+ * to shard b % n_shards.  Returns how many bands `shard` owns and writes the first owned row of each to
+ * first_rows (may be NULL; capacity >= the return value); a band's rows are [row, min(row + RTC_BAND_ROWS, height)). */
+#define RTC_BAND_ROWS 8
+int rtc_shard_bands(uint32_t height, int32_t shard, int32_t n_shards, uint32_t* first_rows);
 /* As rtc_render but with the detailed work counters (node visits, primitive tests, flops). */
 int rtc_render_detailed(RtcScene*, int32_t depth, float* rgb_f32, uint8_t* rgb_u8, RtcStats* stats);
 /* World::color_at (world.rs:88-101) for caller-supplied rays: origins / directions are n*3 f32; out_rgb n*3;

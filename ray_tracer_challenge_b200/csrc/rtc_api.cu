@@ -842,6 +842,16 @@ int rtc_scene_commit(RtcScene* s, int32_t n_devices, const int32_t* device_ids) 
     return 0;
 }
 
+int rtc_shard_bands(uint32_t height, int32_t shard, int32_t n_shards, uint32_t* first_rows) {
+    static_assert(RTC_BAND_ROWS == kBandRows, "public band height must match the kernel tile height");
+    if (n_shards < 1 || shard < 0 || shard >= n_shards) return fail(RTC_ERR_INVALID, "bad shard index");
+    const int total = ((int)height + kBandRows - 1) / kBandRows;
+    int n = 0;
+    for (int b = shard; b < total; b += n_shards, n++)
+        if (first_rows) first_rows[n] = (uint32_t)b * kBandRows;
+    return n;
+}
+
 int rtc_render(RtcScene* s, int32_t depth, float* rgb, uint8_t* u8, RtcStats* stats) {
     return render_impl(s, depth, 0, 0, rgb, u8, stats, false);
 }

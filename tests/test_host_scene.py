@@ -1,0 +1,133 @@
+"""Host-side logic of the product (librtc_host.so: scene model, cofactor inverse, group baking, divide, OBJ
+loader, flattener) checked against the CPU oracle — no GPU needed.  The two libraries share no code, so equality
+here is an independent check of both restatements of the reference's scene construction."""
+import math
+
+import numpy as np
+import pytest
+
+from ray_tracer_challenge_b200 import scenes
+
+
+@pytest.fixture(scope="module")
+def host():
+    import ray_tracer_challenge_b200 as rt
+
+    return rt.new_session()
+
+
+def bits(a):
+    return np.asarray(a, np.float32).view(np.uint32)
+
+
+def test_matrix_routines_are_bit_identical(host, oracle):
+    rng = np.random.default_rng(7)
+    for _ in range(200):
+        a = rng.normal(size=(4, 4)).astype(np.float32)
+        b = rng.normal(size=(4, 4)).astype(np.float32)
+        a[3] = b[3] = (0, 0, 0, 1)
+        ha, oa = host.Matrix(a), oracle.Matrix(a)
+        hb, ob = host.Matrix(b), oracle.Matrix(b)
+        assert np.array_equal(bits(ha.inverse().m), bits(oa.inverse().m))
+        assert np.array_equal(bits((ha * hb).m), bits((oa * ob).m))
+        assert bits(ha.determinant()) == bits(oa.determinant())
+    for args in ((0.3,), (-2.1,), (math.pi / 5,)):
+        for fn in ("rotation_x", "rotation_y", "rotation_z"):
+            assert np.array_equal(bits(getattr(host, fn)(*args).m), bits(getattr(oracle, fn)(*args).m))
+    h = host.view_transform((1, 3, 2), (4, -2, 8), (1, 1, 0))
+    o = oracle.view_transform((1, 3, 2), (4, -2, 8), (1, 1, 0))
+    assert np.array_equal(bits(h.m), bits(o.m))
+
+
+def walk(shape):
+    """Depth-first (kind, transform bits, bbox bits) of a shape tree."""
+    out = [(shape.kind(), bits(shape.transformation().m).tobytes(), bits(np.concatenate(shape.bounding_box())).tobytes())]
+    if shape.kind() in (7, 8):
+        for c in shape.get_children():
+            out += walk(c)
+    return out
+
+
+@pytest.mark.parametrize("name,kw", [
+    ("hexagons", dict(width=32, height=16)),
+    ("shapes_zoo", dict(width=32, height=16)),
+    ("csg_gallery", dict(width=32, height=16)),
+    ("dragon_element", dict(width=32, height=16, n_u=12, n_v=6)),
+    ("dragon_element", dict(width=32, height=16, n_u=12, n_v=6, smooth=True, divide=2)),
+    ("stress", dict(width=32, height=16, n_spheres=300, n_each=3, n_csg=3, divide=4)),
+])
+def test_scene_construction_matches_oracle(host, oracle, name, kw):
+    """Group baking, cached boxes, divide() structure and OBJ loading agree object by object."""
+    _, hw = getattr(scenes, name)(host, **kw)
+    _, ow = getattr(scenes, name)(oracle, **kw)
+    assert len(hw.objects) == len(ow.objects)
+    for a, b in zip(hw.objects, ow.objects):
+        assert walk(a) == walk(b)
+
+
+def test_flattener_emits_depth_first_leaves(host):
+    cam, world = scenes.csg_gallery(host, width=16, height=8)
+    prims, nodes, refs, shapes, counts = host.flatten(world)
+
+    def leaves(shape):
+        if shape.kind() in (7, 8):
+            return [h for c in shape.get_children() for h in leaves(c)]
+        return [shape.handle]
+
+    expected = [h for o in world.objects for h in leaves(o)]
+    assert shapes == expected  # RtcPrim order == the reference's emission (tie-break) order
+    # every CSG node has exactly two children and a valid operator; parents form a forest
+    for n in nodes:
+        assert n.parent < len(nodes)
+        if n.kind == 1:
+            assert n.child_count == 2 and 0 <= n.op <= 2
+    # child references resolve to primitives or nodes that name this node as their parent
+    for idx, n in enumerate(nodes):
+        for r in refs[n.child_begin:n.child_begin + n.child_count]:
+            if r >= 0:
+                assert prims[r].parent == idx
+            else:
+                assert nodes[~r].parent == idx
+
+
+def test_flattener_deduplicates_materials_and_lowers_smooth_triangles(host):
+    cam, world = scenes.dragon_element(host, width=16, height=8, n_u=8, n_v=4, smooth=True)
+    prims, nodes, refs, shapes, counts = host.flatten(world)
+    n_tri = sum(1 for p in prims if p.type == 5)
+    assert n_tri == 2 * 8 * 4  # fan triangulation of the quads; SmoothTriangle lowered to the flat triangle (Q5)
+    assert counts[3] <= 5  # mesh, case, pedestal, floor materials (+ default)
+    tri = next(p for p in prims if p.type == 5)
+    p1, e1, e2, nrm = np.asarray(tri.params[:]).reshape(4, 3)
+    n = np.cross(e2, e1)
+    assert np.allclose(n / np.linalg.norm(n), nrm, atol=1e-6)  # triangle.rs:23
+
+
+def test_flattened_boxes_and_inverses_match_oracle(host, oracle):
+    _, hw = scenes.shapes_zoo(host, width=16, height=8)
+    _, ow = scenes.shapes_zoo(oracle, width=16, height=8)
+    prims, *_ = host.flatten(hw)
+
+    def leaves(shape):
+        if shape.kind() in (7, 8):
+            return [x for c in shape.get_children() for x in leaves(c)]
+        return [shape]
+
+    oleaves = [x for o in ow.objects for x in leaves(o)]
+    assert len(prims) == len(oleaves)
+    for p, o in zip(prims, oleaves):
+        assert np.array_equal(bits(p.inv[:]), bits(o.transformation_inverse().m).reshape(-1))
+        mn, mx = o.parent_space_bounding_box()
+        with np.errstate(invalid="ignore"):
+            assert np.array_equal(bits(p.bbox_min[:]), bits(mn)) and np.array_equal(bits(p.bbox_max[:]), bits(mx))
+
+
+def test_host_rejects_the_oracle_only_test_double(host):
+    import ray_tracer_challenge_b200 as rt
+
+    with pytest.raises(rt.RtcError):
+        host.TestShape()
+    with pytest.raises(rt.RtcError):
+        g = host.GroupShape()
+        s = host.Sphere()
+        g.add_child(s)
+        g.add_child(s)  # already owned (Rust: moved)
