@@ -23,6 +23,14 @@ class SharedCanvas:
             self.shm = shared_memory.SharedMemory(name=name, create=True, size=size)
         else:
             self.shm = shared_memory.SharedMemory(name=name)
+            # Python < 3.13 registers attached segments with the resource tracker, which then tries to unlink them a
+            # second time at exit; only the creating rank owns the segment
+            try:
+                from multiprocessing import resource_tracker
+
+                resource_tracker.unregister(self.shm._name, "shared_memory")
+            except Exception:
+                pass
         self.owner = create
         self.buf = np.ndarray((size,), np.uint8, buffer=self.shm.buf)
         self.rgb = self.buf[: width * height * 12].view(np.float32).reshape(height, width, 3)
