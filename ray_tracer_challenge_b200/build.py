@@ -22,9 +22,11 @@ LIB_DEVICE = os.path.join(PKG, "librtc_b200.so")
 LIB_HOST = os.path.join(PKG, "librtc_host.so")
 
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+# tuning aid: RTC_NVCC_DEFINES="-DRTC_SMALL_MINBLOCKS=8 ..." is appended to every nvcc compile line
+EXTRA_DEFINES = os.environ.get("RTC_NVCC_DEFINES", "").split()
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-    "-Xcompiler", "-fPIC,-ffp-contract=off", "--expt-relaxed-constexpr",
+    "-Xcompiler", "-fPIC,-ffp-contract=off", "--expt-relaxed-constexpr", *EXTRA_DEFINES,
 ]
 
 

@@ -229,7 +229,7 @@ int max_hits(int type) {
 
 struct Flattened {
     std::vector<int4> head;  // 2 * n_pos entries: [pos] main, [n_pos + pos] {cull-chain parent node, api prim, 0, 0}
-    std::vector<float4> xform, tri, bound;
+    std::vector<float4> xform, tri, bound, rec;
     std::vector<DevBvhNode> bvh;
     std::vector<int> linear;
     std::vector<DevNode> nodes;
@@ -341,7 +341,9 @@ int flatten(RtcScene* s, Flattened& f) {
         }
     }
     if (!build_items.empty()) {
-        Builder builder{build_items, f.bvh, std::min(std::max(s->leaf_size, 1), 16)};
+        int leaf = s->leaf_size;
+        if (const char* env = getenv("RTC_BVH_LEAF")) leaf = atoi(env);  // tuning aid
+        Builder builder{build_items, f.bvh, std::min(std::max(leaf, 1), 16)};
         f.bvh.reserve(build_items.size());
         int root = builder.build(0, (int)build_items.size(), 0);
         if (root < 0) {  // a single leaf: wrap it so the traversal always starts at an inner node
@@ -477,6 +479,17 @@ int flatten(RtcScene* s, Flattened& f) {
     if (emitter.max_depth > kCsgRayDepth - 1)
         return fail(RTC_ERR_CAPACITY, "CSG nesting depth " + std::to_string(emitter.max_depth) + " exceeds " + std::to_string(kCsgRayDepth - 1));
 
+    // ---- traversal records: head + the rows the intersection test needs, one 64 B fetch per primitive
+    f.rec.assign(4 * (size_t)f.n_pos, make_float4(0.f, 0.f, 0.f, 0.f));
+    for (int pos = 0; pos < f.n_pos; pos++) {
+        int4 h = f.head[pos];
+        memcpy(&f.rec[4 * (size_t)pos], &h, sizeof(h));
+        int type = h.x & 15;
+        if (type == T_CSG) continue;
+        const float4* src = (type == T_TRIANGLE) ? &f.tri[3 * (size_t)h.z] : &f.xform[3 * (size_t)h.y];
+        for (int r = 0; r < 3; r++) f.rec[4 * (size_t)pos + 1 + r] = src[r];
+    }
+
     // ---- shading tables
     for (const RtcMaterial& m : s->materials) {
         DevMaterial d{};
@@ -574,6 +587,7 @@ int upload_replica(RtcScene* s, const Flattened& f, Replica& r) {
     if ((rc = upload(r, s->jitter, &d.jitter))) return rc;
     if ((rc = upload(r, f.samples, &d.samples))) return rc;
     if ((rc = upload(r, f.head, &d.head))) return rc;
+    if ((rc = upload(r, f.rec, &d.rec))) return rc;
     if ((rc = upload(r, f.xform, &d.xform))) return rc;
     if ((rc = upload(r, f.tri, &d.tri))) return rc;
     if ((rc = upload(r, f.bound, &d.bound))) return rc;

@@ -68,13 +68,16 @@ constexpr float kInfF = __builtin_huge_valf();
 constexpr float kAcne = 1.1920929e-7f * 10000.0f;  // world.rs:210
 constexpr float kCloseToZero = 0.000001f;           // cylinder.rs:82, cone.rs:87
 
-// Work counters.  The plain build keeps only the four ray/shade counts (one register each); the detailed
-// build (STATS) also counts every unit of Appendix E.
+// Work counters.  Every kernel keeps the four ray / shade counts (Rays: one register each, only touched by
+// inlined code so they never leave the register file); the detailed build (STATS) also counts every unit of
+// SURVEY.md Appendix E in Ctr<true>, which is what the out-of-line helpers receive (Ctr<false> is empty).
+struct Rays {
+    unsigned primary = 0, secondary = 0, shadow = 0, shades = 0;
+};
 template <bool STATS>
 struct Ctr;
 template <>
 struct Ctr<false> {
-    unsigned primary = 0, secondary = 0, shadow = 0, shades = 0;
     __device__ __forceinline__ void node() {}
     __device__ __forceinline__ void prim(int) {}
     __device__ __forceinline__ void xform() {}
@@ -86,7 +89,6 @@ struct Ctr<false> {
 };
 template <>
 struct Ctr<true> {
-    unsigned primary = 0, secondary = 0, shadow = 0, shades = 0;
     unsigned nodes = 0, prims[8] = {0, 0, 0, 0, 0, 0, 0, 0}, xforms = 0, patterns = 0, cells = 0, schlicks = 0, refr_dirs = 0,
              overflows = 0;
     __device__ __forceinline__ void node() { nodes++; }
@@ -119,7 +121,8 @@ __device__ __forceinline__ bool aabb_ref(V3 o, V3 d, V3 mn, V3 mx, float& lo, fl
 
 // Shape::local_intersect of every leaf kind.  Writes the distances in the reference's emission order and
 // returns how many there are (0..4).
-__device__ __forceinline__ int local_intersect(const DevScene& S, int type, int aux, float4 bd, V3 o, V3 d, float t[4]) {
+__device__ __forceinline__ int local_intersect(const DevScene& S, int type, int aux, float4 bd, V3 o, V3 d, float t[4],
+                                               const float4* tri = nullptr) {
     switch (type) {
         case T_SPHERE: {  // sphere.rs:47-70 (centre is the origin)
             float a = dot(d, d);
@@ -215,7 +218,7 @@ __device__ __forceinline__ int local_intersect(const DevScene& S, int type, int 
             return n;
         }
         default: {  // T_TRIANGLE — triangle.rs:45-76
-            const float4* tp = S.tri + 3 * (size_t)aux;
+            const float4* tp = tri ? tri : S.tri + 3 * (size_t)aux;
             float4 q0 = __ldg(tp), q1 = __ldg(tp + 1), q2 = __ldg(tp + 2);
             V3 p1 = mk(q0.x, q0.y, q0.z), e1 = mk(q0.w, q1.x, q1.y), e2 = mk(q1.z, q1.w, q2.x);
             V3 dce2 = mk(d.y * e2.z - d.z * e2.y, d.z * e2.x - d.x * e2.z, d.x * e2.y - d.y * e2.x);
@@ -243,7 +246,8 @@ __device__ __forceinline__ float4 load_bound(const DevScene& S, int type, int au
 // Same arithmetic as local_intersect, minus the work whose result cannot be the answer: for a sphere the
 // far root is only divided out when the near root is negative (the sign of a quotient by 2a > 0 is the sign
 // of its numerator).
-__device__ __forceinline__ float nearest_t(const DevScene& S, int type, int aux, float4 bd, V3 o, V3 d) {
+__device__ __forceinline__ float nearest_t(const DevScene& S, int type, int aux, float4 bd, V3 o, V3 d,
+                                           const float4* tri = nullptr) {
     {
         if (type == T_SPHERE) {  // sphere.rs:47-70
             float a = dot(d, d);
@@ -274,7 +278,7 @@ __device__ __forceinline__ float nearest_t(const DevScene& S, int type, int aux,
         }
         {
             float t[4];
-            int n = local_intersect(S, type, aux, bd, o, d, t);
+            int n = local_intersect(S, type, aux, bd, o, d, t, tri);
             float tn = -1.0f;
             for (int i = 0; i < n; i++)
                 if (t[i] >= 0.0f && (!(tn >= 0.0f) || t[i] < tn)) tn = t[i];
@@ -473,7 +477,8 @@ __device__ __noinline__ int csg_eval(const DevScene& S, int pc, V3 wo, V3 wd, fl
 // Test one stored primitive against the world ray for the nearest-hit search.
 template <bool STATS>
 __device__ __forceinline__ void test_prim(const DevScene& S, int pos, V3 o, V3 d, ObjRay& cache, Hit& best, Ctr<STATS>& k) {
-    int4 h = __ldg(&S.head[pos]);
+    const float4* rec = S.rec + 4 * (size_t)pos;
+    int4 h = __ldg(reinterpret_cast<const int4*>(rec));
     int type = h.x & 15;
     if (type == T_CSG) {
         float ht[kCsgHitCap];
@@ -487,15 +492,23 @@ __device__ __forceinline__ void test_prim(const DevScene& S, int pos, V3 o, V3 d
         }
         return;
     }
-    if (h.y != cache.xf_id) {  // shape.rs:60-70 / ray.rs:26-31
-        Xf m = load_xf(S.xform + 3 * (size_t)h.y);
-        cache.o = xf_point(m, o);
-        cache.d = xf_vec(m, d);
-        cache.xf_id = h.y;
-        k.xform();
-    }
+    float tn;
     k.prim(type);
-    float tn = nearest_t(S, type, h.z, load_bound(S, type, h.z), cache.o, cache.d);
+    if (type == T_TRIANGLE) {
+        // a mesh's triangles share one transform: the object-space ray is kept across primitives (shape.rs:60-70)
+        if (h.y != cache.xf_id) {
+            Xf m = load_xf(S.xform + 3 * (size_t)h.y);
+            cache.o = xf_point(m, o);
+            cache.d = xf_vec(m, d);
+            cache.xf_id = h.y;
+            k.xform();
+        }
+        tn = nearest_t(S, T_TRIANGLE, h.z, make_float4(0.f, 0.f, 0.f, 0.f), cache.o, cache.d, rec + 1);
+    } else {
+        Xf m = load_xf(rec + 1);  // the primitive's own inverse transform travels in its record
+        k.xform();
+        tn = nearest_t(S, type, h.z, load_bound(S, type, h.z), xf_point(m, o), xf_vec(m, d));
+    }
     if (!(tn >= 0.0f)) return;
     if (((h.x >> 4) & kFlagHasParent) && !ancestors_pass(S, __ldg(&S.head[pos + S.n_prims]).x, o, d)) return;
     consider(best, tn, pos, h.w);
@@ -521,7 +534,7 @@ __device__ __forceinline__ bool slab(V3 o, V3 inv, float lx, float ly, float lz,
 // depth-first tie-break, searched through the BVH.  `best.t` on entry is the search limit (exclusive).
 // ANY: stop at the first hit (shadow rays when every primitive casts a shadow).
 template <bool STATS, bool ANY>
-__device__ __forceinline__ void nearest_hit(const DevScene& S, V3 o, V3 d, Hit& best, Ctr<STATS>& k) {
+__device__ __noinline__ void nearest_hit(const DevScene& S, V3 o, V3 d, Hit& best, Ctr<STATS>& k) {
     ObjRay cache;
     for (int i = 0; i < S.n_linear; i++) {
         test_prim<STATS>(S, __ldg(&S.linear[i]), o, d, cache, best, k);
@@ -865,7 +878,7 @@ __device__ __forceinline__ void cache_origins(const Env& E, V3 o) {
 
 // One item of a small scene of any kind (primitive or CSG root), honouring the cull chain: the general form.
 template <bool STATS, bool CACHED>
-__device__ __forceinline__ void test_small(const Env& E, int i, V3 o, V3 d, Hit& best, Ctr<STATS>& k) {
+__device__ __noinline__ void test_small(const Env& E, int i, V3 o, V3 d, Hit& best, Ctr<STATS>& k) {
     const float4* tab = small_tab();
     const int4 head = *reinterpret_cast<const int4*>(tab + i * 5);
     const int type = head.x & 15;
@@ -977,9 +990,9 @@ __device__ __forceinline__ void find_hit(const Env& E, V3 o, V3 d, Hit& best, Ct
 // (t, depth-first order) comparison as Intersection::hit) can un-shadow the point.  Same predicate as the
 // reference's, evaluated with fewer intersection tests.
 template <bool STATS, bool SMALL, bool CACHED>
-__device__ __forceinline__ bool is_shadowed(const Env& E, V3 light_position, V3 p, Ctr<STATS>& k) {
+__device__ __forceinline__ bool is_shadowed(const Env& E, V3 light_position, V3 p, Rays& r, Ctr<STATS>& k) {
     const DevScene& S = E.S;
-    k.shadow++;
+    r.shadow++;
     V3 v = light_position - p;
     float distance = magnitude(v);
     V3 direction = mk(v.x / distance, v.y / distance, v.z / distance);
@@ -1009,9 +1022,9 @@ __device__ __forceinline__ bool is_shadowed(const Env& E, V3 light_position, V3 
 
 // Light::intensity_at (point_light.rs:28-34, rectangle_light.rs:76-88)
 template <bool STATS, bool SMALL>
-__device__ __forceinline__ float intensity_at(const Env& E, V3 p, unsigned pixel, unsigned path, Ctr<STATS>& k) {
+__device__ __forceinline__ float intensity_at(const Env& E, V3 p, unsigned pixel, unsigned path, Rays& r, Ctr<STATS>& k) {
     const DevScene& S = E.S;
-    if (!S.light_is_rect) return is_shadowed<STATS, SMALL, false>(E, ld3(S.light_pos), p, k) ? 0.f : 1.f;
+    if (!S.light_is_rect) return is_shadowed<STATS, SMALL, false>(E, ld3(S.light_pos), p, r, k) ? 0.f : 1.f;
     if (SMALL) cache_origins(E, p);
     float total = 0.f;
     int cell = 0;
@@ -1028,7 +1041,7 @@ __device__ __forceinline__ float intensity_at(const Env& E, V3 p, unsigned pixel
                 // rectangle_light.rs:60-66
                 lp = ld3(S.corner) + ld3(S.u_vec) * ((float)u + j1) + ld3(S.v_vec) * ((float)v + j2);
             }
-            if (!is_shadowed<STATS, SMALL, SMALL>(E, lp, p, k)) total += 1.0f;
+            if (!is_shadowed<STATS, SMALL, SMALL>(E, lp, p, r, k)) total += 1.0f;
         }
     }
     return total / (float)S.cells;
@@ -1062,8 +1075,8 @@ __device__ __forceinline__ V3 combine(V3 surface, V3 reflected, V3 refracted, fl
 // reflection subtree, then the whole refraction subtree) and combined bottom-up with the same arithmetic.
 // out_t / out_pos (optional) receive the primary hit.
 template <bool STATS, bool SMALL>
-__device__ __forceinline__ V3 color_at(const Env& E, V3 ro, V3 rd, int depth, unsigned pixel, Ctr<STATS>& k, float* out_t,
-                                       int* out_pos) {
+__device__ __forceinline__ V3 color_at(const Env& E, V3 ro, V3 rd, int depth, unsigned pixel, Rays& r, Ctr<STATS>& k,
+                                       float* out_t, int* out_pos) {
     const DevScene& S = E.S;
     Frame stack[kMaxFrames];
     int sp = 0;
@@ -1081,7 +1094,7 @@ __device__ __forceinline__ V3 color_at(const Env& E, V3 ro, V3 rd, int depth, un
         V3 c = mk(0.f, 0.f, 0.f);
         if (best.pos >= 0) {
             // ---- precompute_values (world.rs:212-283)
-            k.shades++;
+            r.shades++;
             int4 h = __ldg(&S.head[best.pos]);
             int type = h.x & 15;
             const DevMaterial& mat = S.materials[h.x >> 8];
@@ -1094,7 +1107,7 @@ __device__ __forceinline__ V3 color_at(const Env& E, V3 ro, V3 rd, int depth, un
             if (dot(n, eye) < 0.0f) n = -n;
             V3 over_point = point + n * kAcne;
             // ---- shade_hit (world.rs:62-86): light intensity first, then Phong (phong_lighting.rs:12-63)
-            float li = intensity_at<STATS, SMALL>(E, over_point, pixel, path, k);
+            float li = intensity_at<STATS, SMALL>(E, over_point, pixel, path, r, k);
             V3 material_color = ld3(mat.color);
             if (mat.pattern >= 0) {
                 k.pattern();
@@ -1173,7 +1186,7 @@ __device__ __forceinline__ V3 color_at(const Env& E, V3 ro, V3 rd, int depth, un
                 f.remaining = remaining;
                 f.path = path;
                 f.has_refr = want_refr;
-                k.secondary++;
+                r.secondary++;
                 remaining = remaining - 1;
                 if (want_refl) {
                     f.stage = 1;
@@ -1202,7 +1215,7 @@ __device__ __forceinline__ V3 color_at(const Env& E, V3 ro, V3 rd, int depth, un
                     rd = f.refr_d;
                     remaining = f.remaining - 1;
                     path = f.path * 3u + 2u;
-                    k.secondary++;
+                    r.secondary++;
                     break;
                 }
                 c = combine(f.surface, f.refl, mk(0.f, 0.f, 0.f), f.reflectance);

@@ -16,29 +16,37 @@
 #include "rtc_device.cuh"
 #include "rtc_launch.h"
 
+// resident 128-thread blocks per SM the compiler must make room for (register budget = 65536 / (128 * blocks))
+#ifndef RTC_SMALL_MINBLOCKS
+#define RTC_SMALL_MINBLOCKS 6
+#endif
+#ifndef RTC_BVH_MINBLOCKS
+#define RTC_BVH_MINBLOCKS 5
+#endif
+
 namespace rtc {
 namespace RTC_NS {
 
 template <bool STATS>
-__device__ __forceinline__ void flush_counters(const Ctr<STATS>& k, DevCounters* out);
+__device__ __forceinline__ void flush_counters(const Rays& r, const Ctr<STATS>& k, DevCounters* out);
 
 __device__ __forceinline__ void warp_add(unsigned long long* dst, unsigned v) {
     unsigned s = __reduce_add_sync(0xffffffffu, v);
     if ((threadIdx.x & 31) == 0 && s) atomicAdd(dst, (unsigned long long)s);
 }
-template <>
-__device__ __forceinline__ void flush_counters<false>(const Ctr<false>& k, DevCounters* out) {
-    warp_add(&out->primary, k.primary);
-    warp_add(&out->secondary, k.secondary);
-    warp_add(&out->shadow, k.shadow);
-    warp_add(&out->shades, k.shades);
+__device__ __forceinline__ void flush_rays(const Rays& r, DevCounters* out) {
+    warp_add(&out->primary, r.primary);
+    warp_add(&out->secondary, r.secondary);
+    warp_add(&out->shadow, r.shadow);
+    warp_add(&out->shades, r.shades);
 }
 template <>
-__device__ __forceinline__ void flush_counters<true>(const Ctr<true>& k, DevCounters* out) {
-    warp_add(&out->primary, k.primary);
-    warp_add(&out->secondary, k.secondary);
-    warp_add(&out->shadow, k.shadow);
-    warp_add(&out->shades, k.shades);
+__device__ __forceinline__ void flush_counters<false>(const Rays& r, const Ctr<false>&, DevCounters* out) {
+    flush_rays(r, out);
+}
+template <>
+__device__ __forceinline__ void flush_counters<true>(const Rays& r, const Ctr<true>& k, DevCounters* out) {
+    flush_rays(r, out);
     warp_add(&out->node_visits, k.nodes);
     for (int i = 0; i < 8; i++) warp_add(&out->prim_tests[i], k.prims[i]);
     warp_add(&out->xforms, k.xforms);
@@ -50,7 +58,7 @@ __device__ __forceinline__ void flush_counters<true>(const Ctr<true>& k, DevCoun
 }
 
 template <bool STATS, bool SMALL>
-__global__ void __launch_bounds__(128) render_tiles(const __grid_constant__ DevScene S, const __grid_constant__ SmallScene SS,
+__global__ void __launch_bounds__(128, SMALL ? RTC_SMALL_MINBLOCKS : RTC_BVH_MINBLOCKS) render_tiles(const __grid_constant__ DevScene S, const __grid_constant__ SmallScene SS,
                                                     const DevFrame F, DevCounters* counters) {
     // small scenes: primitive table + per-thread shadow-origin cache in dynamic shared memory (kSmallSmemBytes)
     if (SMALL) stage_small_scene(SS);
@@ -61,14 +69,15 @@ __global__ void __launch_bounds__(128) render_tiles(const __grid_constant__ DevS
     const int x = blockIdx.x * kTileW + (warp & 1) * 8 + (lane & 7);
     const int y = band * kBandRows + (warp >> 1) * 4 + (lane >> 3);
     Ctr<STATS> k;
+    Rays r;
     V3 c = mk(0.f, 0.f, 0.f);
     const bool inside = x < S.width && y < S.height;
     // camera.rs:80-81 — the last row and the last column are never rendered and stay black (canvas.rs:23)
     if (inside && x < S.width - 1 && y < S.height - 1) {
         V3 o, d;
         ray_for_pixel(S, x, y, o, d);
-        k.primary++;
-        c = color_at<STATS, SMALL>(E, o, d, F.depth, (unsigned)(y * S.width + x), k, nullptr, nullptr);
+        r.primary++;
+        c = color_at<STATS, SMALL>(E, o, d, F.depth, (unsigned)(y * S.width + x), r, k, nullptr, nullptr);
     }
     if (inside) {
         size_t idx = ((size_t)y * S.width + x) * 3;
@@ -83,7 +92,7 @@ __global__ void __launch_bounds__(128) render_tiles(const __grid_constant__ DevS
             F.u8[idx + 2] = scale_color(c.z);
         }
     }
-    flush_counters<STATS>(k, counters);
+    flush_counters<STATS>(r, k, counters);
 }
 
 template <bool SMALL>
@@ -94,18 +103,19 @@ __global__ void __launch_bounds__(128) trace_rays(const __grid_constant__ DevSce
     const Env E{S, SS};
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     Ctr<false> k;
+    Rays r;
     if (i < n) {
         V3 o = ld3(origins + 3 * (size_t)i), d = ld3(directions + 3 * (size_t)i);
         float t;
         int pos;
-        V3 c = color_at<false, SMALL>(E, o, d, depth, (unsigned)i, k, &t, &pos);
+        V3 c = color_at<false, SMALL>(E, o, d, depth, (unsigned)i, r, k, &t, &pos);
         out_rgb[3 * (size_t)i] = c.x;
         out_rgb[3 * (size_t)i + 1] = c.y;
         out_rgb[3 * (size_t)i + 2] = c.z;
         if (out_t) out_t[i] = t;
         if (out_pos) out_pos[i] = pos;
     }
-    flush_counters<false>(k, counters);
+    flush_counters<false>(r, k, counters);
 }
 
 void launch_render(const DevScene& S, const SmallScene& SS, const DevFrame& F, DevCounters* counters, bool detailed,

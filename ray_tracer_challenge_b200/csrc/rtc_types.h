@@ -89,6 +89,8 @@ struct DevScene {
     unsigned long long seed;   // counter mode
     // geometry
     const int4* head;
+    const float4* rec;    // traversal records, 64 B / primitive: {head, 3 x float4}: the inverse-transform rows, or for a
+                          // triangle its p1 / e1 / e2 / normal (its transform is shared: head.y indexes `xform`)
     const float4* xform;
     const float4* tri;
     const float4* bound;
