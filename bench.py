@@ -222,13 +222,14 @@ def main() -> None:
     while time.perf_counter() - t_spin < 0.4:
         prepared.render(depth, want_rgb=False, want_u8=False, shard=rank, n_shards=n_shards, fma=args.fma)
     barrier()
-    kernel_ms, rays = 0.0, 0
+    kernel_ms, rays, launches = 0.0, 0, 0
     wall0 = time.perf_counter()
     for _ in range(args.steps):
         prepared.flush_l2()  # evict the scene and the previous frame between timed iterations
         prepared.render(depth, want_rgb=False, want_u8=False, shard=rank, n_shards=n_shards, fma=args.fma)
         kernel_ms += prepared.last_stats.kernel_ms
         rays += prepared.last_stats.rays
+        launches += prepared.last_stats.launches
     barrier()
     wall_ms = (time.perf_counter() - wall0) * 1e3
     stop.set()
@@ -351,7 +352,7 @@ def main() -> None:
                        "l2": "flushed between timed iterations (256 MiB memset)",
                        "sharding": f"{world_size} rank(s), interleaved 8-row bands"},
             "rays_per_frame": rays_total / args.steps, "wall_ms_per_step_incl_flush": round(wall_ms / args.steps, 3),
-            "e2e": e2e, "gpu_launches": args.steps * world_size, "clocks": clocks_summary(clock_samples),
+            "e2e": e2e, "gpu_launches": int(multi.reduce_scalar(dist, launches, "sum", "cuda")) if False else launches * world_size, "clocks": clocks_summary(clock_samples),
         }
         if roofline:
             line["roofline"] = roofline

@@ -123,6 +123,8 @@ typedef struct RtcStats {
     double total_ms;         /* host wall time of the call including D2H copies */
     int32_t n_devices;
     int32_t detailed;
+    int32_t launches; /* render kernel launches of this call, over all devices */
+    int32_t reserved;
 } RtcStats;
 
 const char* rtc_last_error(void);
@@ -155,7 +157,13 @@ int rtc_set_rect_light(RtcScene*, const float intensity[3], const float corner[3
  * build: a few percent faster, but its last-place differences flip ill-conditioned threshold tests (the
  * discriminant of a distant sphere cancels catastrophically in f32), so it meets the <= 1 LSB bar only on
  * well-conditioned scenes.  It may be changed between renders; the BVH options only before commit. */
-enum { RTC_OPT_FMA_CONTRACTION = 1, RTC_OPT_BVH_LEAF_SIZE = 2, RTC_OPT_BVH_MIN_PRIMS = 3 };
+enum {
+    RTC_OPT_FMA_CONTRACTION = 1,
+    RTC_OPT_BVH_LEAF_SIZE = 2,
+    RTC_OPT_BVH_MIN_PRIMS = 3,
+    RTC_OPT_RENDER_SLICES = 4 /* kernel launches a frame is cut into when it is copied to host memory, so the
+                                 copy of one slice overlaps the kernel of the next (default 6) */
+};
 int rtc_set_option(RtcScene*, int32_t option, int64_t value);
 
 /* Validate, build the BVH over the primitives' bounding boxes and upload one scene replica per device.

@@ -10,6 +10,7 @@
 #include <cstdio>
 #include <cstring>
 #include <map>
+#include <mutex>
 #include <string>
 #include <tuple>
 #include <vector>
@@ -53,19 +54,96 @@ struct Box {
     }
 };
 
-// One committed replica of the scene on one device.
-struct Replica {
+// Device-side resources that outlive a scene: creating streams / events and allocating the frame and scene
+// buffers costs more than rendering a small frame, so they are pooled per device and leased to a scene at
+// commit (Camera::render_b200 commits a fresh scene on every call, like the reference's render takes its
+// World by value).
+struct DeviceSlot {
     int device = -1;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;       // kernels
+    cudaStream_t copy_stream = nullptr;  // device-to-host copies, overlapped with the kernels of later slices
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    std::vector<void*> allocs;
-    DevScene scene{};
-    SmallScene small{};
+    std::vector<cudaEvent_t> slice_done;
     float* d_rgb = nullptr;
     unsigned char* d_u8 = nullptr;
+    size_t frame_px = 0;
     DevCounters* d_counters = nullptr;
+    char* arena = nullptr;  // scene arrays, one allocation
+    size_t arena_bytes = 0;
+    char* staging = nullptr;  // pinned host mirror of the arena for one asynchronous upload
+    size_t staging_bytes = 0;
     void* d_flush = nullptr;
     size_t flush_bytes = 0;
+};
+
+std::mutex g_pool_mutex;
+std::vector<DeviceSlot*> g_pool;  // idle slots
+
+int lease_slot(int device, DeviceSlot** out) {
+    {
+        std::lock_guard<std::mutex> lock(g_pool_mutex);
+        for (size_t i = 0; i < g_pool.size(); i++)
+            if (g_pool[i]->device == device) {
+                *out = g_pool[i];
+                g_pool.erase(g_pool.begin() + i);
+                return 0;
+            }
+    }
+    CUDA_TRY(cudaSetDevice(device));
+    DeviceSlot* d = new DeviceSlot();
+    d->device = device;
+    CUDA_TRY(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&d->copy_stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreate(&d->ev0));
+    CUDA_TRY(cudaEventCreate(&d->ev1));
+    CUDA_TRY(cudaMalloc(&d->d_counters, sizeof(DevCounters)));
+    // the kernels keep their bounce and traversal stacks in local memory
+    size_t have = 0;
+    cudaDeviceGetLimit(&have, cudaLimitStackSize);
+    if (have < 8192) CUDA_TRY(cudaDeviceSetLimit(cudaLimitStackSize, 8192));
+    *out = d;
+    return 0;
+}
+void return_slot(DeviceSlot* d) {
+    if (!d) return;
+    std::lock_guard<std::mutex> lock(g_pool_mutex);
+    g_pool.push_back(d);
+}
+int ensure_frame(DeviceSlot* d, size_t px) {
+    if (px <= d->frame_px) return 0;
+    CUDA_TRY(cudaSetDevice(d->device));
+    if (d->d_rgb) cudaFree(d->d_rgb);
+    if (d->d_u8) cudaFree(d->d_u8);
+    d->d_rgb = nullptr, d->d_u8 = nullptr, d->frame_px = 0;
+    CUDA_TRY(cudaMalloc(&d->d_rgb, std::max<size_t>(px * 3 * sizeof(float), 16)));
+    CUDA_TRY(cudaMalloc(&d->d_u8, std::max<size_t>(px * 3, 16)));
+    d->frame_px = px;
+    return 0;
+}
+int ensure_arena(DeviceSlot* d, size_t bytes) {
+    CUDA_TRY(cudaSetDevice(d->device));
+    if (bytes > d->arena_bytes) {
+        if (d->arena) cudaFree(d->arena);
+        d->arena = nullptr, d->arena_bytes = 0;
+        size_t cap = std::max<size_t>(bytes + bytes / 4, 1 << 16);
+        CUDA_TRY(cudaMalloc(&d->arena, cap));
+        d->arena_bytes = cap;
+    }
+    if (bytes > d->staging_bytes) {
+        if (d->staging) cudaFreeHost(d->staging);
+        d->staging = nullptr, d->staging_bytes = 0;
+        size_t cap = std::max<size_t>(bytes + bytes / 4, 1 << 16);
+        CUDA_TRY(cudaHostAlloc(&d->staging, cap, cudaHostAllocDefault));
+        d->staging_bytes = cap;
+    }
+    return 0;
+}
+
+// One committed replica of the scene on one device.
+struct Replica {
+    DeviceSlot* slot = nullptr;
+    DevScene scene{};
+    SmallScene small{};
 };
 
 }  // namespace
@@ -87,7 +165,9 @@ struct RtcScene {
     std::vector<float> jitter;
     uint64_t seed = 0;
     int strict_fp = 1, leaf_size = 4, bvh_min_prims = kSmallCap + 1;
+    int render_slices = 6;  // kernel / copy pipeline depth when rendering into host memory
     std::vector<Replica> replicas;
+    std::vector<int> replica_devices;
     std::vector<int> pos_to_prim;  // device position -> API primitive index (-1 for CSG pseudo-primitives)
     // commit statistics
     int n_bvh_nodes = 0, n_linear = 0, n_xforms = 0;
@@ -97,28 +177,35 @@ namespace {
 
 void release(RtcScene* s) {
     for (Replica& r : s->replicas) {
-        cudaSetDevice(r.device);
-        for (void* p : r.allocs) cudaFree(p);
-        if (r.d_flush) cudaFree(r.d_flush);
-        if (r.ev0) cudaEventDestroy(r.ev0);
-        if (r.ev1) cudaEventDestroy(r.ev1);
-        if (r.stream) cudaStreamDestroy(r.stream);
+        if (!r.slot) continue;
+        cudaSetDevice(r.slot->device);
+        cudaStreamSynchronize(r.slot->stream);
+        cudaStreamSynchronize(r.slot->copy_stream);
+        return_slot(r.slot);
+        r.slot = nullptr;
     }
     s->replicas.clear();
     s->committed = false;
 }
 
-template <class T>
-int upload(Replica& r, const std::vector<T>& v, const T** out) {
-    *out = nullptr;
-    if (v.empty()) return 0;
-    void* p = nullptr;
-    CUDA_TRY(cudaMalloc(&p, v.size() * sizeof(T)));
-    r.allocs.push_back(p);
-    CUDA_TRY(cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
-    *out = reinterpret_cast<const T*>(p);
-    return 0;
-}
+// Packs the scene arrays into one staging buffer (256-byte aligned sections) for a single upload.
+struct ArenaWriter {
+    size_t bytes = 0;
+    struct Part {
+        const void* src;
+        size_t n, off;
+    };
+    std::vector<Part> parts;
+    template <class T>
+    size_t add(const std::vector<T>& v) {
+        size_t off = bytes;
+        if (!v.empty()) {
+            parts.push_back({v.data(), v.size() * sizeof(T), off});
+            bytes = (bytes + v.size() * sizeof(T) + 255) & ~size_t(255);
+        }
+        return off;
+    }
+};
 
 void rows3(const float m[16], float4 out[3]) {
     for (int r = 0; r < 3; r++) out[r] = make_float4(m[r * 4], m[r * 4 + 1], m[r * 4 + 2], m[r * 4 + 3]);
@@ -564,11 +651,11 @@ int flatten(RtcScene* s, Flattened& f) {
     return 0;
 }
 
-int upload_replica(RtcScene* s, const Flattened& f, Replica& r) {
-    CUDA_TRY(cudaSetDevice(r.device));
-    CUDA_TRY(cudaStreamCreateWithFlags(&r.stream, cudaStreamNonBlocking));
-    CUDA_TRY(cudaEventCreate(&r.ev0));
-    CUDA_TRY(cudaEventCreate(&r.ev1));
+int upload_replica(RtcScene* s, const Flattened& f, Replica& r, int device) {
+    int rc;
+    if ((rc = lease_slot(device, &r.slot))) return rc;
+    DeviceSlot* slot = r.slot;
+    CUDA_TRY(cudaSetDevice(device));
     DevScene& d = r.scene;
     memset(&d, 0, sizeof(d));
     rows3(s->cam_inv, d.cam_inv);
@@ -583,42 +670,35 @@ int upload_replica(RtcScene* s, const Flattened& f, Replica& r) {
     d.u_steps = s->u_steps, d.v_steps = s->v_steps, d.cells = s->u_steps * s->v_steps;
     d.jitter_len = (int)s->jitter.size();
     d.seed = s->seed;
-    int rc;
-    if ((rc = upload(r, s->jitter, &d.jitter))) return rc;
-    if ((rc = upload(r, f.samples, &d.samples))) return rc;
-    if ((rc = upload(r, f.head, &d.head))) return rc;
-    if ((rc = upload(r, f.rec, &d.rec))) return rc;
-    if ((rc = upload(r, f.xform, &d.xform))) return rc;
-    if ((rc = upload(r, f.tri, &d.tri))) return rc;
-    if ((rc = upload(r, f.bound, &d.bound))) return rc;
-    if ((rc = upload(r, f.bvh, &d.bvh))) return rc;
-    if ((rc = upload(r, f.linear, &d.linear))) return rc;
-    if ((rc = upload(r, f.nodes, &d.nodes))) return rc;
-    if ((rc = upload(r, f.ops, &d.csg_ops))) return rc;
-    if ((rc = upload(r, f.materials, &d.materials))) return rc;
-    if ((rc = upload(r, f.patterns, &d.patterns))) return rc;
-    if ((rc = upload(r, f.uvs, &d.uvs))) return rc;
+    ArenaWriter w;
+    size_t o_jitter = w.add(s->jitter), o_samples = w.add(f.samples), o_head = w.add(f.head), o_rec = w.add(f.rec);
+    size_t o_xform = w.add(f.xform), o_tri = w.add(f.tri), o_bound = w.add(f.bound), o_bvh = w.add(f.bvh);
+    size_t o_linear = w.add(f.linear), o_nodes = w.add(f.nodes), o_ops = w.add(f.ops), o_mat = w.add(f.materials);
+    size_t o_pat = w.add(f.patterns), o_uv = w.add(f.uvs);
+    if ((rc = ensure_arena(slot, std::max<size_t>(w.bytes, 256)))) return rc;
+    for (const auto& p : w.parts) memcpy(slot->staging + p.off, p.src, p.n);
+    if (w.bytes) CUDA_TRY(cudaMemcpyAsync(slot->arena, slot->staging, w.bytes, cudaMemcpyHostToDevice, slot->stream));
+    auto at = [&](size_t off, bool present) -> const void* { return present ? slot->arena + off : nullptr; };
+    d.jitter = (const float*)at(o_jitter, !s->jitter.empty());
+    d.samples = (const float4*)at(o_samples, !f.samples.empty());
+    d.head = (const int4*)at(o_head, !f.head.empty());
+    d.rec = (const float4*)at(o_rec, !f.rec.empty());
+    d.xform = (const float4*)at(o_xform, !f.xform.empty());
+    d.tri = (const float4*)at(o_tri, !f.tri.empty());
+    d.bound = (const float4*)at(o_bound, !f.bound.empty());
+    d.bvh = (const DevBvhNode*)at(o_bvh, !f.bvh.empty());
+    d.linear = (const int*)at(o_linear, !f.linear.empty());
+    d.nodes = (const DevNode*)at(o_nodes, !f.nodes.empty());
+    d.csg_ops = (const DevCsgOp*)at(o_ops, !f.ops.empty());
+    d.materials = (const DevMaterial*)at(o_mat, !f.materials.empty());
+    d.patterns = (const DevPattern*)at(o_pat, !f.patterns.empty());
+    d.uvs = (const DevUvPattern*)at(o_uv, !f.uvs.empty());
     d.n_linear = (int)f.linear.size();
     d.bvh_root = f.bvh_root;
     d.n_prims = f.n_pos;
     d.all_cast_shadow = f.all_cast_shadow;
     r.small = f.small;
-    size_t px = (size_t)s->width * s->height;
-    void* p = nullptr;
-    CUDA_TRY(cudaMalloc(&p, std::max<size_t>(px * 3 * sizeof(float), 16)));
-    r.allocs.push_back(p);
-    r.d_rgb = (float*)p;
-    CUDA_TRY(cudaMalloc(&p, std::max<size_t>(px * 3, 16)));
-    r.allocs.push_back(p);
-    r.d_u8 = (unsigned char*)p;
-    CUDA_TRY(cudaMalloc(&p, sizeof(DevCounters)));
-    r.allocs.push_back(p);
-    r.d_counters = (DevCounters*)p;
-    // the kernels keep their bounce and traversal stacks in local memory
-    size_t want = 8192;
-    size_t have = 0;
-    cudaDeviceGetLimit(&have, cudaLimitStackSize);
-    if (have < want) CUDA_TRY(cudaDeviceSetLimit(cudaLimitStackSize, want));
+    if ((rc = ensure_frame(slot, (size_t)s->width * s->height))) return rc;
     return 0;
 }
 
@@ -639,26 +719,30 @@ void add_counters(RtcStats& st, const DevCounters& c) {
     st.refr_dirs += c.refr_dirs, st.capacity_overflows += c.overflows;
 }
 
-// Copy the rows of this shard's bands from the device frame into the caller's full-size canvas.
-int copy_bands(Replica& r, const RtcScene* s, int shard, int n_shards, int n_bands, const void* src, void* dst, size_t px_bytes) {
+// Copy the rows of bands [b0, b1) of this shard's band list from the device frame into the caller's full-size
+// canvas (band j of the list is frame band `shard + j * n_shards`).
+int copy_bands(DeviceSlot* slot, const RtcScene* s, int shard, int n_shards, int b0, int b1, const void* src, void* dst,
+               size_t px_bytes) {
     const size_t row = (size_t)s->width * px_bytes;
     const size_t band = row * kBandRows;
-    if (n_bands <= 0) return 0;
-    if (n_shards == 1) {
-        CUDA_TRY(cudaMemcpyAsync(dst, src, row * s->height, cudaMemcpyDeviceToHost, r.stream));
+    if (b1 <= b0) return 0;
+    const int first_band = shard + b0 * n_shards, last_band = shard + (b1 - 1) * n_shards;
+    const int last_rows = std::min<int>(kBandRows, (int)s->height - last_band * kBandRows);
+    if (n_shards == 1) {  // contiguous rows
+        size_t off = (size_t)first_band * band;
+        size_t bytes = (size_t)(b1 - b0 - 1) * band + row * last_rows;
+        CUDA_TRY(cudaMemcpyAsync((char*)dst + off, (const char*)src + off, bytes, cudaMemcpyDeviceToHost, slot->copy_stream));
         return 0;
     }
-    // every band but possibly the last one is full height
-    int last_band = shard + (n_bands - 1) * n_shards;
-    int last_rows = std::min<int>(kBandRows, (int)s->height - last_band * kBandRows);
-    int full = (last_rows == kBandRows) ? n_bands : n_bands - 1;
-    size_t off = (size_t)shard * band;
+    const int full = (last_rows == kBandRows) ? (b1 - b0) : (b1 - b0 - 1);  // every band but possibly the last is full
+    size_t off = (size_t)first_band * band;
     if (full > 0)
         CUDA_TRY(cudaMemcpy2DAsync((char*)dst + off, band * n_shards, (const char*)src + off, band * n_shards, band, full,
-                                   cudaMemcpyDeviceToHost, r.stream));
-    if (full < n_bands) {
+                                   cudaMemcpyDeviceToHost, slot->copy_stream));
+    if (full < b1 - b0) {
         size_t o2 = (size_t)last_band * band;
-        CUDA_TRY(cudaMemcpyAsync((char*)dst + o2, (const char*)src + o2, row * last_rows, cudaMemcpyDeviceToHost, r.stream));
+        CUDA_TRY(cudaMemcpyAsync((char*)dst + o2, (const char*)src + o2, row * last_rows, cudaMemcpyDeviceToHost,
+                                 slot->copy_stream));
     }
     return 0;
 }
@@ -675,39 +759,58 @@ int render_impl(RtcScene* s, int depth, int shard0, int n_shards_ext, float* rgb
     if (external && (shard0 < 0 || shard0 >= n_shards_ext)) return fail(RTC_ERR_INVALID, "bad shard index");
     const int n_shards = external ? n_shards_ext : ndev;
     const int total_bands = ((int)s->height + kBandRows - 1) / kBandRows;
+    const bool copy_out = rgb || u8;
     RtcStats st;
     memset(&st, 0, sizeof(st));
     st.n_devices = ndev;
     st.detailed = detailed;
-    std::vector<int> bands(ndev, 0);
     for (int i = 0; i < ndev; i++) {
         Replica& r = s->replicas[i];
-        int shard = external ? shard0 : i;
-        int nb = shard < total_bands ? (total_bands - shard + n_shards - 1) / n_shards : 0;
-        bands[i] = nb;
-        CUDA_TRY(cudaSetDevice(r.device));
-        CUDA_TRY(cudaMemsetAsync(r.d_counters, 0, sizeof(DevCounters), r.stream));
-        DevFrame F{r.d_rgb, r.d_u8, shard, n_shards, depth, nb};
-        CUDA_TRY(cudaEventRecord(r.ev0, r.stream));
-        if (s->strict_fp)
-            strict::launch_render(r.scene, r.small, F, r.d_counters, detailed, r.stream);
-        else
-            fast::launch_render(r.scene, r.small, F, r.d_counters, detailed, r.stream);
-        CUDA_TRY(cudaGetLastError());
-        CUDA_TRY(cudaEventRecord(r.ev1, r.stream));
-        int rc;
-        if (rgb && (rc = copy_bands(r, s, shard, n_shards, nb, r.d_rgb, rgb, 3 * sizeof(float)))) return rc;
-        if (u8 && (rc = copy_bands(r, s, shard, n_shards, nb, r.d_u8, u8, 3))) return rc;
+        DeviceSlot* slot = r.slot;
+        const int shard = external ? shard0 : i;
+        const int nb = shard < total_bands ? (total_bands - shard + n_shards - 1) / n_shards : 0;
+        CUDA_TRY(cudaSetDevice(slot->device));
+        CUDA_TRY(cudaMemsetAsync(slot->d_counters, 0, sizeof(DevCounters), slot->stream));
+        // With a host destination the frame is rendered in a few slices so that the device-to-host copy of one
+        // slice overlaps the kernel of the next (the 4K canvases are 124 MB: ~2.3 ms of PCIe against ~2 ms of
+        // kernel); left on the device it is one launch.
+        const int n_slices = copy_out ? std::max(1, std::min(s->render_slices, nb)) : 1;
+        while ((int)slot->slice_done.size() < n_slices) {
+            cudaEvent_t e;
+            CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            slot->slice_done.push_back(e);
+        }
+        CUDA_TRY(cudaEventRecord(slot->ev0, slot->stream));
+        for (int k = 0; k < n_slices; k++) {
+            const int b0 = (int)((int64_t)nb * k / n_slices), b1 = (int)((int64_t)nb * (k + 1) / n_slices);
+            if (b1 <= b0) continue;
+            DevFrame F{slot->d_rgb, slot->d_u8, shard, n_shards, depth, b1 - b0, b0};
+            if (s->strict_fp)
+                strict::launch_render(r.scene, r.small, F, slot->d_counters, detailed, slot->stream);
+            else
+                fast::launch_render(r.scene, r.small, F, slot->d_counters, detailed, slot->stream);
+            CUDA_TRY(cudaGetLastError());
+            st.launches++;
+            if (copy_out) {
+                CUDA_TRY(cudaEventRecord(slot->slice_done[k], slot->stream));
+                CUDA_TRY(cudaStreamWaitEvent(slot->copy_stream, slot->slice_done[k], 0));
+                int rc;
+                if (rgb && (rc = copy_bands(slot, s, shard, n_shards, b0, b1, slot->d_rgb, rgb, 3 * sizeof(float)))) return rc;
+                if (u8 && (rc = copy_bands(slot, s, shard, n_shards, b0, b1, slot->d_u8, u8, 3))) return rc;
+            }
+        }
+        CUDA_TRY(cudaEventRecord(slot->ev1, slot->stream));
     }
     for (int i = 0; i < ndev; i++) {
-        Replica& r = s->replicas[i];
-        CUDA_TRY(cudaSetDevice(r.device));
-        CUDA_TRY(cudaStreamSynchronize(r.stream));
+        DeviceSlot* slot = s->replicas[i].slot;
+        CUDA_TRY(cudaSetDevice(slot->device));
+        CUDA_TRY(cudaStreamSynchronize(slot->stream));
+        CUDA_TRY(cudaStreamSynchronize(slot->copy_stream));
         float ms = 0.f;
-        CUDA_TRY(cudaEventElapsedTime(&ms, r.ev0, r.ev1));
+        CUDA_TRY(cudaEventElapsedTime(&ms, slot->ev0, slot->ev1));
         st.kernel_ms = std::max(st.kernel_ms, (double)ms);
         DevCounters c;
-        CUDA_TRY(cudaMemcpy(&c, r.d_counters, sizeof(c), cudaMemcpyDeviceToHost));
+        CUDA_TRY(cudaMemcpy(&c, slot->d_counters, sizeof(c), cudaMemcpyDeviceToHost));
         add_counters(st, c);
     }
     st.flops = detailed ? flops_of(st, st.primary_rays) : 0.0;
@@ -819,6 +922,10 @@ int rtc_set_option(RtcScene* s, int32_t option, int64_t value) {
             s->leaf_size = (int)value;
             s->committed = false;
             return 0;
+        case RTC_OPT_RENDER_SLICES:
+            if (value < 1 || value > 64) return fail(RTC_ERR_INVALID, "render slices must be in [1,64]");
+            s->render_slices = (int)value;
+            return 0;
         case RTC_OPT_BVH_MIN_PRIMS:
             s->bvh_min_prims = (int)std::max<int64_t>(0, value);
             s->committed = false;
@@ -841,13 +948,14 @@ int rtc_scene_commit(RtcScene* s, int32_t n_devices, const int32_t* device_ids) 
     int rc = flatten(s, f);
     if (rc) return rc;
     s->replicas.resize(n_devices);
+    s->replica_devices.resize(n_devices);
     for (int i = 0; i < n_devices; i++) {
-        s->replicas[i].device = device_ids ? device_ids[i] : i;
-        if (s->replicas[i].device < 0 || s->replicas[i].device >= visible) {
+        s->replica_devices[i] = device_ids ? device_ids[i] : i;
+        if (s->replica_devices[i] < 0 || s->replica_devices[i] >= visible) {
             release(s);
             return fail(RTC_ERR_INVALID, "bad device id");
         }
-        if ((rc = upload_replica(s, f, s->replicas[i]))) {
+        if ((rc = upload_replica(s, f, s->replicas[i], s->replica_devices[i]))) {
             release(s);
             return rc;
         }
@@ -883,7 +991,14 @@ int rtc_trace_rays(RtcScene* s, uint32_t n, const float* origins, const float* d
     if (!s->committed) return fail(RTC_ERR_STATE, "rtc_trace_rays before rtc_scene_commit");
     if (depth < 0 || depth > kMaxFrames - 1) return fail(RTC_ERR_CAPACITY, "depth out of range");
     if (n == 0) return 0;
-    Replica& r = s->replicas[0];
+    Replica& rep = s->replicas[0];
+    struct {
+        int device;
+        cudaStream_t stream;
+        DevCounters* d_counters;
+        DevScene& scene;
+        SmallScene& small;
+    } r{rep.slot->device, rep.slot->stream, rep.slot->d_counters, rep.scene, rep.small};
     CUDA_TRY(cudaSetDevice(r.device));
     float *d_o = nullptr, *d_d = nullptr, *d_rgb = nullptr, *d_t = nullptr;
     int* d_pos = nullptr;
@@ -934,14 +1049,15 @@ int rtc_host_unregister(void* ptr) {
 
 int rtc_flush_l2(RtcScene* s) {
     if (!s || !s->committed) return fail(RTC_ERR_STATE, "scene not committed");
-    for (Replica& r : s->replicas) {
-        CUDA_TRY(cudaSetDevice(r.device));
-        if (!r.d_flush) {
-            r.flush_bytes = 256u << 20;  // > 126 MB L2
-            CUDA_TRY(cudaMalloc(&r.d_flush, r.flush_bytes));
+    for (Replica& rep : s->replicas) {
+        DeviceSlot* r = rep.slot;
+        CUDA_TRY(cudaSetDevice(r->device));
+        if (!r->d_flush) {
+            r->flush_bytes = 256u << 20;  // > 126 MB L2
+            CUDA_TRY(cudaMalloc(&r->d_flush, r->flush_bytes));
         }
-        CUDA_TRY(cudaMemsetAsync(r.d_flush, 0x5a, r.flush_bytes, r.stream));
-        CUDA_TRY(cudaStreamSynchronize(r.stream));
+        CUDA_TRY(cudaMemsetAsync(r->d_flush, 0x5a, r->flush_bytes, r->stream));
+        CUDA_TRY(cudaStreamSynchronize(r->stream));
     }
     return 0;
 }

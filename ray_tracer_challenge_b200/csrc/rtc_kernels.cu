@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(128, SMALL ? RTC_SMALL_MINBLOCKS : RTC_BVH_MIN
     const Env E{S, SS};
     // block (bx, by) -> tile of 16x8 pixels in band `shard + by * n_shards`; warp w -> 8x4 sub-tile
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int band = F.shard + blockIdx.y * F.n_shards;
+    const int band = F.shard + (F.band_begin + blockIdx.y) * F.n_shards;
     const int x = blockIdx.x * kTileW + (warp & 1) * 8 + (lane & 7);
     const int y = band * kBandRows + (warp >> 1) * 4 + (lane >> 3);
     Ctr<STATS> k;

@@ -137,7 +137,8 @@ struct DevFrame {  // where a render writes
     unsigned char* u8;     // width*height*3 or null
     int shard, n_shards;   // interleaved bands of kBandRows rows
     int depth;
-    int n_bands;           // bands this launch renders
+    int n_bands;           // bands this launch renders ...
+    int band_begin;        // ... starting at this index of the shard's band list
 };
 
 constexpr int kTileW = 16, kTileH = 8;  // pixels per 128-thread block: 4 warps of 8x4

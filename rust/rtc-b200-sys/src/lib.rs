@@ -105,6 +105,8 @@ pub struct RtcStats {
     pub total_ms: f64,
     pub n_devices: i32,
     pub detailed: i32,
+    pub launches: i32,
+    pub reserved: i32,
 }
 
 extern "C" {
