@@ -24,8 +24,10 @@ from .api import (DEFAULT_RAY_RECURSION_DEPTH, REFRACTION_AIR, REFRACTION_DIAMON
                   color_from_hex, constant_jitter, glass, hardcoded_jitter, metal)
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_HOST = os.path.join(_PKG, "librtc_host.so")
-LIB_DEVICE = os.path.join(_PKG, "librtc_b200.so")
+# RTC_LIB_DIR: load another build of the two libraries (A/B timing of kernel variants on one GPU box)
+_LIB_DIR = os.environ.get("RTC_LIB_DIR", _PKG)
+LIB_HOST = os.path.join(_LIB_DIR, "librtc_host.so")
+LIB_DEVICE = os.path.join(_LIB_DIR, "librtc_b200.so")
 
 
 class RtcStats(C.Structure):

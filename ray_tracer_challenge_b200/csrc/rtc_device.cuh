@@ -876,9 +876,10 @@ __device__ __forceinline__ void cache_origins(const Env& E, V3 o) {
     }
 }
 
-// One item of a small scene of any kind (primitive or CSG root), honouring the cull chain: the general form.
-template <bool STATS, bool CACHED>
-__device__ __noinline__ void test_small(const Env& E, int i, V3 o, V3 d, Hit& best, Ctr<STATS>& k) {
+// One item of a small scene of any kind (primitive or CSG root), honouring the cull chain: the general form
+// (out of line: cylinders, cones, triangles and CSG roots are the rare members of small scenes).
+template <bool STATS>
+__device__ __forceinline__ void test_small(const Env& E, int i, bool cached, V3 o, V3 d, Hit& best, Ctr<STATS>& k) {
     const float4* tab = small_tab();
     const int4 head = *reinterpret_cast<const int4*>(tab + i * 5);
     const int type = head.x & 15;
@@ -895,7 +896,7 @@ __device__ __noinline__ void test_small(const Env& E, int i, V3 o, V3 d, Hit& be
         return;
     }
     Xf m{tab[i * 5 + 1], tab[i * 5 + 2], tab[i * 5 + 3]};
-    V3 o2 = small_origin<CACHED>(i, m, o);
+    V3 o2 = cached ? small_origin<true>(i, m, o) : xf_point(m, o);
     V3 d2 = xf_vec(m, d);
     k.xform();
     k.prim(type);
@@ -909,6 +910,7 @@ __device__ __noinline__ void test_small(const Env& E, int i, V3 o, V3 d, Hit& be
 // ANY: return true as soon as some item is hit in [0, best.t) (shadow rays when every object casts a shadow).
 template <bool STATS, bool CACHED, bool ANY>
 __device__ __forceinline__ bool scan_small(const Env& E, int begin, int4 ends, V3 o, V3 d, Hit& best, Ctr<STATS>& k) {
+    constexpr bool cached = CACHED, any = ANY;
     const float4* tab = small_tab();
     int i = begin;
     for (; i < ends.x; i++) {  // spheres — sphere.rs:47-70
@@ -918,16 +920,13 @@ __device__ __forceinline__ bool scan_small(const Env& E, int begin, int4 ends, V
         k.xform();
         k.prim(T_SPHERE);
         float t = nearest_t(E.S, T_SPHERE, 0, make_float4(0.f, 0.f, 0.f, 0.f), o2, d2);
-        if (ANY) {
-            if (t >= 0.0f && t < best.t) return true;
-        } else {
-            consider(best, t, i, __float_as_int(tab[i * 5].w));
-        }
+        if (any && t >= 0.0f && t < best.t) return true;
+        consider(best, t, i, __float_as_int(tab[i * 5].w));
     }
     for (; i < ends.y; i++) {  // planes — plane.rs:45-56 only reads the y components of the object-space ray
         float4 r1 = tab[i * 5 + 2];
         float oy;
-        if (CACHED && i < kOrgCache)
+        if (cached && i < kOrgCache)
             oy = small_org()[(i * 3 + 1) * 128];
         else
             oy = r1.x * o.x + r1.y * o.y + r1.z * o.z + r1.w;
@@ -935,11 +934,8 @@ __device__ __forceinline__ bool scan_small(const Env& E, int begin, int4 ends, V
         k.xform();
         k.prim(T_PLANE);
         float t = (fabsf(dy) < kAcne) ? -1.0f : -oy / dy;
-        if (ANY) {
-            if (t >= 0.0f && t < best.t) return true;
-        } else {
-            consider(best, t, i, __float_as_int(tab[i * 5].w));
-        }
+        if (any && t >= 0.0f && t < best.t) return true;
+        consider(best, t, i, __float_as_int(tab[i * 5].w));
     }
     for (; i < ends.z; i++) {  // cubes — cube.rs:55-63
         Xf m{tab[i * 5 + 1], tab[i * 5 + 2], tab[i * 5 + 3]};
@@ -948,20 +944,13 @@ __device__ __forceinline__ bool scan_small(const Env& E, int begin, int4 ends, V
         k.xform();
         k.prim(T_CUBE);
         float t = nearest_t(E.S, T_CUBE, 0, make_float4(0.f, 0.f, 0.f, 0.f), o2, d2);
-        if (ANY) {
-            if (t >= 0.0f && t < best.t) return true;
-        } else {
-            consider(best, t, i, __float_as_int(tab[i * 5].w));
-        }
+        if (any && t >= 0.0f && t < best.t) return true;
+        consider(best, t, i, __float_as_int(tab[i * 5].w));
     }
     for (; i < ends.w; i++) {  // cylinders, cones, triangles, CSG roots
-        if (ANY) {
-            Hit h{best.t, -1, -1};
-            test_small<STATS, CACHED>(E, i, o, d, h, k);
-            if (h.pos >= 0) return true;
-        } else {
-            test_small<STATS, CACHED>(E, i, o, d, best, k);
-        }
+        const int before = best.pos;
+        test_small<STATS>(E, i, cached, o, d, best, k);
+        if (any && best.pos != before) return true;
     }
     return false;
 }
@@ -972,10 +961,16 @@ __device__ __forceinline__ void find_hit(const Env& E, V3 o, V3 d, Hit& best, Ct
     if (SMALL) {
         const SmallScene& SS = E.SS;
         if (SS.has_cull_chain) {
-            for (int i = 0; i < SS.n; i++) test_small<STATS, false>(E, i, o, d, best, k);
+            for (int i = 0; i < SS.n; i++) test_small<STATS>(E, i, false, o, d, best, k);
         } else {
-            scan_small<STATS, false, false>(E, 0, SS.caster_end, o, d, best, k);
-            scan_small<STATS, false, false>(E, SS.caster_end.w, SS.other_end, o, d, best, k);
+            int begin = 0;
+            int4 ends = SS.caster_end;
+#pragma unroll 1
+            for (int seg = 0; seg < 2; seg++) {  // casters, then non-casters: one copy of the loops
+                scan_small<STATS, false, false>(E, begin, ends, o, d, best, k);
+                begin = ends.w;
+                ends = SS.other_end;
+            }
         }
     } else {
         nearest_hit<STATS, false>(E.S, o, d, best, k);
@@ -991,6 +986,7 @@ __device__ __forceinline__ void find_hit(const Env& E, V3 o, V3 d, Hit& best, Ct
 // reference's, evaluated with fewer intersection tests.
 template <bool STATS, bool SMALL, bool CACHED>
 __device__ __forceinline__ bool is_shadowed(const Env& E, V3 light_position, V3 p, Rays& r, Ctr<STATS>& k) {
+    constexpr bool cached = CACHED;
     const DevScene& S = E.S;
     r.shadow++;
     V3 v = light_position - p;
@@ -1001,10 +997,10 @@ __device__ __forceinline__ bool is_shadowed(const Env& E, V3 light_position, V3 
     if (SMALL) {
         const SmallScene& SS = E.SS;
         if (!SS.two_pass_shadows || SS.has_cull_chain) {  // a CSG root or a cull chain: plain nearest-hit search
-            for (int i = 0; i < SS.n; i++) test_small<STATS, CACHED>(E, i, p, direction, best, k);
+            for (int i = 0; i < SS.n; i++) test_small<STATS>(E, i, cached, p, direction, best, k);
             return best.pos >= 0 && ((__ldg(&S.head[best.pos]).x >> 4) & kFlagCastsShadow);
         }
-        if (S.all_cast_shadow)  // any hit in [0, distance) shadows the point
+        if (S.all_cast_shadow)  // every object casts: any hit in [0, distance) shadows the point
             return scan_small<STATS, CACHED, true>(E, 0, SS.caster_end, p, direction, best, k);
         scan_small<STATS, CACHED, false>(E, 0, SS.caster_end, p, direction, best, k);
         if (best.pos < 0) return false;

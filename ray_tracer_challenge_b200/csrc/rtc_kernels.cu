@@ -58,7 +58,7 @@ __device__ __forceinline__ void flush_counters<true>(const Rays& r, const Ctr<tr
 }
 
 template <bool STATS, bool SMALL>
-__global__ void __launch_bounds__(128, SMALL ? RTC_SMALL_MINBLOCKS : RTC_BVH_MINBLOCKS) render_tiles(const __grid_constant__ DevScene S, const __grid_constant__ SmallScene SS,
+__global__ void __launch_bounds__(128) render_tiles(const __grid_constant__ DevScene S, const __grid_constant__ SmallScene SS,
                                                     const DevFrame F, DevCounters* counters) {
     // small scenes: primitive table + per-thread shadow-origin cache in dynamic shared memory (kSmallSmemBytes)
     if (SMALL) stage_small_scene(SS);
