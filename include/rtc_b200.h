@@ -161,8 +161,11 @@ enum {
     RTC_OPT_FMA_CONTRACTION = 1,
     RTC_OPT_BVH_LEAF_SIZE = 2,
     RTC_OPT_BVH_MIN_PRIMS = 3,
-    RTC_OPT_RENDER_SLICES = 4 /* kernel launches a frame is cut into when it is copied to host memory, so the
-                                 copy of one slice overlaps the kernel of the next (default 6) */
+    RTC_OPT_RENDER_SLICES = 4, /* kernel launches a frame is cut into when it is copied to host memory, so the
+                                  copy of one slice overlaps the kernel of the next (default 6) */
+    RTC_OPT_ADAPTIVE_ORDER = 5 /* default 1: a repeated render of the same shard launches its bands
+                                  most-expensive-first (rays per band counted by the previous render); changes no
+                                  pixel, shortens the tail of the launch */
 };
 int rtc_set_option(RtcScene*, int32_t option, int64_t value);
 

@@ -68,6 +68,10 @@ struct DeviceSlot {
     unsigned char* d_u8 = nullptr;
     size_t frame_px = 0;
     DevCounters* d_counters = nullptr;
+    unsigned* d_band_cost = nullptr;  // rays per frame band of the last render
+    int* d_band_order = nullptr;      // launch order of this shard's bands
+    int band_capacity = 0;
+    int sm_count = 148;
     char* arena = nullptr;  // scene arrays, one allocation
     size_t arena_bytes = 0;
     char* staging = nullptr;  // pinned host mirror of the arena for one asynchronous upload
@@ -97,6 +101,7 @@ int lease_slot(int device, DeviceSlot** out) {
     CUDA_TRY(cudaEventCreate(&d->ev0));
     CUDA_TRY(cudaEventCreate(&d->ev1));
     CUDA_TRY(cudaMalloc(&d->d_counters, sizeof(DevCounters)));
+    CUDA_TRY(cudaDeviceGetAttribute(&d->sm_count, cudaDevAttrMultiProcessorCount, device));
     // the kernels keep their bounce and traversal stacks in local memory
     size_t have = 0;
     cudaDeviceGetLimit(&have, cudaLimitStackSize);
@@ -118,6 +123,17 @@ int ensure_frame(DeviceSlot* d, size_t px) {
     CUDA_TRY(cudaMalloc(&d->d_rgb, std::max<size_t>(px * 3 * sizeof(float), 16)));
     CUDA_TRY(cudaMalloc(&d->d_u8, std::max<size_t>(px * 3, 16)));
     d->frame_px = px;
+    return 0;
+}
+int ensure_bands(DeviceSlot* d, int total_bands) {
+    if (total_bands <= d->band_capacity) return 0;
+    CUDA_TRY(cudaSetDevice(d->device));
+    if (d->d_band_cost) cudaFree(d->d_band_cost);
+    if (d->d_band_order) cudaFree(d->d_band_order);
+    d->band_capacity = 0;
+    CUDA_TRY(cudaMalloc(&d->d_band_cost, (size_t)total_bands * sizeof(unsigned)));
+    CUDA_TRY(cudaMalloc(&d->d_band_order, (size_t)total_bands * sizeof(int)));
+    d->band_capacity = total_bands;
     return 0;
 }
 int ensure_arena(DeviceSlot* d, size_t bytes) {
@@ -144,6 +160,9 @@ struct Replica {
     DeviceSlot* slot = nullptr;
     DevScene scene{};
     SmallScene small{};
+    // Longest-first launch order learnt from the previous render of the same shard (see render_impl)
+    std::vector<int> band_order;
+    int order_shard = -1, order_n_shards = -1, order_depth = -1;
 };
 
 }  // namespace
@@ -166,6 +185,7 @@ struct RtcScene {
     uint64_t seed = 0;
     int strict_fp = 1, leaf_size = 4, bvh_min_prims = kSmallCap + 1;
     int render_slices = 6;  // kernel / copy pipeline depth when rendering into host memory
+    int adaptive_order = 1;  // launch a shard's bands longest-first, learnt from the previous render
     std::vector<Replica> replicas;
     std::vector<int> replica_devices;
     std::vector<int> pos_to_prim;  // device position -> API primitive index (-1 for CSG pseudo-primitives)
@@ -771,6 +791,24 @@ int render_impl(RtcScene* s, int depth, int shard0, int n_shards_ext, float* rgb
         const int nb = shard < total_bands ? (total_bands - shard + n_shards - 1) / n_shards : 0;
         CUDA_TRY(cudaSetDevice(slot->device));
         CUDA_TRY(cudaMemsetAsync(slot->d_counters, 0, sizeof(DevCounters), slot->stream));
+        // Longest-processing-time-first: a frame's cost is concentrated in a few bands (deep reflection trees:
+        // one block there runs ~10x longer than the average), and a long block that starts late is the tail of
+        // the launch — the term that limits strong scaling over shards.  The kernel counts the rays traced per
+        // band; the next render of the same shard launches its bands most-expensive-first.  The order changes
+        // no pixel.  It needs one copy-free launch, so it is used when the frame stays on the device or is
+        // copied in one piece — and only for launches of fewer than ~24 waves of blocks: measured on B200, the
+        // natural top-to-bottom order is 6 % faster for a whole 4K frame (73 waves; neighbouring bands of unlike
+        // cost share the SMs) while longest-first is 10-15 % faster for a 1/4 or 1/8 shard, where the tail counts.
+        int rc0;
+        if ((rc0 = ensure_bands(slot, total_bands))) return rc0;
+        CUDA_TRY(cudaMemsetAsync(slot->d_band_cost, 0, (size_t)total_bands * sizeof(unsigned), slot->stream));
+        const long long launch_blocks = (long long)nb * ((s->width + kTileW - 1) / kTileW);
+        const bool use_order = s->adaptive_order && !copy_out && r.order_shard == shard && r.order_n_shards == n_shards &&
+                               r.order_depth == depth && (int)r.band_order.size() == nb &&
+                               launch_blocks < 24LL * 6 * slot->sm_count;
+        if (use_order)
+            CUDA_TRY(cudaMemcpyAsync(slot->d_band_order, r.band_order.data(), (size_t)nb * sizeof(int), cudaMemcpyHostToDevice,
+                                     slot->stream));
         // With a host destination the frame is rendered in a few slices so that the device-to-host copy of one
         // slice overlaps the kernel of the next (the 4K canvases are 124 MB: ~2.3 ms of PCIe against ~2 ms of
         // kernel); left on the device it is one launch.
@@ -784,7 +822,8 @@ int render_impl(RtcScene* s, int depth, int shard0, int n_shards_ext, float* rgb
         for (int k = 0; k < n_slices; k++) {
             const int b0 = (int)((int64_t)nb * k / n_slices), b1 = (int)((int64_t)nb * (k + 1) / n_slices);
             if (b1 <= b0) continue;
-            DevFrame F{slot->d_rgb, slot->d_u8, shard, n_shards, depth, b1 - b0, b0};
+            DevFrame F{slot->d_rgb, slot->d_u8, shard, n_shards, depth, b1 - b0, b0, use_order ? slot->d_band_order : nullptr,
+                       s->adaptive_order ? slot->d_band_cost : nullptr};
             if (s->strict_fp)
                 strict::launch_render(r.scene, r.small, F, slot->d_counters, detailed, slot->stream);
             else
@@ -812,6 +851,16 @@ int render_impl(RtcScene* s, int depth, int shard0, int n_shards_ext, float* rgb
         DevCounters c;
         CUDA_TRY(cudaMemcpy(&c, slot->d_counters, sizeof(c), cudaMemcpyDeviceToHost));
         add_counters(st, c);
+        if (s->adaptive_order) {  // learn the launch order for the next render of this shard
+            Replica& r = s->replicas[i];
+            const int shard = external ? shard0 : i;
+            std::vector<unsigned> cost(total_bands);
+            CUDA_TRY(cudaMemcpy(cost.data(), slot->d_band_cost, (size_t)total_bands * sizeof(unsigned), cudaMemcpyDeviceToHost));
+            r.band_order.clear();
+            for (int b = shard; b < total_bands; b += n_shards) r.band_order.push_back(b);
+            std::stable_sort(r.band_order.begin(), r.band_order.end(), [&](int a, int b) { return cost[a] > cost[b]; });
+            r.order_shard = shard, r.order_n_shards = n_shards, r.order_depth = depth;
+        }
     }
     st.flops = detailed ? flops_of(st, st.primary_rays) : 0.0;
     st.total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
@@ -837,6 +886,7 @@ int rtc_device_count(void) {
 int rtc_scene_create(RtcScene** out) {
     if (!out) return fail(RTC_ERR_INVALID, "null out pointer");
     *out = new RtcScene();
+    if (const char* env = getenv("RTC_ADAPTIVE_ORDER")) (*out)->adaptive_order = atoi(env) != 0;  // tuning aid
     return 0;
 }
 void rtc_scene_destroy(RtcScene* s) {
@@ -921,6 +971,9 @@ int rtc_set_option(RtcScene* s, int32_t option, int64_t value) {
             if (value < 1 || value > 16) return fail(RTC_ERR_INVALID, "leaf size must be in [1,16]");
             s->leaf_size = (int)value;
             s->committed = false;
+            return 0;
+        case RTC_OPT_ADAPTIVE_ORDER:
+            s->adaptive_order = value != 0;
             return 0;
         case RTC_OPT_RENDER_SLICES:
             if (value < 1 || value > 64) return fail(RTC_ERR_INVALID, "render slices must be in [1,64]");

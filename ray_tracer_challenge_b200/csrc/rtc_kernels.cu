@@ -40,6 +40,10 @@ __device__ __forceinline__ void flush_rays(const Rays& r, DevCounters* out) {
     warp_add(&out->shadow, r.shadow);
     warp_add(&out->shades, r.shades);
 }
+__device__ __forceinline__ void warp_add_u32(unsigned* dst, unsigned v) {
+    unsigned s = __reduce_add_sync(0xffffffffu, v);
+    if ((threadIdx.x & 31) == 0 && s) atomicAdd(dst, s);
+}
 template <>
 __device__ __forceinline__ void flush_counters<false>(const Rays& r, const Ctr<false>&, DevCounters* out) {
     flush_rays(r, out);
@@ -65,7 +69,7 @@ __global__ void __launch_bounds__(128) render_tiles(const __grid_constant__ DevS
     const Env E{S, SS};
     // block (bx, by) -> tile of 16x8 pixels in band `shard + by * n_shards`; warp w -> 8x4 sub-tile
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int band = F.shard + (F.band_begin + blockIdx.y) * F.n_shards;
+    const int band = F.band_order ? F.band_order[F.band_begin + blockIdx.y] : F.shard + (F.band_begin + blockIdx.y) * F.n_shards;
     const int x = blockIdx.x * kTileW + (warp & 1) * 8 + (lane & 7);
     const int y = band * kBandRows + (warp >> 1) * 4 + (lane >> 3);
     Ctr<STATS> k;
@@ -93,6 +97,7 @@ __global__ void __launch_bounds__(128) render_tiles(const __grid_constant__ DevS
         }
     }
     flush_counters<STATS>(r, k, counters);
+    if (F.band_cost) warp_add_u32(&F.band_cost[band], r.primary + r.secondary + r.shadow);
 }
 
 template <bool SMALL>

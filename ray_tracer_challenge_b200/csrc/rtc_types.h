@@ -139,6 +139,8 @@ struct DevFrame {  // where a render writes
     int depth;
     int n_bands;           // bands this launch renders ...
     int band_begin;        // ... starting at this index of the shard's band list
+    const int* band_order; // the shard's band list in launch order (frame band indices), or null: shard + j * n_shards
+    unsigned* band_cost;   // per frame band: rays traced in it (feeds the next frame's launch order), or null
 };
 
 constexpr int kTileW = 16, kTileH = 8;  // pixels per 128-thread block: 4 warps of 8x4
