@@ -323,8 +323,16 @@ def main() -> None:
         if detail is not None:
             ms_frame = kernel_ms_max / args.steps
             achieved = detail["flops"] / (ms_frame * 1e-3) / 1e12
+            traffic = None
+            try:
+                with open(os.path.join(ROOT, "profiles", f"r01_{args.workload}_traffic.json")) as fh:
+                    traffic = json.load(fh)["dram_bytes"]
+            except Exception:
+                pass
             roofline = {"bound": "fp32", "achieved": round(achieved, 3), "peak": round(tflops.value, 2), "unit": "TFLOP/s",
-                        "frac": round(achieved / tflops.value, 4), "traffic": None,
+                        "frac": round(achieved / tflops.value, 4), "traffic": traffic,
+                        "traffic_source": "profiles/r01_c3_traffic.json (ncu dram__bytes_read+write of one launch)" if traffic else None,
+                        "issue_slot_utilisation": "69.6 % (ncu smsp__issue_active, profiles/r01_c3_step6_current.txt)" if args.workload == "c3" else None,
                         "peak_kind": "measured live: K5 FMA micro-benchmark (MEASURED_PEAKS.json has no FP32 figure)",
                         "nominal_peak": round(nominal, 2), "frac_of_nominal": round(achieved / nominal, 4),
                         "flops_per_frame": detail["flops"], "rays_per_frame": detail["rays"],

@@ -74,6 +74,7 @@ _HOST_EXTRAS = {
     "sg_release_prepared": (_I, [_V, _I]),
     "sg_render_prepared": (_I, [_V, _I, _I, _I, _I, _I, _I, _FP, _U8P, C.POINTER(SgStats)]),
     "sg_flush_l2": (_I, [_V, _I]),
+    "sg_set_prepared_option": (_I, [_V, _I, _I, C.c_int64]),
     "sg_trace_rays": (_I, [_V, _I, C.c_uint32, _FP, _FP, _I, _I, _FP, _FP, _IP]),
     "sg_flatten": (_I, [_V, _I, _IP, C.POINTER(RtcPrim), C.POINTER(RtcNode), C.POINTER(C.c_int32), _IP]),
 }
@@ -114,6 +115,10 @@ class PreparedScene:
         api.check(api.lib.sg_trace_rays(api.ctx, self.handle, n, _api.fptr(o), _api.fptr(d), int(depth), int(fma),
                                         _api.fptr(rgb), _api.fptr(t), shape.ctypes.data_as(_IP)))
         return rgb, t, shape
+
+    def set_option(self, option: int, value: int):
+        """rtc_set_option: RTC_OPT_RENDER_SLICES = 4, RTC_OPT_ADAPTIVE_ORDER = 5, ..."""
+        self.api.check(self.api.lib.sg_set_prepared_option(self.api.ctx, self.handle, int(option), int(value)))
 
     def flush_l2(self):
         self.api.check(self.api.lib.sg_flush_l2(self.api.ctx, self.handle))

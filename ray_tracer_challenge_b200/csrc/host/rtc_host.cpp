@@ -426,6 +426,11 @@ int sg_render_prepared(sg_ctx* c, int h, int depth, int shard, int n_shards, int
     to_sg_stats(c->last_stats, stats);
     return rc ? fail(rtc_last_error()) : 0;
 }
+// rtc_set_option on a prepared scene (RTC_OPT_* of include/rtc_b200.h)
+int sg_set_prepared_option(sg_ctx* c, int h, int option, int64_t value) {
+    if (h < 0 || h >= (int)c->prepared.size() || !c->prepared[h]) return fail("bad prepared handle");
+    return rtc_set_option(c->prepared[h]->scene, option, value) ? fail(rtc_last_error()) : 0;
+}
 int sg_flush_l2(sg_ctx* c, int h) {
     if (h < 0 || h >= (int)c->prepared.size() || !c->prepared[h]) return fail("bad prepared handle");
     return rtc_flush_l2(c->prepared[h]->scene) ? fail(rtc_last_error()) : 0;

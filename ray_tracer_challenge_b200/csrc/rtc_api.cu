@@ -799,11 +799,12 @@ int render_impl(RtcScene* s, int depth, int shard0, int n_shards_ext, float* rgb
         // copied in one piece — and only for launches of fewer than ~24 waves of blocks: measured on B200, the
         // natural top-to-bottom order is 6 % faster for a whole 4K frame (73 waves; neighbouring bands of unlike
         // cost share the SMs) while longest-first is 10-15 % faster for a 1/4 or 1/8 shard, where the tail counts.
+        const int n_slices = copy_out ? std::max(1, std::min(s->render_slices, nb)) : 1;
         int rc0;
         if ((rc0 = ensure_bands(slot, total_bands))) return rc0;
         CUDA_TRY(cudaMemsetAsync(slot->d_band_cost, 0, (size_t)total_bands * sizeof(unsigned), slot->stream));
         const long long launch_blocks = (long long)nb * ((s->width + kTileW - 1) / kTileW);
-        const bool use_order = s->adaptive_order && !copy_out && r.order_shard == shard && r.order_n_shards == n_shards &&
+        const bool use_order = s->adaptive_order && n_slices == 1 && r.order_shard == shard && r.order_n_shards == n_shards &&
                                r.order_depth == depth && (int)r.band_order.size() == nb &&
                                launch_blocks < 24LL * 6 * slot->sm_count;
         if (use_order)
@@ -812,7 +813,6 @@ int render_impl(RtcScene* s, int depth, int shard0, int n_shards_ext, float* rgb
         // With a host destination the frame is rendered in a few slices so that the device-to-host copy of one
         // slice overlaps the kernel of the next (the 4K canvases are 124 MB: ~2.3 ms of PCIe against ~2 ms of
         // kernel); left on the device it is one launch.
-        const int n_slices = copy_out ? std::max(1, std::min(s->render_slices, nb)) : 1;
         while ((int)slot->slice_done.size() < n_slices) {
             cudaEvent_t e;
             CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));

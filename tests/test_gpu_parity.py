@@ -116,6 +116,25 @@ def test_band_sharding_is_bit_identical(gpu):
         p.release()
 
 
+def test_longest_first_band_order_changes_no_pixel(gpu):
+    """RTC_OPT_ADAPTIVE_ORDER: the second render of a shard launches its bands most-expensive-first."""
+    cam, world = scenes.soft_shadows(gpu, width=203, height=177, u_steps=2, v_steps=2)
+    p = cam.prepare(world)
+    try:
+        p.set_option(4, 1)  # RTC_OPT_RENDER_SLICES = 1: one launch, so the learnt order is used with a host canvas too
+        for shard, n_shards in ((0, 0), (1, 3)):
+            p.set_option(5, 0)
+            ref = p.render(5, shard=shard, n_shards=n_shards)
+            p.set_option(5, 1)
+            first = p.render(5, shard=shard, n_shards=n_shards)   # natural order, learns the cost
+            second = p.render(5, shard=shard, n_shards=n_shards)  # longest-first
+            for got in (first, second):
+                assert np.array_equal(got.data.view(np.uint32), ref.data.view(np.uint32))
+                assert np.array_equal(got.to_u8(), ref.to_u8())
+    finally:
+        p.release()
+
+
 def test_depth_semantics(gpu, oracle):
     """remaining-depth guards (world.rs:126,140): depth 0 and 1 frames match the oracle."""
     for depth in (0, 1, 2):
