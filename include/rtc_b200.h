@@ -114,7 +114,8 @@ typedef struct RtcStats {
     uint64_t shadow_rays;    /* is_shadowed calls (world.rs:104) */
     uint64_t shades;         /* shade_hit calls */
     uint64_t node_visits;    /* BVH boxes tested (detailed pass only) */
-    uint64_t prim_tests[8];  /* local_intersect calls by RTC_* type; [6] = CSG evaluations (detailed pass only) */
+    uint64_t prim_tests[8];  /* local_intersect calls by RTC_* type; [6] = CSG evaluations; [7] = shadow rays the
+                                shadow filter handed to the exact test (detailed pass only) */
     uint64_t xforms;         /* ray -> object transforms actually performed (detailed pass only) */
     uint64_t patterns, cells, schlicks, refr_dirs;
     uint64_t capacity_overflows; /* CSG hit-buffer overflows: must be 0 for a valid frame */
@@ -163,9 +164,13 @@ enum {
     RTC_OPT_BVH_MIN_PRIMS = 3,
     RTC_OPT_RENDER_SLICES = 4, /* kernel launches a frame is cut into when it is copied to host memory, so the
                                   copy of one slice overlaps the kernel of the next (default 6) */
-    RTC_OPT_ADAPTIVE_ORDER = 5 /* default 1: a repeated render of the same shard launches its bands
+    RTC_OPT_ADAPTIVE_ORDER = 5, /* default 1: a repeated render of the same shard launches its bands
                                   most-expensive-first (rays per band counted by the previous render); changes no
                                   pixel, shortens the tail of the launch */
+    RTC_OPT_SHADOW_FILTER = 6   /* default 1: in small scenes of spheres, planes and axis-aligned cubes a shadow ray is
+                                  first decided on the un-normalised point->light segment with error bounds; only
+                                  undecided rays run the reference's arithmetic.  Changes no pixel (0 = always run
+                                  the exact test: the A/B switch the parity tests use) */
 };
 int rtc_set_option(RtcScene*, int32_t option, int64_t value);
 

@@ -160,6 +160,8 @@ struct Replica {
     DeviceSlot* slot = nullptr;
     DevScene scene{};
     SmallScene small{};
+    int cell_masks_eligible = 0;
+    int filter_eligible = 0;  // SmallScene::filter_ok as computed at commit (RTC_OPT_SHADOW_FILTER masks it per render)
     // Longest-first launch order learnt from the previous render of the same shard (see render_impl)
     std::vector<int> band_order;
     int order_shard = -1, order_n_shards = -1, order_depth = -1;
@@ -186,6 +188,7 @@ struct RtcScene {
     int strict_fp = 1, leaf_size = 4, bvh_min_prims = kSmallCap + 1;
     int render_slices = 6;  // kernel / copy pipeline depth when rendering into host memory
     int adaptive_order = 1;  // launch a shard's bands longest-first, learnt from the previous render
+    int shadow_filter = 1;   // RTC_OPT_SHADOW_FILTER
     std::vector<Replica> replicas;
     std::vector<int> replica_devices;
     std::vector<int> pos_to_prim;  // device position -> API primitive index (-1 for CSG pseudo-primitives)
@@ -664,6 +667,41 @@ int flatten(RtcScene* s, Flattened& f) {
         }
         f.small.caster_end = make_int4(ends[0], ends[1], ends[2], ends[3]);
         f.small.other_end = make_int4(ends[4], ends[5], ends[6], ends[7]);
+        // ---- shadow-filter eligibility (rtc_device.cuh: shadow_filter): spheres whose transform is well conditioned
+        // (the filter's error bound scales with the condition number), planes (term-wise bound: any transform),
+        // cubes whose inverse has a diagonal 3x3 part (every direction component is a single product)
+        bool ok = f.small.two_pass_shadows && !f.small.has_cull_chain && ends[2] == ends[3] && ends[6] == ends[7];
+        double worst = 1.0;
+        for (int i = 0; i < n_items && ok; i++) {
+            const SmallPrim& sp = f.small.p[i];
+            const int type = sp.head.x & 15;
+            const double m[3][3] = {{sp.r0.x, sp.r0.y, sp.r0.z}, {sp.r1.x, sp.r1.y, sp.r1.z}, {sp.r2.x, sp.r2.y, sp.r2.z}};
+            for (int a = 0; a < 3; a++)
+                for (int b = 0; b < 3; b++) ok = ok && std::isfinite(m[a][b]);
+            if (type == T_CUBE) {
+                for (int a = 0; a < 3; a++)
+                    for (int b = 0; b < 3; b++) ok = ok && (a == b ? m[a][b] != 0.0 : m[a][b] == 0.0);
+            } else if (type == T_SPHERE) {
+                const double det = m[0][0] * (m[1][1] * m[2][2] - m[1][2] * m[2][1]) - m[0][1] * (m[1][0] * m[2][2] - m[1][2] * m[2][0]) +
+                                   m[0][2] * (m[1][0] * m[2][1] - m[1][1] * m[2][0]);
+                double norm_m = 0.0, norm_i = 0.0;
+                for (int a = 0; a < 3; a++) {
+                    double row_m = 0.0, row_i = 0.0;
+                    for (int b = 0; b < 3; b++) {
+                        const int a1 = (a + 1) % 3, a2 = (a + 2) % 3, b1 = (b + 1) % 3, b2 = (b + 2) % 3;
+                        row_m += std::fabs(m[a][b]);
+                        row_i += std::fabs((m[b1][a1] * m[b2][a2] - m[b1][a2] * m[b2][a1]) / det);  // inverse = adjugate / det
+                    }
+                    norm_m = std::max(norm_m, row_m), norm_i = std::max(norm_i, row_i);
+                }
+                const double cond = norm_m * norm_i;
+                ok = ok && std::isfinite(cond) && cond <= 64.0;
+                if (ok) worst = std::max(worst, cond);
+            }
+        }
+        f.small.filter_ok = ok ? 1 : 0;
+        f.small.cell_masks = ok && !f.samples.empty() && f.samples.size() <= (size_t)kSampleCap;
+        f.small.tol_sphere = (float)(std::ldexp(1.0, -24) * 64.0 * (worst + 1.0));
     }
     s->n_bvh_nodes = (int)f.bvh.size();
     s->n_linear = (int)f.linear.size();
@@ -718,6 +756,8 @@ int upload_replica(RtcScene* s, const Flattened& f, Replica& r, int device) {
     d.n_prims = f.n_pos;
     d.all_cast_shadow = f.all_cast_shadow;
     r.small = f.small;
+    r.filter_eligible = f.small.filter_ok;
+    r.cell_masks_eligible = f.small.cell_masks;
     if ((rc = ensure_frame(slot, (size_t)s->width * s->height))) return rc;
     return 0;
 }
@@ -788,6 +828,8 @@ int render_impl(RtcScene* s, int depth, int shard0, int n_shards_ext, float* rgb
         Replica& r = s->replicas[i];
         DeviceSlot* slot = r.slot;
         const int shard = external ? shard0 : i;
+        r.small.filter_ok = r.filter_eligible && s->shadow_filter;
+        r.small.cell_masks = r.cell_masks_eligible && s->shadow_filter;
         const int nb = shard < total_bands ? (total_bands - shard + n_shards - 1) / n_shards : 0;
         CUDA_TRY(cudaSetDevice(slot->device));
         CUDA_TRY(cudaMemsetAsync(slot->d_counters, 0, sizeof(DevCounters), slot->stream));
@@ -886,7 +928,8 @@ int rtc_device_count(void) {
 int rtc_scene_create(RtcScene** out) {
     if (!out) return fail(RTC_ERR_INVALID, "null out pointer");
     *out = new RtcScene();
-    if (const char* env = getenv("RTC_ADAPTIVE_ORDER")) (*out)->adaptive_order = atoi(env) != 0;  // tuning aid
+    if (const char* env = getenv("RTC_ADAPTIVE_ORDER")) (*out)->adaptive_order = atoi(env) != 0;  // tuning aids
+    if (const char* env = getenv("RTC_SHADOW_FILTER")) (*out)->shadow_filter = atoi(env) != 0;
     return 0;
 }
 void rtc_scene_destroy(RtcScene* s) {
@@ -975,6 +1018,9 @@ int rtc_set_option(RtcScene* s, int32_t option, int64_t value) {
         case RTC_OPT_ADAPTIVE_ORDER:
             s->adaptive_order = value != 0;
             return 0;
+        case RTC_OPT_SHADOW_FILTER:  // may change between renders
+            s->shadow_filter = value != 0;
+            return 0;
         case RTC_OPT_RENDER_SLICES:
             if (value < 1 || value > 64) return fail(RTC_ERR_INVALID, "render slices must be in [1,64]");
             s->render_slices = (int)value;
@@ -1045,6 +1091,8 @@ int rtc_trace_rays(RtcScene* s, uint32_t n, const float* origins, const float* d
     if (depth < 0 || depth > kMaxFrames - 1) return fail(RTC_ERR_CAPACITY, "depth out of range");
     if (n == 0) return 0;
     Replica& rep = s->replicas[0];
+    rep.small.filter_ok = rep.filter_eligible && s->shadow_filter;
+    rep.small.cell_masks = rep.cell_masks_eligible && s->shadow_filter;
     struct {
         int device;
         cudaStream_t stream;

@@ -86,11 +86,12 @@ struct Ctr<false> {
     __device__ __forceinline__ void schlick() {}
     __device__ __forceinline__ void refr_dir() {}
     __device__ __forceinline__ void overflow() {}
+    __device__ __forceinline__ void refiltered() {}
 };
 template <>
 struct Ctr<true> {
     unsigned nodes = 0, prims[8] = {0, 0, 0, 0, 0, 0, 0, 0}, xforms = 0, patterns = 0, cells = 0, schlicks = 0, refr_dirs = 0,
-             overflows = 0;
+             overflows = 0, refilters = 0;
     __device__ __forceinline__ void node() { nodes++; }
     __device__ __forceinline__ void prim(int t) { prims[t]++; }
     __device__ __forceinline__ void xform() { xforms++; }
@@ -99,6 +100,7 @@ struct Ctr<true> {
     __device__ __forceinline__ void schlick() { schlicks++; }
     __device__ __forceinline__ void refr_dir() { refr_dirs++; }
     __device__ __forceinline__ void overflow() { overflows++; }
+    __device__ __forceinline__ void refiltered() { refilters++; }
 };
 
 // ---------------------------------------------------------------------------------------------------
@@ -844,10 +846,18 @@ __device__ __forceinline__ float* small_org() {
     extern __shared__ float4 rtc_smem[];
     return reinterpret_cast<float*>(rtc_smem + kSmallCap * 5) + threadIdx.x;
 }
-__device__ __forceinline__ void stage_small_scene(const SmallScene& SS) {
+__device__ __forceinline__ const float4* small_samples() {  // table-mode light samples (SmallScene::cell_masks)
+    extern __shared__ float4 rtc_smem[];
+    return rtc_smem + kSmallCap * 5 + kOrgCache * 3 * 128 / 4;
+}
+__device__ __forceinline__ void stage_small_scene(const DevScene& S, const SmallScene& SS) {
     extern __shared__ float4 rtc_smem[];
     const float4* src = reinterpret_cast<const float4*>(SS.p);
     for (int i = threadIdx.x; i < SS.n * 5; i += blockDim.x) rtc_smem[i] = src[i];
+    if (SS.cell_masks) {
+        float4* dst = rtc_smem + kSmallCap * 5 + kOrgCache * 3 * 128 / 4;
+        for (int i = threadIdx.x; i < S.cells; i += blockDim.x) dst[i] = __ldg(&S.samples[i]);
+    }
     __syncthreads();
 }
 
@@ -977,6 +987,183 @@ __device__ __forceinline__ void find_hit(const Env& E, V3 o, V3 d, Hit& best, Ct
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Shadow filter (small scenes made of spheres, planes and axis-aligned cubes only — SmallScene::filter_ok).
+//
+// World::is_shadowed only needs a BOOLEAN per light sample: "is the nearest hit in [0, distance) a shadow caster".
+// The reference gets it the expensive way: normalise the direction (sqrt + 3 divisions), intersect everything,
+// divide out every root.  Away from the decision boundaries the boolean does not depend on any of that rounding, so
+// the filter evaluates the same predicate on the UN-normalised segment point -> light (parameter s in [0, 1),
+// t = s * distance) with fused multiply-adds and approximate reciprocals, carries a forward error bound that covers
+// both its own rounding and the reference's (object-space origins are the reference's own values, bit for bit; only
+// the direction differs), and answers only when every comparison it needs is decided by a margin larger than that
+// bound.  Anything closer than the margin — tangent rays, roots at the light, ties between objects, NaN / inf —
+// returns F_UNSURE and the caller runs the exact test.  Frames are therefore bit-identical with the filter on or off
+// (tests/test_gpu_parity.py::test_shadow_filter_changes_no_pixel).
+enum : int { F_MISS = 0, F_HIT = 1, F_UNSURE = 2 };
+struct FRes {
+    int code;
+    float s, e;  // F_HIT: segment parameter of the nearest hit and its error bound
+};
+constexpr float kTolP = 3.814697265625e-06f;  // 2^-18 = 64 ulp: planes and cubes (bounds are term-wise, no conditioning)
+__device__ __forceinline__ float fma_(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+__device__ __forceinline__ float rcp_(float a) { return __fdividef(1.0f, a); }
+
+// sphere.rs:47-70 on the segment o + s * d, d = M * (light - point).  `tol` = SmallScene::tol_sphere, which scales
+// with the worst condition number of the spheres' transforms (set at commit).
+// The part that runs once the discriminant is clearly positive: which root is Intersection::hit's, is it in [0, 1).
+__device__ __forceinline__ FRes sphere_roots(float a, float b, float oo, float spread, float disc, float tol) {
+    const float rs = rsqrtf(disc), ia = rcp_(a);
+    const float sq = disc * rs;
+    const float s0 = (-b - sq) * ia, s1 = (-b + sq) * ia;
+    const float x = oo * ia;
+    // |error of a root| <= tol * (sqrt(oo / a) + spread / sqrt(disc) + |root|); + tol for the comparison with 1
+    const float e = tol * (x * rsqrtf(x + 1e-30f) + spread * rs + fmaxf(fabsf(s0), fabsf(s1)) + 1.0f);
+    const bool p0 = s0 > e, n0 = s0 < -e, p1 = s1 > e, n1 = s1 < -e;
+    if (n0 && n1) return FRes{F_MISS, 0.f, 0.f};
+    if (!(p0 || (n0 && p1))) return FRes{F_UNSURE, 0.f, 0.f};
+    const float cand = p0 ? s0 : s1;  // Intersection::hit: the smallest non-negative root
+    if (cand < 1.0f - e) return FRes{F_HIT, cand, e};
+    if (cand > 1.0f + e) return FRes{F_MISS, 0.f, 0.f};
+    return FRes{F_UNSURE, 0.f, 0.f};
+}
+__device__ __forceinline__ FRes filter_sphere(const Xf& m, V3 o, V3 v, float tol) {
+    const float dx = fma_(m.r0.x, v.x, fma_(m.r0.y, v.y, m.r0.z * v.z));
+    const float dy = fma_(m.r1.x, v.x, fma_(m.r1.y, v.y, m.r1.z * v.z));
+    const float dz = fma_(m.r2.x, v.x, fma_(m.r2.y, v.y, m.r2.z * v.z));
+    const float a = fma_(dx, dx, fma_(dy, dy, dz * dz));
+    const float b = fma_(dx, o.x, fma_(dy, o.y, dz * o.z));  // half the reference's b
+    const float oo = fma_(o.x, o.x, fma_(o.y, o.y, o.z * o.z));
+    const float c = oo - 1.0f;
+    const float disc = fma_(b, b, -(a * c));                 // a quarter of the reference's discriminant (times |v|^2)
+    const float spread = oo + fabsf(c);
+    const float td = tol * (a * spread);                     // a * spread >= b^2 + |a c|
+    if (disc < -td) return FRes{F_MISS, 0.f, 0.f};
+    if (!(disc > td)) return FRes{F_UNSURE, 0.f, 0.f};
+    return sphere_roots(a, b, oo, spread, disc, tol);
+}
+
+// plane.rs:45-56: only the y row of the inverse is needed.  `len` ~ |light - point| (the reference compares the
+// NORMALISED direction's y with EPSILON).
+// `upper`: len is only an upper bound of the length (the cell-mask path passes the 1-norm): a direction that is not
+// clearly steeper than EPSILON against the bound is undecided rather than a miss.
+template <bool NEED_S>
+__device__ __forceinline__ FRes filter_plane(float4 r1, float oy, V3 v, float len, bool upper = false) {
+    const float px = r1.x * v.x, py = r1.y * v.y, pz = r1.z * v.z;
+    const float dy = px + py + pz;
+    const float edy = kTolP * (fabsf(px) + fabsf(py) + fabsf(pz));
+    const float mag = fabsf(dy), thr = kAcne * len;
+    if (!upper && mag + edy < thr * (1.0f - kTolP)) return FRes{F_MISS, 0.f, 0.f};  // plane.rs:49
+    if (!(mag - edy > thr * (1.0f + kTolP)) || oy == 0.0f) return FRes{F_UNSURE, 0.f, 0.f};
+    if ((oy < 0.0f) == (dy < 0.0f)) return FRes{F_MISS, 0.f, 0.f};  // t = -oy / dy < 0
+    const float aoy = fabsf(oy);
+    if (aoy < (mag - edy) * (1.0f - kTolP)) {
+        if (!NEED_S) return FRes{F_HIT, 0.f, 0.f};
+        const float im = rcp_(mag), s = aoy * im;
+        return FRes{F_HIT, s, s * (edy * im + 4.0f * kTolP)};
+    }
+    if (aoy > (mag + edy) * (1.0f + kTolP)) return FRes{F_MISS, 0.f, 0.f};
+    return FRes{F_UNSURE, 0.f, 0.f};
+}
+
+// cube.rs:55-63 + 90-129 for a cube whose inverse has a diagonal 3x3 part (checked at commit): every direction
+// component is ONE product, so each slab distance differs from the reference's by a few ulp, never by cancellation.
+__device__ __forceinline__ FRes filter_cube(const Xf& m, V3 o, V3 v) {
+    const float dx = m.r0.x * v.x, dy = m.r1.y * v.y, dz = m.r2.z * v.z;
+    if (dx == 0.0f || dy == 0.0f || dz == 0.0f) return FRes{F_UNSURE, 0.f, 0.f};
+    const float ix = rcp_(dx), iy = rcp_(dy), iz = rcp_(dz);
+    float p = (-1.0f - o.x) * ix, q = (1.0f - o.x) * ix;
+    float lo = fminf(p, q), hi = fmaxf(p, q);
+    p = (-1.0f - o.y) * iy, q = (1.0f - o.y) * iy;
+    lo = fmaxf(lo, fminf(p, q)), hi = fminf(hi, fmaxf(p, q));
+    p = (-1.0f - o.z) * iz, q = (1.0f - o.z) * iz;
+    lo = fmaxf(lo, fminf(p, q)), hi = fminf(hi, fmaxf(p, q));
+    const float e = kTolP * (fabsf(lo) + fabsf(hi) + 1.0f);
+    const float g = hi - fmaxf(lo, 0.0f);
+    if (g < -e) return FRes{F_MISS, 0.f, 0.f};
+    if (!(g > e) || !(fabsf(lo) > e)) return FRes{F_UNSURE, 0.f, 0.f};
+    const float cand = lo > 0.0f ? lo : hi;
+    if (cand < 1.0f - e) return FRes{F_HIT, cand, e};
+    if (cand > 1.0f + e) return FRes{F_MISS, 0.f, 0.f};
+    return FRes{F_UNSURE, 0.f, 0.f};
+}
+
+// The items [begin, ends.z) of the small-scene table against the segment.  MODE 0: casters, any hit decides
+// (every object casts); MODE 1: casters, keep the nearest hit (s_c, e_c); MODE 2: non-casters against the nearest
+// caster hit.  Returns F_UNSURE as soon as some test is undecided; otherwise F_HIT / F_MISS, meaning
+//   MODE 0/1: some / no caster is hit in [0, 1);  MODE 2: F_HIT = a non-caster is clearly nearer than every caster.
+template <bool STATS, bool CACHED, int MODE>
+__device__ __forceinline__ int filter_scan(const Env& E, int begin, int4 ends, V3 p, V3 v, float len, float& s_c, float& e_c,
+                                           Ctr<STATS>& k) {
+    const float4* tab = small_tab();
+    const float tol = E.SS.tol_sphere;
+    int result = F_MISS;
+    auto take = [&](const FRes& r) -> bool {  // true: the scan is decided
+        if (r.code == F_UNSURE) {
+            result = F_UNSURE;
+            return true;
+        }
+        if (r.code == F_MISS) return false;
+        if (MODE == 0) {
+            result = F_HIT;
+            return true;
+        }
+        if (MODE == 1) {
+            result = F_HIT;
+            e_c = r.s < s_c ? r.e : e_c;
+            s_c = fminf(s_c, r.s);
+            return false;
+        }
+        if (r.s + r.e < s_c - e_c) {  // clearly in front of the nearest caster: the point is lit (world.rs:113-118)
+            result = F_HIT;
+            return true;
+        }
+        if (r.s - r.e > s_c + e_c) return false;  // clearly behind it
+        result = F_UNSURE;
+        return true;
+    };
+    int i = begin;
+    for (; i < ends.x; i++) {
+        Xf m{tab[i * 5 + 1], tab[i * 5 + 2], tab[i * 5 + 3]};
+        k.xform();
+        k.prim(T_SPHERE);
+        if (take(filter_sphere(m, small_origin<CACHED>(i, m, p), v, tol))) return result;
+    }
+    for (; i < ends.y; i++) {
+        float4 r1 = tab[i * 5 + 2];
+        float oy;
+        if (CACHED && i < kOrgCache)
+            oy = small_org()[(i * 3 + 1) * 128];
+        else
+            oy = r1.x * p.x + r1.y * p.y + r1.z * p.z + r1.w;
+        k.xform();
+        k.prim(T_PLANE);
+        if (take(filter_plane<MODE != 0>(r1, oy, v, len))) return result;
+    }
+    for (; i < ends.z; i++) {
+        Xf m{tab[i * 5 + 1], tab[i * 5 + 2], tab[i * 5 + 3]};
+        k.xform();
+        k.prim(T_CUBE);
+        if (take(filter_cube(m, small_origin<CACHED>(i, m, p), v))) return result;
+    }
+    return result;
+}
+
+// 0: lit, 1: shadowed, 2: undecided (run the exact test)
+template <bool STATS, bool CACHED>
+__device__ __forceinline__ int shadow_filter(const Env& E, V3 light_position, V3 p, Ctr<STATS>& k) {
+    const SmallScene& SS = E.SS;
+    const V3 v = light_position - p;
+    const float vv = fma_(v.x, v.x, fma_(v.y, v.y, v.z * v.z));
+    const float len = vv * rsqrtf(vv);
+    float s_c = kInfF, e_c = 0.0f;
+    if (E.S.all_cast_shadow) return filter_scan<STATS, CACHED, 0>(E, 0, SS.caster_end, p, v, len, s_c, e_c, k);
+    int r = filter_scan<STATS, CACHED, 1>(E, 0, SS.caster_end, p, v, len, s_c, e_c, k);
+    if (r != F_HIT) return r == F_MISS ? 0 : 2;
+    r = filter_scan<STATS, CACHED, 2>(E, SS.caster_end.w, SS.other_end, p, v, len, s_c, e_c, k);
+    return r == F_UNSURE ? 2 : (r == F_HIT ? 0 : 1);
+}
+
 // World::is_shadowed (world.rs:104-119): nearest hit on the point->light ray; shadowed iff that object
 // casts a shadow and is nearer than the light (Q9).
 //
@@ -985,10 +1172,9 @@ __device__ __forceinline__ void find_hit(const Env& E, V3 o, V3 d, Hit& best, Ct
 // (t, depth-first order) comparison as Intersection::hit) can un-shadow the point.  Same predicate as the
 // reference's, evaluated with fewer intersection tests.
 template <bool STATS, bool SMALL, bool CACHED>
-__device__ __forceinline__ bool is_shadowed(const Env& E, V3 light_position, V3 p, Rays& r, Ctr<STATS>& k) {
+__device__ __forceinline__ bool shadow_exact(const Env& E, V3 light_position, V3 p, Ctr<STATS>& k) {
     constexpr bool cached = CACHED;
     const DevScene& S = E.S;
-    r.shadow++;
     V3 v = light_position - p;
     float distance = magnitude(v);
     V3 direction = mk(v.x / distance, v.y / distance, v.z / distance);
@@ -1015,12 +1201,136 @@ __device__ __forceinline__ bool is_shadowed(const Env& E, V3 light_position, V3 
     nearest_hit<STATS, false>(S, p, direction, best, k);
     return best.pos >= 0 && ((__ldg(&S.head[best.pos]).x >> 4) & kFlagCastsShadow);
 }
+// the filter's fallback: out of line so the rarely-taken exact test stays out of the light-cell loop
+template <bool STATS, bool CACHED>
+__device__ __noinline__ bool shadow_exact_cold(const Env& E, V3 light_position, V3 p, Ctr<STATS>& k) {
+    return shadow_exact<STATS, true, CACHED>(E, light_position, p, k);
+}
+template <bool STATS, bool SMALL, bool CACHED>
+__device__ __forceinline__ bool is_shadowed(const Env& E, V3 light_position, V3 p, Rays& r, Ctr<STATS>& k) {
+    r.shadow++;
+    if (SMALL && E.SS.filter_ok) {
+        const int f = shadow_filter<STATS, CACHED>(E, light_position, p, k);
+        if (f != 2) return f == 1;
+        k.refiltered();
+        return shadow_exact_cold<STATS, CACHED>(E, light_position, p, k);
+    }
+    return shadow_exact<STATS, SMALL, CACHED>(E, light_position, p, k);
+}
+
+// RectangleLight::intensity_at (rectangle_light.rs:76-88) for filter_ok scenes with a table-mode light: the light
+// samples are the same for every shade (staged in shared memory), so the loops are turned inside out — primitive
+// outside, light cell inside — and the per-shade part of every test (object-space origin, |o|^2, ...) leaves the
+// cell loop.  Pass 1 runs the shadow filter of every CASTER against up to 32 cells at a time and keeps two bit
+// masks: cells where some caster is clearly hit, cells where some test was undecided.  Cells in neither mask are
+// lit.  Pass 2 revisits the others one by one: hit cells need the nearest-caster / non-caster comparison
+// (shadow_filter) when the scene has non-casting objects, undecided cells run the exact test.
+template <bool STATS>
+__device__ __noinline__ int shadow_cell_cold(const Env& E, V3 lp, V3 p, bool exact, Ctr<STATS>& k) {
+    int f = exact ? 2 : shadow_filter<STATS, false>(E, lp, p, k);
+    if (f == 2) {
+        k.refiltered();
+        f = shadow_exact<STATS, true, false>(E, lp, p, k) ? 1 : 0;
+    }
+    return f;
+}
+template <bool STATS>
+__device__ __forceinline__ float intensity_cells(const Env& E, V3 p, Rays& r, Ctr<STATS>& k) {
+    const DevScene& S = E.S;
+    const SmallScene& SS = E.SS;
+    const float4* tab = small_tab();
+    const float4* smp = small_samples();
+    const int cells = S.cells;
+    const float tol = SS.tol_sphere;
+    const int4 ends = SS.caster_end;
+    r.shadow += cells;
+    int lit = 0;
+    for (int c0 = 0; c0 < cells; c0 += 32) {
+        const int nc = min(32, cells - c0);
+        const unsigned full = nc == 32 ? 0xffffffffu : ((1u << nc) - 1u);
+        unsigned hit = 0u, unsure = 0u;
+        int i = 0;
+        for (; i < ends.x && (hit | unsure) != full; i++) {  // caster spheres
+            const Xf m{tab[i * 5 + 1], tab[i * 5 + 2], tab[i * 5 + 3]};
+            const V3 o = xf_point(m, p);  // the reference's object-space origin (shape.rs:60-70), once per shade
+            const float oo = fma_(o.x, o.x, fma_(o.y, o.y, o.z * o.z));
+            const float c = oo - 1.0f;
+            const float spread = oo + fabsf(c);
+            const float ts = tol * spread;
+#pragma unroll 4
+            for (int j = 0; j < nc; j++) {
+                const float4 L = smp[c0 + j];
+                const float vx = L.x - p.x, vy = L.y - p.y, vz = L.z - p.z;
+                const float dx = fma_(m.r0.x, vx, fma_(m.r0.y, vy, m.r0.z * vz));
+                const float dy = fma_(m.r1.x, vx, fma_(m.r1.y, vy, m.r1.z * vz));
+                const float dz = fma_(m.r2.x, vx, fma_(m.r2.y, vy, m.r2.z * vz));
+                const float a = fma_(dx, dx, fma_(dy, dy, dz * dz));
+                const float b = fma_(dx, o.x, fma_(dy, o.y, dz * o.z));
+                const float disc = fma_(b, b, -(a * c));
+                const float td = a * ts;
+                if (!(disc < -td)) {  // not a clear miss
+                    const int code = disc > td ? sphere_roots(a, b, oo, spread, disc, tol).code : F_UNSURE;
+                    hit |= (unsigned)(code == F_HIT) << j;
+                    unsure |= (unsigned)(code == F_UNSURE) << j;
+                }
+            }
+            for (int j = 0; j < nc; j++) {
+                k.xform();
+                k.prim(T_SPHERE);
+            }
+        }
+        for (i = ends.x; i < ends.y && (hit | unsure) != full; i++) {  // caster planes
+            const float4 r1 = tab[i * 5 + 2];
+            const float oy = r1.x * p.x + r1.y * p.y + r1.z * p.z + r1.w;
+#pragma unroll 4
+            for (int j = 0; j < nc; j++) {
+                const float4 L = smp[c0 + j];
+                const V3 v = mk(L.x - p.x, L.y - p.y, L.z - p.z);
+                // |v| <= |v|_1: a conservative stand-in for the length in the `direction.y.abs() < EPSILON` test
+                const int code = filter_plane<false>(r1, oy, v, fabsf(v.x) + fabsf(v.y) + fabsf(v.z), true).code;
+                hit |= (unsigned)(code == F_HIT) << j;
+                unsure |= (unsigned)(code == F_UNSURE) << j;
+            }
+            for (int j = 0; j < nc; j++) {
+                k.xform();
+                k.prim(T_PLANE);
+            }
+        }
+        for (i = ends.y; i < ends.z && (hit | unsure) != full; i++) {  // caster cubes
+            const Xf m{tab[i * 5 + 1], tab[i * 5 + 2], tab[i * 5 + 3]};
+            const V3 o = xf_point(m, p);
+#pragma unroll 2
+            for (int j = 0; j < nc; j++) {
+                const float4 L = smp[c0 + j];
+                const int code = filter_cube(m, o, mk(L.x - p.x, L.y - p.y, L.z - p.z)).code;
+                hit |= (unsigned)(code == F_HIT) << j;
+                unsure |= (unsigned)(code == F_UNSURE) << j;
+            }
+            for (int j = 0; j < nc; j++) {
+                k.xform();
+                k.prim(T_CUBE);
+            }
+        }
+        for (int j = 0; j < nc; j++) k.cell();
+        // pass 2
+        unsigned todo = S.all_cast_shadow ? unsure : (hit | unsure);
+        lit += __popc(full & ~(hit | unsure));
+        while (todo) {
+            const int j = __ffs(todo) - 1;
+            todo &= todo - 1u;
+            const float4 L = smp[c0 + j];
+            lit += shadow_cell_cold<STATS>(E, mk(L.x, L.y, L.z), p, (unsure >> j) & 1u, k) == 0;
+        }
+    }
+    return (float)lit / (float)cells;  // `total += 1.0` per lit cell is exact in f32
+}
 
 // Light::intensity_at (point_light.rs:28-34, rectangle_light.rs:76-88)
 template <bool STATS, bool SMALL>
 __device__ __forceinline__ float intensity_at(const Env& E, V3 p, unsigned pixel, unsigned path, Rays& r, Ctr<STATS>& k) {
     const DevScene& S = E.S;
     if (!S.light_is_rect) return is_shadowed<STATS, SMALL, false>(E, ld3(S.light_pos), p, r, k) ? 0.f : 1.f;
+    if (SMALL && E.SS.cell_masks) return intensity_cells<STATS>(E, p, r, k);
     if (SMALL) cache_origins(E, p);
     float total = 0.f;
     int cell = 0;

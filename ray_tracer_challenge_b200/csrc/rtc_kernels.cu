@@ -59,13 +59,14 @@ __device__ __forceinline__ void flush_counters<true>(const Rays& r, const Ctr<tr
     warp_add(&out->schlicks, k.schlicks);
     warp_add(&out->refr_dirs, k.refr_dirs);
     warp_add(&out->overflows, k.overflows);
+    warp_add(&out->prim_tests[7], k.refilters);  // shadow-filter fallbacks to the exact test
 }
 
 template <bool STATS, bool SMALL>
 __global__ void __launch_bounds__(128) render_tiles(const __grid_constant__ DevScene S, const __grid_constant__ SmallScene SS,
                                                     const DevFrame F, DevCounters* counters) {
     // small scenes: primitive table + per-thread shadow-origin cache in dynamic shared memory (kSmallSmemBytes)
-    if (SMALL) stage_small_scene(SS);
+    if (SMALL) stage_small_scene(S, SS);
     const Env E{S, SS};
     // block (bx, by) -> tile of 16x8 pixels in band `shard + by * n_shards`; warp w -> 8x4 sub-tile
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -104,7 +105,7 @@ template <bool SMALL>
 __global__ void __launch_bounds__(128) trace_rays(const __grid_constant__ DevScene S, const __grid_constant__ SmallScene SS, int n,
                                                   const float* origins, const float* directions, int depth, float* out_rgb,
                                                   float* out_t, int* out_pos, DevCounters* counters) {
-    if (SMALL) stage_small_scene(SS);
+    if (SMALL) stage_small_scene(S, SS);
     const Env E{S, SS};
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     Ctr<false> k;

@@ -126,11 +126,15 @@ struct SmallScene {
     int n;                      // 0: the scene does not qualify, use the general path
     int two_pass_shadows;       // no CSG roots among them: shadow rays may test casters first (see is_shadowed)
     int has_cull_chain;         // some unbounded primitive sits inside a group whose cull must be honoured (Q6)
-    int pad;
+    int filter_ok;              // spheres / planes / axis-aligned cubes only: shadow rays go through the filter first
+    float tol_sphere;           // the filter's relative error bound for spheres (grows with the transforms' condition)
+    int cell_masks;             // filter_ok, table-mode area light with <= kSampleCap cells: intensity_cells path
+    int pad[2];
     int4 caster_end, other_end;
     SmallPrim p[kSmallCap];
 };
-constexpr int kSmallSmemBytes = kSmallCap * 80 + kOrgCache * 3 * 128 * 4;
+constexpr int kSampleCap = 128;  // table-mode light samples staged in shared memory
+constexpr int kSmallSmemBytes = kSmallCap * 80 + kOrgCache * 3 * 128 * 4 + kSampleCap * 16;
 
 struct DevFrame {  // where a render writes
     float* rgb;            // width*height*3 f32 or null

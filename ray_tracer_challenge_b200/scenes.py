@@ -5,6 +5,7 @@ Parameters are transcribed from the reference's demos:
   soft_shadows      demos/src/bin/soft_shadows.rs:33-169      (BASELINE configs 1 and 3)
   reflect_refract   demos/src/bin/reflect_refract.rs:35-178   (config 2)
   hexagons          demos/src/bin/hexagons.rs:33-103
+  filter_zoo        parity scene for the shadow filter (spheres / planes / axis-aligned cubes, area light)
   dragon_element    demos/src/bin/here_be_dragons.rs:242-338  (config 4, with a synthetic OBJ: lib/resources
                     holds no mesh besides test/triangles.obj)
   stress            SURVEY.md §8d config 5 (100 k spheres + cylinders/cones/cubes + CSG + checker plane)
@@ -54,6 +55,41 @@ def soft_shadows(rt, width=1000, height=400, u_steps=10, v_steps=10, jitter="tab
                               Material(color=(0.5, 0.5, 1), ambient=0.1, specular=0.0, diffuse=0.6, reflective=0.3))
     world = rt.World([lampshade, floor, sphere1, sphere2], light)
     camera = rt.Camera(width, height, PI / 4.0, rt.view_transform((-3, 1, 2.5), (0, 0.5, 0), (0, 1, 0)))
+    return camera, world
+
+
+def filter_zoo(rt, width=320, height=200, area_light=True, jitter=None, seed=11):
+    """Parity scene for the shadow filter (rtc_device.cuh: shadow_filter): only spheres, planes and axis-aligned
+    cubes, so every shadow ray goes through the filter — with rotated / sheared / squashed spheres, tilted planes,
+    objects touching each other and the floor (tangent shadow rays), a non-casting sphere and cube between the light
+    and the floor, and a light sample grid whose edge grazes a cube.  Not a reference demo."""
+    if area_light:
+        light = RectangleLight((1.2, 1.2, 1.2), (-2.0, 4.0, -3.0), (3.0, 0, 0), 3, (0, 0.5, 2.0), 2,
+                               jitter_table(12) if jitter == "table" else jitter, seed)
+    else:
+        light = PointLight((-3.0, 5.0, -4.0), (1, 1, 1))
+    floor = rt.Plane.build(rt.identity_4x4(), Material(color=(0.9, 0.9, 0.9), specular=0.0, reflective=0.1,
+                                                       pattern=rt.Checkers((0.9, 0.9, 0.9), (0.3, 0.3, 0.35))))
+    wall = rt.Plane.build(rt.translation(0.0, 0.0, 6.0) * rt.rotation_x(PI / 2.0 - 0.2) * rt.rotation_z(0.15),
+                          Material(color=(0.7, 0.8, 1.0), specular=0.1))
+    ball = rt.Sphere.build(rt.translation(0.0, 1.0, 0.0), Material(color=(1, 0.3, 0.2), reflective=0.2))
+    egg = rt.Sphere.build(rt.translation(1.8, 0.6, -0.5) * rt.rotation_z(0.5) * rt.rotation_y(0.9) * rt.scaling(0.9, 0.45, 0.6),
+                          Material(color=(0.2, 0.8, 0.3), shininess=50.0))
+    sheared = rt.Sphere.build(rt.translation(-2.0, 0.7, 0.8) * rt.shearing(0.5, 0.0, 0.0, 0.3, 0.0, 0.0) * rt.scaling(0.7, 0.7, 0.7),
+                              Material(color=(0.3, 0.4, 0.9)))
+    disc = rt.Sphere.build(rt.translation(0.5, 0.05, -2.0) * rt.scaling(0.8, 0.05, 0.8), Material(color=(0.8, 0.8, 0.2)))
+    touching = rt.Sphere.build(rt.translation(0.0, 0.4, -1.4) * rt.scaling(0.4, 0.4, 0.4),
+                               Material(color=(0.9, 0.5, 0.9), reflective=0.3))
+    box = rt.Cube.build(rt.translation(-0.9, 0.5, -2.2) * rt.scaling(0.4, 0.5, 0.3), Material(color=(0.6, 0.4, 0.2)))
+    slab = rt.Cube.build(rt.translation(2.5, 1.5, 2.0) * rt.scaling(0.2, 1.5, 1.0), Material(color=(0.4, 0.7, 0.7), reflective=0.4))
+    shade = rt.Cube.build(rt.translation(-0.5, 4.0, -2.0) * rt.scaling(1.5, 0.02, 1.0),
+                          Material(color=(1.2, 1.2, 1.0), ambient=1.0, diffuse=0.0, specular=0.0))
+    shade.set_casts_shadow(False)
+    ghost = rt.Sphere.build(rt.translation(-1.0, 2.2, -1.0) * rt.scaling(0.5, 0.5, 0.5),
+                            Material(color=(0.1, 0.1, 0.1), transparency=0.9, refractive_index=1.0, diffuse=0.1, ambient=0.0))
+    ghost.set_casts_shadow(False)
+    world = rt.World([floor, wall, ball, egg, sheared, disc, touching, box, slab, shade, ghost], light)
+    camera = rt.Camera(width, height, PI / 3.0, rt.view_transform((0.5, 2.5, -7.0), (0, 1.0, 0), (0, 1, 0)))
     return camera, world
 
 

@@ -24,6 +24,9 @@ SCENES = {
     "csg_gallery": (scenes.csg_gallery, dict(width=320, height=200)),
     "dragon_element": (scenes.dragon_element, dict(width=240, height=135, n_u=32, n_v=16)),
     "dragon_smooth_nodivide": (scenes.dragon_element, dict(width=160, height=90, n_u=16, n_v=8, divide=0, smooth=True)),
+    "filter_zoo_area": (scenes.filter_zoo, dict(width=320, height=200)),
+    "filter_zoo_table": (scenes.filter_zoo, dict(width=200, height=120, jitter="table")),
+    "filter_zoo_point": (scenes.filter_zoo, dict(width=320, height=200, area_light=False)),
     "stress_small": (scenes.stress, dict(width=240, height=135, n_spheres=3000, n_each=8, n_csg=6)),
 }
 
@@ -131,6 +134,40 @@ def test_longest_first_band_order_changes_no_pixel(gpu):
             for got in (first, second):
                 assert np.array_equal(got.data.view(np.uint32), ref.data.view(np.uint32))
                 assert np.array_equal(got.to_u8(), ref.to_u8())
+    finally:
+        p.release()
+
+
+FILTERED = ["default_world", "soft_shadows_table", "soft_shadows_constant", "soft_shadows_counter_rng", "filter_zoo_area",
+            "filter_zoo_table", "filter_zoo_point"]
+
+
+@pytest.mark.parametrize("name", FILTERED)
+def test_shadow_filter_changes_no_pixel(name, gpu):
+    """RTC_OPT_SHADOW_FILTER: the filter decides a shadow ray only when every comparison clears its error bound, so a
+    frame is bit-identical with the filter on (default) and off (every shadow ray through the reference arithmetic)."""
+    build, kw = SCENES[name]
+    kw = dict(kw, width=kw["width"] * 2, height=kw["height"] * 2)
+    cam, world = build(gpu, **kw)
+    p = cam.prepare(world)
+    try:
+        for fma in (False, True):
+            p.set_option(6, 0)
+            off = p.render(5, fma=fma)
+            rays_off = p.last_stats.rays
+            p.set_option(6, 1)
+            on = p.render(5, fma=fma, detailed=True)
+            st = p.last_stats
+            assert st.rays == rays_off
+            assert np.array_equal(on.data.view(np.uint32), off.data.view(np.uint32)), (name, fma)
+            assert np.array_equal(on.to_u8(), off.to_u8())
+            # the filter is in use and hands only a small fraction of the shadow rays to the exact test
+            fallbacks = st.prim_tests[7]
+            assert fallbacks <= 0.05 * st.shadow_rays, (name, fallbacks, st.shadow_rays)
+            p.set_option(6, 0)
+            p.render(5, fma=fma, detailed=True)
+            assert p.last_stats.prim_tests[7] == 0
+            p.set_option(6, 1)
     finally:
         p.release()
 
