@@ -68,9 +68,9 @@ struct DeviceSlot {
     unsigned char* d_u8 = nullptr;
     size_t frame_px = 0;
     DevCounters* d_counters = nullptr;
-    unsigned* d_band_cost = nullptr;  // rays per frame band of the last render
-    int* d_band_order = nullptr;      // launch order of this shard's bands
-    int band_capacity = 0;
+    unsigned* d_tile_cost = nullptr;  // clock cycles per frame tile, recorded by the render that learns the order
+    int* d_tile_order = nullptr;      // launch order of this shard's tiles
+    int tile_capacity = 0;
     int sm_count = 148;
     char* arena = nullptr;  // scene arrays, one allocation
     size_t arena_bytes = 0;
@@ -125,15 +125,15 @@ int ensure_frame(DeviceSlot* d, size_t px) {
     d->frame_px = px;
     return 0;
 }
-int ensure_bands(DeviceSlot* d, int total_bands) {
-    if (total_bands <= d->band_capacity) return 0;
+int ensure_tiles(DeviceSlot* d, int total_tiles) {
+    if (total_tiles <= d->tile_capacity) return 0;
     CUDA_TRY(cudaSetDevice(d->device));
-    if (d->d_band_cost) cudaFree(d->d_band_cost);
-    if (d->d_band_order) cudaFree(d->d_band_order);
-    d->band_capacity = 0;
-    CUDA_TRY(cudaMalloc(&d->d_band_cost, (size_t)total_bands * sizeof(unsigned)));
-    CUDA_TRY(cudaMalloc(&d->d_band_order, (size_t)total_bands * sizeof(int)));
-    d->band_capacity = total_bands;
+    if (d->d_tile_cost) cudaFree(d->d_tile_cost);
+    if (d->d_tile_order) cudaFree(d->d_tile_order);
+    d->tile_capacity = 0;
+    CUDA_TRY(cudaMalloc(&d->d_tile_cost, (size_t)total_tiles * sizeof(unsigned)));
+    CUDA_TRY(cudaMalloc(&d->d_tile_order, (size_t)total_tiles * sizeof(int)));
+    d->tile_capacity = total_tiles;
     return 0;
 }
 int ensure_arena(DeviceSlot* d, size_t bytes) {
@@ -160,11 +160,11 @@ struct Replica {
     DeviceSlot* slot = nullptr;
     DevScene scene{};
     SmallScene small{};
-    int cell_masks_eligible = 0;
+    int cell_masks_eligible = 0, plane_cells_eligible = 0;
     int filter_eligible = 0;  // SmallScene::filter_ok as computed at commit (RTC_OPT_SHADOW_FILTER masks it per render)
     // Longest-first launch order learnt from the previous render of the same shard (see render_impl)
-    std::vector<int> band_order;
-    int order_shard = -1, order_n_shards = -1, order_depth = -1;
+    int order_shard = -1, order_n_shards = -1, order_depth = -1, order_filter = -1;  // what d_tile_order was learnt for
+    bool learning = false;  // this render records the tile costs
 };
 
 }  // namespace
@@ -189,6 +189,7 @@ struct RtcScene {
     int render_slices = 6;  // kernel / copy pipeline depth when rendering into host memory
     int adaptive_order = 1;  // launch a shard's bands longest-first, learnt from the previous render
     int shadow_filter = 1;   // RTC_OPT_SHADOW_FILTER
+    int order_max_waves = 24;  // longest-first order only for launches shorter than this many waves of blocks
     std::vector<Replica> replicas;
     std::vector<int> replica_devices;
     std::vector<int> pos_to_prim;  // device position -> API primitive index (-1 for CSG pseudo-primitives)
@@ -701,6 +702,51 @@ int flatten(RtcScene* s, Flattened& f) {
         }
         f.small.filter_ok = ok ? 1 : 0;
         f.small.cell_masks = ok && !f.samples.empty() && f.samples.size() <= (size_t)kSampleCap;
+        if (f.small.cell_masks) {
+            // the bundle reject (rtc_device.cuh: bundle_misses): a ball around the light samples, and for every sphere /
+            // cube its world-space bounding ball — centre = forward transform of the origin, radius = the largest
+            // stretch of the forward 3x3 (bounded by sqrt(|T|_1 |T|_inf)), times sqrt(3) for a cube's corners
+            double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+            for (const float4& q : f.samples) {
+                const double v[3] = {q.x, q.y, q.z};
+                for (int a = 0; a < 3; a++) lo[a] = std::min(lo[a], v[a]), hi[a] = std::max(hi[a], v[a]);
+            }
+            const double lc[3] = {0.5 * (lo[0] + hi[0]), 0.5 * (lo[1] + hi[1]), 0.5 * (lo[2] + hi[2])};
+            double rl = 0.0;
+            for (const float4& q : f.samples)
+                rl = std::max(rl, std::sqrt((q.x - lc[0]) * (q.x - lc[0]) + (q.y - lc[1]) * (q.y - lc[1]) + (q.z - lc[2]) * (q.z - lc[2])));
+            f.small.light_ball = make_float4((float)lc[0], (float)lc[1], (float)lc[2], (float)(rl * 1.001 + 1e-6));
+            for (int i = 0; i < n_items; i++) {
+                SmallPrim& sp = f.small.p[i];
+                const int type = sp.head.x & 15;
+                if (type != T_SPHERE && type != T_CUBE) continue;
+                const double m[3][4] = {{sp.r0.x, sp.r0.y, sp.r0.z, sp.r0.w}, {sp.r1.x, sp.r1.y, sp.r1.z, sp.r1.w}, {sp.r2.x, sp.r2.y, sp.r2.z, sp.r2.w}};
+                const double det = m[0][0] * (m[1][1] * m[2][2] - m[1][2] * m[2][1]) - m[0][1] * (m[1][0] * m[2][2] - m[1][2] * m[2][0]) +
+                                   m[0][2] * (m[1][0] * m[2][1] - m[1][1] * m[2][0]);
+                double t[3][3], n1 = 0.0, ninf = 0.0, mi = 0.0;  // t = forward 3x3 = inverse of m's 3x3
+                for (int a = 0; a < 3; a++)
+                    for (int b = 0; b < 3; b++) {
+                        const int a1 = (a + 1) % 3, a2 = (a + 2) % 3, b1 = (b + 1) % 3, b2 = (b + 2) % 3;
+                        t[a][b] = (m[b1][a1] * m[b2][a2] - m[b1][a2] * m[b2][a1]) / det;
+                    }
+                for (int a = 0; a < 3; a++) {
+                    n1 = std::max(n1, std::fabs(t[0][a]) + std::fabs(t[1][a]) + std::fabs(t[2][a]));
+                    ninf = std::max(ninf, std::fabs(t[a][0]) + std::fabs(t[a][1]) + std::fabs(t[a][2]));
+                    mi = std::max(mi, std::fabs(m[a][0]) + std::fabs(m[a][1]) + std::fabs(m[a][2]));
+                }
+                const double stretch = std::sqrt(n1 * ninf), cond = std::max(1.0, mi * ninf);
+                const double radius = stretch * (type == T_CUBE ? std::sqrt(3.0) : 1.0);
+                double c[3];  // centre: -T * (translation column of the inverse)
+                for (int a = 0; a < 3; a++) c[a] = -(t[a][0] * m[0][3] + t[a][1] * m[1][3] + t[a][2] * m[2][3]);
+                const bool finite = std::isfinite(radius) && std::isfinite(c[0]) && std::isfinite(c[1]) && std::isfinite(c[2]) && radius > 0.0;
+                // a non-finite ball never rejects (NaN comparisons are false)
+                sp.bound = finite ? make_float4((float)c[0], (float)c[1], (float)c[2], (float)(radius * 1.001 + 1e-6)) : make_float4(NAN, NAN, NAN, NAN);
+                const float pad = (float)(std::ldexp(1.0, -17) * cond * cond / radius);
+                memcpy(&sp.head.y, &pad, sizeof(float));
+            }
+            const int n_planes = ends[1] - ends[0];
+            f.small.plane_cells = n_planes > 0 && (size_t)n_planes * f.samples.size() <= (size_t)kPlaneCellCap;
+        }
         f.small.tol_sphere = (float)(std::ldexp(1.0, -24) * 64.0 * (worst + 1.0));
     }
     s->n_bvh_nodes = (int)f.bvh.size();
@@ -758,6 +804,7 @@ int upload_replica(RtcScene* s, const Flattened& f, Replica& r, int device) {
     r.small = f.small;
     r.filter_eligible = f.small.filter_ok;
     r.cell_masks_eligible = f.small.cell_masks;
+    r.plane_cells_eligible = f.small.plane_cells;
     if ((rc = ensure_frame(slot, (size_t)s->width * s->height))) return rc;
     return 0;
 }
@@ -830,28 +877,31 @@ int render_impl(RtcScene* s, int depth, int shard0, int n_shards_ext, float* rgb
         const int shard = external ? shard0 : i;
         r.small.filter_ok = r.filter_eligible && s->shadow_filter;
         r.small.cell_masks = r.cell_masks_eligible && s->shadow_filter;
+        r.small.plane_cells = r.plane_cells_eligible && r.small.cell_masks;
         const int nb = shard < total_bands ? (total_bands - shard + n_shards - 1) / n_shards : 0;
         CUDA_TRY(cudaSetDevice(slot->device));
         CUDA_TRY(cudaMemsetAsync(slot->d_counters, 0, sizeof(DevCounters), slot->stream));
-        // Longest-processing-time-first: a frame's cost is concentrated in a few bands (deep reflection trees:
-        // one block there runs ~10x longer than the average), and a long block that starts late is the tail of
-        // the launch — the term that limits strong scaling over shards.  The kernel counts the rays traced per
-        // band; the next render of the same shard launches its bands most-expensive-first.  The order changes
-        // no pixel.  It needs one copy-free launch, so it is used when the frame stays on the device or is
-        // copied in one piece — and only for launches of fewer than ~24 waves of blocks: measured on B200, the
-        // natural top-to-bottom order is 6 % faster for a whole 4K frame (73 waves; neighbouring bands of unlike
-        // cost share the SMs) while longest-first is 10-15 % faster for a 1/4 or 1/8 shard, where the tail counts.
+        // Longest-processing-time-first: a frame's cost is concentrated in a few tiles (deep reflection trees: one
+        // block there runs ~10x longer than the average), and a long block that starts late is the tail of the
+        // launch — the term that limits strong scaling over shards (c3, 1/8 of the frame: the SMs were busy for
+        // only 53 % of the launch).  The first render of a (shard, depth) configuration runs in natural order and
+        // records how many clock cycles every tile's block took; later renders launch the shard's tiles
+        // most-expensive-first from a list kept on the device.  The order changes no pixel.  It needs one
+        // copy-free launch, so it is used when the frame stays on the device or is copied in one piece — and only
+        // for launches of fewer than `order_max_waves` waves of blocks (a whole 4K frame, 73 waves, has no tail to
+        // speak of and runs a few percent faster in natural order: neighbouring tiles share their cache lines).
         const int n_slices = copy_out ? std::max(1, std::min(s->render_slices, nb)) : 1;
+        const int tiles_x = ((int)s->width + kTileW - 1) / kTileW;
         int rc0;
-        if ((rc0 = ensure_bands(slot, total_bands))) return rc0;
-        CUDA_TRY(cudaMemsetAsync(slot->d_band_cost, 0, (size_t)total_bands * sizeof(unsigned), slot->stream));
-        const long long launch_blocks = (long long)nb * ((s->width + kTileW - 1) / kTileW);
-        const bool use_order = s->adaptive_order && n_slices == 1 && r.order_shard == shard && r.order_n_shards == n_shards &&
-                               r.order_depth == depth && (int)r.band_order.size() == nb &&
-                               launch_blocks < 24LL * 6 * slot->sm_count;
-        if (use_order)
-            CUDA_TRY(cudaMemcpyAsync(slot->d_band_order, r.band_order.data(), (size_t)nb * sizeof(int), cudaMemcpyHostToDevice,
-                                     slot->stream));
+        if ((rc0 = ensure_tiles(slot, total_bands * tiles_x))) return rc0;
+        const long long launch_blocks = (long long)nb * tiles_x;
+        const bool order_wanted = s->adaptive_order && n_slices == 1 && nb > 0 &&
+                                  launch_blocks < (long long)s->order_max_waves * 5 * slot->sm_count;
+        const bool learnt = r.order_shard == shard && r.order_n_shards == n_shards && r.order_depth == depth &&
+                            r.order_filter == s->shadow_filter;
+        const bool use_order = order_wanted && learnt;
+        r.learning = order_wanted && !learnt;
+        if (r.learning) CUDA_TRY(cudaMemsetAsync(slot->d_tile_cost, 0, (size_t)total_bands * tiles_x * sizeof(unsigned), slot->stream));
         // With a host destination the frame is rendered in a few slices so that the device-to-host copy of one
         // slice overlaps the kernel of the next (the 4K canvases are 124 MB: ~2.3 ms of PCIe against ~2 ms of
         // kernel); left on the device it is one launch.
@@ -864,8 +914,8 @@ int render_impl(RtcScene* s, int depth, int shard0, int n_shards_ext, float* rgb
         for (int k = 0; k < n_slices; k++) {
             const int b0 = (int)((int64_t)nb * k / n_slices), b1 = (int)((int64_t)nb * (k + 1) / n_slices);
             if (b1 <= b0) continue;
-            DevFrame F{slot->d_rgb, slot->d_u8, shard, n_shards, depth, b1 - b0, b0, use_order ? slot->d_band_order : nullptr,
-                       s->adaptive_order ? slot->d_band_cost : nullptr};
+            DevFrame F{slot->d_rgb, slot->d_u8, shard, n_shards, depth, b1 - b0, b0, use_order ? slot->d_tile_order : nullptr,
+                       r.learning ? slot->d_tile_cost : nullptr};
             if (s->strict_fp)
                 strict::launch_render(r.scene, r.small, F, slot->d_counters, detailed, slot->stream);
             else
@@ -893,15 +943,25 @@ int render_impl(RtcScene* s, int depth, int shard0, int n_shards_ext, float* rgb
         DevCounters c;
         CUDA_TRY(cudaMemcpy(&c, slot->d_counters, sizeof(c), cudaMemcpyDeviceToHost));
         add_counters(st, c);
-        if (s->adaptive_order) {  // learn the launch order for the next render of this shard
-            Replica& r = s->replicas[i];
+        Replica& r = s->replicas[i];
+        if (r.learning) {  // sort this shard's tiles by the cycles their blocks took: the launch order from now on
             const int shard = external ? shard0 : i;
-            std::vector<unsigned> cost(total_bands);
-            CUDA_TRY(cudaMemcpy(cost.data(), slot->d_band_cost, (size_t)total_bands * sizeof(unsigned), cudaMemcpyDeviceToHost));
-            r.band_order.clear();
-            for (int b = shard; b < total_bands; b += n_shards) r.band_order.push_back(b);
-            std::stable_sort(r.band_order.begin(), r.band_order.end(), [&](int a, int b) { return cost[a] > cost[b]; });
-            r.order_shard = shard, r.order_n_shards = n_shards, r.order_depth = depth;
+            const int tiles_x = ((int)s->width + kTileW - 1) / kTileW;
+            std::vector<unsigned> cost((size_t)total_bands * tiles_x);
+            CUDA_TRY(cudaMemcpy(cost.data(), slot->d_tile_cost, cost.size() * sizeof(unsigned), cudaMemcpyDeviceToHost));
+            std::vector<int> order;
+            for (int b = shard; b < total_bands; b += n_shards)
+                for (int x = 0; x < tiles_x; x++) order.push_back(b * tiles_x + x);
+            std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return cost[a] > cost[b]; });
+            if (const char* dump = getenv("RTC_DUMP_TILE_COST")) {  // tuning aid: the learnt costs, in launch order
+                if (FILE* fh = fopen(dump, "w")) {
+                    for (int id : order) fprintf(fh, "%d %d %u\n", id / tiles_x, id % tiles_x, cost[id]);
+                    fclose(fh);
+                }
+            }
+            CUDA_TRY(cudaMemcpy(slot->d_tile_order, order.data(), order.size() * sizeof(int), cudaMemcpyHostToDevice));
+            r.order_shard = shard, r.order_n_shards = n_shards, r.order_depth = depth, r.order_filter = s->shadow_filter;
+            r.learning = false;
         }
     }
     st.flops = detailed ? flops_of(st, st.primary_rays) : 0.0;
@@ -930,6 +990,7 @@ int rtc_scene_create(RtcScene** out) {
     *out = new RtcScene();
     if (const char* env = getenv("RTC_ADAPTIVE_ORDER")) (*out)->adaptive_order = atoi(env) != 0;  // tuning aids
     if (const char* env = getenv("RTC_SHADOW_FILTER")) (*out)->shadow_filter = atoi(env) != 0;
+    if (const char* env = getenv("RTC_ORDER_MAX_WAVES")) (*out)->order_max_waves = atoi(env);
     return 0;
 }
 void rtc_scene_destroy(RtcScene* s) {
@@ -1093,6 +1154,7 @@ int rtc_trace_rays(RtcScene* s, uint32_t n, const float* origins, const float* d
     Replica& rep = s->replicas[0];
     rep.small.filter_ok = rep.filter_eligible && s->shadow_filter;
     rep.small.cell_masks = rep.cell_masks_eligible && s->shadow_filter;
+    rep.small.plane_cells = rep.plane_cells_eligible && rep.small.cell_masks;
     struct {
         int device;
         cudaStream_t stream;

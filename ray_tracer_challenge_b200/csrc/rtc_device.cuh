@@ -846,6 +846,19 @@ __device__ __forceinline__ float* small_org() {
     extern __shared__ float4 rtc_smem[];
     return reinterpret_cast<float*>(rtc_smem + kSmallCap * 5) + threadIdx.x;
 }
+// Shadow filter, plane test with the light sample folded in (SmallScene::plane_cells): for light point L and shading
+// point p the object-space direction's y is r1.L - r1.p, so everything that depends on L alone is staged once per
+// block: {r1.L, tol * sum|r1_k L_k|, EPSILON' * |L|_1}.  See filter_plane_cell.
+constexpr float kTolP = 3.814697265625e-06f;  // 2^-18 = 64 ulp: planes and cubes (bounds are term-wise, no conditioning)
+__device__ __forceinline__ float4 plane_cell_constants(float4 r1, float4 L) {
+    const float px = r1.x * L.x, py = r1.y * L.y, pz = r1.z * L.z;
+    return make_float4(px + py + pz, kTolP * (fabsf(px) + fabsf(py) + fabsf(pz)),
+                       (1.1920929e-3f * (1.0f + 2.0f * kTolP)) * (fabsf(L.x) + fabsf(L.y) + fabsf(L.z)), 0.0f);
+}
+__device__ __forceinline__ const float4* small_plane_cells() {
+    extern __shared__ float4 rtc_smem[];
+    return rtc_smem + kSmallCap * 5 + kOrgCache * 3 * 128 / 4 + kSampleCap;
+}
 __device__ __forceinline__ const float4* small_samples() {  // table-mode light samples (SmallScene::cell_masks)
     extern __shared__ float4 rtc_smem[];
     return rtc_smem + kSmallCap * 5 + kOrgCache * 3 * 128 / 4;
@@ -857,6 +870,14 @@ __device__ __forceinline__ void stage_small_scene(const DevScene& S, const Small
     if (SS.cell_masks) {
         float4* dst = rtc_smem + kSmallCap * 5 + kOrgCache * 3 * 128 / 4;
         for (int i = threadIdx.x; i < S.cells; i += blockDim.x) dst[i] = __ldg(&S.samples[i]);
+        if (SS.plane_cells) {  // see plane_cell_constants
+            const int n_planes = SS.caster_end.y - SS.caster_end.x;
+            for (int i = threadIdx.x; i < n_planes * S.cells; i += blockDim.x) {
+                const float4 r1 = SS.p[SS.caster_end.x + i / S.cells].r1;
+                const float4 L = __ldg(&S.samples[i % S.cells]);
+                dst[kSampleCap + i] = plane_cell_constants(r1, L);
+            }
+        }
     }
     __syncthreads();
 }
@@ -864,9 +885,8 @@ __device__ __forceinline__ void stage_small_scene(const DevScene& S, const Small
 // Object-space origin of primitive i: from the per-shade cache (all shadow rays of one shade share their
 // origin, so `inverse * origin`, shape.rs:60-70, is evaluated once per primitive instead of once per light
 // cell — the same arithmetic, hoisted) or computed.
-template <bool CACHED>
-__device__ __forceinline__ V3 small_origin(int i, const Xf& m, V3 o) {
-    if (CACHED && i < kOrgCache) {
+__device__ __forceinline__ V3 small_origin(bool cached, int i, const Xf& m, V3 o) {
+    if (cached && i < kOrgCache) {
         const float* org = small_org();
         return mk(org[(i * 3 + 0) * 128], org[(i * 3 + 1) * 128], org[(i * 3 + 2) * 128]);
     }
@@ -889,7 +909,7 @@ __device__ __forceinline__ void cache_origins(const Env& E, V3 o) {
 // One item of a small scene of any kind (primitive or CSG root), honouring the cull chain: the general form
 // (out of line: cylinders, cones, triangles and CSG roots are the rare members of small scenes).
 template <bool STATS>
-__device__ __forceinline__ void test_small(const Env& E, int i, bool cached, V3 o, V3 d, Hit& best, Ctr<STATS>& k) {
+__device__ __noinline__ void test_small(const Env& E, int i, bool cached, V3 o, V3 d, Hit& best, Ctr<STATS>& k) {
     const float4* tab = small_tab();
     const int4 head = *reinterpret_cast<const int4*>(tab + i * 5);
     const int type = head.x & 15;
@@ -906,7 +926,7 @@ __device__ __forceinline__ void test_small(const Env& E, int i, bool cached, V3 
         return;
     }
     Xf m{tab[i * 5 + 1], tab[i * 5 + 2], tab[i * 5 + 3]};
-    V3 o2 = cached ? small_origin<true>(i, m, o) : xf_point(m, o);
+    V3 o2 = cached ? small_origin(true, i, m, o) : xf_point(m, o);
     V3 d2 = xf_vec(m, d);
     k.xform();
     k.prim(type);
@@ -918,14 +938,14 @@ __device__ __forceinline__ void test_small(const Env& E, int i, bool cached, V3 
 // Nearest hit among the items [begin, ends.w) of a small scene, which are runs of spheres, planes, cubes and
 // "everything else" ending at ends.x / .y / .z / .w: one tight loop per kind, no per-item dispatch.
 // ANY: return true as soon as some item is hit in [0, best.t) (shadow rays when every object casts a shadow).
-template <bool STATS, bool CACHED, bool ANY>
-__device__ __forceinline__ bool scan_small(const Env& E, int begin, int4 ends, V3 o, V3 d, Hit& best, Ctr<STATS>& k) {
-    constexpr bool cached = CACHED, any = ANY;
+template <bool STATS, bool ANY>
+__device__ __forceinline__ bool scan_small(const Env& E, bool cached, int begin, int4 ends, V3 o, V3 d, Hit& best, Ctr<STATS>& k) {
+    constexpr bool any = ANY;
     const float4* tab = small_tab();
     int i = begin;
     for (; i < ends.x; i++) {  // spheres — sphere.rs:47-70
         Xf m{tab[i * 5 + 1], tab[i * 5 + 2], tab[i * 5 + 3]};
-        V3 o2 = small_origin<CACHED>(i, m, o);
+        V3 o2 = small_origin(cached, i, m, o);
         V3 d2 = xf_vec(m, d);
         k.xform();
         k.prim(T_SPHERE);
@@ -949,7 +969,7 @@ __device__ __forceinline__ bool scan_small(const Env& E, int begin, int4 ends, V
     }
     for (; i < ends.z; i++) {  // cubes — cube.rs:55-63
         Xf m{tab[i * 5 + 1], tab[i * 5 + 2], tab[i * 5 + 3]};
-        V3 o2 = small_origin<CACHED>(i, m, o);
+        V3 o2 = small_origin(cached, i, m, o);
         V3 d2 = xf_vec(m, d);
         k.xform();
         k.prim(T_CUBE);
@@ -977,7 +997,7 @@ __device__ __forceinline__ void find_hit(const Env& E, V3 o, V3 d, Hit& best, Ct
             int4 ends = SS.caster_end;
 #pragma unroll 1
             for (int seg = 0; seg < 2; seg++) {  // casters, then non-casters: one copy of the loops
-                scan_small<STATS, false, false>(E, begin, ends, o, d, best, k);
+                scan_small<STATS, false>(E, false, begin, ends, o, d, best, k);
                 begin = ends.w;
                 ends = SS.other_end;
             }
@@ -1005,7 +1025,6 @@ struct FRes {
     int code;
     float s, e;  // F_HIT: segment parameter of the nearest hit and its error bound
 };
-constexpr float kTolP = 3.814697265625e-06f;  // 2^-18 = 64 ulp: planes and cubes (bounds are term-wise, no conditioning)
 __device__ __forceinline__ float fma_(float a, float b, float c) { return __fmaf_rn(a, b, c); }
 __device__ __forceinline__ float rcp_(float a) { return __fdividef(1.0f, a); }
 
@@ -1092,9 +1111,9 @@ __device__ __forceinline__ FRes filter_cube(const Xf& m, V3 o, V3 v) {
 // (every object casts); MODE 1: casters, keep the nearest hit (s_c, e_c); MODE 2: non-casters against the nearest
 // caster hit.  Returns F_UNSURE as soon as some test is undecided; otherwise F_HIT / F_MISS, meaning
 //   MODE 0/1: some / no caster is hit in [0, 1);  MODE 2: F_HIT = a non-caster is clearly nearer than every caster.
-template <bool STATS, bool CACHED, int MODE>
-__device__ __forceinline__ int filter_scan(const Env& E, int begin, int4 ends, V3 p, V3 v, float len, float& s_c, float& e_c,
-                                           Ctr<STATS>& k) {
+template <bool STATS, int MODE>
+__device__ __forceinline__ int filter_scan(const Env& E, bool cached, int begin, int4 ends, V3 p, V3 v, float len, float& s_c,
+                                           float& e_c, Ctr<STATS>& k) {
     const float4* tab = small_tab();
     const float tol = E.SS.tol_sphere;
     int result = F_MISS;
@@ -1127,12 +1146,12 @@ __device__ __forceinline__ int filter_scan(const Env& E, int begin, int4 ends, V
         Xf m{tab[i * 5 + 1], tab[i * 5 + 2], tab[i * 5 + 3]};
         k.xform();
         k.prim(T_SPHERE);
-        if (take(filter_sphere(m, small_origin<CACHED>(i, m, p), v, tol))) return result;
+        if (take(filter_sphere(m, small_origin(cached, i, m, p), v, tol))) return result;
     }
     for (; i < ends.y; i++) {
         float4 r1 = tab[i * 5 + 2];
         float oy;
-        if (CACHED && i < kOrgCache)
+        if (cached && i < kOrgCache)
             oy = small_org()[(i * 3 + 1) * 128];
         else
             oy = r1.x * p.x + r1.y * p.y + r1.z * p.z + r1.w;
@@ -1144,23 +1163,23 @@ __device__ __forceinline__ int filter_scan(const Env& E, int begin, int4 ends, V
         Xf m{tab[i * 5 + 1], tab[i * 5 + 2], tab[i * 5 + 3]};
         k.xform();
         k.prim(T_CUBE);
-        if (take(filter_cube(m, small_origin<CACHED>(i, m, p), v))) return result;
+        if (take(filter_cube(m, small_origin(cached, i, m, p), v))) return result;
     }
     return result;
 }
 
 // 0: lit, 1: shadowed, 2: undecided (run the exact test)
-template <bool STATS, bool CACHED>
-__device__ __forceinline__ int shadow_filter(const Env& E, V3 light_position, V3 p, Ctr<STATS>& k) {
+template <bool STATS>
+__device__ __forceinline__ int shadow_filter(const Env& E, bool cached, V3 light_position, V3 p, Ctr<STATS>& k) {
     const SmallScene& SS = E.SS;
     const V3 v = light_position - p;
     const float vv = fma_(v.x, v.x, fma_(v.y, v.y, v.z * v.z));
     const float len = vv * rsqrtf(vv);
     float s_c = kInfF, e_c = 0.0f;
-    if (E.S.all_cast_shadow) return filter_scan<STATS, CACHED, 0>(E, 0, SS.caster_end, p, v, len, s_c, e_c, k);
-    int r = filter_scan<STATS, CACHED, 1>(E, 0, SS.caster_end, p, v, len, s_c, e_c, k);
+    if (E.S.all_cast_shadow) return filter_scan<STATS, 0>(E, cached, 0, SS.caster_end, p, v, len, s_c, e_c, k);
+    int r = filter_scan<STATS, 1>(E, cached, 0, SS.caster_end, p, v, len, s_c, e_c, k);
     if (r != F_HIT) return r == F_MISS ? 0 : 2;
-    r = filter_scan<STATS, CACHED, 2>(E, SS.caster_end.w, SS.other_end, p, v, len, s_c, e_c, k);
+    r = filter_scan<STATS, 2>(E, cached, SS.caster_end.w, SS.other_end, p, v, len, s_c, e_c, k);
     return r == F_UNSURE ? 2 : (r == F_HIT ? 0 : 1);
 }
 
@@ -1171,51 +1190,54 @@ __device__ __forceinline__ int shadow_filter(const Env& E, V3 light_position, V3
 // the non-casting objects do, and otherwise only a non-casting object NEARER than the nearest caster (same
 // (t, depth-first order) comparison as Intersection::hit) can un-shadow the point.  Same predicate as the
 // reference's, evaluated with fewer intersection tests.
-template <bool STATS, bool SMALL, bool CACHED>
-__device__ __forceinline__ bool shadow_exact(const Env& E, V3 light_position, V3 p, Ctr<STATS>& k) {
-    constexpr bool cached = CACHED;
+template <bool STATS>
+__device__ __forceinline__ bool shadow_exact_small(const Env& E, bool cached, V3 light_position, V3 p, Ctr<STATS>& k) {
     const DevScene& S = E.S;
+    const SmallScene& SS = E.SS;
     V3 v = light_position - p;
     float distance = magnitude(v);
     V3 direction = mk(v.x / distance, v.y / distance, v.z / distance);
     // order -1: a hit AT the light distance is never accepted (`<`, world.rs:116)
     Hit best{distance, -1, -1};
-    if (SMALL) {
-        const SmallScene& SS = E.SS;
-        if (!SS.two_pass_shadows || SS.has_cull_chain) {  // a CSG root or a cull chain: plain nearest-hit search
-            for (int i = 0; i < SS.n; i++) test_small<STATS>(E, i, cached, p, direction, best, k);
-            return best.pos >= 0 && ((__ldg(&S.head[best.pos]).x >> 4) & kFlagCastsShadow);
-        }
-        if (S.all_cast_shadow)  // every object casts: any hit in [0, distance) shadows the point
-            return scan_small<STATS, CACHED, true>(E, 0, SS.caster_end, p, direction, best, k);
-        scan_small<STATS, CACHED, false>(E, 0, SS.caster_end, p, direction, best, k);
-        if (best.pos < 0) return false;
-        const int caster = best.pos;
-        scan_small<STATS, CACHED, false>(E, SS.caster_end.w, SS.other_end, p, direction, best, k);
-        return best.pos == caster;
+    if (!SS.two_pass_shadows || SS.has_cull_chain) {  // a CSG root or a cull chain: plain nearest-hit search
+        for (int i = 0; i < SS.n; i++) test_small<STATS>(E, i, cached, p, direction, best, k);
+        return best.pos >= 0 && ((__ldg(&S.head[best.pos]).x >> 4) & kFlagCastsShadow);
     }
+    if (S.all_cast_shadow)  // every object casts: any hit in [0, distance) shadows the point
+        return scan_small<STATS, true>(E, cached, 0, SS.caster_end, p, direction, best, k);
+    scan_small<STATS, false>(E, cached, 0, SS.caster_end, p, direction, best, k);
+    if (best.pos < 0) return false;
+    const int caster = best.pos;
+    scan_small<STATS, false>(E, cached, SS.caster_end.w, SS.other_end, p, direction, best, k);
+    return best.pos == caster;
+}
+// One shadow ray of a small scene, out of line (ONE copy of the filter and of the exact test in the kernel: the
+// kernel's instruction footprint, not its arithmetic, limits the issue rate).  skip_filter: the caller already
+// knows the filter cannot decide this ray.
+template <bool STATS>
+__device__ __noinline__ bool shadow_query_small(const Env& E, bool cached, bool skip_filter, V3 light_position, V3 p, Ctr<STATS>& k) {
+    if (E.SS.filter_ok) {
+        const int f = skip_filter ? 2 : shadow_filter<STATS>(E, cached, light_position, p, k);
+        if (f != 2) return f == 1;
+        k.refiltered();
+    }
+    return shadow_exact_small<STATS>(E, cached, light_position, p, k);
+}
+template <bool STATS, bool SMALL, bool CACHED>
+__device__ __forceinline__ bool is_shadowed(const Env& E, V3 light_position, V3 p, Rays& r, Ctr<STATS>& k) {
+    r.shadow++;
+    if (SMALL) return shadow_query_small<STATS>(E, CACHED, false, light_position, p, k);
+    const DevScene& S = E.S;
+    V3 v = light_position - p;
+    float distance = magnitude(v);
+    V3 direction = mk(v.x / distance, v.y / distance, v.z / distance);
+    Hit best{distance, -1, -1};  // order -1: a hit AT the light distance is never accepted (`<`, world.rs:116)
     if (S.all_cast_shadow) {
         nearest_hit<STATS, true>(S, p, direction, best, k);
         return best.pos >= 0;
     }
     nearest_hit<STATS, false>(S, p, direction, best, k);
     return best.pos >= 0 && ((__ldg(&S.head[best.pos]).x >> 4) & kFlagCastsShadow);
-}
-// the filter's fallback: out of line so the rarely-taken exact test stays out of the light-cell loop
-template <bool STATS, bool CACHED>
-__device__ __noinline__ bool shadow_exact_cold(const Env& E, V3 light_position, V3 p, Ctr<STATS>& k) {
-    return shadow_exact<STATS, true, CACHED>(E, light_position, p, k);
-}
-template <bool STATS, bool SMALL, bool CACHED>
-__device__ __forceinline__ bool is_shadowed(const Env& E, V3 light_position, V3 p, Rays& r, Ctr<STATS>& k) {
-    r.shadow++;
-    if (SMALL && E.SS.filter_ok) {
-        const int f = shadow_filter<STATS, CACHED>(E, light_position, p, k);
-        if (f != 2) return f == 1;
-        k.refiltered();
-        return shadow_exact_cold<STATS, CACHED>(E, light_position, p, k);
-    }
-    return shadow_exact<STATS, SMALL, CACHED>(E, light_position, p, k);
 }
 
 // RectangleLight::intensity_at (rectangle_light.rs:76-88) for filter_ok scenes with a table-mode light: the light
@@ -1225,15 +1247,54 @@ __device__ __forceinline__ bool is_shadowed(const Env& E, V3 light_position, V3 
 // masks: cells where some caster is clearly hit, cells where some test was undecided.  Cells in neither mask are
 // lit.  Pass 2 revisits the others one by one: hit cells need the nearest-caster / non-caster comparison
 // (shadow_filter) when the scene has non-casting objects, undecided cells run the exact test.
-template <bool STATS>
-__device__ __noinline__ int shadow_cell_cold(const Env& E, V3 lp, V3 p, bool exact, Ctr<STATS>& k) {
-    int f = exact ? 2 : shadow_filter<STATS, false>(E, lp, p, k);
-    if (f == 2) {
-        k.refiltered();
-        f = shadow_exact<STATS, true, false>(E, lp, p, k) ? 1 : 0;
-    }
-    return f;
+// Distances from p to a bounding ball {centre, radius}: no point of the ball is farther than ball_reach, none is
+// nearer than ball_gap (negative inside).  Approximate square roots: the callers compare with a 0.1 % margin.
+__device__ __forceinline__ float ball_reach(float4 ball, V3 p) {
+    const float dx = p.x - ball.x, dy = p.y - ball.y, dz = p.z - ball.z;
+    const float ww = fma_(dx, dx, fma_(dy, dy, dz * dz));
+    return ww * rsqrtf(ww + 1e-30f) + ball.w;
 }
+__device__ __forceinline__ float ball_gap(float4 ball, V3 p) {
+    const float dx = p.x - ball.x, dy = p.y - ball.y, dz = p.z - ball.z;
+    const float ww = fma_(dx, dx, fma_(dy, dy, dz * dz));
+    return ww * rsqrtf(ww + 1e-30f) - ball.w;
+}
+
+// filter_plane with the per-(plane, cell) constants of plane_cell_constants: q = {r1.L, tol*|r1||L|, eps'*|L|_1},
+// rp = r1.p, erp = tol * sum|r1_k p_k|, p1 = eps' * |p|_1 (per shade).  |L - p| <= |L|_1 + |p|_1 stands in for the length
+// in the reference's `direction.y.abs() < EPSILON` test (plane.rs:49), so a direction that is not clearly steeper than
+// that is undecided rather than a miss.
+__device__ __forceinline__ int filter_plane_cell(float4 q, float oy, float rp, float erp, float p1) {
+    const float dy = q.x - rp;
+    const float edy = q.y + erp;
+    const float mag = fabsf(dy), lo = mag - edy;
+    if (!(lo > q.z + p1) || oy == 0.0f) return F_UNSURE;
+    if ((oy < 0.0f) == (dy < 0.0f)) return F_MISS;  // t = -oy / dy < 0
+    const float aoy = fabsf(oy);
+    if (aoy < lo * (1.0f - kTolP)) return F_HIT;
+    if (aoy > (mag + edy) * (1.0f + kTolP)) return F_MISS;
+    return F_UNSURE;
+}
+
+// Bundle reject: every shadow segment of a shade runs from p to a light sample inside the ball (Lc, Rl), so all of
+// them lie in the cone-like solid { x : |x - (p + s (Lc - p))| <= s Rl, 0 <= s <= 1 }.  A primitive whose bounding ball
+// (C, R) stays outside it — f(s) = |w + s u|^2 - (R + s Rl)^2 > 0 on [0, 1], w = p - C, u = Lc - p — cannot be hit by
+// any of them.  R is padded by 0.1 % plus 2^-17 * |w|^2 / R: beyond that clearance neither this filter nor the
+// reference's f32 discriminant (whose rounding error grows with |w|^2 / R^2) can report a hit.
+__device__ __forceinline__ bool bundle_misses(float4 ball, float pad_over_r, float4 light_ball, V3 p) {
+    const V3 w = mk(p.x - ball.x, p.y - ball.y, p.z - ball.z);
+    const V3 u = mk(light_ball.x - p.x, light_ball.y - p.y, light_ball.z - p.z);
+    const float ww = fma_(w.x, w.x, fma_(w.y, w.y, w.z * w.z));
+    const float R = fma_(pad_over_r, ww, ball.w), Rl = light_ball.w;
+    const float A = fma_(u.x, u.x, fma_(u.y, u.y, u.z * u.z)) - Rl * Rl;
+    const float B = fma_(w.x, u.x, fma_(w.y, u.y, w.z * u.z)) - R * Rl;
+    const float C = ww - R * R;
+    if (!(C > 0.0f) || !(A + 2.0f * B + C > 0.0f)) return false;  // an end of the bundle touches the ball
+    if (!(A > 0.0f)) return A <= 0.0f;      // concave or linear: the minimum over [0, 1] is at an end (NaN: no reject)
+    if (B >= 0.0f || -B >= A) return true;  // convex, vertex outside (0, 1)
+    return C * A > B * B * 1.0001f;
+}
+
 template <bool STATS>
 __device__ __forceinline__ float intensity_cells(const Env& E, V3 p, Rays& r, Ctr<STATS>& k) {
     const DevScene& S = E.S;
@@ -1249,8 +1310,11 @@ __device__ __forceinline__ float intensity_cells(const Env& E, V3 p, Rays& r, Ct
         const int nc = min(32, cells - c0);
         const unsigned full = nc == 32 ? 0xffffffffu : ((1u << nc) - 1u);
         unsigned hit = 0u, unsure = 0u;
+        float far_hit = 0.0f;  // no caster hit of this chunk is farther from p than this (bounding balls)
         int i = 0;
         for (; i < ends.x && (hit | unsure) != full; i++) {  // caster spheres
+            if (bundle_misses(tab[i * 5 + 4], tab[i * 5].y, SS.light_ball, p)) continue;
+            const unsigned hit_before = hit;
             const Xf m{tab[i * 5 + 1], tab[i * 5 + 2], tab[i * 5 + 3]};
             const V3 o = xf_point(m, p);  // the reference's object-space origin (shape.rs:60-70), once per shade
             const float oo = fma_(o.x, o.x, fma_(o.y, o.y, o.z * o.z));
@@ -1278,10 +1342,31 @@ __device__ __forceinline__ float intensity_cells(const Env& E, V3 p, Rays& r, Ct
                 k.xform();
                 k.prim(T_SPHERE);
             }
+            if (hit != hit_before) far_hit = fmaxf(far_hit, ball_reach(tab[i * 5 + 4], p));
         }
         for (i = ends.x; i < ends.y && (hit | unsure) != full; i++) {  // caster planes
+            const unsigned hit_before = hit;
             const float4 r1 = tab[i * 5 + 2];
-            const float oy = r1.x * p.x + r1.y * p.y + r1.z * p.z + r1.w;
+            const float tx = r1.x * p.x, ty = r1.y * p.y, tz = r1.z * p.z;
+            const float rp = tx + ty + tz;
+            const float oy = rp + r1.w;  // the reference's object-space origin.y (shape.rs:60-70)
+            if (SS.plane_cells) {
+                const float4* pc = small_plane_cells() + (i - ends.x) * cells + c0;
+                const float erp = kTolP * (fabsf(tx) + fabsf(ty) + fabsf(tz));
+                const float p1 = (kAcne * (1.0f + 2.0f * kTolP)) * (fabsf(p.x) + fabsf(p.y) + fabsf(p.z));
+#pragma unroll 4
+                for (int j = 0; j < nc; j++) {
+                    const int code = filter_plane_cell(pc[j], oy, rp, erp, p1);
+                    hit |= (unsigned)(code == F_HIT) << j;
+                    unsure |= (unsigned)(code == F_UNSURE) << j;
+                }
+                for (int j = 0; j < nc; j++) {
+                    k.xform();
+                    k.prim(T_PLANE);
+                }
+                if (hit != hit_before) far_hit = kInfF;  // a plane has no bounding ball
+                continue;
+            }
 #pragma unroll 4
             for (int j = 0; j < nc; j++) {
                 const float4 L = smp[c0 + j];
@@ -1295,8 +1380,11 @@ __device__ __forceinline__ float intensity_cells(const Env& E, V3 p, Rays& r, Ct
                 k.xform();
                 k.prim(T_PLANE);
             }
+            if (hit != hit_before) far_hit = kInfF;
         }
         for (i = ends.y; i < ends.z && (hit | unsure) != full; i++) {  // caster cubes
+            if (bundle_misses(tab[i * 5 + 4], tab[i * 5].y, SS.light_ball, p)) continue;
+            const unsigned hit_before = hit;
             const Xf m{tab[i * 5 + 1], tab[i * 5 + 2], tab[i * 5 + 3]};
             const V3 o = xf_point(m, p);
 #pragma unroll 2
@@ -1310,16 +1398,29 @@ __device__ __forceinline__ float intensity_cells(const Env& E, V3 p, Rays& r, Ct
                 k.xform();
                 k.prim(T_CUBE);
             }
+            if (hit != hit_before) far_hit = fmaxf(far_hit, ball_reach(tab[i * 5 + 4], p));
         }
         for (int j = 0; j < nc; j++) k.cell();
-        // pass 2
-        unsigned todo = S.all_cast_shadow ? unsure : (hit | unsure);
+        // pass 2.  A non-caster only matters where it is NEARER than the nearest caster hit (world.rs:113-118): when
+        // every non-caster's bounding ball begins beyond the reach of every caster that was hit, the hit cells are
+        // shadowed as they stand.
+        bool hits_final = S.all_cast_shadow != 0;
+        if (!hits_final && (hit & ~unsure) != 0u) {
+            float near_other = kInfF;
+            for (int q = ends.w; q < SS.other_end.z; q++) {
+                const float4 ball = tab[q * 5 + 4];
+                const bool has_ball = q < SS.other_end.x || q >= SS.other_end.y;  // spheres and cubes; planes have none
+                near_other = fminf(near_other, has_ball ? ball_gap(ball, p) : 0.0f);
+            }
+            hits_final = far_hit * 1.001f < near_other;  // false for NaN
+        }
+        unsigned todo = hits_final ? unsure : (hit | unsure);
         lit += __popc(full & ~(hit | unsure));
         while (todo) {
             const int j = __ffs(todo) - 1;
             todo &= todo - 1u;
             const float4 L = smp[c0 + j];
-            lit += shadow_cell_cold<STATS>(E, mk(L.x, L.y, L.z), p, (unsure >> j) & 1u, k) == 0;
+            lit += !shadow_query_small<STATS>(E, false, (unsure >> j) & 1u, mk(L.x, L.y, L.z), p, k);
         }
     }
     return (float)lit / (float)cells;  // `total += 1.0` per lit cell is exact in f32

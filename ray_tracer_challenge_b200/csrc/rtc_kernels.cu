@@ -18,10 +18,10 @@
 
 // resident 128-thread blocks per SM the compiler must make room for (register budget = 65536 / (128 * blocks))
 #ifndef RTC_SMALL_MINBLOCKS
-#define RTC_SMALL_MINBLOCKS 6
+#define RTC_SMALL_MINBLOCKS 1
 #endif
 #ifndef RTC_BVH_MINBLOCKS
-#define RTC_BVH_MINBLOCKS 5
+#define RTC_BVH_MINBLOCKS 1
 #endif
 
 namespace rtc {
@@ -63,15 +63,22 @@ __device__ __forceinline__ void flush_counters<true>(const Rays& r, const Ctr<tr
 }
 
 template <bool STATS, bool SMALL>
-__global__ void __launch_bounds__(128) render_tiles(const __grid_constant__ DevScene S, const __grid_constant__ SmallScene SS,
+__global__ void __launch_bounds__(128, SMALL ? RTC_SMALL_MINBLOCKS : RTC_BVH_MINBLOCKS) render_tiles(const __grid_constant__ DevScene S, const __grid_constant__ SmallScene SS,
                                                     const DevFrame F, DevCounters* counters) {
     // small scenes: primitive table + per-thread shadow-origin cache in dynamic shared memory (kSmallSmemBytes)
     if (SMALL) stage_small_scene(S, SS);
     const Env E{S, SS};
-    // block (bx, by) -> tile of 16x8 pixels in band `shard + by * n_shards`; warp w -> 8x4 sub-tile
+    // block -> tile of 16x8 pixels: natural order = (tile column bx, band `shard + by * n_shards`), or the learnt
+    // longest-first list; warp w -> 8x4 sub-tile
+    const long long t_start = F.tile_cost ? clock64() : 0;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int band = F.band_order ? F.band_order[F.band_begin + blockIdx.y] : F.shard + (F.band_begin + blockIdx.y) * F.n_shards;
-    const int x = blockIdx.x * kTileW + (warp & 1) * 8 + (lane & 7);
+    int band = F.shard + (F.band_begin + blockIdx.y) * F.n_shards, bx = blockIdx.x;
+    if (F.tile_order) {
+        const int id = F.tile_order[blockIdx.y * gridDim.x + blockIdx.x];
+        band = id / (int)gridDim.x;
+        bx = id - band * (int)gridDim.x;
+    }
+    const int x = bx * kTileW + (warp & 1) * 8 + (lane & 7);
     const int y = band * kBandRows + (warp >> 1) * 4 + (lane >> 3);
     Ctr<STATS> k;
     Rays r;
@@ -98,7 +105,8 @@ __global__ void __launch_bounds__(128) render_tiles(const __grid_constant__ DevS
         }
     }
     flush_counters<STATS>(r, k, counters);
-    if (F.band_cost) warp_add_u32(&F.band_cost[band], r.primary + r.secondary + r.shadow);
+    if (F.tile_cost && lane == 0)  // a block lasts as long as its slowest warp
+        atomicMax(&F.tile_cost[band * gridDim.x + bx], (unsigned)min(clock64() - t_start, 0xffffffffLL));
 }
 
 template <bool SMALL>

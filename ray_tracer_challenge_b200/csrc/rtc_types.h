@@ -116,7 +116,8 @@ constexpr int kOrgCache = 8;    // object-space shadow-ray origins cached per th
 struct SmallPrim {              // 80 B
     int4 head;                  // type | flags << 4 | material << 8, cull-chain parent node, aux, dfs order
     float4 r0, r1, r2;          // rows of the inverse transform
-    float4 bound;               // cylinder / cone: minimum_y, maximum_y, closed
+    float4 bound;               // cylinder / cone: minimum_y, maximum_y, closed.  filter_ok scenes, sphere / cube: the
+                                // world-space bounding ball {centre, radius * 1.001} (head.y then holds 2^-17 / radius)
 };
 // The table is sorted by (casts shadow first, then kind) so every loop over it is a run of ONE kind:
 //   casters:     spheres [0, c.x) planes [c.x, c.y) cubes [c.y, c.z) everything else [c.z, c.w)
@@ -129,12 +130,15 @@ struct SmallScene {
     int filter_ok;              // spheres / planes / axis-aligned cubes only: shadow rays go through the filter first
     float tol_sphere;           // the filter's relative error bound for spheres (grows with the transforms' condition)
     int cell_masks;             // filter_ok, table-mode area light with <= kSampleCap cells: intensity_cells path
-    int pad[2];
+    int plane_cells;            // cell_masks and (caster planes x cells) <= kPlaneCellCap: per-(plane, cell) constants staged
+    int pad;
+    float4 light_ball;          // cell_masks: ball around the light samples (centre, radius) for the bundle reject
     int4 caster_end, other_end;
     SmallPrim p[kSmallCap];
 };
-constexpr int kSampleCap = 128;  // table-mode light samples staged in shared memory
-constexpr int kSmallSmemBytes = kSmallCap * 80 + kOrgCache * 3 * 128 * 4 + kSampleCap * 16;
+constexpr int kSampleCap = 128;     // table-mode light samples staged in shared memory
+constexpr int kPlaneCellCap = 256;  // (caster plane, light cell) constants staged in shared memory
+constexpr int kSmallSmemBytes = kSmallCap * 80 + kOrgCache * 3 * 128 * 4 + kSampleCap * 16 + kPlaneCellCap * 16;
 
 struct DevFrame {  // where a render writes
     float* rgb;            // width*height*3 f32 or null
@@ -143,8 +147,8 @@ struct DevFrame {  // where a render writes
     int depth;
     int n_bands;           // bands this launch renders ...
     int band_begin;        // ... starting at this index of the shard's band list
-    const int* band_order; // the shard's band list in launch order (frame band indices), or null: shard + j * n_shards
-    unsigned* band_cost;   // per frame band: rays traced in it (feeds the next frame's launch order), or null
+    const int* tile_order; // this shard's tiles (band * tiles_x + tile column) in launch order, or null: natural order
+    unsigned* tile_cost;   // per frame tile: clock cycles its block ran (learns the launch order), or null
 };
 
 constexpr int kTileW = 16, kTileH = 8;  // pixels per 128-thread block: 4 warps of 8x4
