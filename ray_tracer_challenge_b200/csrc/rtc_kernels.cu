@@ -18,10 +18,10 @@
 
 // resident 128-thread blocks per SM the compiler must make room for (register budget = 65536 / (128 * blocks))
 #ifndef RTC_SMALL_MINBLOCKS
-#define RTC_SMALL_MINBLOCKS 1
+#define RTC_SMALL_MINBLOCKS 4
 #endif
 #ifndef RTC_BVH_MINBLOCKS
-#define RTC_BVH_MINBLOCKS 1
+#define RTC_BVH_MINBLOCKS 5
 #endif
 
 namespace rtc {
