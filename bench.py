@@ -114,7 +114,9 @@ def cpu_baseline(workload: str, threads: int, target_seconds: float = 12.0) -> d
     mrays = st.rays / dt / 1e6
     return {"value": round(mrays, 4), "unit": "Mrays/s", "cores": threads, "kind": "port",
             "sample": f"rows {ystep // 2}::{ystep} of the {cam.width_pixels}x{h} frame ({rows} rows, {st.rays} rays, {dt:.2f} s)",
-            "est_frame_ms": round(dt * (h - 1) / rows * 1e3, 1)}
+            "est_frame_ms": round(dt * (h - 1) / rows * 1e3, 1),
+            # the reference algorithm's own work for the frame (every ray against every object, Appendix E units)
+            "reference_flops_per_frame": float(st.flops) * (h - 1) / rows}
 
 
 def run_reference(args) -> None:
@@ -323,16 +325,19 @@ def main() -> None:
         if detail is not None:
             ms_frame = kernel_ms_max / args.steps
             achieved = detail["flops"] / (ms_frame * 1e-3) / 1e12
-            traffic = None
-            try:
-                with open(os.path.join(ROOT, "profiles", f"r01_{args.workload}_traffic.json")) as fh:
-                    traffic = json.load(fh)["dram_bytes"]
+            prof = {}
+            try:  # the committed ncu capture of this workload's kernel (tools/ncu_profile_json.py)
+                with open(os.path.join(ROOT, "profiles", f"r01_{args.workload}_profile.json")) as fh:
+                    prof = json.load(fh)
             except Exception:
                 pass
             roofline = {"bound": "fp32", "achieved": round(achieved, 3), "peak": round(tflops.value, 2), "unit": "TFLOP/s",
-                        "frac": round(achieved / tflops.value, 4), "traffic": traffic,
-                        "traffic_source": "profiles/r01_c3_traffic.json (ncu dram__bytes_read+write of one launch)" if traffic else None,
-                        "issue_slot_utilisation": "69.6 % (ncu smsp__issue_active, profiles/r01_c3_step6_current.txt)" if args.workload == "c3" else None,
+                        "frac": round(achieved / tflops.value, 4), "traffic": prof.get("dram_bytes"),
+                        "traffic_source": prof.get("source"),
+                        "issue_slot_utilisation_pct": prof.get("issue_active_pct"),
+                        "fma_pipe_utilisation_pct": prof.get("pipe_fma_pct"),
+                        "what": "achieved = algorithmic FP32 flops of the units the kernel EXECUTED (SURVEY.md Appendix E table x the "
+                                "detailed pass's counters: tests skipped by the shadow filter's bundle reject are not counted) / kernel time",
                         "peak_kind": "measured live: K5 FMA micro-benchmark (MEASURED_PEAKS.json has no FP32 figure)",
                         "nominal_peak": round(nominal, 2), "frac_of_nominal": round(achieved / nominal, 4),
                         "flops_per_frame": detail["flops"], "rays_per_frame": detail["rays"],
@@ -341,6 +346,13 @@ def main() -> None:
                         "prim_tests_per_ray": round(sum(detail["prim_tests"]) / max(detail["rays"], 1), 2)}
         if world_size == 1 and not args.no_cpu_baseline:
             cpu = cpu_baseline(args.workload, 1)
+            if roofline and cpu.get("reference_flops_per_frame"):
+                ref_flops = cpu["reference_flops_per_frame"]
+                ref_tf = ref_flops / (kernel_ms_max / args.steps * 1e-3) / 1e12
+                roofline["reference_algorithm"] = {
+                    "flops_per_frame": ref_flops, "achieved": round(ref_tf, 3), "frac": round(ref_tf / tflops.value, 4),
+                    "what": "the same frame's flops as the REFERENCE algorithm spends them (the oracle's counters: every ray "
+                            "against every object) / our kernel time: work-equivalent throughput, not hardware utilisation"}
             try:
                 from tests.oracle_binding import load_oracle
 
