@@ -92,7 +92,7 @@ enum {
     RTC_PAT_TEXTURE_MAP = 6,
     RTC_PAT_CUBIC_MAP = 7
 };
-enum { RTC_UV_CHECKERS = 0, RTC_UV_ALIGN_CHECK = 1 };
+enum { RTC_UV_CHECKERS = 0, RTC_UV_ALIGN_CHECK = 1, RTC_UV_IMAGE = 2 };
 enum { RTC_MAP_SPHERICAL = 0, RTC_MAP_PLANAR = 1, RTC_MAP_CYLINDRICAL = 2 };
 typedef struct RtcPattern {
     int32_t kind;
@@ -105,8 +105,14 @@ typedef struct RtcPattern {
 } RtcPattern;
 typedef struct RtcUvPattern {
     int32_t kind;
-    float params[15]; /* UVCheckers: width, height, a.rgb, b.rgb; AlignCheck: main, ul, ur, bl, br */
+    float params[15]; /* UVCheckers: width, height, a.rgb, b.rgb; AlignCheck: main, ul, ur, bl, br;
+                         UVImage (uv.rs:346-377): params[0] = texture index (rtc_set_textures) */
 } RtcUvPattern;
+/* The Canvas behind a UVImage (canvas.rs:6-10): width * height * 3 f32, row-major, row 0 at the top. */
+typedef struct RtcTexture {
+    uint32_t width, height;
+    const float* rgb; /* caller keeps ownership; copied by rtc_set_textures */
+} RtcTexture;
 
 typedef struct RtcStats {
     uint64_t primary_rays;   /* color_at calls from render (camera.rs:83) */
@@ -141,6 +147,10 @@ int rtc_set_primitives(RtcScene*, uint32_t n, const RtcPrim* prims);
 int rtc_set_nodes(RtcScene*, uint32_t n_nodes, const RtcNode* nodes, uint32_t n_refs, const int32_t* child_refs);
 int rtc_set_materials(RtcScene*, uint32_t n, const RtcMaterial* materials);
 int rtc_set_patterns(RtcScene*, uint32_t n, const RtcPattern* patterns, uint32_t n_uv, const RtcUvPattern* uv);
+/* Image textures referenced by RTC_UV_IMAGE patterns.  UVImage::color_at (uv.rs:366-377): x = round(u * (width - 1)),
+ * y = round((1 - v) * (height - 1)), nearest pixel; where the reference would index outside the canvas and panic
+ * (u or v outside [0, 1]) the device clamps to the edge. */
+int rtc_set_textures(RtcScene*, uint32_t n, const RtcTexture* textures);
 /* PointLight (point_light.rs:7-18) */
 int rtc_set_point_light(RtcScene*, const float position[3], const float intensity[3]);
 /* RectangleLight after construction (rectangle_light.rs:48-58): u_cell / v_cell are the per-cell edges,

@@ -62,7 +62,7 @@ enum {
 };
 
 /* uv patterns and mappings (lib/src/pattern/uv.rs) */
-enum { SG_UV_CHECKERS = 0, SG_UV_ALIGN_CHECK = 1 };
+enum { SG_UV_CHECKERS = 0, SG_UV_ALIGN_CHECK = 1, SG_UV_IMAGE = 2 };
 enum { SG_MAP_SPHERICAL = 0, SG_MAP_PLANAR = 1, SG_MAP_CYLINDRICAL = 2 };
 
 const char* sg_last_error(void);
@@ -92,6 +92,21 @@ int sg_uv_pattern_new(sg_ctx*, int kind, const float* params, int n_params);
 int sg_texture_map_new(sg_ctx*, int uv_pattern, int mapping);
 /* order Front, Back, Left, Right, Up, Down (uv.rs:229-249) */
 int sg_cubic_map_new(sg_ctx*, const int uv_patterns[6]);
+
+/* ---- canvases as data (canvas.rs) and image textures (uv.rs:346-377) ----
+ * sg_canvas_new: Canvas::new (black) or, with rgb != NULL, width*height*3 f32 pixels row-major.
+ * sg_canvas_from_ppm: canvas_from_ppm (canvas.rs:119-182): P3 text, comment / empty lines skipped, triplets may span
+ *   lines, values divided by the file's scale.  Errors (negative return, sg_last_error()) carry the reference's
+ *   ParseError kind: "IncorrectFormat: ...", "MalformedDimensionHeader: ...", "ParseIntError: ...".
+ * sg_canvas_to_ppm: Canvas::to_ppm (canvas.rs:58-96), byte for byte: "P3", "w h", "255", then rows of 8-bit values
+ *   (truncating scale_color) wrapped at 70 columns.  Returns the length; writes min(length, capacity) bytes.
+ * sg_uv_image_new: UVImage::new(canvas) -> a uv pattern handle for sg_texture_map_new / sg_cubic_map_new. */
+int sg_canvas_new(sg_ctx*, int width, int height, const float* rgb);
+int sg_canvas_from_ppm(sg_ctx*, const char* text, int64_t n_bytes);
+int sg_canvas_size(sg_ctx*, int canvas, int* width, int* height);
+int sg_canvas_pixels(sg_ctx*, int canvas, float* out_rgb);
+int64_t sg_canvas_to_ppm(sg_ctx*, int canvas, char* out, int64_t capacity);
+int sg_uv_image_new(sg_ctx*, int canvas);
 
 /* ---- materials (material.rs:19-51) ----
  * params = {color.r, color.g, color.b, ambient, diffuse, specular, shininess, reflective, transparency,

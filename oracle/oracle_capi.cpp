@@ -31,6 +31,7 @@ static int fail(const std::string& m) {
 struct sg_ctx {
     std::vector<std::shared_ptr<Pattern>> patterns;
     std::vector<std::shared_ptr<UVPattern>> uvs;
+    std::vector<Canvas> canvases;
     std::vector<Material> materials;
     std::vector<std::unique_ptr<Shape>> owned;  // slot is released when a parent takes the shape
     std::vector<Shape*> shapes;                 // handle -> shape (stays valid after adoption)
@@ -116,6 +117,46 @@ int sg_uv_pattern_new(sg_ctx* c, int kind, const float* p, int n) {
     } else {
         return fail("bad uv pattern kind");
     }
+    return (int)c->uvs.size() - 1;
+}
+int sg_canvas_new(sg_ctx* c, int w, int h, const float* rgb) {
+    if (w < 0 || h < 0) return fail("bad canvas size");
+    Canvas cv((size_t)w, (size_t)h);
+    if (rgb)
+        for (size_t i = 0; i < cv.data.size(); i++) cv.data[i] = Color{rgb[3 * i], rgb[3 * i + 1], rgb[3 * i + 2]};
+    c->canvases.push_back(std::move(cv));
+    return (int)c->canvases.size() - 1;
+}
+int sg_canvas_from_ppm(sg_ctx* c, const char* text, int64_t n) {
+    try {
+        c->canvases.push_back(canvas_from_ppm(std::string(text, (size_t)n)));
+    } catch (const std::exception& e) {
+        return fail(e.what());
+    }
+    return (int)c->canvases.size() - 1;
+}
+int sg_canvas_size(sg_ctx* c, int cv, int* w, int* h) {
+    if (cv < 0 || cv >= (int)c->canvases.size()) return fail("bad canvas handle");
+    *w = (int)c->canvases[cv].width, *h = (int)c->canvases[cv].height;
+    return 0;
+}
+int sg_canvas_pixels(sg_ctx* c, int cv, float* out) {
+    if (cv < 0 || cv >= (int)c->canvases.size()) return fail("bad canvas handle");
+    const Canvas& k = c->canvases[cv];
+    for (size_t i = 0; i < k.data.size(); i++) out[3 * i] = k.data[i].r, out[3 * i + 1] = k.data[i].g, out[3 * i + 2] = k.data[i].b;
+    return 0;
+}
+int64_t sg_canvas_to_ppm(sg_ctx* c, int cv, char* out, int64_t capacity) {
+    if (cv < 0 || cv >= (int)c->canvases.size()) return fail("bad canvas handle");
+    std::string ppm = c->canvases[cv].to_ppm();
+    if (out && capacity > 0) memcpy(out, ppm.data(), (size_t)std::min<int64_t>(capacity, (int64_t)ppm.size()));
+    return (int64_t)ppm.size();
+}
+int sg_uv_image_new(sg_ctx* c, int cv) {
+    if (cv < 0 || cv >= (int)c->canvases.size()) return fail("bad canvas handle");
+    auto u = std::make_shared<UVImage>();
+    u->canvas = c->canvases[cv];
+    c->uvs.push_back(u);
     return (int)c->uvs.size() - 1;
 }
 int sg_texture_map_new(sg_ctx* c, int uv, int mapping) {
@@ -703,7 +744,11 @@ int orc_pattern_color_at(sg_ctx* c, int pattern, int shape, const float p[3], fl
 }
 int orc_uv_pattern_color_at(sg_ctx* c, int uv, float u, float v, float out[3]) {
     if (uv < 0 || uv >= (int)c->uvs.size()) return fail("bad uv handle");
-    put3(out, c->uvs[uv]->color_at(u, v));
+    try {
+        put3(out, c->uvs[uv]->color_at(u, v));
+    } catch (const std::exception& e) {  // UVImage outside [0, 1]: the reference panics (canvas.rs:35)
+        return fail(std::string("index out of bounds: ") + e.what());
+    }
     return 0;
 }
 void orc_uv_map(int mapping, const float p[3], float out[2]) {

@@ -19,11 +19,13 @@
 #pragma once
 
 #include <algorithm>
+#include <cctype>
 #include <cmath>
 #include <cstdint>
 #include <cstring>
 #include <limits>
 #include <memory>
+#include <stdexcept>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -333,6 +335,127 @@ inline bool BoundingBox::intersects(const Ray& r) const {
     return aabb_intersection(r, min, max, a, b);
 }
 
+// ---------------------------------------------------------------- canvas.rs
+// Canvas (canvas.rs:5-43), to_ppm (canvas.rs:45-96) and canvas_from_ppm (canvas.rs:119-200), restated line by line:
+// P3 text, lines of at most 70 columns, 8-bit values through the truncating scale_color.
+struct Canvas {
+    size_t width = 0, height = 0;
+    std::vector<Color> data;  // [y][x], black (canvas.rs:19-25)
+    Canvas() = default;
+    Canvas(size_t w, size_t h) : width(w), height(h), data(w * h, Color{0, 0, 0}) {}
+    void write_pixel(size_t x, size_t y, Color c) {  // canvas.rs:26-32 (`<=`: an index equal to the size panics there)
+        if (x < width && y < height) data[y * width + x] = c;
+    }
+    Color pixel_at(size_t x, size_t y) const { return data.at(y * width + x); }  // canvas.rs:34-36 (out of range: panic)
+    static uint8_t scale_color(float rgb) {  // canvas.rs:39-43: f32::min / max return the non-NaN operand; `as u8` saturates
+        float v = rgb * 255.0f;
+        v = (v != v) ? 255.0f : (v < 255.0f ? v : 255.0f);
+        v = v > 0.0f ? v : 0.0f;
+        return (uint8_t)v;
+    }
+    static void write_rgb_separator(std::string& line, std::string& ppm) {  // canvas.rs:47-55
+        if (line.size() < 70 - 3) {
+            line.push_back(' ');
+        } else {
+            ppm += line;
+            ppm.push_back('\n');
+            line.clear();
+        }
+    }
+    std::string to_ppm() const {  // canvas.rs:58-96
+        std::string ppm = "P3\n" + std::to_string(width) + " " + std::to_string(height) + "\n255\n";
+        std::string line;
+        for (size_t row = 0; row < height; row++) {
+            line.clear();
+            for (size_t i = 0; i < width; i++) {
+                Color c = pixel_at(i, row);
+                line += std::to_string((unsigned)scale_color(c.r));
+                write_rgb_separator(line, ppm);
+                line += std::to_string((unsigned)scale_color(c.g));
+                write_rgb_separator(line, ppm);
+                line += std::to_string((unsigned)scale_color(c.b));
+                if (i != width - 1) write_rgb_separator(line, ppm);
+            }
+            if (!line.empty()) {
+                ppm += line;
+                ppm.push_back('\n');
+            }
+        }
+        return ppm;
+    }
+};
+
+struct PpmError : std::runtime_error {
+    using std::runtime_error::runtime_error;
+};
+inline std::string trim_ws(const std::string& s) {
+    size_t a = 0, b = s.size();
+    while (a < b && std::isspace((unsigned char)s[a])) a++;
+    while (b > a && std::isspace((unsigned char)s[b - 1])) b--;
+    return s.substr(a, b - a);
+}
+inline std::vector<std::string> split_ws(const std::string& s) {
+    std::vector<std::string> out;
+    size_t i = 0;
+    while (i < s.size()) {
+        while (i < s.size() && std::isspace((unsigned char)s[i])) i++;
+        size_t j = i;
+        while (j < s.size() && !std::isspace((unsigned char)s[j])) j++;
+        if (j > i) out.push_back(s.substr(i, j - i));
+        i = j;
+    }
+    return out;
+}
+inline uint64_t parse_unsigned(const std::string& s, uint64_t max_value) {  // str::parse::<u32 / usize>: digits, optional '+'
+    size_t i = 0;
+    if (!s.empty() && s[0] == '+') i = 1;
+    if (i >= s.size()) throw PpmError("ParseIntError: cannot parse integer from '" + s + "'");
+    uint64_t v = 0;
+    for (; i < s.size(); i++) {
+        if (s[i] < '0' || s[i] > '9') throw PpmError("ParseIntError: invalid digit found in '" + s + "'");
+        v = v * 10 + (uint64_t)(s[i] - '0');
+        if (v > max_value) throw PpmError("ParseIntError: number too large in '" + s + "'");
+    }
+    return v;
+}
+inline Canvas canvas_from_ppm(const std::string& text) {  // canvas.rs:119-182
+    // BufRead::lines + clean_line (canvas.rs:184-200): trimmed, comment and empty lines dropped
+    std::vector<std::string> lines;
+    size_t pos = 0;
+    while (pos <= text.size()) {
+        size_t nl = text.find('\n', pos);
+        std::string line = text.substr(pos, nl == std::string::npos ? std::string::npos : nl - pos);
+        pos = nl == std::string::npos ? text.size() + 1 : nl + 1;
+        std::string t = trim_ws(line);
+        if (t.empty() || t[0] == '#') continue;
+        lines.push_back(t);
+    }
+    if (lines.size() < 3) throw PpmError("unexpected end of file in the PPM header");  // the reference unwrap()s: a panic
+    if (lines[0] != "P3") throw PpmError("IncorrectFormat: Incorrect magic number at line 1: expected P3, found " + lines[0]);
+    std::vector<std::string> dims = split_ws(lines[1]);
+    if (dims.size() != 2) throw PpmError("MalformedDimensionHeader: Expected width and height at line 2; found " + lines[1]);
+    size_t width = (size_t)parse_unsigned(dims[0], UINT64_MAX / 16), height = (size_t)parse_unsigned(dims[1], UINT64_MAX / 16);
+    float scale = (float)(uint32_t)parse_unsigned(lines[2], 0xffffffffull);
+    Canvas canvas(width, height);
+    std::vector<uint32_t> raw;
+    size_t head = 0, x = 0, y = 0;
+    for (size_t li = 3; li < lines.size(); li++) {
+        for (const std::string& tok : split_ws(lines[li])) raw.push_back((uint32_t)parse_unsigned(tok, 0xffffffffull));
+        while (raw.size() - head >= 3) {
+            float r = (float)raw[head] / scale, g = (float)raw[head + 1] / scale, b = (float)raw[head + 2] / scale;
+            head += 3;
+            if (y >= height && x < width) throw PpmError("more pixel data than width x height");  // data[y][x] panics there
+            canvas.write_pixel(x, y, Color{r, g, b});
+            x += 1;
+            if (x >= width) {
+                x = 0;
+                y += 1;
+            }
+        }
+    }
+    return canvas;
+}
+
 // ---------------------------------------------------------------- pattern/*.rs
 struct Shape;
 
@@ -362,6 +485,24 @@ struct AlignCheck : UVPattern {  // uv.rs:136-176
             if (u > 0.8f) return br;
         }
         return main;
+    }
+};
+
+struct UVImage : UVPattern {  // uv.rs:346-377
+    Canvas canvas;
+    Color color_at(float u, float v) const override {
+        v = 1.0f - v;  // flip v over so it matches the image layout, with y at the top
+        float x = u * (float)(canvas.width - 1);
+        float y = v * (float)(canvas.height - 1);
+        // `x.round() as usize`: half away from zero, saturating (NaN and negatives give 0); an index beyond the canvas
+        // panics in the reference (canvas.rs:35) — here it throws
+        auto index = [](float f) -> size_t {
+            float r = roundf(f);
+            if (!(r > 0.0f)) return 0;
+            if (r >= 1.8446744e19f) return SIZE_MAX;
+            return (size_t)r;
+        };
+        return canvas.pixel_at(index(x), index(y));
     }
 };
 

@@ -104,7 +104,7 @@ class PreparedScene:
             _api.fptr(out_rgb) if want_rgb else None, out_u8.ctypes.data_as(_U8P) if want_u8 else None,
             C.byref(stats)))
         self.last_stats = api.last_rtc_stats()
-        return Canvas(w, h, out_rgb if want_rgb else None, out_u8 if want_u8 else None)
+        return Canvas(w, h, out_rgb if want_rgb else None, out_u8 if want_u8 else None, api=api)
 
     def trace_rays(self, origins, directions, depth=DEFAULT_RAY_RECURSION_DEPTH, fma=False):
         """World::color_at (world.rs:88-101) for arbitrary rays: returns (rgb[n,3], t[n], shape_handle[n])."""

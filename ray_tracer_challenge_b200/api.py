@@ -27,7 +27,7 @@ U8P = C.POINTER(C.c_uint8)
 
 SG_SPHERE, SG_PLANE, SG_CUBE, SG_CYLINDER, SG_CONE, SG_TRIANGLE, SG_SMOOTH_TRIANGLE, SG_GROUP, SG_CSG, SG_TEST_SHAPE = range(10)
 SG_PAT_STRIPES, SG_PAT_GRADIENT, SG_PAT_RINGS, SG_PAT_CHECKERS, SG_PAT_SINE2D, SG_PAT_TEST = range(6)
-SG_UV_CHECKERS, SG_UV_ALIGN_CHECK = 0, 1
+SG_UV_CHECKERS, SG_UV_ALIGN_CHECK, SG_UV_IMAGE = 0, 1, 2
 SG_MAP_SPHERICAL, SG_MAP_PLANAR, SG_MAP_CYLINDRICAL = 0, 1, 2
 
 
@@ -69,6 +69,12 @@ _SIGNATURES = {
     "sg_pattern_set_transform": (C.c_int, [C.c_void_p, C.c_int, FP]),
     "sg_uv_pattern_new": (C.c_int, [C.c_void_p, C.c_int, FP, C.c_int]),
     "sg_texture_map_new": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "sg_canvas_new": (C.c_int, [C.c_void_p, C.c_int, C.c_int, FP]),
+    "sg_canvas_from_ppm": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int64]),
+    "sg_canvas_size": (C.c_int, [C.c_void_p, C.c_int, IP, IP]),
+    "sg_canvas_pixels": (C.c_int, [C.c_void_p, C.c_int, FP]),
+    "sg_canvas_to_ppm": (C.c_int64, [C.c_void_p, C.c_int, C.c_char_p, C.c_int64]),
+    "sg_uv_image_new": (C.c_int, [C.c_void_p, C.c_int]),
     "sg_cubic_map_new": (C.c_int, [C.c_void_p, IP]),
     "sg_material_new": (C.c_int, [C.c_void_p, FP, C.c_int]),
     "sg_shape_new": (C.c_int, [C.c_void_p, C.c_int]),
@@ -189,10 +195,15 @@ class RectangleLight:
 class Canvas:
     """canvas.rs:6-43 — f32 RGB framebuffer, row-major [y][x]."""
 
-    def __init__(self, width: int, height: int, data: Optional[np.ndarray] = None, u8: Optional[np.ndarray] = None):
+    def __init__(self, width: int, height: int, data: Optional[np.ndarray] = None, u8: Optional[np.ndarray] = None, api=None):
         self.width, self.height = width, height
         self.data = data if data is not None else np.zeros((height, width, 3), np.float32)
         self._u8 = u8
+        self.api = api  # the native library that serialises this canvas (to_ppm) and binds it to UVImage
+
+    def write_pixel(self, x: int, y: int, color):
+        self.data[y, x] = color
+        self._u8 = None
 
     def pixel_at(self, x: int, y: int):
         return tuple(float(v) for v in self.data[y, x])
@@ -204,7 +215,10 @@ class Canvas:
         return self._u8
 
     def to_ppm(self) -> str:
-        """canvas.rs:58-96 (P3, 70-column wrap) — host-side serialisation, outside the hot path."""
+        """canvas.rs:58-96 (P3, 70-column wrap): the native writer of the library this canvas came from, or, for a
+        canvas with no library behind it, the pure-Python spelling below."""
+        if self.api is not None:
+            return self.api.canvas_to_ppm(self)
         u8 = self.to_u8()
         out = [f"P3\n{self.width} {self.height}\n255\n"]
         for row in u8.reshape(self.height, self.width * 3):
@@ -335,7 +349,15 @@ class Api:
                 ids = (C.c_int * 6)(*[p.handle for p in (front, back, left, right, up, down)])
                 self.handle = api.check(api.lib.sg_cubic_map_new(api.ctx, ids))
 
+        class UVImage:
+            """uv.rs:346-377 — `canvas` is an api.Canvas (its f32 pixels are handed to the library)."""
+
+            def __init__(self, canvas):
+                self.canvas_handle = api.native_canvas(canvas)
+                self.handle = api.check(api.lib.sg_uv_image_new(api.ctx, self.canvas_handle))
+
         self.UVCheckers, self.AlignCheck, self.TextureMap, self.CubicMap = UVCheckers, AlignCheck, TextureMap, CubicMap
+        self.UVImage = UVImage
 
         # ---------------------------------------------------------------- shapes
         class Shape:
@@ -538,7 +560,7 @@ class Api:
                     api.ctx, self.handle, world.handle, int(reflection_recursion_depth), fptr(rgb),
                     u8.ctypes.data_as(U8P) if u8 is not None else None, C.byref(stats)))
                 self.last_stats = stats
-                return Canvas(w, h, rgb, u8)
+                return Canvas(w, h, rgb, u8, api=api)
 
         self.World, self.Camera = World, Camera
         self.Material, self.PointLight, self.RectangleLight, self.Canvas = Material, PointLight, RectangleLight, Canvas
@@ -548,6 +570,35 @@ class Api:
         if rc < 0:
             raise RtcError(self.lib.sg_last_error().decode())
         return rc
+
+    # ---- canvases as data: canvas.rs:58-200
+    def native_canvas(self, canvas) -> int:
+        """Hand an api.Canvas's f32 pixels to the library (sg_canvas_new); returns the native handle."""
+        data = np.ascontiguousarray(canvas.data, dtype=np.float32)
+        return self.check(self.lib.sg_canvas_new(self.ctx, int(canvas.width), int(canvas.height), fptr(data)))
+
+    def canvas_from_ppm(self, text) -> "Canvas":
+        """canvas_from_ppm (canvas.rs:119-182).  Raises RtcError carrying the reference's ParseError kind."""
+        raw = text.encode() if isinstance(text, str) else bytes(text)
+        h = self.check(self.lib.sg_canvas_from_ppm(self.ctx, raw, len(raw)))
+        w, ht = C.c_int(), C.c_int()
+        self.check(self.lib.sg_canvas_size(self.ctx, h, C.byref(w), C.byref(ht)))
+        data = np.zeros((ht.value, w.value, 3), np.float32)
+        if data.size:
+            self.check(self.lib.sg_canvas_pixels(self.ctx, h, fptr(data)))
+        return Canvas(w.value, ht.value, data, api=self)
+
+    def canvas_to_ppm(self, canvas) -> str:
+        """Canvas::to_ppm (canvas.rs:58-96) by the library's native writer."""
+        h = self.native_canvas(canvas)
+        n = self.check(self.lib.sg_canvas_to_ppm(self.ctx, h, None, 0))
+        buf = C.create_string_buffer(int(n))
+        self.check(self.lib.sg_canvas_to_ppm(self.ctx, h, buf, n))
+        return buf.raw[:n].decode("ascii")
+
+    def new_canvas(self, width: int, height: int) -> "Canvas":
+        """Canvas::new (canvas.rs:19-25): black."""
+        return Canvas(width, height, api=self)
 
     def material_handle(self, m: Material) -> int:
         p = m.params()

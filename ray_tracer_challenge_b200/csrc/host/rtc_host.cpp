@@ -217,6 +217,44 @@ int sg_uv_pattern_new(sg_ctx* c, int kind, const float* params, int n) {
     c->graph.uvs.push_back(u);
     return (int)c->graph.uvs.size() - 1;
 }
+int sg_canvas_new(sg_ctx* c, int w, int h, const float* rgb) {
+    if (w < 0 || h < 0) return fail("bad canvas size");
+    CanvasRec cv;
+    cv.width = w, cv.height = h;
+    cv.rgb.assign((size_t)w * h * 3, 0.0f);  // Canvas::new: black (canvas.rs:19-25)
+    if (rgb) memcpy(cv.rgb.data(), rgb, cv.rgb.size() * sizeof(float));
+    c->graph.canvases.push_back(std::move(cv));
+    return (int)c->graph.canvases.size() - 1;
+}
+int sg_canvas_from_ppm(sg_ctx* c, const char* text, int64_t n) {
+    SG_GUARD(c->graph.canvases.push_back(canvas_from_ppm(text, (size_t)n)); return (int)c->graph.canvases.size() - 1;)
+}
+int sg_canvas_size(sg_ctx* c, int cv, int* w, int* h) {
+    if (cv < 0 || cv >= (int)c->graph.canvases.size()) return fail("bad canvas handle");
+    *w = c->graph.canvases[cv].width, *h = c->graph.canvases[cv].height;
+    return 0;
+}
+int sg_canvas_pixels(sg_ctx* c, int cv, float* out) {
+    if (cv < 0 || cv >= (int)c->graph.canvases.size()) return fail("bad canvas handle");
+    const CanvasRec& k = c->graph.canvases[cv];
+    memcpy(out, k.rgb.data(), k.rgb.size() * sizeof(float));
+    return 0;
+}
+int64_t sg_canvas_to_ppm(sg_ctx* c, int cv, char* out, int64_t capacity) {
+    if (cv < 0 || cv >= (int)c->graph.canvases.size()) return fail("bad canvas handle");
+    SG_GUARD(std::string ppm = canvas_to_ppm(c->graph.canvases[cv]);
+             if (out && capacity > 0) memcpy(out, ppm.data(), (size_t)std::min<int64_t>(capacity, (int64_t)ppm.size()));
+             return (int64_t)ppm.size();)
+}
+int sg_uv_image_new(sg_ctx* c, int cv) {
+    if (cv < 0 || cv >= (int)c->graph.canvases.size()) return fail("bad canvas handle");
+    if (c->graph.canvases[cv].width < 1 || c->graph.canvases[cv].height < 1) return fail("UVImage needs a non-empty canvas");
+    UvPattern u;
+    u.kind = SG_UV_IMAGE;
+    u.canvas = cv;
+    c->graph.uvs.push_back(u);
+    return (int)c->graph.uvs.size() - 1;
+}
 int sg_texture_map_new(sg_ctx* c, int uv, int mapping) {
     if (uv < 0 || uv >= (int)c->graph.uvs.size()) return fail("bad uv handle");
     if (mapping < 0 || mapping > 2) return fail("bad mapping");

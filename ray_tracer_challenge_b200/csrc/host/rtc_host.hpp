@@ -205,6 +205,11 @@ struct Pattern {  // pattern/*.rs
 struct UvPattern {
     int kind = 0;
     float params[15] = {0};
+    int canvas = -1;  // UVImage (uv.rs:346-377): the canvas handle
+};
+struct CanvasRec {  // canvas.rs:6-10 as data: width * height * 3 f32, row-major, row 0 at the top
+    int width = 0, height = 0;
+    std::vector<float> rgb;
 };
 struct Material {  // material.rs:19-51
     float color[3] = {1, 1, 1};
@@ -243,6 +248,7 @@ class SceneGraph {
     std::vector<ShapeRec> shapes;
     std::vector<Pattern> patterns;
     std::vector<UvPattern> uvs;
+    std::vector<CanvasRec> canvases;
 
     int add(int kind) {
         ShapeRec s;
@@ -452,6 +458,126 @@ inline Light rectangle_light(const float intensity[3], const float corner[3], co
 // ------------------------------------------------------------------------------------------- flattener
 // World -> the POD arrays of include/rtc_b200.h.  Leaves are emitted in depth-first order of
 // World::objects / children / (s1, s2): the reference's emission order, hence its tie-break order.
+// ------------------------------------------------------------------------------------------- PPM (canvas.rs)
+// Canvas::to_ppm (canvas.rs:58-96), byte for byte, written for speed: one pass over the pixels, a 256-entry table of
+// decimal strings, the output reserved up front.  The reference's rule after every value but a row's last: append a
+// space if the line is shorter than 70 - 3 columns, else end the line (canvas.rs:47-55); rows end their line.
+inline unsigned char scale_color(float rgb) {  // canvas.rs:39-43: f32::min / max keep the non-NaN operand, `as u8` truncates
+    float v = rgb * 255.0f;
+    v = (v != v) ? 255.0f : (v < 255.0f ? v : 255.0f);
+    v = v > 0.0f ? v : 0.0f;
+    return (unsigned char)v;
+}
+inline std::string canvas_to_ppm(const CanvasRec& c) {
+    static const struct Table {
+        char text[256][4];
+        unsigned char len[256];
+        Table() {
+            for (int v = 0; v < 256; v++) len[v] = (unsigned char)snprintf(text[v], 4, "%d", v);
+        }
+    } table;
+    std::string out = "P3\n" + std::to_string(c.width) + " " + std::to_string(c.height) + "\n255\n";
+    out.reserve(out.size() + (size_t)c.width * c.height * 12 + 16);
+    const size_t n = (size_t)c.width * 3;
+    for (int row = 0; row < c.height; row++) {
+        const float* px = c.rgb.data() + (size_t)row * n;
+        size_t line = 0;
+        for (size_t i = 0; i < n; i++) {
+            const unsigned v = scale_color(px[i]);
+            out.append(table.text[v], table.len[v]);
+            line += table.len[v];
+            if (i + 1 == n) break;
+            if (line < 70 - 3) {
+                out.push_back(' ');
+                line++;
+            } else {
+                out.push_back('\n');
+                line = 0;
+            }
+        }
+        if (line) out.push_back('\n');
+    }
+    return out;
+}
+
+// canvas_from_ppm (canvas.rs:119-182) + clean_line (184-200).  Error texts start with the reference's ParseError kind.
+inline CanvasRec canvas_from_ppm(const char* text, size_t n) {
+    auto is_space = [](char ch) { return ch == ' ' || (ch >= '\t' && ch <= '\r'); };
+    size_t pos = 0;
+    // next line that is neither empty nor a comment, trimmed: [a, b)
+    auto next_line = [&](size_t& a, size_t& b) {
+        while (pos <= n) {
+            size_t end = pos;
+            while (end < n && text[end] != '\n') end++;
+            a = pos, b = end;
+            pos = end + 1;
+            while (a < b && is_space(text[a])) a++;
+            while (b > a && is_space(text[b - 1])) b--;
+            if (a < b && text[a] != '#') return true;
+            if (end >= n) break;
+        }
+        return false;
+    };
+    auto parse = [&](size_t a, size_t b, uint64_t limit) -> uint64_t {  // str::parse::<u32 / usize>
+        const std::string tok(text + a, b - a);
+        size_t i = a;
+        if (i < b && text[i] == '+') i++;
+        if (i >= b) throw Error("ParseIntError: cannot parse integer from '" + tok + "'");
+        uint64_t v = 0;
+        for (; i < b; i++) {
+            if (text[i] < '0' || text[i] > '9') throw Error("ParseIntError: invalid digit found in '" + tok + "'");
+            v = v * 10 + (uint64_t)(text[i] - '0');
+            if (v > limit) throw Error("ParseIntError: number too large in '" + tok + "'");
+        }
+        return v;
+    };
+    size_t a, b;
+    if (!next_line(a, b)) throw Error("unexpected end of file in the PPM header");
+    if (!(b - a == 2 && text[a] == 'P' && text[a + 1] == '3'))
+        throw Error("IncorrectFormat: Incorrect magic number at line 1: expected P3, found " + std::string(text + a, b - a));
+    if (!next_line(a, b)) throw Error("unexpected end of file in the PPM header");
+    size_t tok[3][2];
+    int n_tok = 0;
+    for (size_t i = a; i < b;) {
+        while (i < b && is_space(text[i])) i++;
+        size_t j = i;
+        while (j < b && !is_space(text[j])) j++;
+        if (j > i) {
+            if (n_tok < 3) tok[n_tok][0] = i, tok[n_tok][1] = j;
+            n_tok++;
+        }
+        i = j;
+    }
+    if (n_tok != 2)
+        throw Error("MalformedDimensionHeader: Expected width and height at line 2; found " + std::string(text + a, b - a));
+    CanvasRec c;
+    c.width = (int)parse(tok[0][0], tok[0][1], 1u << 30);
+    c.height = (int)parse(tok[1][0], tok[1][1], 1u << 30);
+    if (!next_line(a, b)) throw Error("unexpected end of file in the PPM header");
+    const float scale = (float)(uint32_t)parse(a, b, 0xffffffffull);
+    const size_t total = (size_t)c.width * c.height * 3;
+    c.rgb.assign(total, 0.0f);
+    size_t count = 0;  // values consumed; a pixel is written when its third value arrives (canvas.rs:163-176)
+    float pending[3];
+    while (next_line(a, b)) {
+        for (size_t i = a; i < b;) {
+            while (i < b && is_space(text[i])) i++;
+            size_t j = i;
+            while (j < b && !is_space(text[j])) j++;
+            if (j > i) {
+                pending[count % 3] = (float)(uint32_t)parse(i, j, 0xffffffffull) / scale;
+                count++;
+                if (count % 3 == 0) {
+                    if (count > total) throw Error("more pixel data than width x height");  // data[y][x] panics there
+                    memcpy(&c.rgb[count - 3], pending, sizeof(pending));
+                }
+            }
+            i = j;
+        }
+    }
+    return c;
+}
+
 struct FlatScene {
     std::vector<RtcPrim> prims;
     std::vector<RtcNode> nodes;
@@ -459,6 +585,7 @@ struct FlatScene {
     std::vector<RtcMaterial> materials;
     std::vector<RtcPattern> patterns;
     std::vector<RtcUvPattern> uvs;
+    std::vector<RtcTexture> textures;  // point into the scene graph's canvases
     std::vector<int> prim_shape;  // primitive index -> shape handle
 };
 
@@ -473,7 +600,7 @@ class Flattener {
     SceneGraph& g_;
     FlatScene& out_;
     std::map<std::vector<uint32_t>, int> material_ids_;
-    std::map<int, int> pattern_ids_, uv_ids_;
+    std::map<int, int> pattern_ids_, uv_ids_, texture_ids_;
 
     int uv_index(int h) {
         if (h < 0 || h >= (int)g_.uvs.size()) throw Error("bad uv pattern handle");
@@ -482,6 +609,16 @@ class Flattener {
         RtcUvPattern u;
         u.kind = g_.uvs[h].kind;
         memcpy(u.params, g_.uvs[h].params, sizeof(u.params));
+        if (u.kind == RTC_UV_IMAGE) {  // the canvas travels once, however many patterns share it
+            const int cv = g_.uvs[h].canvas;
+            auto t = texture_ids_.find(cv);
+            if (t == texture_ids_.end()) {
+                const CanvasRec& c = g_.canvases.at(cv);
+                out_.textures.push_back(RtcTexture{(uint32_t)c.width, (uint32_t)c.height, c.rgb.data()});
+                t = texture_ids_.emplace(cv, (int)out_.textures.size() - 1).first;
+            }
+            u.params[0] = (float)t->second;
+        }
         out_.uvs.push_back(u);
         return uv_ids_[h] = (int)out_.uvs.size() - 1;
     }
@@ -598,6 +735,7 @@ inline void fill_scene(RtcScene* scene, SceneGraph& g, const World& w, const Cam
     ck(rtc_set_nodes(scene, (uint32_t)flat.nodes.size(), flat.nodes.data(), (uint32_t)flat.refs.size(), flat.refs.data()));
     ck(rtc_set_materials(scene, (uint32_t)flat.materials.size(), flat.materials.data()));
     ck(rtc_set_patterns(scene, (uint32_t)flat.patterns.size(), flat.patterns.data(), (uint32_t)flat.uvs.size(), flat.uvs.data()));
+    ck(rtc_set_textures(scene, (uint32_t)flat.textures.size(), flat.textures.data()));
     const Light& l = w.light;
     if (l.rect)
         ck(rtc_set_rect_light(scene, l.intensity, l.corner, l.u_cell, l.u_steps, l.v_cell, l.v_steps, l.position,

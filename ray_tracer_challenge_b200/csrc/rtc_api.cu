@@ -180,6 +180,11 @@ struct RtcScene {
     std::vector<RtcMaterial> materials;
     std::vector<RtcPattern> patterns;
     std::vector<RtcUvPattern> uvs;
+    struct Texture {
+        uint32_t width, height;
+        std::vector<float> rgb;
+    };
+    std::vector<Texture> textures;
     bool light_is_rect = false;
     float light_pos[3], light_rgb[3], corner[3], u_cell[3], v_cell[3];
     int u_steps = 1, v_steps = 1;
@@ -348,6 +353,7 @@ struct Flattened {
     std::vector<DevMaterial> materials;
     std::vector<DevPattern> patterns;
     std::vector<DevUvPattern> uvs;
+    std::vector<float4> texels;
     std::vector<float4> samples;
     SmallScene small{};
     int bvh_root = -1;
@@ -619,10 +625,24 @@ int flatten(RtcScene* s, Flattened& f) {
         memcpy(d.uv, p.uv, sizeof(d.uv));
         f.patterns.push_back(d);
     }
+    std::vector<size_t> texel_base;
+    for (const RtcScene::Texture& t : s->textures) {
+        texel_base.push_back(f.texels.size());
+        for (size_t i = 0; i < (size_t)t.width * t.height; i++)
+            f.texels.push_back(make_float4(t.rgb[3 * i], t.rgb[3 * i + 1], t.rgb[3 * i + 2], 0.f));
+    }
+    if (f.texels.size() >= (1u << 30)) return fail(RTC_ERR_CAPACITY, "image textures exceed 2^30 pixels");
     for (const RtcUvPattern& u : s->uvs) {
         DevUvPattern d{};
         d.kind = u.kind;
         memcpy(d.p, u.params, sizeof(d.p));
+        if (u.kind == RTC_UV_IMAGE) {  // {first texel, width, height} as integers
+            const int t = (int)u.params[0];
+            if (t < 0 || t >= (int)s->textures.size() || (float)t != u.params[0]) return fail(RTC_ERR_INVALID, "uv image: bad texture index");
+            const int base = (int)texel_base[t], w = (int)s->textures[t].width, h = (int)s->textures[t].height;
+            if (w < 1 || h < 1) return fail(RTC_ERR_INVALID, "uv image: empty canvas");
+            memcpy(&d.p[0], &base, 4), memcpy(&d.p[1], &w, 4), memcpy(&d.p[2], &h, 4);
+        }
         f.uvs.push_back(d);
     }
     // ---- table-mode light samples: point_on_light (rectangle_light.rs:60-66) is the same for every shade
@@ -778,7 +798,7 @@ int upload_replica(RtcScene* s, const Flattened& f, Replica& r, int device) {
     size_t o_jitter = w.add(s->jitter), o_samples = w.add(f.samples), o_head = w.add(f.head), o_rec = w.add(f.rec);
     size_t o_xform = w.add(f.xform), o_tri = w.add(f.tri), o_bound = w.add(f.bound), o_bvh = w.add(f.bvh);
     size_t o_linear = w.add(f.linear), o_nodes = w.add(f.nodes), o_ops = w.add(f.ops), o_mat = w.add(f.materials);
-    size_t o_pat = w.add(f.patterns), o_uv = w.add(f.uvs);
+    size_t o_pat = w.add(f.patterns), o_uv = w.add(f.uvs), o_tex = w.add(f.texels);
     if ((rc = ensure_arena(slot, std::max<size_t>(w.bytes, 256)))) return rc;
     for (const auto& p : w.parts) memcpy(slot->staging + p.off, p.src, p.n);
     if (w.bytes) CUDA_TRY(cudaMemcpyAsync(slot->arena, slot->staging, w.bytes, cudaMemcpyHostToDevice, slot->stream));
@@ -797,6 +817,7 @@ int upload_replica(RtcScene* s, const Flattened& f, Replica& r, int device) {
     d.materials = (const DevMaterial*)at(o_mat, !f.materials.empty());
     d.patterns = (const DevPattern*)at(o_pat, !f.patterns.empty());
     d.uvs = (const DevUvPattern*)at(o_uv, !f.uvs.empty());
+    d.texels = (const float4*)at(o_tex, !f.texels.empty());
     d.n_linear = (int)f.linear.size();
     d.bvh_root = f.bvh_root;
     d.n_prims = f.n_pos;
@@ -1033,6 +1054,19 @@ int rtc_set_patterns(RtcScene* s, uint32_t n, const RtcPattern* p, uint32_t n_uv
     if (!s || (n && !p) || (n_uv && !uv)) return fail(RTC_ERR_INVALID, "null argument");
     s->patterns.assign(p, p + n);
     s->uvs.assign(uv, uv + n_uv);
+    s->committed = false;
+    return 0;
+}
+int rtc_set_textures(RtcScene* s, uint32_t n, const RtcTexture* t) {
+    if (!s || (n && !t)) return fail(RTC_ERR_INVALID, "null argument");
+    s->textures.clear();
+    for (uint32_t i = 0; i < n; i++) {
+        if (!t[i].rgb && t[i].width * t[i].height) return fail(RTC_ERR_INVALID, "texture without pixels");
+        RtcScene::Texture x;
+        x.width = t[i].width, x.height = t[i].height;
+        x.rgb.assign(t[i].rgb, t[i].rgb + (size_t)t[i].width * t[i].height * 3);
+        s->textures.push_back(std::move(x));
+    }
     s->committed = false;
     return 0;
 }

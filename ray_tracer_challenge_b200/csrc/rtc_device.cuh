@@ -734,6 +734,17 @@ __device__ __forceinline__ V3 uv_color(const DevScene& S, int id, float u, float
         int s = (int)((unsigned)u2 + (unsigned)v2);
         return (s % 2 == 0) ? ld3(p.p + 2) : ld3(p.p + 5);
     }
+    if (p.kind == 2) {  // UVImage, uv.rs:366-377: nearest pixel, v flipped (row 0 is the top of the image)
+        const int w = __float_as_int(p.p[1]), h = __float_as_int(p.p[2]);
+        const float x = u * (float)(w - 1);
+        const float y = (1.f - v) * (float)(h - 1);
+        // `x.round() as usize`: half away from zero; the cast saturates and maps NaN to 0.  Beyond the canvas the
+        // reference panics (canvas.rs:35); the device clamps to the edge.
+        const int xi = min(max(__float2int_rz(roundf(x)), 0), w - 1);
+        const int yi = min(max(__float2int_rz(roundf(y)), 0), h - 1);
+        const float4 t = __ldg(&S.texels[(size_t)__float_as_int(p.p[0]) + (size_t)yi * w + xi]);
+        return mk(t.x, t.y, t.z);
+    }
     // AlignCheck, uv.rs:155-176
     if (v > 0.8f) {
         if (u < 0.2f) return ld3(p.p + 3);

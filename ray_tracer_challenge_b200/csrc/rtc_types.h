@@ -105,6 +105,7 @@ struct DevScene {
     const DevMaterial* materials;
     const DevPattern* patterns;
     const DevUvPattern* uvs;
+    const float4* texels;  // image textures, one float4 {r, g, b, 0} per pixel, all canvases back to back
     int all_cast_shadow;  // every primitive casts a shadow: shadow rays may stop at the first hit
 };
 

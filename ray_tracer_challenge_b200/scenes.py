@@ -5,6 +5,7 @@ Parameters are transcribed from the reference's demos:
   soft_shadows      demos/src/bin/soft_shadows.rs:33-169      (BASELINE configs 1 and 3)
   reflect_refract   demos/src/bin/reflect_refract.rs:35-178   (config 2)
   hexagons          demos/src/bin/hexagons.rs:33-103
+  textured          first_textures.rs / skybox.rs in miniature (UVImage over every mapping, synthetic PPMs)
   filter_zoo        parity scene for the shadow filter (spheres / planes / axis-aligned cubes, area light)
   dragon_element    demos/src/bin/here_be_dragons.rs:242-338  (config 4, with a synthetic OBJ: lib/resources
                     holds no mesh besides test/triangles.obj)
@@ -90,6 +91,53 @@ def filter_zoo(rt, width=320, height=200, area_light=True, jitter=None, seed=11)
     ghost.set_casts_shadow(False)
     world = rt.World([floor, wall, ball, egg, sheared, disc, touching, box, slab, shade, ghost], light)
     camera = rt.Camera(width, height, PI / 3.0, rt.view_transform((0.5, 2.5, -7.0), (0, 1.0, 0), (0, 1, 0)))
+    return camera, world
+
+
+def synthetic_ppm(width=48, height=32, seed=5, scale=255):
+    """A deterministic P3 image (colour ramps + a checker overlay + a comment line and wrapped rows), as text."""
+    rows, state = [f"P3\n# synthetic texture {width}x{height}\n{width} {height}\n{scale}"], seed
+    for y in range(height):
+        vals = []
+        for x in range(width):
+            state = (state * 1103515245 + 12345) & 0x7FFFFFFF
+            check = ((x // 4) + (y // 4)) % 2
+            r = (x * scale) // max(width - 1, 1)
+            g = (y * scale) // max(height - 1, 1)
+            b = (scale if check else scale // 4) - (state % (scale // 8 + 1))
+            vals += [r, g, max(b, 0)]
+        cut = len(vals) // 2 + 1  # not a multiple of 3: triplets span lines (canvas.rs ppm_parsing_allows_rgb_triplet_to_span_lines)
+        rows.append(" ".join(str(v) for v in vals[:cut]) + "\n  " + " ".join(str(v) for v in vals[cut:]))
+    return "\n".join(rows) + "\n"
+
+
+def textured(rt, width=320, height=200):
+    """first_textures.rs:34-171 / skybox.rs:26-129 in miniature, with synthetic PPMs instead of the external image
+    files: UVImage (uv.rs:346-377) through the spherical, planar and cylindrical mappings and a six-image cube map."""
+    from .api import SG_MAP_CYLINDRICAL, SG_MAP_PLANAR, SG_MAP_SPHERICAL
+
+    earth = rt.UVImage(rt.canvas_from_ppm(synthetic_ppm(64, 32, seed=1)))
+    tiles = rt.UVImage(rt.canvas_from_ppm(synthetic_ppm(16, 16, seed=2, scale=100)))
+    label = rt.UVImage(rt.canvas_from_ppm(synthetic_ppm(40, 20, seed=3)))
+    faces = [rt.UVImage(rt.canvas_from_ppm(synthetic_ppm(24, 24, seed=10 + i))) for i in range(6)]
+    floor_map = rt.TextureMap(tiles, SG_MAP_PLANAR)
+    floor = rt.Plane.build(rt.identity_4x4(), Material(pattern=floor_map, specular=0.0, reflective=0.2))
+    globe_map = rt.TextureMap(earth, SG_MAP_SPHERICAL)
+    globe_map.set_transformation(rt.rotation_y(1.9))
+    globe = rt.Sphere.build(rt.translation(0.0, 1.1, 0.0) * rt.rotation_z(0.3), Material(pattern=globe_map, diffuse=0.9, specular=0.1, shininess=10.0))
+    can_map = rt.TextureMap(label, SG_MAP_CYLINDRICAL)
+    can_map.set_transformation(rt.scaling(1.0, 1.0 / PI, 1.0))
+    can = rt.Cylinder()
+    can.minimum_y, can.maximum_y, can.closed = 0.0, 1.0, True
+    can.set_transformation(rt.translation(-2.4, 0.0, 0.5) * rt.scaling(0.6, 1.6, 0.6))
+    can.set_material(Material(pattern=can_map, specular=0.6, shininess=15.0))
+    box = rt.Cube.build(rt.translation(2.4, 0.8, 0.3) * rt.rotation_y(0.6) * rt.rotation_x(0.3) * rt.scaling(0.8, 0.8, 0.8),
+                        Material(pattern=rt.CubicMap(*faces), specular=0.0))
+    sky = rt.Cube.build(rt.scaling(50.0, 50.0, 50.0),
+                        Material(pattern=rt.CubicMap(*faces), diffuse=0.0, specular=0.0, ambient=1.0))
+    sky.set_casts_shadow(False)
+    world = rt.World([floor, globe, can, box, sky], PointLight((-5.0, 8.0, -6.0), (1, 1, 1)))
+    camera = rt.Camera(width, height, PI / 3.0, rt.view_transform((0.0, 2.2, -6.5), (0, 0.9, 0), (0, 1, 0)))
     return camera, world
 
 

@@ -168,3 +168,30 @@ def test_patterns_on_gpu_match_golden_tables(gpu):
     rgb, t, _ = p.trace_rays(origins, dirs, 0)
     p.release()
     assert_abs_diff_eq(rgb, np.asarray(expected, np.float32), epsilon=0)
+
+
+def test_uv_image_on_gpu_matches_golden_table(gpu, oracle):
+    """uv.rs:640-672 (uv_mapping_an_image) on the device: a planar-mapped UVImage on an ambient-only plane, probed at
+    the table's (u, v) — planar map: u = x mod 1, v = z mod 1 (uv.rs:97-103) — plus a dense sweep against the oracle."""
+    from tests.test_canvas_ppm import UV_IMAGE_PPM
+    from ray_tracer_challenge_b200.api import SG_MAP_PLANAR
+
+    def build(rt):
+        pattern = rt.TextureMap(rt.UVImage(rt.canvas_from_ppm(UV_IMAGE_PPM)), SG_MAP_PLANAR)
+        plane = rt.Plane.build(rt.identity_4x4(), rt.Material(pattern=pattern, ambient=1.0, diffuse=0.0, specular=0.0))
+        return rt.World([plane], rt.PointLight((0, 100, 0), (1, 1, 1)))
+
+    gw, ow = build(gpu), build(oracle)
+    cam = gpu.Camera(4, 4, PI / 2, gpu.identity_4x4())
+    p = cam.prepare(gw)
+    table = [(0.0, 0.0, 0.9), (0.3, 0.0, 0.2), (0.6, 0.3, 0.1)]  # (1, 1) is the same texel as (0, 0) after `mod 1`
+    origins = [(u, 1.0, v) for u, v, _ in table]
+    rgb, _, _ = p.trace_rays(origins, [(0, -1, 0)] * len(origins), 0)
+    assert_abs_diff_eq(rgb, np.asarray([[c, c, c] for _, _, c in table], np.float32), epsilon=0)
+    rng = np.random.default_rng(3)
+    pts = rng.uniform(-3, 3, size=(500, 2)).astype(np.float32)
+    origins = [(float(x), 2.0, float(z)) for x, z in pts]
+    rgb, _, _ = p.trace_rays(origins, [(0, -1, 0)] * len(origins), 0)
+    want = np.asarray([oracle.probe.color_at(ow, o, (0, -1, 0), 0) for o in origins], np.float32)
+    p.release()
+    assert_abs_diff_eq(rgb, want, epsilon=0)

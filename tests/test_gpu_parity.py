@@ -24,6 +24,7 @@ SCENES = {
     "csg_gallery": (scenes.csg_gallery, dict(width=320, height=200)),
     "dragon_element": (scenes.dragon_element, dict(width=240, height=135, n_u=32, n_v=16)),
     "dragon_smooth_nodivide": (scenes.dragon_element, dict(width=160, height=90, n_u=16, n_v=8, divide=0, smooth=True)),
+    "textured": (scenes.textured, dict(width=320, height=200)),
     "filter_zoo_area": (scenes.filter_zoo, dict(width=320, height=200)),
     "filter_zoo_table": (scenes.filter_zoo, dict(width=200, height=120, jitter="table")),
     "filter_zoo_point": (scenes.filter_zoo, dict(width=320, height=200, area_light=False)),
