@@ -85,6 +85,15 @@ pub struct RtcUvPattern {
     pub params: [f32; 15],
 }
 
+/// The Canvas behind a UVImage (canvas.rs:6-10): width * height * 3 f32, row-major, row 0 at the top.
+#[repr(C)]
+#[derive(Clone, Copy)]
+pub struct RtcTexture {
+    pub width: u32,
+    pub height: u32,
+    pub rgb: *const f32,
+}
+
 #[repr(C)]
 #[derive(Clone, Copy, Default)]
 pub struct RtcStats {
@@ -120,6 +129,7 @@ extern "C" {
     pub fn rtc_set_nodes(scene: *mut RtcScene, n_nodes: u32, nodes: *const RtcNode, n_refs: u32, refs: *const i32) -> c_int;
     pub fn rtc_set_materials(scene: *mut RtcScene, n: u32, materials: *const RtcMaterial) -> c_int;
     pub fn rtc_set_patterns(scene: *mut RtcScene, n: u32, patterns: *const RtcPattern, n_uv: u32, uv: *const RtcUvPattern) -> c_int;
+    pub fn rtc_set_textures(scene: *mut RtcScene, n: u32, textures: *const RtcTexture) -> c_int;
     pub fn rtc_set_point_light(scene: *mut RtcScene, position: *const f32, intensity: *const f32) -> c_int;
     pub fn rtc_set_rect_light(scene: *mut RtcScene, intensity: *const f32, corner: *const f32, u_cell: *const f32,
                               u_steps: i32, v_cell: *const f32, v_steps: i32, position: *const f32,
