@@ -5,6 +5,8 @@ Parameters are transcribed from the reference's demos:
   soft_shadows      demos/src/bin/soft_shadows.rs:33-169      (BASELINE configs 1 and 3)
   reflect_refract   demos/src/bin/reflect_refract.rs:35-178   (config 2)
   hexagons          demos/src/bin/hexagons.rs:33-103
+  first_scene / first_plane / first_patterns / first_textures / skybox / here_be_dragons
+                    the remaining camera demos of demos/src/bin/ (external image / mesh files replaced by synthetic ones)
   textured          first_textures.rs / skybox.rs in miniature (UVImage over every mapping, synthetic PPMs)
   filter_zoo        parity scene for the shadow filter (spheres / planes / axis-aligned cubes, area light)
   dragon_element    demos/src/bin/here_be_dragons.rs:242-338  (config 4, with a synthetic OBJ: lib/resources
@@ -91,6 +93,121 @@ def filter_zoo(rt, width=320, height=200, area_light=True, jitter=None, seed=11)
     ghost.set_casts_shadow(False)
     world = rt.World([floor, wall, ball, egg, sheared, disc, touching, box, slab, shade, ghost], light)
     camera = rt.Camera(width, height, PI / 3.0, rt.view_transform((0.5, 2.5, -7.0), (0, 1.0, 0), (0, 1, 0)))
+    return camera, world
+
+
+def _three_spheres(rt, pattern=None):
+    """The left / middle / right spheres shared by first_scene.rs:54-87, first_plane.rs:34-67, first_patterns.rs:40-70."""
+    def mat(color):
+        return Material(color=color, diffuse=0.7, specular=0.3) if pattern is None else Material(pattern=pattern, diffuse=0.7, specular=0.3)
+    middle = rt.Sphere.build(rt.translation(-0.5, 1.0, 0.5), mat((0.1, 1, 0.5)))
+    right = rt.Sphere.build(rt.shearing(0.0, 1.0, 0.0, 0.0, 0.0, 1.0) * rt.translation(1.5, 0.5, -0.5) * rt.scaling(0.5, 0.5, 0.5),
+                            mat((0.5, 1, 0.1)))
+    left = rt.Sphere.build(rt.translation(-1.5, 0.33, -0.75) * rt.scaling(0.33, 0.33, 0.33), mat((1, 0.8, 0.1)))
+    return left, middle, right
+
+
+def _first_camera(rt, width, height):
+    return rt.Camera(width, height, PI / 3.0, rt.view_transform((0, 1.5, -5), (0, 1, 0), (0, 1, 0)))
+
+
+def first_scene(rt, width=1000, height=500):
+    """demos/src/bin/first_scene.rs:25-107 — the room is made of extremely flattened spheres."""
+    room = Material(color=(1, 0.9, 0.9), specular=0.0)
+    floor = rt.Sphere.build(rt.scaling(10.0, 0.01, 10.0), room)
+    left_wall = rt.Sphere.build(rt.translation(0.0, 0.0, 5.0) * rt.rotation_y(-PI / 4.0) * rt.rotation_x(PI / 2.0)
+                                * rt.scaling(10.0, 0.01, 10.0), room)
+    right_wall = rt.Sphere.build(rt.translation(0.0, 0.0, 5.0) * rt.rotation_y(PI / 4.0) * rt.rotation_x(PI / 2.0)
+                                 * rt.scaling(10.0, 0.01, 10.0), room)
+    left, middle, right = _three_spheres(rt)
+    world = rt.World([floor, left_wall, right_wall, left, middle, right], PointLight((-10, 10, -10), (1, 1, 1)))
+    return _first_camera(rt, width, height), world
+
+
+def first_plane(rt, width=100, height=50):
+    """demos/src/bin/first_plane.rs:24-86"""
+    floor = rt.Plane.build(rt.scaling(10.0, 0.01, 10.0), Material(color=(1, 0.9, 0.9), specular=0.0))
+    left, middle, right = _three_spheres(rt)
+    world = rt.World([floor, left, middle, right], PointLight((-10, 10, -10), (1, 1, 1)))
+    return _first_camera(rt, width, height), world
+
+
+def first_patterns(rt, width=100, height=50):
+    """demos/src/bin/first_patterns.rs:28-92"""
+    stripes = rt.Stripes((1.0, 0.2, 0.4), (0.1, 0.1, 0.1))
+    stripes.set_transformation(rt.scaling(0.3, 0.3, 0.3) * rt.rotation_z(3.0 * PI / 4.0))
+    sine2d = rt.Sine2D((0.1, 1, 0.5), (0.9, 0.2, 0.6))
+    sine2d.set_transformation(rt.scaling(0.005, 1.0, 0.005) * rt.translation(-5.0, 1.0, 0.5))
+    floor = rt.Plane.build(rt.scaling(10.0, 0.01, 10.0), Material(pattern=sine2d, specular=0.0))
+    left, middle, right = _three_spheres(rt, stripes)
+    world = rt.World([floor, left, middle, right], PointLight((-10, 10, -10), (1, 1, 1)))
+    return _first_camera(rt, width, height), world
+
+
+# constants.rs:8-46 colours used by uv.rs:328-344
+_YELLOW, _CYAN, _RED, _BLUE, _BROWN = (1, 1, 0), (0, 1, 1), (1, 0, 0), (0, 0, 1), (1, 0.5, 0)
+_GREEN, _PURPLE, _WHITE = (0, 1, 0), (1, 0, 1), (1, 1, 1)
+
+
+def align_check_cubic_map(rt):
+    """get_align_check_cubic_map_pattern, uv.rs:328-344"""
+    left = rt.AlignCheck(_YELLOW, _CYAN, _RED, _BLUE, _BROWN)
+    front = rt.AlignCheck(_CYAN, _RED, _YELLOW, _BROWN, _GREEN)
+    right = rt.AlignCheck(_RED, _YELLOW, _PURPLE, _GREEN, _WHITE)
+    back = rt.AlignCheck(_GREEN, _PURPLE, _CYAN, _WHITE, _BLUE)
+    up = rt.AlignCheck(_BROWN, _CYAN, _PURPLE, _RED, _YELLOW)
+    down = rt.AlignCheck(_PURPLE, _BROWN, _GREEN, _BLUE, _WHITE)
+    return rt.CubicMap(front, back, left, right, up, down)
+
+
+def first_textures(rt, width=1000, height=500, earth_ppm=None, u_steps=10, v_steps=10, seed=3):
+    """demos/src/bin/first_textures.rs:34-171.  The earth image is an external file there; here a synthetic PPM.  The
+    light is the demo's 10x10 RectangleLight with jitter `None` (first_textures.rs:161-171): the counter-based
+    generator stands in for thread_rng on both sides."""
+    from .api import SG_MAP_CYLINDRICAL, SG_MAP_PLANAR, SG_MAP_SPHERICAL
+
+    black, white = (0, 0, 0), (1, 1, 1)
+    floor = rt.Plane.build(rt.scaling(10.0, 0.01, 10.0),
+                           Material(specular=0.0, pattern=rt.TextureMap(rt.UVCheckers(16.0, 8.0, black, white), SG_MAP_PLANAR)))
+    sphere = rt.Sphere.build(rt.translation(-2.5, 1.3, 3.0),
+                             Material(pattern=rt.TextureMap(rt.UVCheckers(16.0, 8.0, black, white), SG_MAP_SPHERICAL),
+                                      diffuse=0.7, specular=0.3))
+    canvas = rt.canvas_from_ppm(earth_ppm if earth_ppm is not None else synthetic_ppm(128, 64, seed=7))
+    earth = rt.Sphere.build(rt.translation(0.0, 1.0, 0.0) * rt.rotation_x(-0.5) * rt.rotation_y(-1.5),
+                            Material(pattern=rt.TextureMap(rt.UVImage(canvas), SG_MAP_SPHERICAL), diffuse=0.9, specular=0.1,
+                                     shininess=10.0, ambient=0.1))
+    pedestal = rt.Cylinder()
+    pedestal.maximum_y, pedestal.minimum_y, pedestal.closed = 0.0, -0.15, True
+    pedestal.set_material(Material(color=(0.2, 0.2, 0.2), ambient=0.0, diffuse=0.8, specular=0.0, reflective=0.2))
+    earth_display = rt.GroupShape()
+    earth_display.add_child(earth)
+    earth_display.add_child(pedestal)
+    earth_display.set_transformation(rt.translation(-0.2, 0.15, 0.5))
+    cylinder = rt.Cylinder()
+    cylinder.set_transformation(rt.translation(2.0, 2.0, 2.0))
+    cylinder.set_material(Material(ambient=0.1, specular=0.6, shininess=15.0, diffuse=0.8,
+                                   pattern=rt.TextureMap(rt.UVCheckers(16.0, 16.0, (0, 0.5, 0), white), SG_MAP_CYLINDRICAL)))
+    cylinder.maximum_y, cylinder.minimum_y = 3.0, -3.0
+    cube = rt.Cube()
+    cube.set_transformation(rt.translation(5.0, 2.0, 2.0) * rt.rotation_x(-PI / 4.0))
+    cube.set_material(Material(pattern=align_check_cubic_map(rt)))
+    light = RectangleLight((1.5, 1.5, 1.5), (-10, 10, -10), (2, 0, 0), u_steps, (0, 2, 0), v_steps, None, seed)
+    world = rt.World([floor, sphere, cylinder, cube, earth_display], light)
+    camera = rt.Camera(width, height, PI / 3.0, rt.view_transform((0, 1.5, -10), (2, 2.8, 0), (0, 1, 0)))
+    return camera, world
+
+
+def skybox(rt, width=800, height=400, face_size=64):
+    """demos/src/bin/skybox.rs:26-129 with synthetic face images (the demo reads six external PPMs).  Note the demo's
+    own assignment: left <- posx.ppm, right <- negx.ppm (skybox.rs:88-91)."""
+    sphere = rt.Sphere.build(rt.scaling(0.75, 0.75, 0.75) * rt.translation(0.0, 0.0, 5.0),
+                             Material(diffuse=0.4, specular=0.6, shininess=20.0, reflective=0.6, ambient=0.0))
+    names = ["posz", "negz", "posx", "negx", "posy", "negy"]  # front, back, left, right, up, down
+    faces = [rt.UVImage(rt.canvas_from_ppm(synthetic_ppm(face_size, face_size, seed=20 + i))) for i, _ in enumerate(names)]
+    box = rt.Cube.build(rt.scaling(1000.0, 1000.0, 1000.0),
+                        Material(diffuse=0.0, specular=0.0, ambient=1.0, pattern=rt.CubicMap(*faces)))
+    world = rt.World([sphere, box], PointLight((0, 100, 0), (1, 1, 1)))
+    camera = rt.Camera(width, height, 1.2, rt.view_transform((0, 0, 0), (0, 0, 5), (0, 1, 0)))
     return camera, world
 
 
@@ -404,6 +521,58 @@ def dragon_element(rt, width=480, height=270, n_u=48, n_v=24, divide=4, case=Tru
         element.divide(divide)
     floor = rt.Plane.build(rt.translation(0.0, 0.35, 0.0), Material(color=(0.6, 0.6, 0.65), specular=0.0, reflective=0.1))
     world = rt.World([element, floor], PointLight((-10, 100, -100), (1, 1, 1)))
+    camera = rt.Camera(width, height, 1.2, rt.view_transform((0, 2.5, -10), (0, 1, 0), (0, 1, 0)))
+    return camera, world
+
+
+def here_be_dragons(rt, width=500, height=200, n_u=32, n_v=16):
+    """demos/src/bin/here_be_dragons.rs:36-218: six display elements (transforms / materials :42-138, element builder
+    :298-338 with divide(4), display case :242-250, pedestal :264-281, mesh lift :291) around clones of one mesh — a
+    synthetic OBJ here, the demo reads an external dragon.obj."""
+    def dragon_mat(color):
+        return Material(color=color, ambient=0.1, diffuse=0.6, specular=0.3, shininess=15.0)
+
+    def case_mat(diffuse, transparency):
+        return Material(ambient=0.0, diffuse=diffuse, specular=0.0, transparency=transparency)
+
+    elements = [  # (transform, dragon material, case material), in the demo's order :143-180
+        (rt.translation(0.0, 0.5, -4.0) * rt.rotation_y(PI), dragon_mat((1, 1, 1)), None),
+        (rt.translation(0.0, 2.0, 2.0), dragon_mat((1, 0, 0.1)), case_mat(0.4, 0.6)),
+        (rt.translation(-2.0, 0.75, -1.0) * rt.rotation_y(-PI / 8.0) * rt.scaling(0.75, 0.75, 0.75), dragon_mat((0.9, 0.5, 0.1)),
+         case_mat(0.2, 0.8)),
+        (rt.translation(-4.0, 0.0, -2.0) * rt.rotation_y(-PI / 16.0) * rt.scaling(0.5, 0.5, 0.5), dragon_mat((1, 0.9, 0.1)),
+         case_mat(0.1, 0.9)),
+        (rt.translation(2.0, 1.0, -1.0) * rt.rotation_y(5.0 * PI / 4.0) * rt.scaling(0.75, 0.75, 0.75), dragon_mat((1, 0.5, 0.1)),
+         case_mat(0.2, 0.8)),
+        (rt.translation(4.0, 0.0, -2.0) * rt.rotation_y(21.0 * PI / 20.0) * rt.scaling(0.5, 0.5, 0.5), dragon_mat((0.9, 1, 0.1)),
+         case_mat(0.1, 0.9)),
+    ]
+    dragon = rt.parse_obj(synthetic_obj(n_u, n_v))
+    dragon.set_transformation(rt.translation(0.0, 0.69, 0.0))
+    objects = []
+    for i, (transform, d_mat, c_mat) in enumerate(elements):
+        mesh = dragon.clone() if i + 1 < len(elements) else dragon
+        element = rt.GroupShape()
+        element.set_transformation(transform)
+        mesh.set_material(d_mat)
+        if c_mat is not None:
+            case = rt.Cube()
+            case.set_casts_shadow(False)
+            case.set_transformation(rt.scaling(1.1, 0.77, 0.49) * rt.translation(0.0, 1.001, 0.0))
+            case.set_material(c_mat)
+            box = rt.GroupShape()
+            box.add_child(mesh)
+            box.add_child(case)
+        else:
+            box = mesh
+        element.add_child(box)
+        pedestal = rt.Cylinder()
+        pedestal.maximum_y, pedestal.minimum_y, pedestal.closed = 0.0, -0.15, True
+        pedestal.set_material(Material(color=(0.2, 0.2, 0.2), ambient=0.0, diffuse=0.8, specular=0.0, reflective=0.2))
+        element.add_child(pedestal)
+        element.divide(4)
+        objects.append(element)
+    world = rt.World(objects, PointLight((-10, 100, -100), (1, 1, 1)))
     camera = rt.Camera(width, height, 1.2, rt.view_transform((0, 2.5, -10), (0, 1, 0), (0, 1, 0)))
     return camera, world
 

@@ -25,6 +25,13 @@ SCENES = {
     "dragon_element": (scenes.dragon_element, dict(width=240, height=135, n_u=32, n_v=16)),
     "dragon_smooth_nodivide": (scenes.dragon_element, dict(width=160, height=90, n_u=16, n_v=8, divide=0, smooth=True)),
     "textured": (scenes.textured, dict(width=320, height=200)),
+    # the remaining camera demos of demos/src/bin/ at reduced size (full-size c1-c4 are in test_gpu_full_size.py)
+    "first_scene": (scenes.first_scene, dict(width=300, height=150)),
+    "first_plane": (scenes.first_plane, dict(width=100, height=50)),
+    "first_patterns": (scenes.first_patterns, dict(width=200, height=100)),
+    "first_textures": (scenes.first_textures, dict(width=300, height=150, u_steps=4, v_steps=4)),
+    "skybox": (scenes.skybox, dict(width=320, height=160)),
+    "here_be_dragons": (scenes.here_be_dragons, dict(width=300, height=120)),
     "filter_zoo_area": (scenes.filter_zoo, dict(width=320, height=200)),
     "filter_zoo_table": (scenes.filter_zoo, dict(width=200, height=120, jitter="table")),
     "filter_zoo_point": (scenes.filter_zoo, dict(width=320, height=200, area_light=False)),
