@@ -244,7 +244,8 @@ void rows3(const float m[16], float4 out[3]) {
 struct BuildItem {
     Box box;
     float centroid[3];
-    int item;  // index into the bounded item list
+    int item;     // index into the bounded item list
+    bool closed;  // sphere or cube: it has an odd number of hits behind a ray origin only if the origin is inside it
 };
 struct Builder {
     std::vector<BuildItem>& items;
@@ -326,7 +327,11 @@ struct Builder {
         n.a = make_float4(b0.lo[0], b0.lo[1], b0.lo[2], b0.hi[0]);
         n.b = make_float4(b0.hi[1], b0.hi[2], b1.lo[0], b1.lo[1]);
         n.c = make_float4(b1.lo[2], b1.hi[0], b1.hi[1], b1.hi[2]);
-        n.d = make_int4(c0, c1, 0, 0);
+        // d.z bit i: child i holds closed primitives only (find_containers may cull it with a point-in-box test)
+        bool closed0 = true, closed1 = true;
+        for (int i = b; i < mid; i++) closed0 = closed0 && items[i].closed;
+        for (int i = mid; i < e; i++) closed1 = closed1 && items[i].closed;
+        n.d = make_int4(c0, c1, (closed0 ? 1 : 0) | (closed1 ? 2 : 0), 0);
         return idx;
     }
 };
@@ -448,6 +453,7 @@ int flatten(RtcScene* s, Flattened& f) {
         BuildItem& b = build_items[i];
         b.box = bounded[i].box;
         b.item = (int)i;
+        b.closed = bounded[i].prim >= 0 && (s->prims[bounded[i].prim].type == RTC_SPHERE || s->prims[bounded[i].prim].type == RTC_CUBE);
         for (int a = 0; a < 3; a++) {
             // pad: the tree must never reject a hit the reference would report (it is only an accelerator)
             float ext = b.box.hi[a] - b.box.lo[a];

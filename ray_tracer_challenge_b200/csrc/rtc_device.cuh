@@ -681,8 +681,20 @@ __device__ __noinline__ void find_containers(const DevScene& S, V3 o, V3 d, int 
                 float t0, t1;
                 k.node();
                 k.node();
-                bool h0 = slab(o, inv, a.x, a.y, a.z, a.w, b.x, b.y, kInfF, t0);
-                bool h1 = slab(o, inv, b.z, b.w, cc.x, cc.y, cc.z, cc.w, kInfF, t1);
+                // A sphere or a cube has an odd number of hits behind the origin only when the origin is inside it (both
+                // roots of an outside origin have one sign, cube.rs:124-128 rejects a box that is not straddled), and
+                // the tree's boxes are padded far beyond f32 rounding: subtrees of such primitives are culled with a
+                // point-in-box test instead of the unbounded backward ray (a refraction hit deep in a 100 k-sphere
+                // field no longer walks every node along the whole half-line).
+                bool h0, h1;
+                if (link.z & 1)
+                    h0 = o.x >= a.x && o.x <= a.w && o.y >= a.y && o.y <= b.x && o.z >= a.z && o.z <= b.y;
+                else
+                    h0 = slab(o, inv, a.x, a.y, a.z, a.w, b.x, b.y, kInfF, t0);
+                if (link.z & 2)
+                    h1 = o.x >= b.z && o.x <= cc.y && o.y >= b.w && o.y <= cc.z && o.z >= cc.x && o.z <= cc.w;
+                else
+                    h1 = slab(o, inv, b.z, b.w, cc.x, cc.y, cc.z, cc.w, kInfF, t1);
                 if (h0 && h1) {
                     if (sp < kBvhStack) stack[sp++] = link.y;
                     node = link.x;
