@@ -194,6 +194,8 @@ struct RtcScene {
     int render_slices = 6;  // kernel / copy pipeline depth when rendering into host memory
     int adaptive_order = 1;  // launch a shard's bands longest-first, learnt from the previous render
     int shadow_filter = 1;   // RTC_OPT_SHADOW_FILTER
+    int converge = -1;         // color_at warp vote: -1 automatic (branching ray trees), 0 / 1 forced (RTC_CONVERGE)
+    bool has_branching_materials = false;  // some material is reflective AND transparent (set at commit)
     int order_max_waves = 24;  // longest-first order only for launches shorter than this many waves of blocks
     std::vector<Replica> replicas;
     std::vector<int> replica_devices;
@@ -614,7 +616,9 @@ int flatten(RtcScene* s, Flattened& f) {
     }
 
     // ---- shading tables
+    s->has_branching_materials = false;
     for (const RtcMaterial& m : s->materials) {
+        if (m.reflective != 0.0f && m.transparency != 0.0f) s->has_branching_materials = true;
         DevMaterial d{};
         memcpy(d.color, m.color, sizeof(d.color));
         d.ambient = m.ambient, d.diffuse = m.diffuse, d.specular = m.specular, d.shininess = m.shininess;
@@ -942,7 +946,7 @@ int render_impl(RtcScene* s, int depth, int shard0, int n_shards_ext, float* rgb
             const int b0 = (int)((int64_t)nb * k / n_slices), b1 = (int)((int64_t)nb * (k + 1) / n_slices);
             if (b1 <= b0) continue;
             DevFrame F{slot->d_rgb, slot->d_u8, shard, n_shards, depth, b1 - b0, b0, use_order ? slot->d_tile_order : nullptr,
-                       r.learning ? slot->d_tile_cost : nullptr};
+                       r.learning ? slot->d_tile_cost : nullptr, s->converge < 0 ? (int)s->has_branching_materials : s->converge};
             if (s->strict_fp)
                 strict::launch_render(r.scene, r.small, F, slot->d_counters, detailed, slot->stream);
             else
@@ -1018,6 +1022,7 @@ int rtc_scene_create(RtcScene** out) {
     if (const char* env = getenv("RTC_ADAPTIVE_ORDER")) (*out)->adaptive_order = atoi(env) != 0;  // tuning aids
     if (const char* env = getenv("RTC_SHADOW_FILTER")) (*out)->shadow_filter = atoi(env) != 0;
     if (const char* env = getenv("RTC_ORDER_MAX_WAVES")) (*out)->order_max_waves = atoi(env);
+    if (const char* env = getenv("RTC_CONVERGE")) (*out)->converge = atoi(env);
     return 0;
 }
 void rtc_scene_destroy(RtcScene* s) {

@@ -62,7 +62,7 @@ __device__ __forceinline__ void flush_counters<true>(const Rays& r, const Ctr<tr
     warp_add(&out->prim_tests[7], k.refilters);  // shadow-filter fallbacks to the exact test
 }
 
-template <bool STATS, bool SMALL>
+template <bool STATS, bool SMALL, bool CONVERGE>
 __global__ void __launch_bounds__(128, SMALL ? RTC_SMALL_MINBLOCKS : RTC_BVH_MINBLOCKS) render_tiles(const __grid_constant__ DevScene S, const __grid_constant__ SmallScene SS,
                                                     const DevFrame F, DevCounters* counters) {
     // small scenes: primitive table + per-thread shadow-origin cache in dynamic shared memory (kSmallSmemBytes)
@@ -85,12 +85,14 @@ __global__ void __launch_bounds__(128, SMALL ? RTC_SMALL_MINBLOCKS : RTC_BVH_MIN
     V3 c = mk(0.f, 0.f, 0.f);
     const bool inside = x < S.width && y < S.height;
     // camera.rs:80-81 — the last row and the last column are never rendered and stay black (canvas.rs:23)
-    if (inside && x < S.width - 1 && y < S.height - 1) {
-        V3 o, d;
+    const bool rendered = inside && x < S.width - 1 && y < S.height - 1;
+    V3 o = mk(0.f, 0.f, 0.f), d = mk(0.f, 0.f, 1.f);
+    if (rendered) {
         ray_for_pixel(S, x, y, o, d);
         r.primary++;
-        c = color_at<STATS, SMALL>(E, o, d, F.depth, (unsigned)(y * S.width + x), r, k, nullptr, nullptr);
     }
+    if (CONVERGE || rendered)
+        c = color_at<STATS, SMALL, CONVERGE>(E, rendered, o, d, F.depth, (unsigned)(y * S.width + x), r, k, nullptr, nullptr);
     if (inside) {
         size_t idx = ((size_t)y * S.width + x) * 3;
         if (F.rgb) {
@@ -118,11 +120,13 @@ __global__ void __launch_bounds__(128) trace_rays(const __grid_constant__ DevSce
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     Ctr<false> k;
     Rays r;
-    if (i < n) {
-        V3 o = ld3(origins + 3 * (size_t)i), d = ld3(directions + 3 * (size_t)i);
-        float t;
-        int pos;
-        V3 c = color_at<false, SMALL>(E, o, d, depth, (unsigned)i, r, k, &t, &pos);
+    const bool active = i < n;
+    V3 o = mk(0.f, 0.f, 0.f), d = mk(0.f, 0.f, 1.f);
+    if (active) o = ld3(origins + 3 * (size_t)i), d = ld3(directions + 3 * (size_t)i);
+    float t = -1.0f;
+    int pos = -1;
+    const V3 c = color_at<false, SMALL, true>(E, active, o, d, depth, (unsigned)i, r, k, &t, &pos);
+    if (active) {
         out_rgb[3 * (size_t)i] = c.x;
         out_rgb[3 * (size_t)i + 1] = c.y;
         out_rgb[3 * (size_t)i + 2] = c.z;
@@ -137,16 +141,22 @@ void launch_render(const DevScene& S, const SmallScene& SS, const DevFrame& F, D
     dim3 grid((S.width + kTileW - 1) / kTileW, F.n_bands);
     if (grid.x == 0 || grid.y == 0) return;
     const bool small = SS.n > 0;
+    // the detailed (counting) pass always uses the converging build; the timed kernels pick by DevFrame::converge
     if (detailed) {
         if (small)
-            render_tiles<true, true><<<grid, 128, kSmallSmemBytes, stream>>>(S, SS, F, counters);
+            render_tiles<true, true, true><<<grid, 128, kSmallSmemBytes, stream>>>(S, SS, F, counters);
         else
-            render_tiles<true, false><<<grid, 128, 0, stream>>>(S, SS, F, counters);
+            render_tiles<true, false, true><<<grid, 128, 0, stream>>>(S, SS, F, counters);
+    } else if (small) {
+        if (F.converge)
+            render_tiles<false, true, true><<<grid, 128, kSmallSmemBytes, stream>>>(S, SS, F, counters);
+        else
+            render_tiles<false, true, false><<<grid, 128, kSmallSmemBytes, stream>>>(S, SS, F, counters);
     } else {
-        if (small)
-            render_tiles<false, true><<<grid, 128, kSmallSmemBytes, stream>>>(S, SS, F, counters);
+        if (F.converge)
+            render_tiles<false, false, true><<<grid, 128, 0, stream>>>(S, SS, F, counters);
         else
-            render_tiles<false, false><<<grid, 128, 0, stream>>>(S, SS, F, counters);
+            render_tiles<false, false, false><<<grid, 128, 0, stream>>>(S, SS, F, counters);
     }
 }
 

@@ -150,6 +150,7 @@ struct DevFrame {  // where a render writes
     int band_begin;        // ... starting at this index of the shard's band list
     const int* tile_order; // this shard's tiles (band * tiles_x + tile column) in launch order, or null: natural order
     unsigned* tile_cost;   // per frame tile: clock cycles its block ran (learns the launch order), or null
+    int converge;          // color_at: all lanes of a warp meet at a vote before every ray (see color_at)
 };
 
 constexpr int kTileW = 16, kTileH = 8;  // pixels per 128-thread block: 4 warps of 8x4

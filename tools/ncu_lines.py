@@ -36,21 +36,24 @@ rows = list(csv.reader(io.StringIO(src)))
 hi = next(i for i, r in enumerate(rows) if "Source" in r and "Instructions Executed" in r)
 hdr = rows[hi]
 ia, iaddr, ist = hdr.index("Instructions Executed"), hdr.index("Address"), hdr.index("# Samples")
+ith = hdr.index("Thread Instructions Executed")
 data = []
 for r in rows[hi + 1:]:
     try:
-        data.append((int(r[iaddr], 16) if r[iaddr].startswith("0x") else int(r[iaddr]), int(r[ia]), int(r[ist] or 0)))
+        data.append((int(r[iaddr], 16) if r[iaddr].startswith("0x") else int(r[iaddr]), int(r[ia]), int(r[ist] or 0), int(r[ith] or 0)))
     except (ValueError, IndexError):
         pass
 base = min(d[0] for d in data)
 by_line = collections.Counter()
 samples = collections.Counter()
 n_inst = collections.Counter()
-for addr, n, st in data:
+threads = collections.Counter()
+for addr, n, st, th in data:
     key = line_of.get(addr - base, (("?", 0), ""))[0]
     by_line[key] += n
     samples[key] += st
     n_inst[key] += 1
+    threads[key] += th
 tot, tots = sum(by_line.values()), max(sum(samples.values()), 1)
 print(f"{tot} warp instructions, {len(data)} SASS instructions, {len(by_line)} source lines")
 srcs = {}
@@ -64,7 +67,7 @@ for (f, l), n in by_line.most_common(top):
         else:
             srcs[f] = []
     text = srcs[f][l - 1].strip()[:90] if 0 < l <= len(srcs[f]) else ""
-    print(f"{n / tot:6.2%} instr {samples[(f, l)] / tots:6.2%} stall  {n_inst[(f, l)]:4d} sass  {f}:{l:<5d} {text}")
+    print(f"{n / tot:6.2%} instr {samples[(f, l)] / tots:6.2%} stall  {threads[(f, l)] / max(n, 1):5.1f} lanes {n_inst[(f, l)]:4d} sass  {f}:{l:<5d} {text}")
 
 # ---- the same, grouped by the device function a line belongs to
 print("\nby function:")
@@ -76,7 +79,7 @@ for f, lines in srcs.items():
         if m and not text.strip().startswith("//"):
             starts.append((i + 1, m.group(1)))
     fn_start[f] = starts
-by_fn, st_fn = collections.Counter(), collections.Counter()
+by_fn, st_fn, th_fn = collections.Counter(), collections.Counter(), collections.Counter()
 for (f, l), n in by_line.items():
     if f not in srcs:
         for root in ("ray_tracer_challenge_b200/csrc", "."):
@@ -98,5 +101,6 @@ for (f, l), n in by_line.items():
             name = nm
     by_fn[name] += n
     st_fn[name] += samples[(f, l)]
+    th_fn[name] += threads[(f, l)]
 for name, n in by_fn.most_common(30):
-    print(f"{n / tot:6.2%} instr {st_fn[name] / tots:6.2%} stall  {name}")
+    print(f"{n / tot:6.2%} instr {st_fn[name] / tots:6.2%} stall  {th_fn[name] / max(n, 1):5.1f} lanes  {name}")
