@@ -547,8 +547,12 @@ __device__ __noinline__ void nearest_hit(const DevScene& S, V3 o, V3 d, Hit& bes
     int stack[kBvhStack];
     int sp = 0;
     int node = S.bvh_root;
+    // "while-while" traversal: every lane first descends to its next leaf (lanes that are there already wait), then
+    // all lanes test their leaf's primitives together — instead of serialising an inner-node step for some lanes with
+    // a leaf for the others in every iteration (ncu: 4.5 of 32 lanes active in the primitive tests before).
+    constexpr int kDone = -0x7fffffff - 1;  // never a leaf code: ~((first << 4) | (count - 1)) > INT_MIN
     for (;;) {
-        if (node >= 0) {
+        while (node >= 0) {
             const float4* np = reinterpret_cast<const float4*>(S.bvh + node);
             float4 a = __ldg(np), b = __ldg(np + 1), c = __ldg(np + 2);
             int4 link = __ldg(reinterpret_cast<const int4*>(np + 3));
@@ -565,17 +569,16 @@ __device__ __noinline__ void nearest_hit(const DevScene& S, V3 o, V3 d, Hit& bes
                 }
                 if (sp < kBvhStack) stack[sp++] = far;
                 node = near;
-                continue;
-            }
-            if (h0) {
+            } else if (h0) {
                 node = link.x;
-                continue;
-            }
-            if (h1) {
+            } else if (h1) {
                 node = link.y;
-                continue;
+            } else {
+                node = sp == 0 ? kDone : stack[--sp];
             }
-        } else {
+        }
+        if (node == kDone) return;
+        {
             int code = ~node;
             int first = code >> 4, count = (code & 15) + 1;
             for (int i = 0; i < count; i++) {
@@ -673,8 +676,9 @@ __device__ __noinline__ void find_containers(const DevScene& S, V3 o, V3 d, int 
         int stack[kBvhStack];
         int sp = 0;
         int node = S.bvh_root;
-        for (;;) {
-            if (node >= 0) {
+        constexpr int kDone = -0x7fffffff - 1;
+        for (;;) {  // while-while, as in nearest_hit
+            while (node >= 0) {
                 const float4* np = reinterpret_cast<const float4*>(S.bvh + node);
                 float4 a = __ldg(np), b = __ldg(np + 1), cc = __ldg(np + 2);
                 int4 link = __ldg(reinterpret_cast<const int4*>(np + 3));
@@ -698,17 +702,16 @@ __device__ __noinline__ void find_containers(const DevScene& S, V3 o, V3 d, int 
                 if (h0 && h1) {
                     if (sp < kBvhStack) stack[sp++] = link.y;
                     node = link.x;
-                    continue;
-                }
-                if (h0) {
+                } else if (h0) {
                     node = link.x;
-                    continue;
-                }
-                if (h1) {
+                } else if (h1) {
                     node = link.y;
-                    continue;
+                } else {
+                    node = sp == 0 ? kDone : stack[--sp];
                 }
-            } else {
+            }
+            if (node == kDone) break;
+            {
                 int code = ~node;
                 int first = code >> 4, count = (code & 15) + 1;
                 for (int i = 0; i < count; i++) container_prim<STATS>(S, first + i, o, d, cache, hit_pos, c, k);
