@@ -170,7 +170,7 @@ int rtc_set_rect_light(RtcScene*, const float intensity[3], const float corner[3
  * well-conditioned scenes.  It may be changed between renders; the BVH options only before commit. */
 enum {
     RTC_OPT_FMA_CONTRACTION = 1,
-    RTC_OPT_BVH_LEAF_SIZE = 2,
+    RTC_OPT_BVH_LEAF_SIZE = 2, /* primitives per BVH leaf, 1..16; 0 (default) = 4 for triangle meshes, 1 otherwise */
     RTC_OPT_BVH_MIN_PRIMS = 3,
     RTC_OPT_RENDER_SLICES = 4, /* kernel launches a frame is cut into when it is copied to host memory, so the
                                   copy of one slice overlaps the kernel of the next (default 6) */

@@ -190,7 +190,7 @@ struct RtcScene {
     int u_steps = 1, v_steps = 1;
     std::vector<float> jitter;
     uint64_t seed = 0;
-    int strict_fp = 1, leaf_size = 4, bvh_min_prims = kSmallCap + 1;
+    int strict_fp = 1, leaf_size = 0 /* automatic */, bvh_min_prims = kSmallCap + 1;
     int render_slices = 6;  // kernel / copy pipeline depth when rendering into host memory
     int adaptive_order = 1;  // launch a shard's bands longest-first, learnt from the previous render
     int shadow_filter = 1;   // RTC_OPT_SHADOW_FILTER
@@ -466,7 +466,12 @@ int flatten(RtcScene* s, Flattened& f) {
         }
     }
     if (!build_items.empty()) {
-        int leaf = s->leaf_size;
+        // Leaf size: a mesh's triangles share one transform (the object-space ray is cached), so a few per leaf cost
+        // less than the extra boxes; every other primitive pays its own ray transform, and one per leaf wins
+        // (measured on B200: 102 k triangles 0.50 ms at 4 vs 0.58 at 1; 100 k spheres 38.7 ms at 1 vs 51.7 at 4).
+        size_t n_triangles = 0;
+        for (const Item& it : bounded) n_triangles += it.prim >= 0 && s->prims[it.prim].type == RTC_TRIANGLE;
+        int leaf = s->leaf_size > 0 ? s->leaf_size : (2 * n_triangles > bounded.size() ? 4 : 1);
         if (const char* env = getenv("RTC_BVH_LEAF")) leaf = atoi(env);  // tuning aid
         Builder builder{build_items, f.bvh, std::min(std::max(leaf, 1), 16)};
         f.bvh.reserve(build_items.size());
@@ -1117,7 +1122,7 @@ int rtc_set_option(RtcScene* s, int32_t option, int64_t value) {
     switch (option) {
         case RTC_OPT_FMA_CONTRACTION: s->strict_fp = value == 0; return 0;  // may change between renders
         case RTC_OPT_BVH_LEAF_SIZE:
-            if (value < 1 || value > 16) return fail(RTC_ERR_INVALID, "leaf size must be in [1,16]");
+            if (value < 0 || value > 16) return fail(RTC_ERR_INVALID, "leaf size must be in [1,16], or 0 = automatic");
             s->leaf_size = (int)value;
             s->committed = false;
             return 0;
