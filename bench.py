@@ -283,6 +283,13 @@ def main() -> None:
         for _ in range(e_steps):
             prepared.render(depth, out_rgb=rgb, out_u8=u8, fma=args.fma)
         e2e["resident_scene_ms_per_frame"] = round((time.perf_counter() - t0) / e_steps * 1e3, 3)
+        # the Canvas the reference returns is the f32 plane alone (canvas.rs:6-10; 8-bit values are made by to_ppm)
+        for _ in range(2):
+            prepared.render(depth, out_rgb=rgb, want_u8=False, fma=args.fma)
+        t0 = time.perf_counter()
+        for _ in range(e_steps):
+            prepared.render(depth, out_rgb=rgb, want_u8=False, fma=args.fma)
+        e2e["resident_scene_f32_only_ms_per_frame"] = round((time.perf_counter() - t0) / e_steps * 1e3, 3)
         lib.rtc_host_free(p_rgb)
         lib.rtc_host_free(p_u8)
     else:

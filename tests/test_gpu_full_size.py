@@ -9,7 +9,10 @@ from tests.parity import assert_parity, compare_frames
 pytestmark = pytest.mark.gpu
 
 # workload -> (row stride of the oracle sample, minimum fraction of sampled pixels that must be bit-identical in 8 bits)
-CASES = {"c1": (8, 1.0), "c2": (24, 1.0), "c3": (48, 1.0), "c4": (24, 1.0)}
+# c5 (100 k spheres): the reference's sphere test is noise-dominated at the silhouettes of far, tiny spheres, where its
+# own group boxes decide whether a phantom hit is reported (see test_sphere_field_parity_at_scale): all but a few
+# 1e-5 of the pixels are identical.
+CASES = {"c1": (8, 1.0), "c2": (24, 1.0), "c3": (48, 1.0), "c4": (24, 1.0), "c5": (48, 0.9995)}
 
 
 @pytest.fixture(scope="module")
@@ -39,7 +42,10 @@ def test_full_size_frame_matches_oracle_rows(workload, gpu, oracle):
     rgb, u8, ost = oracle.probe.render_rows(ocam, oworld, depth, ystep // 2, h, ystep, want_u8=True)
     rows = np.arange(ystep // 2, h - 1, ystep)
     rep = compare_frames(got.to_u8()[rows], u8[rows], got.data[rows], rgb[rows])
-    assert_parity(rep, min_within=0.9999, max_gross=0.0001, label=f"{workload} rows {ystep // 2}::{ystep}")
+    loose = min_exact < 1.0
+    assert_parity(rep, min_within=0.9995 if loose else 0.9999, max_gross=0.0005 if loose else 0.0001,
+                  label=f"{workload} rows {ystep // 2}::{ystep}")
+    print(workload, rep)
     assert rep["exact_u8"] >= min_exact - 1e-4, rep
 
 
