@@ -781,6 +781,27 @@ int flatten(RtcScene* s, Flattened& f) {
             }
             const int n_planes = ends[1] - ends[0];
             f.small.plane_cells = n_planes > 0 && (size_t)n_planes * f.samples.size() <= (size_t)kPlaneCellCap;
+            // bounds of the per-(plane, cell) constants over all cells (rtc_device.cuh: plane_cell_constants), padded
+            // beyond the f32 rounding of the device's own evaluation: lets a shade settle the plane for every cell at once
+            for (int q = 0; q < 2; q++) {
+                f.small.plane_bundle[q] = make_float4(NAN, NAN, NAN, NAN);  // NaN: the bundle test never decides
+                if (!f.small.plane_cells || q >= n_planes) continue;
+                const float4 r1 = f.small.p[ends[0] + q].r1;
+                double lo = 1e300, hi = -1e300, e_max = 0.0, l1_max = 0.0;
+                for (const float4& L : f.samples) {
+                    const double px = (double)r1.x * L.x, py = (double)r1.y * L.y, pz = (double)r1.z * L.z;
+                    const double a = std::fabs(px) + std::fabs(py) + std::fabs(pz);
+                    lo = std::min(lo, px + py + pz - 1e-6 * a), hi = std::max(hi, px + py + pz + 1e-6 * a);
+                    e_max = std::max(e_max, 3.814697265625e-06 * a * 1.000001);
+                    l1_max = std::max(l1_max, 1.1920929e-3 * (1.0 + 7.7e-6) * (std::fabs(L.x) + std::fabs(L.y) + std::fabs(L.z)) * 1.000001);
+                }
+                f.small.plane_bundle[q] = make_float4((float)lo, (float)hi, (float)e_max, (float)l1_max);
+                // round outwards
+                f.small.plane_bundle[q].x = std::nextafter(f.small.plane_bundle[q].x, -INFINITY);
+                f.small.plane_bundle[q].y = std::nextafter(f.small.plane_bundle[q].y, INFINITY);
+                f.small.plane_bundle[q].z = std::nextafter(f.small.plane_bundle[q].z, INFINITY);
+                f.small.plane_bundle[q].w = std::nextafter(f.small.plane_bundle[q].w, INFINITY);
+            }
         }
         f.small.tol_sphere = (float)(std::ldexp(1.0, -24) * 64.0 * (worst + 1.0));
     }

@@ -1380,6 +1380,14 @@ __device__ __forceinline__ float intensity_cells(const Env& E, V3 p, Rays& r, Ct
                 const float4* pc = small_plane_cells() + (i - ends.x) * cells + c0;
                 const float erp = kTolP * (fabsf(tx) + fabsf(ty) + fabsf(tz));
                 const float p1 = (kAcne * (1.0f + 2.0f * kTolP)) * (fabsf(p.x) + fabsf(p.y) + fabsf(p.z));
+                if (i - ends.x < 2) {
+                    // the whole bundle at once: with the bounds of the cell constants, every cell's direction is clearly
+                    // steep and points away from the plane's side the point is on (a floor under a light above it):
+                    // filter_plane_cell would answer F_MISS for each of them
+                    const float4 pb = SS.plane_bundle[i - ends.x];
+                    const float slack = pb.z + erp + pb.w + p1;
+                    if ((oy > 0.0f && (pb.x - rp) > slack) || (oy < 0.0f && (rp - pb.y) > slack)) continue;
+                }
 #pragma unroll 4
                 for (int j = 0; j < nc; j++) {
                     const int code = filter_plane_cell(pc[j], oy, rp, erp, p1);
