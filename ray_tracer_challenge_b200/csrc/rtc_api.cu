@@ -736,19 +736,30 @@ int flatten(RtcScene* s, Flattened& f) {
             }
         }
         f.small.filter_ok = ok ? 1 : 0;
-        f.small.cell_masks = ok && !f.samples.empty() && f.samples.size() <= (size_t)kSampleCap;
+        // cell-mask path: a table-mode light whose samples fit the staging area, or the counter-mode generator
+        const bool table_light = s->light_is_rect && !f.samples.empty() && f.samples.size() <= (size_t)kSampleCap;
+        const bool counter_light = s->light_is_rect && s->jitter.empty() && s->u_steps > 0 && s->v_steps > 0;
+        f.small.cell_masks = ok && (table_light || counter_light);
         if (f.small.cell_masks) {
             // the bundle reject (rtc_device.cuh: bundle_misses): a ball around the light samples, and for every sphere /
             // cube its world-space bounding ball — centre = forward transform of the origin, radius = the largest
             // stretch of the forward 3x3 (bounded by sqrt(|T|_1 |T|_inf)), times sqrt(3) for a cube's corners
+            // the light's possible sample points: the table's, or (counter mode: jitter in (0, 1]) the whole rectangle
+            std::vector<float4> pts = f.samples;
+            if (pts.empty())
+                for (int cu = 0; cu < 2; cu++)
+                    for (int cv = 0; cv < 2; cv++)
+                        pts.push_back(make_float4(s->corner[0] + s->u_cell[0] * (cu * s->u_steps) + s->v_cell[0] * (cv * s->v_steps),
+                                                  s->corner[1] + s->u_cell[1] * (cu * s->u_steps) + s->v_cell[1] * (cv * s->v_steps),
+                                                  s->corner[2] + s->u_cell[2] * (cu * s->u_steps) + s->v_cell[2] * (cv * s->v_steps), 0.f));
             double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
-            for (const float4& q : f.samples) {
+            for (const float4& q : pts) {
                 const double v[3] = {q.x, q.y, q.z};
                 for (int a = 0; a < 3; a++) lo[a] = std::min(lo[a], v[a]), hi[a] = std::max(hi[a], v[a]);
             }
             const double lc[3] = {0.5 * (lo[0] + hi[0]), 0.5 * (lo[1] + hi[1]), 0.5 * (lo[2] + hi[2])};
             double rl = 0.0;
-            for (const float4& q : f.samples)
+            for (const float4& q : pts)
                 rl = std::max(rl, std::sqrt((q.x - lc[0]) * (q.x - lc[0]) + (q.y - lc[1]) * (q.y - lc[1]) + (q.z - lc[2]) * (q.z - lc[2])));
             f.small.light_ball = make_float4((float)lc[0], (float)lc[1], (float)lc[2], (float)(rl * 1.001 + 1e-6));
             for (int i = 0; i < n_items; i++) {
@@ -780,7 +791,7 @@ int flatten(RtcScene* s, Flattened& f) {
                 memcpy(&sp.head.y, &pad, sizeof(float));
             }
             const int n_planes = ends[1] - ends[0];
-            f.small.plane_cells = n_planes > 0 && (size_t)n_planes * f.samples.size() <= (size_t)kPlaneCellCap;
+            f.small.plane_cells = table_light && n_planes > 0 && (size_t)n_planes * f.samples.size() <= (size_t)kPlaneCellCap;
             // bounds of the per-(plane, cell) constants over all cells (rtc_device.cuh: plane_cell_constants), padded
             // beyond the f32 rounding of the device's own evaluation: lets a shade settle the plane for every cell at once
             for (int q = 0; q < 2; q++) {

@@ -893,7 +893,7 @@ __device__ __forceinline__ void stage_small_scene(const DevScene& S, const Small
     extern __shared__ float4 rtc_smem[];
     const float4* src = reinterpret_cast<const float4*>(SS.p);
     for (int i = threadIdx.x; i < SS.n * 5; i += blockDim.x) rtc_smem[i] = src[i];
-    if (SS.cell_masks) {
+    if (SS.cell_masks && S.jitter_len > 0) {
         float4* dst = rtc_smem + kSmallCap * 5 + kOrgCache * 3 * 128 / 4;
         for (int i = threadIdx.x; i < S.cells; i += blockDim.x) dst[i] = __ldg(&S.samples[i]);
         if (SS.plane_cells) {  // see plane_cell_constants
@@ -1321,20 +1321,37 @@ __device__ __forceinline__ bool bundle_misses(float4 ball, float pad_over_r, flo
     return C * A > B * B * 1.0001f;
 }
 
-template <bool STATS>
-__device__ __forceinline__ float intensity_cells(const Env& E, V3 p, Rays& r, Ctr<STATS>& k) {
+// TABLE: the light samples are the staged table.  Otherwise (jitter `None`, rectangle_light.rs:46: the counter-based
+// generator) a chunk's sample points are drawn first — two jitter values per cell in the reference's order
+// `for v { for u { j_u, j_v } }`, point_on_light's arithmetic (rectangle_light.rs:60-66) — into a per-thread array,
+// and the same loops read them from there.
+template <bool STATS, bool TABLE>
+__device__ __forceinline__ float intensity_cells(const Env& E, V3 p, unsigned pixel, unsigned path, Rays& r, Ctr<STATS>& k) {
     const DevScene& S = E.S;
     const SmallScene& SS = E.SS;
     const float4* tab = small_tab();
-    const float4* smp = small_samples();
+    const float4* table = small_samples();
     const int cells = S.cells;
     const float tol = SS.tol_sphere;
     const int4 ends = SS.caster_end;
     r.shadow += cells;
     int lit = 0;
+    float4 drawn[TABLE ? 1 : 32];
     for (int c0 = 0; c0 < cells; c0 += 32) {
         const int nc = min(32, cells - c0);
         const unsigned full = nc == 32 ? 0xffffffffu : ((1u << nc) - 1u);
+        if (!TABLE) {
+            const V3 corner = ld3(S.corner), u_vec = ld3(S.u_vec), v_vec = ld3(S.v_vec);
+            for (int j = 0; j < nc; j++) {
+                const unsigned cell = (unsigned)(c0 + j);
+                const int v = (int)cell / S.u_steps, u = (int)cell - v * S.u_steps;
+                const float j1 = jitter_value(S.seed, pixel, path, 2u * cell);
+                const float j2 = jitter_value(S.seed, pixel, path, 2u * cell + 1u);
+                const V3 lp = corner + u_vec * ((float)u + j1) + v_vec * ((float)v + j2);
+                drawn[j] = make_float4(lp.x, lp.y, lp.z, 0.f);
+            }
+        }
+        const float4* smp = TABLE ? table + c0 : drawn;
         unsigned hit = 0u, unsure = 0u;
         float far_hit = 0.0f;  // no caster hit of this chunk is farther from p than this (bounding balls)
         int i = 0;
@@ -1349,7 +1366,7 @@ __device__ __forceinline__ float intensity_cells(const Env& E, V3 p, Rays& r, Ct
             const float ts = tol * spread;
 #pragma unroll 4
             for (int j = 0; j < nc; j++) {
-                const float4 L = smp[c0 + j];
+                const float4 L = smp[j];
                 const float vx = L.x - p.x, vy = L.y - p.y, vz = L.z - p.z;
                 const float dx = fma_(m.r0.x, vx, fma_(m.r0.y, vy, m.r0.z * vz));
                 const float dy = fma_(m.r1.x, vx, fma_(m.r1.y, vy, m.r1.z * vz));
@@ -1403,7 +1420,7 @@ __device__ __forceinline__ float intensity_cells(const Env& E, V3 p, Rays& r, Ct
             }
 #pragma unroll 4
             for (int j = 0; j < nc; j++) {
-                const float4 L = smp[c0 + j];
+                const float4 L = smp[j];
                 const V3 v = mk(L.x - p.x, L.y - p.y, L.z - p.z);
                 // |v| <= |v|_1: a conservative stand-in for the length in the `direction.y.abs() < EPSILON` test
                 const int code = filter_plane<false>(r1, oy, v, fabsf(v.x) + fabsf(v.y) + fabsf(v.z), true).code;
@@ -1423,7 +1440,7 @@ __device__ __forceinline__ float intensity_cells(const Env& E, V3 p, Rays& r, Ct
             const V3 o = xf_point(m, p);
 #pragma unroll 2
             for (int j = 0; j < nc; j++) {
-                const float4 L = smp[c0 + j];
+                const float4 L = smp[j];
                 const int code = filter_cube(m, o, mk(L.x - p.x, L.y - p.y, L.z - p.z)).code;
                 hit |= (unsigned)(code == F_HIT) << j;
                 unsure |= (unsigned)(code == F_UNSURE) << j;
@@ -1453,19 +1470,21 @@ __device__ __forceinline__ float intensity_cells(const Env& E, V3 p, Rays& r, Ct
         while (todo) {
             const int j = __ffs(todo) - 1;
             todo &= todo - 1u;
-            const float4 L = smp[c0 + j];
+            const float4 L = smp[j];
             lit += !shadow_query_small<STATS>(E, false, (unsure >> j) & 1u, mk(L.x, L.y, L.z), p, k);
         }
     }
     return (float)lit / (float)cells;  // `total += 1.0` per lit cell is exact in f32
 }
 
-// Light::intensity_at (point_light.rs:28-34, rectangle_light.rs:76-88)
-template <bool STATS, bool SMALL>
+// Light::intensity_at (point_light.rs:28-34, rectangle_light.rs:76-88).  DRAWN: the kernel build for small scenes whose
+// area light draws its jitter from the counter-based generator (only that build carries intensity_cells<.., false>).
+template <bool STATS, bool SMALL, bool DRAWN>
 __device__ __forceinline__ float intensity_at(const Env& E, V3 p, unsigned pixel, unsigned path, Rays& r, Ctr<STATS>& k) {
     const DevScene& S = E.S;
     if (!S.light_is_rect) return is_shadowed<STATS, SMALL, false>(E, ld3(S.light_pos), p, r, k) ? 0.f : 1.f;
-    if (SMALL && E.SS.cell_masks) return intensity_cells<STATS>(E, p, r, k);
+    if (SMALL && E.SS.cell_masks)
+        return DRAWN ? intensity_cells<STATS, false>(E, p, pixel, path, r, k) : intensity_cells<STATS, true>(E, p, pixel, path, r, k);
     if (SMALL) cache_origins(E, p);
     float total = 0.f;
     int cell = 0;
@@ -1523,7 +1542,7 @@ __device__ __forceinline__ V3 combine(V3 surface, V3 reflected, V3 refracted, fl
 // Without the vote the compiler's reconvergence points leave lanes that took different exits of the body running
 // their iterations one after the other (c5: 5 of 32 lanes active in the traversal code; 126 -> 64 ms with it).  Scenes
 // whose trees are chains run ~5 % faster without it.
-template <bool STATS, bool SMALL, bool CONVERGE>
+template <bool STATS, bool SMALL, bool CONVERGE, bool DRAWN = false>
 __device__ __forceinline__ V3 color_at(const Env& E, bool active, V3 ro, V3 rd, int depth, unsigned pixel, Rays& r, Ctr<STATS>& k,
                                        float* out_t, int* out_pos) {
     const DevScene& S = E.S;
@@ -1561,7 +1580,7 @@ __device__ __forceinline__ V3 color_at(const Env& E, bool active, V3 ro, V3 rd, 
             if (dot(n, eye) < 0.0f) n = -n;
             V3 over_point = point + n * kAcne;
             // ---- shade_hit (world.rs:62-86): light intensity first, then Phong (phong_lighting.rs:12-63)
-            float li = intensity_at<STATS, SMALL>(E, over_point, pixel, path, r, k);
+            float li = intensity_at<STATS, SMALL, DRAWN>(E, over_point, pixel, path, r, k);
             V3 material_color = ld3(mat.color);
             if (mat.pattern >= 0) {
                 k.pattern();

@@ -62,7 +62,7 @@ __device__ __forceinline__ void flush_counters<true>(const Rays& r, const Ctr<tr
     warp_add(&out->prim_tests[7], k.refilters);  // shadow-filter fallbacks to the exact test
 }
 
-template <bool STATS, bool SMALL, bool CONVERGE>
+template <bool STATS, bool SMALL, bool CONVERGE, bool DRAWN>
 __global__ void __launch_bounds__(128, SMALL ? RTC_SMALL_MINBLOCKS : RTC_BVH_MINBLOCKS) render_tiles(const __grid_constant__ DevScene S, const __grid_constant__ SmallScene SS,
                                                     const DevFrame F, DevCounters* counters) {
     // small scenes: primitive table + per-thread shadow-origin cache in dynamic shared memory (kSmallSmemBytes)
@@ -92,7 +92,7 @@ __global__ void __launch_bounds__(128, SMALL ? RTC_SMALL_MINBLOCKS : RTC_BVH_MIN
         r.primary++;
     }
     if (CONVERGE || rendered)
-        c = color_at<STATS, SMALL, CONVERGE>(E, rendered, o, d, F.depth, (unsigned)(y * S.width + x), r, k, nullptr, nullptr);
+        c = color_at<STATS, SMALL, CONVERGE, DRAWN>(E, rendered, o, d, F.depth, (unsigned)(y * S.width + x), r, k, nullptr, nullptr);
     if (inside) {
         size_t idx = ((size_t)y * S.width + x) * 3;
         if (F.rgb) {
@@ -141,22 +141,31 @@ void launch_render(const DevScene& S, const SmallScene& SS, const DevFrame& F, D
     dim3 grid((S.width + kTileW - 1) / kTileW, F.n_bands);
     if (grid.x == 0 || grid.y == 0) return;
     const bool small = SS.n > 0;
+    // small scenes whose area light draws its samples (jitter None) need the build with the drawn-sample cell loop
+    const bool drawn = small && SS.cell_masks && S.jitter_len == 0;
     // the detailed (counting) pass always uses the converging build; the timed kernels pick by DevFrame::converge
-    if (detailed) {
-        if (small)
-            render_tiles<true, true, true><<<grid, 128, kSmallSmemBytes, stream>>>(S, SS, F, counters);
+    if (drawn) {
+        if (detailed)
+            render_tiles<true, true, true, true><<<grid, 128, kSmallSmemBytes, stream>>>(S, SS, F, counters);
+        else if (F.converge)
+            render_tiles<false, true, true, true><<<grid, 128, kSmallSmemBytes, stream>>>(S, SS, F, counters);
         else
-            render_tiles<true, false, true><<<grid, 128, 0, stream>>>(S, SS, F, counters);
+            render_tiles<false, true, false, true><<<grid, 128, kSmallSmemBytes, stream>>>(S, SS, F, counters);
+    } else if (detailed) {
+        if (small)
+            render_tiles<true, true, true, false><<<grid, 128, kSmallSmemBytes, stream>>>(S, SS, F, counters);
+        else
+            render_tiles<true, false, true, false><<<grid, 128, 0, stream>>>(S, SS, F, counters);
     } else if (small) {
         if (F.converge)
-            render_tiles<false, true, true><<<grid, 128, kSmallSmemBytes, stream>>>(S, SS, F, counters);
+            render_tiles<false, true, true, false><<<grid, 128, kSmallSmemBytes, stream>>>(S, SS, F, counters);
         else
-            render_tiles<false, true, false><<<grid, 128, kSmallSmemBytes, stream>>>(S, SS, F, counters);
+            render_tiles<false, true, false, false><<<grid, 128, kSmallSmemBytes, stream>>>(S, SS, F, counters);
     } else {
         if (F.converge)
-            render_tiles<false, false, true><<<grid, 128, 0, stream>>>(S, SS, F, counters);
+            render_tiles<false, false, true, false><<<grid, 128, 0, stream>>>(S, SS, F, counters);
         else
-            render_tiles<false, false, false><<<grid, 128, 0, stream>>>(S, SS, F, counters);
+            render_tiles<false, false, false, false><<<grid, 128, 0, stream>>>(S, SS, F, counters);
     }
 }
 
