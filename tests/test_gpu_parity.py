@@ -16,6 +16,8 @@ SCENES = {
     "soft_shadows_table": (scenes.soft_shadows, dict(width=250, height=100, u_steps=4, v_steps=4)),
     "soft_shadows_constant": (scenes.soft_shadows, dict(width=200, height=80, u_steps=3, v_steps=2, jitter="constant")),
     "soft_shadows_counter_rng": (scenes.soft_shadows, dict(width=200, height=80, u_steps=3, v_steps=3, jitter=None, seed=7)),
+    # as shipped (soft_shadows.rs:72-82): 10 x 10 cells, jitter None -> four 32-cell chunks of drawn samples
+    "soft_shadows_as_shipped": (scenes.soft_shadows, dict(width=150, height=60, u_steps=10, v_steps=10, jitter=None, seed=3)),
     "reflect_refract": (scenes.reflect_refract, dict(width=320, height=160)),
     "reflect_refract_csg": (scenes.reflect_refract, dict(width=240, height=120, with_csg=True)),
     "hexagons": (scenes.hexagons, dict(width=240, height=120)),
@@ -146,7 +148,8 @@ def test_longest_first_band_order_changes_no_pixel(gpu):
         p.release()
 
 
-FILTERED = ["default_world", "soft_shadows_table", "soft_shadows_constant", "soft_shadows_counter_rng", "filter_zoo_area",
+FILTERED = ["default_world", "soft_shadows_table", "soft_shadows_constant", "soft_shadows_counter_rng", "soft_shadows_as_shipped",
+            "filter_zoo_area",
             "filter_zoo_table", "filter_zoo_point"]
 
 
