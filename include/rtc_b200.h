@@ -174,9 +174,9 @@ enum {
     RTC_OPT_BVH_MIN_PRIMS = 3,
     RTC_OPT_RENDER_SLICES = 4, /* kernel launches a frame is cut into when it is copied to host memory, so the
                                   copy of one slice overlaps the kernel of the next (default 6) */
-    RTC_OPT_ADAPTIVE_ORDER = 5, /* default 1: a repeated render of the same shard launches its bands
-                                  most-expensive-first (rays per band counted by the previous render); changes no
-                                  pixel, shortens the tail of the launch */
+    RTC_OPT_ADAPTIVE_ORDER = 5, /* default 1: a repeated render of the same shard launches its 16x8-pixel tiles
+                                  most-expensive-first (clock cycles per tile recorded by the first render); used
+                                  for launches short enough to have a tail (a shard of a frame); changes no pixel */
     RTC_OPT_SHADOW_FILTER = 6   /* default 1: in small scenes of spheres, planes and axis-aligned cubes a shadow ray is
                                   first decided on the un-normalised point->light segment with error bounds; only
                                   undecided rays run the reference's arithmetic.  Changes no pixel (0 = always run

@@ -130,7 +130,7 @@ def test_band_sharding_is_bit_identical(gpu):
 
 
 def test_longest_first_band_order_changes_no_pixel(gpu):
-    """RTC_OPT_ADAPTIVE_ORDER: the second render of a shard launches its bands most-expensive-first."""
+    """RTC_OPT_ADAPTIVE_ORDER: after the render that records the tile costs, a shard launches its tiles most-expensive-first."""
     cam, world = scenes.soft_shadows(gpu, width=203, height=177, u_steps=2, v_steps=2)
     p = cam.prepare(world)
     try:
