@@ -693,6 +693,7 @@ int flatten(RtcScene* s, Flattened& f) {
             int bucket = (caster ? 0 : 4) + (type == T_SPHERE ? 0 : type == T_PLANE ? 1 : type == T_CUBE ? 2 : 3);
             for (int b = bucket; b < 8; b++) ends[b] = i + 1;
             if ((h.x >> 4) & kFlagHasParent) f.small.has_cull_chain = 1;
+            sp.ball = make_float4(NAN, NAN, NAN, NAN);  // a NaN ball never rejects
             if (type == T_CSG) {
                 f.small.two_pass_shadows = 0;
                 sp.r0 = sp.r1 = sp.r2 = sp.bound = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -700,6 +701,46 @@ int flatten(RtcScene* s, Flattened& f) {
             }
             sp.r0 = f.xform[3 * (size_t)h.y], sp.r1 = f.xform[3 * (size_t)h.y + 1], sp.r2 = f.xform[3 * (size_t)h.y + 2];
             sp.bound = (type == T_CYLINDER || type == T_CONE) ? f.bound[h.z] : make_float4(0.f, 0.f, 0.f, 0.f);
+            // ---- world-space bounding ball (rtc_device.cuh: ball_missed, bundle_misses).  Sphere / cube: centre =
+            // forward transform of the origin, radius = the largest stretch of the forward 3x3 (bounded by
+            // sqrt(|T|_1 |T|_inf)), times sqrt(3) for a cube's corners; other bounded shapes: the ball around their
+            // world box.  bound.w = 2^-17 cond^2 / radius is the rate at which the tested radius grows with the squared
+            // distance of the ray origin: beyond that clearance no f32 intersection test of the reference reports a hit.
+            {
+                const double m[3][4] = {{sp.r0.x, sp.r0.y, sp.r0.z, sp.r0.w}, {sp.r1.x, sp.r1.y, sp.r1.z, sp.r1.w}, {sp.r2.x, sp.r2.y, sp.r2.z, sp.r2.w}};
+                const double det = m[0][0] * (m[1][1] * m[2][2] - m[1][2] * m[2][1]) - m[0][1] * (m[1][0] * m[2][2] - m[1][2] * m[2][0]) +
+                                   m[0][2] * (m[1][0] * m[2][1] - m[1][1] * m[2][0]);
+                double t[3][3], n1 = 0.0, ninf = 0.0, mi = 0.0;  // t = forward 3x3 = inverse of m's 3x3
+                for (int a = 0; a < 3; a++)
+                    for (int b = 0; b < 3; b++) {
+                        const int a1 = (a + 1) % 3, a2 = (a + 2) % 3, b1 = (b + 1) % 3, b2 = (b + 2) % 3;
+                        t[a][b] = (m[b1][a1] * m[b2][a2] - m[b1][a2] * m[b2][a1]) / det;
+                    }
+                for (int a = 0; a < 3; a++) {
+                    n1 = std::max(n1, std::fabs(t[0][a]) + std::fabs(t[1][a]) + std::fabs(t[2][a]));
+                    ninf = std::max(ninf, std::fabs(t[a][0]) + std::fabs(t[a][1]) + std::fabs(t[a][2]));
+                    mi = std::max(mi, std::fabs(m[a][0]) + std::fabs(m[a][1]) + std::fabs(m[a][2]));
+                }
+                const double cond = std::max(1.0, mi * ninf);
+                double c[3], radius;
+                if (type == T_SPHERE || type == T_CUBE) {
+                    radius = std::sqrt(n1 * ninf) * (type == T_CUBE ? std::sqrt(3.0) : 1.0);
+                    for (int a = 0; a < 3; a++) c[a] = -(t[a][0] * m[0][3] + t[a][1] * m[1][3] + t[a][2] * m[2][3]);
+                } else {
+                    const RtcPrim& pr = s->prims[h.w];
+                    double d2 = 0.0;
+                    for (int a = 0; a < 3; a++) {
+                        c[a] = 0.5 * ((double)pr.bbox_min[a] + pr.bbox_max[a]);
+                        d2 += 0.25 * ((double)pr.bbox_max[a] - pr.bbox_min[a]) * ((double)pr.bbox_max[a] - pr.bbox_min[a]);
+                    }
+                    radius = std::sqrt(d2);
+                }
+                if (std::isfinite(radius) && std::isfinite(c[0]) && std::isfinite(c[1]) && std::isfinite(c[2]) && radius > 0.0 &&
+                    std::isfinite(cond)) {
+                    sp.ball = make_float4((float)c[0], (float)c[1], (float)c[2], (float)(radius * 1.001 + 1e-6));
+                    sp.bound.w = (float)(std::ldexp(1.0, -17) * cond * cond / radius);
+                }
+            }
         }
         f.small.caster_end = make_int4(ends[0], ends[1], ends[2], ends[3]);
         f.small.other_end = make_int4(ends[4], ends[5], ends[6], ends[7]);
@@ -762,34 +803,6 @@ int flatten(RtcScene* s, Flattened& f) {
             for (const float4& q : pts)
                 rl = std::max(rl, std::sqrt((q.x - lc[0]) * (q.x - lc[0]) + (q.y - lc[1]) * (q.y - lc[1]) + (q.z - lc[2]) * (q.z - lc[2])));
             f.small.light_ball = make_float4((float)lc[0], (float)lc[1], (float)lc[2], (float)(rl * 1.001 + 1e-6));
-            for (int i = 0; i < n_items; i++) {
-                SmallPrim& sp = f.small.p[i];
-                const int type = sp.head.x & 15;
-                if (type != T_SPHERE && type != T_CUBE) continue;
-                const double m[3][4] = {{sp.r0.x, sp.r0.y, sp.r0.z, sp.r0.w}, {sp.r1.x, sp.r1.y, sp.r1.z, sp.r1.w}, {sp.r2.x, sp.r2.y, sp.r2.z, sp.r2.w}};
-                const double det = m[0][0] * (m[1][1] * m[2][2] - m[1][2] * m[2][1]) - m[0][1] * (m[1][0] * m[2][2] - m[1][2] * m[2][0]) +
-                                   m[0][2] * (m[1][0] * m[2][1] - m[1][1] * m[2][0]);
-                double t[3][3], n1 = 0.0, ninf = 0.0, mi = 0.0;  // t = forward 3x3 = inverse of m's 3x3
-                for (int a = 0; a < 3; a++)
-                    for (int b = 0; b < 3; b++) {
-                        const int a1 = (a + 1) % 3, a2 = (a + 2) % 3, b1 = (b + 1) % 3, b2 = (b + 2) % 3;
-                        t[a][b] = (m[b1][a1] * m[b2][a2] - m[b1][a2] * m[b2][a1]) / det;
-                    }
-                for (int a = 0; a < 3; a++) {
-                    n1 = std::max(n1, std::fabs(t[0][a]) + std::fabs(t[1][a]) + std::fabs(t[2][a]));
-                    ninf = std::max(ninf, std::fabs(t[a][0]) + std::fabs(t[a][1]) + std::fabs(t[a][2]));
-                    mi = std::max(mi, std::fabs(m[a][0]) + std::fabs(m[a][1]) + std::fabs(m[a][2]));
-                }
-                const double stretch = std::sqrt(n1 * ninf), cond = std::max(1.0, mi * ninf);
-                const double radius = stretch * (type == T_CUBE ? std::sqrt(3.0) : 1.0);
-                double c[3];  // centre: -T * (translation column of the inverse)
-                for (int a = 0; a < 3; a++) c[a] = -(t[a][0] * m[0][3] + t[a][1] * m[1][3] + t[a][2] * m[2][3]);
-                const bool finite = std::isfinite(radius) && std::isfinite(c[0]) && std::isfinite(c[1]) && std::isfinite(c[2]) && radius > 0.0;
-                // a non-finite ball never rejects (NaN comparisons are false)
-                sp.bound = finite ? make_float4((float)c[0], (float)c[1], (float)c[2], (float)(radius * 1.001 + 1e-6)) : make_float4(NAN, NAN, NAN, NAN);
-                const float pad = (float)(std::ldexp(1.0, -17) * cond * cond / radius);
-                memcpy(&sp.head.y, &pad, sizeof(float));
-            }
             const int n_planes = ends[1] - ends[0];
             f.small.plane_cells = table_light && n_planes > 0 && (size_t)n_planes * f.samples.size() <= (size_t)kPlaneCellCap;
             // bounds of the per-(plane, cell) constants over all cells (rtc_device.cuh: plane_cell_constants), padded

@@ -64,6 +64,11 @@ __device__ __forceinline__ V3 xf_normal(const Xf& m, V3 n) {
               m.r0.z * n.x + m.r1.z * n.y + m.r2.z * n.z);
 }
 
+// explicitly fused / approximate arithmetic for the conservative pre-tests and the shadow filter (never for values
+// that reach a pixel): the same instructions in the IEEE and the FMA-contracting build
+__device__ __forceinline__ float fma_(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+__device__ __forceinline__ float rcp_(float a) { return __fdividef(1.0f, a); }
+
 constexpr float kInfF = __builtin_huge_valf();
 constexpr float kAcne = 1.1920929e-7f * 10000.0f;  // world.rs:210
 constexpr float kCloseToZero = 0.000001f;           // cylinder.rs:82, cone.rs:87
@@ -870,7 +875,7 @@ __device__ __forceinline__ const float4* small_tab() {
 }
 __device__ __forceinline__ float* small_org() {
     extern __shared__ float4 rtc_smem[];
-    return reinterpret_cast<float*>(rtc_smem + kSmallCap * 5) + threadIdx.x;
+    return reinterpret_cast<float*>(rtc_smem + kSmallCap * kSmallStride) + threadIdx.x;
 }
 // Shadow filter, plane test with the light sample folded in (SmallScene::plane_cells): for light point L and shading
 // point p the object-space direction's y is r1.L - r1.p, so everything that depends on L alone is staged once per
@@ -883,18 +888,18 @@ __device__ __forceinline__ float4 plane_cell_constants(float4 r1, float4 L) {
 }
 __device__ __forceinline__ const float4* small_plane_cells() {
     extern __shared__ float4 rtc_smem[];
-    return rtc_smem + kSmallCap * 5 + kOrgCache * 3 * 128 / 4 + kSampleCap;
+    return rtc_smem + kSmallCap * kSmallStride + kOrgCache * 3 * 128 / 4 + kSampleCap;
 }
 __device__ __forceinline__ const float4* small_samples() {  // table-mode light samples (SmallScene::cell_masks)
     extern __shared__ float4 rtc_smem[];
-    return rtc_smem + kSmallCap * 5 + kOrgCache * 3 * 128 / 4;
+    return rtc_smem + kSmallCap * kSmallStride + kOrgCache * 3 * 128 / 4;
 }
 __device__ __forceinline__ void stage_small_scene(const DevScene& S, const SmallScene& SS) {
     extern __shared__ float4 rtc_smem[];
     const float4* src = reinterpret_cast<const float4*>(SS.p);
-    for (int i = threadIdx.x; i < SS.n * 5; i += blockDim.x) rtc_smem[i] = src[i];
+    for (int i = threadIdx.x; i < SS.n * kSmallStride; i += blockDim.x) rtc_smem[i] = src[i];
     if (SS.cell_masks && S.jitter_len > 0) {
-        float4* dst = rtc_smem + kSmallCap * 5 + kOrgCache * 3 * 128 / 4;
+        float4* dst = rtc_smem + kSmallCap * kSmallStride + kOrgCache * 3 * 128 / 4;
         for (int i = threadIdx.x; i < S.cells; i += blockDim.x) dst[i] = __ldg(&S.samples[i]);
         if (SS.plane_cells) {  // see plane_cell_constants
             const int n_planes = SS.caster_end.y - SS.caster_end.x;
@@ -924,7 +929,7 @@ __device__ __forceinline__ void cache_origins(const Env& E, V3 o) {
     const float4* tab = small_tab();
     float* org = small_org();
     for (int i = 0; i < n; i++) {
-        Xf m{tab[i * 5 + 1], tab[i * 5 + 2], tab[i * 5 + 3]};
+        Xf m{tab[i * kSmallStride + 1], tab[i * kSmallStride + 2], tab[i * kSmallStride + 3]};
         V3 o2 = xf_point(m, o);
         org[(i * 3 + 0) * 128] = o2.x;
         org[(i * 3 + 1) * 128] = o2.y;
@@ -932,12 +937,27 @@ __device__ __forceinline__ void cache_origins(const Env& E, V3 o) {
     }
 }
 
+// Ray-vs-bounding-ball pre-test of the small-scene loops: true when the LINE o + t d stays clear of the primitive's
+// world-space ball {centre, radius} grown by `pad_rate * |centre - o|^2` (SmallPrim::ball / bound.w) — then the
+// reference's intersection test reports no hit either, with any sign of t (its f32 error, which for a far, small
+// object grows with the squared distance over the radius, is inside the padding), and the exact test is skipped.
+// ~14 instructions against ~90 for a sphere and ~250 for a cylinder or cone.  NaN ball (planes, CSG): never true.
+__device__ __forceinline__ bool ball_missed(float4 ball, float pad_rate, V3 o, V3 d) {
+    const float wx = ball.x - o.x, wy = ball.y - o.y, wz = ball.z - o.z;
+    const float ww = fma_(wx, wx, fma_(wy, wy, wz * wz));
+    const float wd = fma_(wx, d.x, fma_(wy, d.y, wz * d.z));
+    const float dd = fma_(d.x, d.x, fma_(d.y, d.y, d.z * d.z));
+    const float R = fma_(pad_rate, ww, ball.w);
+    // squared distance of the centre from the line, times |d|^2, against the squared radius times |d|^2 (0.1 % margin)
+    return fma_(ww, dd, -(wd * wd)) > R * R * dd * 1.001f;
+}
+
 // One item of a small scene of any kind (primitive or CSG root), honouring the cull chain: the general form
 // (out of line: cylinders, cones, triangles and CSG roots are the rare members of small scenes).
 template <bool STATS>
 __device__ __noinline__ void test_small(const Env& E, int i, bool cached, V3 o, V3 d, Hit& best, Ctr<STATS>& k) {
     const float4* tab = small_tab();
-    const int4 head = *reinterpret_cast<const int4*>(tab + i * 5);
+    const int4 head = *reinterpret_cast<const int4*>(tab + i * kSmallStride);
     const int type = head.x & 15;
     if (type == T_CSG) {
         float ht[kCsgHitCap];
@@ -951,12 +971,12 @@ __device__ __noinline__ void test_small(const Env& E, int i, bool cached, V3 o, 
         }
         return;
     }
-    Xf m{tab[i * 5 + 1], tab[i * 5 + 2], tab[i * 5 + 3]};
+    Xf m{tab[i * kSmallStride + 1], tab[i * kSmallStride + 2], tab[i * kSmallStride + 3]};
     V3 o2 = cached ? small_origin(true, i, m, o) : xf_point(m, o);
     V3 d2 = xf_vec(m, d);
     k.xform();
     k.prim(type);
-    float tn = nearest_t(E.S, type, head.z, tab[i * 5 + 4], o2, d2);
+    float tn = nearest_t(E.S, type, head.z, tab[i * kSmallStride + 4], o2, d2);
     if (((head.x >> 4) & kFlagHasParent) && tn >= 0.0f && !ancestors_pass(E.S, head.y, o, d)) return;
     consider(best, tn, i, head.w);
 }
@@ -970,17 +990,18 @@ __device__ __forceinline__ bool scan_small(const Env& E, bool cached, int begin,
     const float4* tab = small_tab();
     int i = begin;
     for (; i < ends.x; i++) {  // spheres — sphere.rs:47-70
-        Xf m{tab[i * 5 + 1], tab[i * 5 + 2], tab[i * 5 + 3]};
+        if (ball_missed(tab[i * kSmallStride + 5], tab[i * kSmallStride + 4].w, o, d)) continue;
+        Xf m{tab[i * kSmallStride + 1], tab[i * kSmallStride + 2], tab[i * kSmallStride + 3]};
         V3 o2 = small_origin(cached, i, m, o);
         V3 d2 = xf_vec(m, d);
         k.xform();
         k.prim(T_SPHERE);
         float t = nearest_t(E.S, T_SPHERE, 0, make_float4(0.f, 0.f, 0.f, 0.f), o2, d2);
         if (any && t >= 0.0f && t < best.t) return true;
-        consider(best, t, i, __float_as_int(tab[i * 5].w));
+        consider(best, t, i, __float_as_int(tab[i * kSmallStride].w));
     }
     for (; i < ends.y; i++) {  // planes — plane.rs:45-56 only reads the y components of the object-space ray
-        float4 r1 = tab[i * 5 + 2];
+        float4 r1 = tab[i * kSmallStride + 2];
         float oy;
         if (cached && i < kOrgCache)
             oy = small_org()[(i * 3 + 1) * 128];
@@ -991,19 +1012,21 @@ __device__ __forceinline__ bool scan_small(const Env& E, bool cached, int begin,
         k.prim(T_PLANE);
         float t = (fabsf(dy) < kAcne) ? -1.0f : -oy / dy;
         if (any && t >= 0.0f && t < best.t) return true;
-        consider(best, t, i, __float_as_int(tab[i * 5].w));
+        consider(best, t, i, __float_as_int(tab[i * kSmallStride].w));
     }
     for (; i < ends.z; i++) {  // cubes — cube.rs:55-63
-        Xf m{tab[i * 5 + 1], tab[i * 5 + 2], tab[i * 5 + 3]};
+        if (ball_missed(tab[i * kSmallStride + 5], tab[i * kSmallStride + 4].w, o, d)) continue;
+        Xf m{tab[i * kSmallStride + 1], tab[i * kSmallStride + 2], tab[i * kSmallStride + 3]};
         V3 o2 = small_origin(cached, i, m, o);
         V3 d2 = xf_vec(m, d);
         k.xform();
         k.prim(T_CUBE);
         float t = nearest_t(E.S, T_CUBE, 0, make_float4(0.f, 0.f, 0.f, 0.f), o2, d2);
         if (any && t >= 0.0f && t < best.t) return true;
-        consider(best, t, i, __float_as_int(tab[i * 5].w));
+        consider(best, t, i, __float_as_int(tab[i * kSmallStride].w));
     }
     for (; i < ends.w; i++) {  // cylinders, cones, triangles, CSG roots
+        if (ball_missed(tab[i * kSmallStride + 5], tab[i * kSmallStride + 4].w, o, d)) continue;
         const int before = best.pos;
         test_small<STATS>(E, i, cached, o, d, best, k);
         if (any && best.pos != before) return true;
@@ -1051,8 +1074,6 @@ struct FRes {
     int code;
     float s, e;  // F_HIT: segment parameter of the nearest hit and its error bound
 };
-__device__ __forceinline__ float fma_(float a, float b, float c) { return __fmaf_rn(a, b, c); }
-__device__ __forceinline__ float rcp_(float a) { return __fdividef(1.0f, a); }
 
 // sphere.rs:47-70 on the segment o + s * d, d = M * (light - point).  `tol` = SmallScene::tol_sphere, which scales
 // with the worst condition number of the spheres' transforms (set at commit).
@@ -1169,13 +1190,13 @@ __device__ __forceinline__ int filter_scan(const Env& E, bool cached, int begin,
     };
     int i = begin;
     for (; i < ends.x; i++) {
-        Xf m{tab[i * 5 + 1], tab[i * 5 + 2], tab[i * 5 + 3]};
+        Xf m{tab[i * kSmallStride + 1], tab[i * kSmallStride + 2], tab[i * kSmallStride + 3]};
         k.xform();
         k.prim(T_SPHERE);
         if (take(filter_sphere(m, small_origin(cached, i, m, p), v, tol))) return result;
     }
     for (; i < ends.y; i++) {
-        float4 r1 = tab[i * 5 + 2];
+        float4 r1 = tab[i * kSmallStride + 2];
         float oy;
         if (cached && i < kOrgCache)
             oy = small_org()[(i * 3 + 1) * 128];
@@ -1186,7 +1207,7 @@ __device__ __forceinline__ int filter_scan(const Env& E, bool cached, int begin,
         if (take(filter_plane<MODE != 0>(r1, oy, v, len))) return result;
     }
     for (; i < ends.z; i++) {
-        Xf m{tab[i * 5 + 1], tab[i * 5 + 2], tab[i * 5 + 3]};
+        Xf m{tab[i * kSmallStride + 1], tab[i * kSmallStride + 2], tab[i * kSmallStride + 3]};
         k.xform();
         k.prim(T_CUBE);
         if (take(filter_cube(m, small_origin(cached, i, m, p), v))) return result;
@@ -1356,9 +1377,9 @@ __device__ __forceinline__ float intensity_cells(const Env& E, V3 p, unsigned pi
         float far_hit = 0.0f;  // no caster hit of this chunk is farther from p than this (bounding balls)
         int i = 0;
         for (; i < ends.x && (hit | unsure) != full; i++) {  // caster spheres
-            if (bundle_misses(tab[i * 5 + 4], tab[i * 5].y, SS.light_ball, p)) continue;
+            if (bundle_misses(tab[i * kSmallStride + 5], tab[i * kSmallStride + 4].w, SS.light_ball, p)) continue;
             const unsigned hit_before = hit;
-            const Xf m{tab[i * 5 + 1], tab[i * 5 + 2], tab[i * 5 + 3]};
+            const Xf m{tab[i * kSmallStride + 1], tab[i * kSmallStride + 2], tab[i * kSmallStride + 3]};
             const V3 o = xf_point(m, p);  // the reference's object-space origin (shape.rs:60-70), once per shade
             const float oo = fma_(o.x, o.x, fma_(o.y, o.y, o.z * o.z));
             const float c = oo - 1.0f;
@@ -1385,11 +1406,11 @@ __device__ __forceinline__ float intensity_cells(const Env& E, V3 p, unsigned pi
                 k.xform();
                 k.prim(T_SPHERE);
             }
-            if (hit != hit_before) far_hit = fmaxf(far_hit, ball_reach(tab[i * 5 + 4], p));
+            if (hit != hit_before) far_hit = fmaxf(far_hit, ball_reach(tab[i * kSmallStride + 5], p));
         }
         for (i = ends.x; i < ends.y && (hit | unsure) != full; i++) {  // caster planes
             const unsigned hit_before = hit;
-            const float4 r1 = tab[i * 5 + 2];
+            const float4 r1 = tab[i * kSmallStride + 2];
             const float tx = r1.x * p.x, ty = r1.y * p.y, tz = r1.z * p.z;
             const float rp = tx + ty + tz;
             const float oy = rp + r1.w;  // the reference's object-space origin.y (shape.rs:60-70)
@@ -1434,9 +1455,9 @@ __device__ __forceinline__ float intensity_cells(const Env& E, V3 p, unsigned pi
             if (hit != hit_before) far_hit = kInfF;
         }
         for (i = ends.y; i < ends.z && (hit | unsure) != full; i++) {  // caster cubes
-            if (bundle_misses(tab[i * 5 + 4], tab[i * 5].y, SS.light_ball, p)) continue;
+            if (bundle_misses(tab[i * kSmallStride + 5], tab[i * kSmallStride + 4].w, SS.light_ball, p)) continue;
             const unsigned hit_before = hit;
-            const Xf m{tab[i * 5 + 1], tab[i * 5 + 2], tab[i * 5 + 3]};
+            const Xf m{tab[i * kSmallStride + 1], tab[i * kSmallStride + 2], tab[i * kSmallStride + 3]};
             const V3 o = xf_point(m, p);
 #pragma unroll 2
             for (int j = 0; j < nc; j++) {
@@ -1449,7 +1470,7 @@ __device__ __forceinline__ float intensity_cells(const Env& E, V3 p, unsigned pi
                 k.xform();
                 k.prim(T_CUBE);
             }
-            if (hit != hit_before) far_hit = fmaxf(far_hit, ball_reach(tab[i * 5 + 4], p));
+            if (hit != hit_before) far_hit = fmaxf(far_hit, ball_reach(tab[i * kSmallStride + 5], p));
         }
         for (int j = 0; j < nc; j++) k.cell();
         // pass 2.  A non-caster only matters where it is NEARER than the nearest caster hit (world.rs:113-118): when
@@ -1459,7 +1480,7 @@ __device__ __forceinline__ float intensity_cells(const Env& E, V3 p, unsigned pi
         if (!hits_final && (hit & ~unsure) != 0u) {
             float near_other = kInfF;
             for (int q = ends.w; q < SS.other_end.z; q++) {
-                const float4 ball = tab[q * 5 + 4];
+                const float4 ball = tab[q * kSmallStride + 5];
                 const bool has_ball = q < SS.other_end.x || q >= SS.other_end.y;  // spheres and cubes; planes have none
                 near_other = fminf(near_other, has_ball ? ball_gap(ball, p) : 0.0f);
             }

@@ -114,11 +114,13 @@ struct DevScene {
 // through the uniform datapath, no global loads, no address arithmetic, no divergence on the type switch.
 constexpr int kSmallCap = 16;   // primitives (or CSG roots) held in the parameter block
 constexpr int kOrgCache = 8;    // object-space shadow-ray origins cached per thread in shared memory
-struct SmallPrim {              // 80 B
+constexpr int kSmallStride = 6;  // float4 per table entry
+struct SmallPrim {              // 96 B
     int4 head;                  // type | flags << 4 | material << 8, cull-chain parent node, aux, dfs order
     float4 r0, r1, r2;          // rows of the inverse transform
-    float4 bound;               // cylinder / cone: minimum_y, maximum_y, closed.  filter_ok scenes, sphere / cube: the
-                                // world-space bounding ball {centre, radius * 1.001} (head.y then holds 2^-17 / radius)
+    float4 bound;               // cylinder / cone: minimum_y, maximum_y, closed; .w = the ball's padding rate (below)
+    float4 ball;                // world-space bounding ball {centre, radius * 1.001} (NaN: unbounded, never rejects);
+                                // tested with radius + bound.w * |centre - origin|^2 (bound.w = 2^-17 cond^2 / radius)
 };
 // The table is sorted by (casts shadow first, then kind) so every loop over it is a run of ONE kind:
 //   casters:     spheres [0, c.x) planes [c.x, c.y) cubes [c.y, c.z) everything else [c.z, c.w)
@@ -141,7 +143,7 @@ struct SmallScene {
 };
 constexpr int kSampleCap = 128;     // table-mode light samples staged in shared memory
 constexpr int kPlaneCellCap = 256;  // (caster plane, light cell) constants staged in shared memory
-constexpr int kSmallSmemBytes = kSmallCap * 80 + kOrgCache * 3 * 128 * 4 + kSampleCap * 16 + kPlaneCellCap * 16;
+constexpr int kSmallSmemBytes = kSmallCap * kSmallStride * 16 + kOrgCache * 3 * 128 * 4 + kSampleCap * 16 + kPlaneCellCap * 16;
 
 struct DevFrame {  // where a render writes
     float* rgb;            // width*height*3 f32 or null
