@@ -343,6 +343,9 @@ def main() -> None:
                         "traffic_source": prof.get("source"),
                         "issue_slot_utilisation_pct": prof.get("issue_active_pct"),
                         "fma_pipe_utilisation_pct": prof.get("pipe_fma_pct"),
+                        # what the hardware executed (ncu SASS counts of the committed capture: FADD + FMUL + 2 FFMA + FMNMX +
+                        # MUFU, predicated-on threads) over this run's kernel time
+                        "executed_fp32_tflops": round(prof["executed_fp32_flops"] / (ms_frame * 1e-3) / 1e12, 3) if prof.get("executed_fp32_flops") else None,
                         "what": "achieved = algorithmic FP32 flops of the units the kernel EXECUTED (SURVEY.md Appendix E table x the "
                                 "detailed pass's counters: tests skipped by the shadow filter's bundle reject are not counted) / kernel time",
                         "peak_kind": "measured live: K5 FMA micro-benchmark (MEASURED_PEAKS.json has no FP32 figure)",

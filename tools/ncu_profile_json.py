@@ -34,8 +34,20 @@ out = {
     "registers_per_thread": get("launch__registers_per_thread"),
     "warps_active_pct": round(get("sm__warps_active.avg.pct_of_peak_sustained_active"), 2),
 }
-for k in ("ffma", "fmul", "fadd"):
-    name = f"smsp__sass_thread_inst_executed_op_{k}_pred_on.sum"
-    if name in hdr:
-        out[f"thread_{k}"] = get(name)
+# FP32 work the hardware executed: predicated-on thread instructions per opcode from the SASS page
+src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+srows = list(csv.reader(io.StringIO(src)))
+hi = next(i for i, r in enumerate(srows) if "Source" in r and "Instructions Executed" in r)
+h = srows[hi]
+isrc, ith = h.index("Source"), h.index("Predicated-On Thread Instructions Executed")
+ops = {}
+for r in srows[hi + 1:]:
+    try:
+        parts = r[isrc].split()
+        op = (parts[1] if parts[0].startswith("@") else parts[0]).split(".")[0]
+        ops[op] = ops.get(op, 0) + int(r[ith])
+    except (IndexError, ValueError):
+        pass
+out["thread_fadd"], out["thread_fmul"], out["thread_ffma"] = ops.get("FADD", 0), ops.get("FMUL", 0), ops.get("FFMA", 0)
+out["executed_fp32_flops"] = ops.get("FADD", 0) + ops.get("FMUL", 0) + 2 * ops.get("FFMA", 0) + ops.get("FMNMX", 0) + ops.get("MUFU", 0)
 print(json.dumps(out, indent=1))
