@@ -17,6 +17,30 @@ pub struct FlatScene {
     pub materials: Vec<sys::RtcMaterial>,
     pub patterns: Vec<sys::RtcPattern>,
     pub uvs: Vec<sys::RtcUvPattern>,
+    /// One entry per distinct UVImage canvas (uv.rs:346-377): its f32 pixels row-major, kept alive until commit.
+    pub texture_pixels: Vec<Vec<f32>>,
+    pub texture_sizes: Vec<(u32, u32)>,
+}
+
+// UVImage lowering (inside uv.rs, where `canvas` is visible): the canvas travels once as an RtcTexture and the uv
+// pattern refers to it by index (params[0]).
+impl UVImage {
+    fn lower_uv(&self, out: &mut FlatScene) -> i32 {
+        let (w, h) = (self.canvas.width, self.canvas.height);
+        let mut px = Vec::with_capacity(w * h * 3);
+        for y in 0..h {
+            for x in 0..w {
+                let c = self.canvas.pixel_at(x, y);
+                px.extend_from_slice(&[c.r, c.g, c.b]);
+            }
+        }
+        out.texture_pixels.push(px);
+        out.texture_sizes.push((w as u32, h as u32));
+        let mut params = [0f32; 15];
+        params[0] = (out.texture_pixels.len() - 1) as f32;
+        out.uvs.push(sys::RtcUvPattern { kind: sys::RTC_UV_IMAGE, params });
+        (out.uvs.len() - 1) as i32
+    }
 }
 
 fn mat16(m: &Matrix) -> [f32; 16] {
@@ -65,6 +89,9 @@ impl Camera {
             check(sys::rtc_set_nodes(scene, flat.nodes.len() as u32, flat.nodes.as_ptr(), flat.refs.len() as u32, flat.refs.as_ptr()));
             check(sys::rtc_set_materials(scene, flat.materials.len() as u32, flat.materials.as_ptr()));
             check(sys::rtc_set_patterns(scene, flat.patterns.len() as u32, flat.patterns.as_ptr(), flat.uvs.len() as u32, flat.uvs.as_ptr()));
+            let textures: Vec<sys::RtcTexture> = flat.texture_pixels.iter().zip(&flat.texture_sizes)
+                .map(|(px, &(w, h))| sys::RtcTexture { width: w, height: h, rgb: px.as_ptr() }).collect();
+            check(sys::rtc_set_textures(scene, textures.len() as u32, textures.as_ptr()));
             world.light.as_ref().expect("World light should be set").lower(scene); // world.rs:66
             check(sys::rtc_scene_commit(scene, 0, std::ptr::null())); // every visible GPU
             let mut stats = sys::RtcStats::default();

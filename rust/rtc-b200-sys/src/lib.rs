@@ -24,6 +24,11 @@ pub const RTC_TRIANGLE: i32 = 5;
 pub const RTC_NODE_GROUP: i32 = 0;
 pub const RTC_NODE_CSG: i32 = 1;
 pub const RTC_OPT_FMA_CONTRACTION: i32 = 1;
+pub const RTC_OPT_BVH_LEAF_SIZE: i32 = 2;
+pub const RTC_OPT_BVH_MIN_PRIMS: i32 = 3;
+pub const RTC_OPT_RENDER_SLICES: i32 = 4;
+pub const RTC_OPT_ADAPTIVE_ORDER: i32 = 5;
+pub const RTC_OPT_SHADOW_FILTER: i32 = 6;
 
 #[repr(C)]
 #[derive(Clone, Copy)]
@@ -77,6 +82,10 @@ pub struct RtcPattern {
     pub a: [f32; 3],
     pub b: [f32; 3],
 }
+
+pub const RTC_UV_CHECKERS: i32 = 0;
+pub const RTC_UV_ALIGN_CHECK: i32 = 1;
+pub const RTC_UV_IMAGE: i32 = 2;
 
 #[repr(C)]
 #[derive(Clone, Copy)]
