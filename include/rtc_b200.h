@@ -184,6 +184,26 @@ enum {
 };
 int rtc_set_option(RtcScene*, int32_t option, int64_t value);
 
+/* What rtc_scene_commit will build for the scene as it stands: runs the host half of the commit (validation, BVH,
+ * CSG programs, small-scene table and its shadow-filter eligibility) without touching a device — for tests and
+ * tooling on machines without a GPU.  Nothing is uploaded or kept. */
+typedef struct RtcCommitInfo {
+    int32_t n_positions;     /* device primitive slots (leaves + CSG pseudo-primitives) */
+    int32_t n_bvh_nodes;     /* 0: no tree */
+    int32_t n_linear;        /* primitives tested for every ray (unbounded shapes, or every item of a small scene) */
+    int32_t n_xforms;        /* distinct inverse transforms */
+    int32_t bvh_leaf_size;   /* the leaf size used (RTC_OPT_BVH_LEAF_SIZE, or the automatic choice) */
+    int32_t small_n;         /* > 0: the small-scene path, with this many table entries */
+    int32_t filter_ok;       /* shadow filter eligible (spheres / planes / axis-aligned cubes only) */
+    int32_t cell_masks;      /* area light handled by the cell-mask loops */
+    int32_t plane_cells;     /* per-(plane, cell) constants staged */
+    int32_t converge;        /* some material is reflective and transparent: the converging kernel build */
+    float tol_sphere;        /* the filter's relative error bound for spheres */
+    float light_ball[4];     /* ball around the light's sample points (cell_masks) */
+    double host_ms;          /* time the host half took */
+} RtcCommitInfo;
+int rtc_scene_inspect(RtcScene*, RtcCommitInfo* out);
+
 /* Validate, build the BVH over the primitives' bounding boxes and upload one scene replica per device.
  * device_ids == NULL selects devices 0..n_devices-1; n_devices == 0 selects every visible device. */
 int rtc_scene_commit(RtcScene*, int32_t n_devices, const int32_t* device_ids);

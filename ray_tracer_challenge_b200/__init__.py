@@ -54,6 +54,20 @@ class RtcStats(C.Structure):
         return d
 
 
+class RtcCommitInfo(C.Structure):
+    """include/rtc_b200.h: RtcCommitInfo"""
+
+    _fields_ = [
+        ("n_positions", C.c_int32), ("n_bvh_nodes", C.c_int32), ("n_linear", C.c_int32), ("n_xforms", C.c_int32),
+        ("bvh_leaf_size", C.c_int32), ("small_n", C.c_int32), ("filter_ok", C.c_int32), ("cell_masks", C.c_int32),
+        ("plane_cells", C.c_int32), ("converge", C.c_int32), ("tol_sphere", C.c_float), ("light_ball", C.c_float * 4),
+        ("host_ms", C.c_double),
+    ]
+
+    def as_dict(self) -> dict:
+        return {name: (list(getattr(self, name)) if name == "light_ball" else getattr(self, name)) for name, _ in self._fields_}
+
+
 class RtcPrim(C.Structure):
     _fields_ = [("type", C.c_int32), ("material", C.c_int32), ("casts_shadow", C.c_int32), ("parent", C.c_int32),
                 ("inv", C.c_float * 16), ("params", C.c_float * 12), ("bbox_min", C.c_float * 3),
@@ -71,6 +85,7 @@ _HOST_EXTRAS = {
     "sg_set_render_options": (_I, [_V, _I, _IP, _I, _I]),
     "sg_last_rtc_stats": (_I, [_V, C.POINTER(RtcStats)]),
     "sg_prepare": (_I, [_V, _I, _I]),
+    "sg_inspect": (_I, [_V, _I, _I, C.c_void_p, C.POINTER(C.c_double)]),
     "sg_release_prepared": (_I, [_V, _I]),
     "sg_render_prepared": (_I, [_V, _I, _I, _I, _I, _I, _I, _FP, _U8P, C.POINTER(SgStats)]),
     "sg_flush_l2": (_I, [_V, _I]),
@@ -162,6 +177,15 @@ class HostApi(_api.Api):
         st = RtcStats()
         self.lib.sg_last_rtc_stats(self.ctx, C.byref(st))
         return st
+
+    def inspect(self, camera, world) -> dict:
+        """rtc_scene_inspect: what a commit of (camera, world) would build — tree size, leaf size, small-scene path and
+        shadow-filter eligibility, host time — without touching a device."""
+        info, flatten_ms = RtcCommitInfo(), C.c_double()
+        self.check(self.lib.sg_inspect(self.ctx, camera.handle, world.handle, C.byref(info), C.byref(flatten_ms)))
+        out = info.as_dict()
+        out["flatten_ms"] = flatten_ms.value
+        return out
 
     def flatten(self, world):
         """The flattener's output (no device needed): (prims, nodes, refs, prim_shape_handles, counts)."""

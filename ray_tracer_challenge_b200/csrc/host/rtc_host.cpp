@@ -423,6 +423,27 @@ int sg_camera_render(sg_ctx* c, int cam, int w, int depth, float* out_rgb, uint8
     return rc ? -1 : 0;
 }
 
+// rtc_scene_inspect for (camera, world): flatten + the host half of the commit, no device needed.  `info` is an
+// RtcCommitInfo (include/rtc_b200.h); flatten_ms receives the time of the scene-graph flattening itself.
+int sg_inspect(sg_ctx* c, int cam, int w, void* info, double* flatten_ms) {
+    if (cam < 0 || cam >= (int)c->cameras.size()) return fail("bad camera handle");
+    if (w < 0 || w >= (int)c->worlds.size()) return fail("bad world handle");
+    RtcScene* scene = nullptr;
+    if (rtc_scene_create(&scene)) return fail(rtc_last_error());
+    int rc = 0;
+    try {
+        FlatScene flat;
+        const auto t0 = std::chrono::steady_clock::now();
+        fill_scene(scene, c->graph, c->worlds[w], c->cameras[cam], flat);
+        if (flatten_ms) *flatten_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        if (rtc_scene_inspect(scene, static_cast<RtcCommitInfo*>(info))) rc = fail(rtc_last_error());
+    } catch (const std::exception& e) {
+        rc = fail(e.what());
+    }
+    rtc_scene_destroy(scene);
+    return rc;
+}
+
 // Keep a committed scene resident on the device(s) for repeated renders (animation / benchmarking).
 int sg_prepare(sg_ctx* c, int cam, int w) {
     if (cam < 0 || cam >= (int)c->cameras.size()) return fail("bad camera handle");

@@ -601,6 +601,7 @@ class Flattener {
     FlatScene& out_;
     std::map<std::vector<uint32_t>, int> material_ids_;
     std::map<int, int> pattern_ids_, uv_ids_, texture_ids_;
+    int last_material_ = -1;
 
     int uv_index(int h) {
         if (h < 0 || h >= (int)g_.uvs.size()) throw Error("bad uv pattern handle");
@@ -652,12 +653,14 @@ class Flattener {
         r.ambient = m.ambient, r.diffuse = m.diffuse, r.specular = m.specular, r.shininess = m.shininess;
         r.reflective = m.reflective, r.transparency = m.transparency, r.refractive_index = m.refractive_index;
         r.pattern = pattern_index(m.pattern);
+        // a mesh's triangles share one material: compare with the previous one before going to the map
+        if (last_material_ >= 0 && memcmp(&out_.materials[last_material_], &r, 11 * sizeof(uint32_t)) == 0) return last_material_;
         std::vector<uint32_t> key(11);
         memcpy(key.data(), &r, 11 * sizeof(uint32_t));
         auto it = material_ids_.find(key);
-        if (it != material_ids_.end()) return it->second;
+        if (it != material_ids_.end()) return last_material_ = it->second;
         out_.materials.push_back(r);
-        return material_ids_[key] = (int)out_.materials.size() - 1;
+        return last_material_ = material_ids_[key] = (int)out_.materials.size() - 1;
     }
     static void put_box(const Bounds& b, float lo[3], float hi[3]) {
         for (int a = 0; a < 3; a++) lo[a] = b.lo[a], hi[a] = b.hi[a];
@@ -670,7 +673,8 @@ class Flattener {
             int node = (int)out_.nodes.size();
             out_.nodes.emplace_back();
             std::vector<int32_t> child_refs;
-            std::vector<int> kids = g_.shapes[id].children;
+            const std::vector<int> kids = g_.shapes[id].children;  // copy: visit() may grow g_.shapes
+            child_refs.reserve(kids.size());
             for (int c : kids) child_refs.push_back(visit(c, node));
             RtcNode n;
             memset(&n, 0, sizeof(n));

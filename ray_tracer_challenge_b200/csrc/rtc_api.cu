@@ -9,8 +9,11 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <future>
 #include <map>
 #include <mutex>
+#include <thread>
+#include <unordered_map>
 #include <string>
 #include <tuple>
 #include <vector>
@@ -317,14 +320,38 @@ struct Builder {
         }
         return make_inner(b, mid, e, depth);
     }
+    // Subtrees of the top `par_depth` levels are built by separate threads into their own node arrays (the ranges of
+    // `items` they partition are disjoint) and appended afterwards with their inner links shifted.
+    int par_depth = 0;
+    static void append(std::vector<DevBvhNode>& dst, std::vector<DevBvhNode>& sub, int& link) {
+        const int off = (int)dst.size();
+        for (DevBvhNode& n : sub) {
+            if (n.d.x >= 0) n.d.x += off;
+            if (n.d.y >= 0) n.d.y += off;
+        }
+        if (link >= 0) link += off;
+        dst.insert(dst.end(), sub.begin(), sub.end());
+    }
     int make_inner(int b, int mid, int e, int depth) {
         int idx = (int)nodes.size();
         nodes.emplace_back();
         Box b0, b1;
         for (int i = b; i < mid; i++) b0.grow(items[i].box);
         for (int i = mid; i < e; i++) b1.grow(items[i].box);
-        int c0 = build(b, mid, depth + 1);
-        int c1 = build(mid, e, depth + 1);
+        int c0, c1;
+        if (depth < par_depth && e - b > 4096) {
+            std::vector<DevBvhNode> left_nodes, right_nodes;
+            Builder left{items, left_nodes, leaf_size}, right{items, right_nodes, leaf_size};
+            left.par_depth = right.par_depth = par_depth;
+            auto task = std::async(std::launch::async, [&] { return left.build(b, mid, depth + 1); });
+            c1 = right.build(mid, e, depth + 1);
+            c0 = task.get();
+            append(nodes, left_nodes, c0);
+            append(nodes, right_nodes, c1);
+        } else {
+            c0 = build(b, mid, depth + 1);
+            c1 = build(mid, e, depth + 1);
+        }
         DevBvhNode& n = nodes[idx];
         n.a = make_float4(b0.lo[0], b0.lo[1], b0.lo[2], b0.hi[0]);
         n.b = make_float4(b0.hi[1], b0.hi[2], b1.lo[0], b1.lo[1]);
@@ -361,6 +388,7 @@ struct Flattened {
     std::vector<DevPattern> patterns;
     std::vector<DevUvPattern> uvs;
     std::vector<float4> texels;
+    int leaf_size = 0;  // the BVH leaf size used
     std::vector<float4> samples;
     SmallScene small{};
     int bvh_root = -1;
@@ -370,6 +398,14 @@ struct Flattened {
 
 int flatten(RtcScene* s, Flattened& f) {
     const int np = (int)s->prims.size(), nn = (int)s->nodes.size();
+    const bool timing = getenv("RTC_TIMING") != nullptr;  // tuning aid: phase times of the host half on stderr
+    auto t_last = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+        if (!timing) return;
+        const auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[rtc commit] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(now - t_last).count());
+        t_last = now;
+    };
     // ---- validate references
     for (int i = 0; i < np; i++) {
         const RtcPrim& p = s->prims[i];
@@ -449,6 +485,7 @@ int flatten(RtcScene* s, Flattened& f) {
         });
     }
 
+    lap("validate + item lists");
     // ---- BVH
     std::vector<BuildItem> build_items(bounded.size());
     for (size_t i = 0; i < bounded.size(); i++) {
@@ -473,7 +510,10 @@ int flatten(RtcScene* s, Flattened& f) {
         for (const Item& it : bounded) n_triangles += it.prim >= 0 && s->prims[it.prim].type == RTC_TRIANGLE;
         int leaf = s->leaf_size > 0 ? s->leaf_size : (2 * n_triangles > bounded.size() ? 4 : 1);
         if (const char* env = getenv("RTC_BVH_LEAF")) leaf = atoi(env);  // tuning aid
-        Builder builder{build_items, f.bvh, std::min(std::max(leaf, 1), 16)};
+        f.leaf_size = std::min(std::max(leaf, 1), 16);
+        Builder builder{build_items, f.bvh, f.leaf_size};
+        const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+        while ((1u << builder.par_depth) < hw && builder.par_depth < 5) builder.par_depth++;  // up to 32 subtree tasks
         f.bvh.reserve(build_items.size());
         int root = builder.build(0, (int)build_items.size(), 0);
         if (root < 0) {  // a single leaf: wrap it so the traversal always starts at an inner node
@@ -490,6 +530,7 @@ int flatten(RtcScene* s, Flattened& f) {
         f.bvh_root = root;
     }
 
+    lap("bvh build");
     // ---- device positions: BVH order, then the linear list, then CSG-internal primitives
     std::vector<int> item_refs;
     for (const BuildItem& b : build_items) item_refs.push_back(bounded[b.item].prim);
@@ -510,17 +551,30 @@ int flatten(RtcScene* s, Flattened& f) {
     for (int i = n_tree; i < n_items; i++) f.linear.push_back(i);
 
     // ---- transforms (deduplicated bitwise), triangle and bound tables, heads
-    std::map<std::vector<uint32_t>, int> xf_ids;
+    struct XfKey {
+        uint32_t w[12];
+        bool operator==(const XfKey& o) const { return memcmp(w, o.w, sizeof(w)) == 0; }
+    };
+    struct XfHash {
+        size_t operator()(const XfKey& k) const {  // FNV-1a over the 12 words
+            uint64_t h = 1469598103934665603ull;
+            for (uint32_t v : k.w) h = (h ^ v) * 1099511628211ull;
+            return (size_t)h;
+        }
+    };
+    std::unordered_map<XfKey, int, XfHash> xf_ids;
+    xf_ids.reserve((size_t)np);
+    f.xform.reserve(3 * (size_t)np);
     auto xform_id = [&](const float m[16]) {
-        std::vector<uint32_t> key(12);
-        memcpy(key.data(), m, 12 * sizeof(float));
+        XfKey key;
+        memcpy(key.w, m, sizeof(key.w));
         auto it = xf_ids.find(key);
         if (it != xf_ids.end()) return it->second;
         int id = (int)f.xform.size() / 3;
         float4 r[3];
         rows3(m, r);
         f.xform.insert(f.xform.end(), r, r + 3);
-        xf_ids.emplace(std::move(key), id);
+        xf_ids.emplace(key, id);
         return id;
     };
     f.head.assign(2 * (size_t)f.n_pos, make_int4(0, 0, 0, 0));
@@ -548,6 +602,7 @@ int flatten(RtcScene* s, Flattened& f) {
         s->pos_to_prim[pos] = i;
     }
 
+    lap("positions, transforms, heads");
     // ---- reference shape-tree nodes
     f.nodes.resize(nn);
     for (int i = 0; i < nn; i++) {
@@ -609,6 +664,7 @@ int flatten(RtcScene* s, Flattened& f) {
     if (emitter.max_depth > kCsgRayDepth - 1)
         return fail(RTC_ERR_CAPACITY, "CSG nesting depth " + std::to_string(emitter.max_depth) + " exceeds " + std::to_string(kCsgRayDepth - 1));
 
+    lap("nodes + csg programs");
     // ---- traversal records: head + the rows the intersection test needs, one 64 B fetch per primitive
     f.rec.assign(4 * (size_t)f.n_pos, make_float4(0.f, 0.f, 0.f, 0.f));
     for (int pos = 0; pos < f.n_pos; pos++) {
@@ -829,6 +885,7 @@ int flatten(RtcScene* s, Flattened& f) {
         }
         f.small.tol_sphere = (float)(std::ldexp(1.0, -24) * 64.0 * (worst + 1.0));
     }
+    lap("records, tables, small scene");
     s->n_bvh_nodes = (int)f.bvh.size();
     s->n_linear = (int)f.linear.size();
     s->n_xforms = (int)f.xform.size() / 3;
@@ -1187,6 +1244,26 @@ int rtc_set_option(RtcScene* s, int32_t option, int64_t value) {
             return 0;
     }
     return fail(RTC_ERR_INVALID, "unknown option");
+}
+
+int rtc_scene_inspect(RtcScene* s, RtcCommitInfo* out) {
+    if (!s || !out) return fail(RTC_ERR_INVALID, "null argument");
+    if (!s->have_camera) return fail(RTC_ERR_STATE, "camera not set");
+    if (!s->have_light) return fail(RTC_ERR_STATE, "World light should be set");
+    const auto t0 = std::chrono::steady_clock::now();
+    Flattened f;
+    int rc = flatten(s, f);
+    if (rc) return rc;
+    memset(out, 0, sizeof(*out));
+    out->host_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    out->n_positions = f.n_pos, out->n_bvh_nodes = (int)f.bvh.size(), out->n_linear = (int)f.linear.size();
+    out->n_xforms = (int)f.xform.size() / 3, out->bvh_leaf_size = f.leaf_size;
+    out->small_n = f.small.n, out->filter_ok = f.small.filter_ok, out->cell_masks = f.small.cell_masks;
+    out->plane_cells = f.small.plane_cells, out->converge = s->has_branching_materials ? 1 : 0;
+    out->tol_sphere = f.small.tol_sphere;
+    out->light_ball[0] = f.small.light_ball.x, out->light_ball[1] = f.small.light_ball.y;
+    out->light_ball[2] = f.small.light_ball.z, out->light_ball[3] = f.small.light_ball.w;
+    return 0;
 }
 
 int rtc_scene_commit(RtcScene* s, int32_t n_devices, const int32_t* device_ids) {

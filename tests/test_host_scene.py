@@ -131,3 +131,45 @@ def test_host_rejects_the_oracle_only_test_double(host):
         s = host.Sphere()
         g.add_child(s)
         g.add_child(s)  # already owned (Rust: moved)
+
+
+def test_commit_plan_without_a_device(host):
+    """rtc_scene_inspect: the host half of the commit (tree, small-scene table, shadow-filter eligibility, kernel build
+    choice) for the BASELINE workloads and a few demo scenes — no GPU needed."""
+    from bench import build_scene
+
+    plans = {}
+    for workload in ("c1", "c2", "c3", "c4"):
+        cam, world, _, _ = build_scene(host, workload)
+        plans[workload] = host.inspect(cam, world)
+    # c1 / c3: four objects (cube, plane, two spheres), table-mode area light: every fast path applies
+    for w in ("c1", "c3"):
+        p = plans[w]
+        assert (p["small_n"], p["n_bvh_nodes"], p["filter_ok"], p["cell_masks"], p["plane_cells"], p["converge"]) == (4, 0, 1, 1, 1, 0), p
+        assert 0 < p["tol_sphere"] < 1e-4 and p["light_ball"][3] > 1.0
+    # c2: cylinder and cone -> exact shadow test; the glass sphere is reflective and transparent -> converging build
+    p = plans["c2"]
+    assert (p["small_n"], p["filter_ok"], p["cell_masks"], p["converge"]) == (6, 0, 0, 1), p
+    # c4: 102 k triangles in one tree with 4-triangle leaves, the plane in the linear list, 4 distinct transforms
+    p = plans["c4"]
+    assert p["small_n"] == 0 and p["n_bvh_nodes"] > 20000 and p["bvh_leaf_size"] == 4 and p["n_linear"] == 1 and p["n_xforms"] == 4, p
+    assert p["n_positions"] == 102403
+    # soft_shadows as shipped (jitter None): filter + drawn-sample cell masks, no staged plane constants
+    cam, world = scenes.soft_shadows(host, width=100, height=40, jitter=None)
+    p = host.inspect(cam, world)
+    assert (p["filter_ok"], p["cell_masks"], p["plane_cells"]) == (1, 1, 0), p
+    # first_scene: the walls are spheres squashed 1000:1 -> condition number far above the filter's limit
+    cam, world = scenes.first_scene(host, width=100, height=50)
+    assert host.inspect(cam, world)["filter_ok"] == 0
+    # a sphere field goes to the tree with one sphere per leaf
+    cam, world = scenes.stress(host, width=64, height=36, n_spheres=500, n_each=2, n_csg=1)
+    p = host.inspect(cam, world)
+    assert p["small_n"] == 0 and p["bvh_leaf_size"] == 1 and p["converge"] == 1, p
+
+
+def test_parallel_tree_build_is_deterministic(host):
+    """The BVH's top levels are built by several threads; the tree (node count, and so the render) does not depend on
+    their timing."""
+    cam, world = scenes.stress(host, width=64, height=36, n_spheres=20000, n_each=4, n_csg=2)
+    seen = {(p["n_bvh_nodes"], p["n_positions"], p["n_xforms"]) for p in (host.inspect(cam, world) for _ in range(4))}
+    assert len(seen) == 1, seen
