@@ -11,6 +11,7 @@
 // Layout: shapes live in an arena (SceneGraph) and are addressed by index; this is deliberately not the
 // reference's Box<dyn Shape> tree — the flattener wants arrays, not pointers.
 #pragma once
+#include <chrono>
 #include <cmath>
 #include <cstdint>
 #include <cstring>
@@ -593,6 +594,8 @@ class Flattener {
    public:
     Flattener(SceneGraph& g, FlatScene& out) : g_(g), out_(out) {}
     void run(const World& w) {
+        out_.prims.reserve(g_.shapes.size());  // every shape is emitted at most once: no regrowth of the 160 B records
+        out_.prim_shape.reserve(g_.shapes.size());
         for (int id : w.objects) visit(id, -1);
     }
 
@@ -733,7 +736,12 @@ inline void fill_scene(RtcScene* scene, SceneGraph& g, const World& w, const Cam
         if (rc) throw Error(rtc_last_error());
     };
     if (!w.light.set) throw Error("World light should be set");  // world.rs:66
+    const bool timing = getenv("RTC_TIMING") != nullptr;
+    const auto t0 = std::chrono::steady_clock::now();
     Flattener(g, flat).run(w);
+    if (timing)
+        fprintf(stderr, "[rtc host]   %-28s %8.3f ms\n", "scene graph -> flat arrays",
+                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
     ck(rtc_set_camera(scene, cam.width, cam.height, cam.half_width, cam.half_height, cam.pixel_size, cam.transform_inverse.m));
     ck(rtc_set_primitives(scene, (uint32_t)flat.prims.size(), flat.prims.data()));
     ck(rtc_set_nodes(scene, (uint32_t)flat.nodes.size(), flat.nodes.data(), (uint32_t)flat.refs.size(), flat.refs.data()));

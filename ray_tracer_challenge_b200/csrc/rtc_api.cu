@@ -565,20 +565,25 @@ int flatten(RtcScene* s, Flattened& f) {
     std::unordered_map<XfKey, int, XfHash> xf_ids;
     xf_ids.reserve((size_t)np);
     f.xform.reserve(3 * (size_t)np);
+    XfKey last_key{};
+    int last_id = -1;
     auto xform_id = [&](const float m[16]) {
         XfKey key;
         memcpy(key.w, m, sizeof(key.w));
+        if (last_id >= 0 && key == last_key) return last_id;  // a mesh's triangles share one transform
+        last_key = key;
         auto it = xf_ids.find(key);
-        if (it != xf_ids.end()) return it->second;
+        if (it != xf_ids.end()) return last_id = it->second;
         int id = (int)f.xform.size() / 3;
         float4 r[3];
         rows3(m, r);
         f.xform.insert(f.xform.end(), r, r + 3);
         xf_ids.emplace(key, id);
-        return id;
+        return last_id = id;
     };
     f.head.assign(2 * (size_t)f.n_pos, make_int4(0, 0, 0, 0));
     s->pos_to_prim.assign(f.n_pos, -1);
+    f.tri.reserve(3 * (size_t)np);
     for (int i = 0; i < np; i++) {
         const RtcPrim& p = s->prims[i];
         int pos = prim_pos[i];
