@@ -258,6 +258,54 @@ def textured(rt, width=320, height=200):
     return camera, world
 
 
+def random_filter_scene(rt, seed, width=160, height=100):
+    """A random filter-eligible scene (spheres with random rotations / shears / squashes, tilted planes, axis-aligned
+    boxes, some touching or interpenetrating, some not casting shadows) under a random area or point light: fuzzing
+    input for the shadow filter's on / off equality test."""
+    rnd = _xorshift64star(0x5EED0000 + seed)
+
+    def u(a, b):
+        return a + (b - a) * rnd()
+
+    def mat():
+        return Material(color=(u(0.2, 1), u(0.2, 1), u(0.2, 1)), reflective=u(0, 0.4) if rnd() < 0.3 else 0.0,
+                        specular=u(0, 0.9), shininess=u(5, 200))
+
+    objects = [rt.Plane.build(rt.identity_4x4(), Material(color=(0.9, 0.9, 0.9), specular=0.0))]
+    if rnd() < 0.6:
+        objects.append(rt.Plane.build(rt.translation(0.0, 0.0, u(4, 8)) * rt.rotation_x(PI / 2.0 + u(-0.3, 0.3)) * rt.rotation_z(u(-0.3, 0.3)), mat()))
+    for _ in range(2 + int(rnd() * 5)):
+        r = u(0.25, 1.1)
+        t = rt.translation(u(-3, 3), r * u(0.6, 1.4), u(-2.5, 3))
+        kind = rnd()
+        if kind < 0.35:
+            t = t * rt.scaling(r, r, r)
+        elif kind < 0.7:
+            t = t * rt.rotation_y(u(0, 6.28)) * rt.rotation_z(u(0, 6.28)) * rt.scaling(r, r * u(0.2, 1.0), r * u(0.4, 1.0))
+        else:
+            t = t * rt.shearing(u(-0.5, 0.5), 0.0, 0.0, u(-0.5, 0.5), 0.0, 0.0) * rt.scaling(r, r, r)
+        sphere = rt.Sphere.build(t, mat())
+        if rnd() < 0.15:
+            sphere.set_casts_shadow(False)
+        objects.append(sphere)
+    for _ in range(int(rnd() * 3)):
+        box = rt.Cube.build(rt.translation(u(-3, 3), u(0.2, 1.5), u(-2, 3)) * rt.scaling(u(0.2, 0.9), u(0.2, 1.2), u(0.2, 0.9)), mat())
+        if rnd() < 0.25:
+            box.set_casts_shadow(False)
+        objects.append(box)
+    if rnd() < 0.7:
+        us, vs = 1 + int(rnd() * 4), 1 + int(rnd() * 4)
+        mode = rnd()
+        jitter = jitter_table(2 * us * vs, seed + 11) if mode < 0.4 else ([0.5] if mode < 0.6 else None)
+        light = RectangleLight((1.2, 1.2, 1.2), (u(-4, 0), u(2.5, 6), u(-5, -1)), (u(0.3, 1.0), 0, u(-0.2, 0.2)), us,
+                               (0, u(0.3, 1.0), u(-0.2, 0.2)), vs, jitter, seed)
+    else:
+        light = PointLight((u(-6, 6), u(3, 9), u(-7, -2)), (1, 1, 1))
+    world = rt.World(objects, light)
+    camera = rt.Camera(width, height, PI / 3.0, rt.view_transform((u(-2, 2), u(1.5, 3.5), u(-8, -6)), (0, 1.0, 0), (0, 1, 0)))
+    return camera, world
+
+
 def reflect_refract(rt, width=1000, height=500, with_csg=False):
     stripes = rt.Stripes((1.0, 0.2, 0.4), (0.1, 0.1, 0.1))
     stripes_t = rt.scaling(0.3, 0.3, 0.3) * rt.rotation_z(3.0 * PI / 4.0)

@@ -183,6 +183,33 @@ def test_shadow_filter_changes_no_pixel(name, gpu):
         p.release()
 
 
+def test_shadow_filter_fuzz(gpu, oracle):
+    """Random filter-eligible scenes: the frame is bit-identical with the filter on and off, and (every third scene)
+    identical to the oracle's in all 8-bit channels."""
+    checked = 0
+    for seed in range(24):
+        cam, world = scenes.random_filter_scene(gpu, seed)
+        p = cam.prepare(world)
+        try:
+            p.set_option(6, 0)
+            off = p.render(5)
+            rays_off = p.last_stats.rays
+            p.set_option(6, 1)
+            on = p.render(5, detailed=True)
+            st = p.last_stats
+            assert st.rays == rays_off, seed
+            assert np.array_equal(on.data.view(np.uint32), off.data.view(np.uint32)), seed
+            checked += st.prim_tests[7] < st.shadow_rays  # the filter decided something
+            if seed % 3 == 0:
+                ocam, oworld = scenes.random_filter_scene(oracle, seed)
+                want = ocam.render(oworld, 5)
+                rep = compare_frames(on.to_u8(), want.to_u8(), on.data, want.data)
+                assert rep["exact_u8"] == 1.0 and st.rays == ocam.last_stats.rays, (seed, rep)
+        finally:
+            p.release()
+    assert checked >= 20
+
+
 def test_depth_semantics(gpu, oracle):
     """remaining-depth guards (world.rs:126,140): depth 0 and 1 frames match the oracle."""
     for depth in (0, 1, 2):
