@@ -863,12 +863,14 @@ struct Env {
     const SmallScene& SS;
 };
 
-// Small scenes keep two things in (dynamic) shared memory:
-//   tab : the primitive table, 5 x float4 per primitive {head, row0, row1, row2, bound}, copied from the
-//         parameter block by stage_small_scene — every thread of a warp reads the same entry, so a row is one
-//         broadcast LDS.128 with an immediate offset;
-//   org : per thread, the object-space origin of the current shade's shadow rays for the first kOrgCache
-//         primitives (element (i, c) of thread t at org[(i * 3 + c) * 128 + t]).
+// Small scenes keep these in (dynamic) shared memory, kSmallSmemBytes in all:
+//   tab     : the primitive table, kSmallStride x float4 per primitive {head, row0, row1, row2, bound, ball}, copied
+//             from the parameter block by stage_small_scene — every thread of a warp reads the same entry, so a row
+//             is one broadcast LDS.128 with an immediate offset;
+//   org     : per thread, the object-space origin of the current shade's shadow rays for the first kOrgCache
+//             primitives (element (i, c) of thread t at org[(i * 3 + c) * 128 + t]) — the per-cell shadow loop;
+//   samples : table-mode area light: the `cells` sample points (cell-mask loops, intensity_cells);
+//   plane cells : per (caster plane, cell) the constants of filter_plane_cell.
 __device__ __forceinline__ const float4* small_tab() {
     extern __shared__ float4 rtc_smem[];
     return rtc_smem;
