@@ -12,6 +12,7 @@
 // reference's Box<dyn Shape> tree — the flattener wants arrays, not pointers.
 #pragma once
 #include <chrono>
+#include <thread>
 #include <cmath>
 #include <cstdint>
 #include <cstring>
@@ -596,7 +597,22 @@ class Flattener {
     void run(const World& w) {
         out_.prims.reserve(g_.shapes.size());  // every shape is emitted at most once: no regrowth of the 160 B records
         out_.prim_shape.reserve(g_.shapes.size());
-        for (int id : w.objects) visit(id, -1);
+        for (int id : w.objects) visit(id, -1);  // depth-first: order, parents, materials (sequential, light)
+        // the heavy part of every leaf record — inverse, parameters, the transformed bounding box — reads the scene
+        // graph only, so a large scene (a 100 k-triangle mesh) is filled by several threads
+        const size_t n = out_.prims.size();
+        const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+        const size_t n_threads = n < 8192 ? 1 : std::min<size_t>(hw, 16);
+        auto fill = [&](size_t b, size_t e) {
+            for (size_t i = b; i < e; i++) fill_leaf(out_.prims[i], out_.prim_shape[i]);
+        };
+        if (n_threads == 1) {
+            fill(0, n);
+        } else {
+            std::vector<std::thread> pool;
+            for (size_t t = 0; t < n_threads; t++) pool.emplace_back(fill, n * t / n_threads, n * (t + 1) / n_threads);
+            for (std::thread& t : pool) t.join();
+        }
     }
 
    private:
@@ -656,8 +672,10 @@ class Flattener {
         r.ambient = m.ambient, r.diffuse = m.diffuse, r.specular = m.specular, r.shininess = m.shininess;
         r.reflective = m.reflective, r.transparency = m.transparency, r.refractive_index = m.refractive_index;
         r.pattern = pattern_index(m.pattern);
-        // a mesh's triangles share one material: compare with the previous one before going to the map
+        // a mesh's triangles share one material: compare with the previous one, then with the first few, before the map
         if (last_material_ >= 0 && memcmp(&out_.materials[last_material_], &r, 11 * sizeof(uint32_t)) == 0) return last_material_;
+        for (size_t i = 0; i < out_.materials.size() && i < 16; i++)
+            if (memcmp(&out_.materials[i], &r, 11 * sizeof(uint32_t)) == 0) return last_material_ = (int)i;
         std::vector<uint32_t> key(11);
         memcpy(key.data(), &r, 11 * sizeof(uint32_t));
         auto it = material_ids_.find(key);
@@ -709,16 +727,19 @@ class Flattener {
         p.material = material_index(s.material);
         p.casts_shadow = s.casts_shadow ? 1 : 0;
         p.parent = parent_node;
+        out_.prims.push_back(p);  // inverse, parameters and box: fill_leaf
+        out_.prim_shape.push_back(id);
+        return (int)out_.prims.size() - 1;
+    }
+    void fill_leaf(RtcPrim& p, int id) const {
+        const ShapeRec& s = g_.shapes[id];
         memcpy(p.inv, s.t_inv.m, sizeof(p.inv));
         if (p.type == RTC_TRIANGLE) {
             memcpy(p.params, s.tri, sizeof(p.params));
         } else if (p.type == RTC_CYLINDER || p.type == RTC_CONE) {
             p.params[0] = s.y_min, p.params[1] = s.y_max, p.params[2] = s.closed ? 1.f : 0.f;
         }
-        put_box(g_.parent_space_box(id), p.bbox_min, p.bbox_max);
-        out_.prims.push_back(p);
-        out_.prim_shape.push_back(id);
-        return (int)out_.prims.size() - 1;
+        put_box(g_.parent_space_box(id), p.bbox_min, p.bbox_max);  // leaves: no cached state is touched
     }
 };
 

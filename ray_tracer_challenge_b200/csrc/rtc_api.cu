@@ -563,11 +563,18 @@ int flatten(RtcScene* s, Flattened& f) {
         }
     };
     std::unordered_map<XfKey, int, XfHash> xf_ids;
-    xf_ids.reserve((size_t)np);
     f.xform.reserve(3 * (size_t)np);
     XfKey last_key{};
     int last_id = -1;
-    auto xform_id = [&](const float m[16]) {
+    // only a mesh's triangles share transforms in practice (and only they profit: the object-space ray is cached by
+    // transform id), so every other primitive gets its own slot without a lookup
+    auto xform_id = [&](const float m[16], bool dedup) {
+        if (!dedup) {
+            float4 r[3];
+            rows3(m, r);
+            f.xform.insert(f.xform.end(), r, r + 3);
+            return (int)f.xform.size() / 3 - 1;
+        }
         XfKey key;
         memcpy(key.w, m, sizeof(key.w));
         if (last_id >= 0 && key == last_key) return last_id;  // a mesh's triangles share one transform
@@ -602,7 +609,7 @@ int flatten(RtcScene* s, Flattened& f) {
         if (!p.casts_shadow) f.all_cast_shadow = 0;
         bool in_linear = pos >= n_tree && pos < n_items;
         if (in_linear && p.parent >= 0) flags |= kFlagHasParent;
-        f.head[pos] = make_int4(p.type | (flags << 4) | (p.material << 8), xform_id(p.inv), aux, i);
+        f.head[pos] = make_int4(p.type | (flags << 4) | (p.material << 8), xform_id(p.inv, p.type == RTC_TRIANGLE), aux, i);
         f.head[f.n_pos + pos] = make_int4(prim_top_csg[i] < 0 ? p.parent : -1, i, 0, 0);
         s->pos_to_prim[pos] = i;
     }
