@@ -218,6 +218,10 @@ def __getattr__(name):
     global _default
     if name.startswith("__"):
         raise AttributeError(name)
+    if name in ("build", "scenes", "sharding", "multi"):  # submodules: `from ray_tracer_challenge_b200 import build`
+        import importlib  # works before the libraries exist (build is how they come to exist)
+
+        return importlib.import_module(f"{__name__}.{name}")
     if _default is None:
         _default = HostApi()
     return getattr(_default, name)

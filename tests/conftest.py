@@ -12,6 +12,17 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
+@pytest.fixture(scope="session", autouse=True)
+def _native_libraries():
+    """A fresh checkout has no built libraries (they are git-ignored): compile them once (nvcc cross-compiles sm_100a
+    without a GPU).  Building is not a fallback — with the libraries missing the package refuses to import."""
+    pkg = os.path.join(ROOT, "ray_tracer_challenge_b200")
+    if not (os.path.exists(os.path.join(pkg, "librtc_b200.so")) and os.path.exists(os.path.join(pkg, "librtc_host.so"))):
+        from ray_tracer_challenge_b200 import build as native
+
+        native.build(verbose=True)
+
+
 @pytest.fixture(scope="session")
 def oracle():
     """The CPU oracle (oracle/librtc_oracle.so) bound to the reference-shaped Python API."""
