@@ -88,3 +88,66 @@ def test_no_device_is_a_loud_error():
         cam.render_b200(world, 1)
     with pytest.raises(rt.RtcError):
         cam.prepare(world)
+
+
+def test_raw_c_abi_validates_scenes_without_a_device():
+    """The C ABI driven the way a foreign host (the Rust -sys crate) drives it: plain structs in, error codes out.
+    rtc_scene_inspect runs the host half of the commit, so bad references are reported without a GPU."""
+    import ray_tracer_challenge_b200 as rt
+
+    lib = C.CDLL(rt.LIB_DEVICE)
+    lib.rtc_last_error.restype = C.c_char_p
+    scene = C.c_void_p()
+    assert lib.rtc_scene_create(C.byref(scene)) == 0
+    ident = (C.c_float * 16)(1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1)
+    lib.rtc_set_camera.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_float, C.c_float, C.c_float, C.POINTER(C.c_float)]
+    assert lib.rtc_set_camera(scene, 64, 32, 1.0, 0.5, 2.0 / 64, ident) == 0
+    info = rt.RtcCommitInfo()
+    # no light yet: the reference's own failure (world.rs:66), as an error code
+    assert lib.rtc_scene_inspect(scene, C.byref(info)) < 0 and b"World light should be set" in lib.rtc_last_error()
+    pos, rgb = (C.c_float * 3)(-10, 10, -10), (C.c_float * 3)(1, 1, 1)
+    assert lib.rtc_set_point_light(scene, pos, rgb) == 0
+
+    class RtcMaterial(C.Structure):
+        _fields_ = [("color", C.c_float * 3), ("v", C.c_float * 7), ("pattern", C.c_int32)]
+
+    class RtcPattern(C.Structure):
+        _fields_ = [("kind", C.c_int32), ("mapping", C.c_int32), ("uv", C.c_int32 * 6), ("inv", C.c_float * 16),
+                    ("a", C.c_float * 3), ("b", C.c_float * 3)]
+
+    class RtcUvPattern(C.Structure):
+        _fields_ = [("kind", C.c_int32), ("params", C.c_float * 15)]
+
+    class RtcTexture(C.Structure):
+        _fields_ = [("width", C.c_uint32), ("height", C.c_uint32), ("rgb", C.POINTER(C.c_float))]
+
+    prim = rt.RtcPrim()
+    prim.type, prim.material, prim.casts_shadow, prim.parent = 0, 0, 1, -1
+    prim.inv[:] = list(ident)
+    prim.bbox_min[:], prim.bbox_max[:] = [-1, -1, -1], [1, 1, 1]
+    assert lib.rtc_set_primitives(scene, 1, C.byref(prim)) == 0
+    mat = RtcMaterial()
+    mat.color[:], mat.v[:], mat.pattern = [1, 1, 1], [0.1, 0.9, 0.9, 200.0, 0.0, 0.0, 1.0], 0
+    assert lib.rtc_set_materials(scene, 1, C.byref(mat)) == 0
+    pat = RtcPattern()
+    pat.kind, pat.mapping = 6, 0  # RTC_PAT_TEXTURE_MAP, spherical
+    pat.uv[:] = [0, -1, -1, -1, -1, -1]
+    pat.inv[:] = list(ident)
+    uv = RtcUvPattern()
+    uv.kind = 2  # RTC_UV_IMAGE
+    uv.params[0] = 3.0  # texture 3 of none
+    assert lib.rtc_set_patterns(scene, 1, C.byref(pat), 1, C.byref(uv)) == 0
+    assert lib.rtc_scene_inspect(scene, C.byref(info)) < 0 and b"texture" in lib.rtc_last_error()
+    pixels = (C.c_float * 12)(*([0.5] * 12))
+    tex = RtcTexture(2, 2, pixels)
+    uv.params[0] = 0.0
+    assert lib.rtc_set_patterns(scene, 1, C.byref(pat), 1, C.byref(uv)) == 0
+    assert lib.rtc_set_textures(scene, 1, C.byref(tex)) == 0
+    assert lib.rtc_scene_inspect(scene, C.byref(info)) == 0
+    assert (info.small_n, info.n_positions, info.filter_ok, info.n_bvh_nodes) == (1, 1, 1, 0)
+    mat.pattern = 5  # a pattern that does not exist
+    assert lib.rtc_set_materials(scene, 1, C.byref(mat)) == 0
+    assert lib.rtc_scene_inspect(scene, C.byref(info)) < 0
+    if lib.rtc_device_count() == 0:
+        assert lib.rtc_scene_commit(scene, 1, None) < 0 and b"no CPU fallback" in lib.rtc_last_error()
+    lib.rtc_scene_destroy(scene)
