@@ -1,6 +1,7 @@
 """In-tree build of the native libraries (sm_100a only; nvcc cross-compiles without a GPU).
 
-    librtc_b200.so  the C ABI of include/rtc_b200.h: csrc/rtc_api.cu + csrc/rtc_kernels.cu compiled twice
+    librtc_b200.so  the C ABI of include/rtc_b200.h: csrc/rtc_api.cu + csrc/rtc_commit.cu (host half of a commit) +
+                    csrc/rtc_kernels.cu compiled twice
                     (FMA-contracting `fast` build and -fmad=false `strict` build)
     librtc_host.so  the C++ host mirror of the reference API + flattener (csrc/host/), linked against
                     librtc_b200.so
@@ -45,14 +46,16 @@ def _run(cmd: list[str]) -> None:
 
 def build(force: bool = False, verbose: bool = False) -> None:
     os.makedirs(BUILD, exist_ok=True)
-    headers = [os.path.join(CSRC, h) for h in ("rtc_types.h", "rtc_device.cuh", "rtc_launch.h")]
+    headers = [os.path.join(CSRC, h) for h in ("rtc_types.h", "rtc_device.cuh", "rtc_launch.h", "rtc_internal.h")]
     headers.append(os.path.join(ROOT, "include", "rtc_b200.h"))
     kernels = os.path.join(CSRC, "rtc_kernels.cu")
     api = os.path.join(CSRC, "rtc_api.cu")
+    commit = os.path.join(CSRC, "rtc_commit.cu")
     objs = {
         os.path.join(BUILD, "kernels_fast.o"): [NVCC, *NVCC_FLAGS, "-c", kernels],
         os.path.join(BUILD, "kernels_strict.o"): [NVCC, *NVCC_FLAGS, "-DRTC_STRICT", "-fmad=false", "-c", kernels],
         os.path.join(BUILD, "api.o"): [NVCC, *NVCC_FLAGS, "-c", api],
+        os.path.join(BUILD, "commit.o"): [NVCC, *NVCC_FLAGS, "-c", commit],
     }
     jobs = []
     for obj, cmd in objs.items():
@@ -62,7 +65,7 @@ def build(force: bool = False, verbose: bool = False) -> None:
     if jobs:
         if verbose:
             print(f"compiling {len(jobs)} CUDA translation unit(s) for sm_100a ...", flush=True)
-        with ThreadPoolExecutor(max_workers=3) as pool:
+        with ThreadPoolExecutor(max_workers=4) as pool:
             list(pool.map(_run, jobs))
     if force or jobs or _newer(LIB_DEVICE, list(objs)):
         _run([NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB_DEVICE, *objs, "-cudart", "shared"])

@@ -20,19 +20,22 @@
 
 #include <cuda_runtime.h>
 
-#include "../../include/rtc_b200.h"
+#include "rtc_internal.h"
 #include "rtc_launch.h"
-#include "rtc_types.h"
 
 using namespace rtc;
 
 namespace {
 
 thread_local std::string g_error;
+}  // namespace
+namespace rtc {
 int fail(int code, const std::string& msg) {
     g_error = msg;
     return code;
 }
+}  // namespace rtc
+namespace {
 #define CUDA_TRY(expr)                                                                                          \
     do {                                                                                                        \
         cudaError_t _e = (expr);                                                                                \
@@ -40,48 +43,7 @@ int fail(int code, const std::string& msg) {
             return fail(RTC_ERR_NO_DEVICE, std::string(#expr) + ": " + cudaGetErrorString(_e));                  \
     } while (0)
 
-struct Box {
-    float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
-    void grow(const Box& o) {
-        for (int a = 0; a < 3; a++) lo[a] = std::min(lo[a], o.lo[a]), hi[a] = std::max(hi[a], o.hi[a]);
-    }
-    float area() const {
-        float dx = hi[0] - lo[0], dy = hi[1] - lo[1], dz = hi[2] - lo[2];
-        if (dx < 0 || dy < 0 || dz < 0) return 0.f;
-        return 2.f * (dx * dy + dy * dz + dz * dx);
-    }
-    bool finite() const {
-        for (int a = 0; a < 3; a++)
-            if (!std::isfinite(lo[a]) || !std::isfinite(hi[a]) || lo[a] > hi[a]) return false;
-        return true;
-    }
-};
 
-// Device-side resources that outlive a scene: creating streams / events and allocating the frame and scene
-// buffers costs more than rendering a small frame, so they are pooled per device and leased to a scene at
-// commit (Camera::render_b200 commits a fresh scene on every call, like the reference's render takes its
-// World by value).
-struct DeviceSlot {
-    int device = -1;
-    cudaStream_t stream = nullptr;       // kernels
-    cudaStream_t copy_stream = nullptr;  // device-to-host copies, overlapped with the kernels of later slices
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    std::vector<cudaEvent_t> slice_done;
-    float* d_rgb = nullptr;
-    unsigned char* d_u8 = nullptr;
-    size_t frame_px = 0;
-    DevCounters* d_counters = nullptr;
-    unsigned* d_tile_cost = nullptr;  // clock cycles per frame tile, recorded by the render that learns the order
-    int* d_tile_order = nullptr;      // launch order of this shard's tiles
-    int tile_capacity = 0;
-    int sm_count = 148;
-    char* arena = nullptr;  // scene arrays, one allocation
-    size_t arena_bytes = 0;
-    char* staging = nullptr;  // pinned host mirror of the arena for one asynchronous upload
-    size_t staging_bytes = 0;
-    void* d_flush = nullptr;
-    size_t flush_bytes = 0;
-};
 
 std::mutex g_pool_mutex;
 std::vector<DeviceSlot*> g_pool;  // idle slots
@@ -158,54 +120,9 @@ int ensure_arena(DeviceSlot* d, size_t bytes) {
     return 0;
 }
 
-// One committed replica of the scene on one device.
-struct Replica {
-    DeviceSlot* slot = nullptr;
-    DevScene scene{};
-    SmallScene small{};
-    int cell_masks_eligible = 0, plane_cells_eligible = 0;
-    int filter_eligible = 0;  // SmallScene::filter_ok as computed at commit (RTC_OPT_SHADOW_FILTER masks it per render)
-    // Longest-first launch order learnt from the previous render of the same shard (see render_impl)
-    int order_shard = -1, order_n_shards = -1, order_depth = -1, order_filter = -1;  // what d_tile_order was learnt for
-    bool learning = false;  // this render records the tile costs
-};
 
 }  // namespace
 
-struct RtcScene {
-    bool have_camera = false, have_light = false, committed = false;
-    uint32_t width = 0, height = 0;
-    float half_w = 0, half_h = 0, pixel_size = 0;
-    float cam_inv[16];
-    std::vector<RtcPrim> prims;
-    std::vector<RtcNode> nodes;
-    std::vector<int32_t> refs;
-    std::vector<RtcMaterial> materials;
-    std::vector<RtcPattern> patterns;
-    std::vector<RtcUvPattern> uvs;
-    struct Texture {
-        uint32_t width, height;
-        std::vector<float> rgb;
-    };
-    std::vector<Texture> textures;
-    bool light_is_rect = false;
-    float light_pos[3], light_rgb[3], corner[3], u_cell[3], v_cell[3];
-    int u_steps = 1, v_steps = 1;
-    std::vector<float> jitter;
-    uint64_t seed = 0;
-    int strict_fp = 1, leaf_size = 0 /* automatic */, bvh_min_prims = kSmallCap + 1;
-    int render_slices = 6;  // kernel / copy pipeline depth when rendering into host memory
-    int adaptive_order = 1;  // launch a shard's bands longest-first, learnt from the previous render
-    int shadow_filter = 1;   // RTC_OPT_SHADOW_FILTER
-    int converge = -1;         // color_at warp vote: -1 automatic (branching ray trees), 0 / 1 forced (RTC_CONVERGE)
-    bool has_branching_materials = false;  // some material is reflective AND transparent (set at commit)
-    int order_max_waves = 24;  // longest-first order only for launches shorter than this many waves of blocks
-    std::vector<Replica> replicas;
-    std::vector<int> replica_devices;
-    std::vector<int> pos_to_prim;  // device position -> API primitive index (-1 for CSG pseudo-primitives)
-    // commit statistics
-    int n_bvh_nodes = 0, n_linear = 0, n_xforms = 0;
-};
 
 namespace {
 
@@ -240,669 +157,6 @@ struct ArenaWriter {
         return off;
     }
 };
-
-void rows3(const float m[16], float4 out[3]) {
-    for (int r = 0; r < 3; r++) out[r] = make_float4(m[r * 4], m[r * 4 + 1], m[r * 4 + 2], m[r * 4 + 3]);
-}
-
-// ---- binned-SAH BVH over the top-level items -----------------------------------------------------------
-struct BuildItem {
-    Box box;
-    float centroid[3];
-    int item;     // index into the bounded item list
-    bool closed;  // sphere or cube: it has an odd number of hits behind a ray origin only if the origin is inside it
-};
-struct Builder {
-    std::vector<BuildItem>& items;
-    std::vector<DevBvhNode>& nodes;
-    int leaf_size;
-    // returns the link for the range [b, e): >= 0 inner node, < 0 leaf code
-    int build(int b, int e, int depth) {
-        int n = e - b;
-        if (n <= leaf_size || depth > 40) {
-            if (n <= 16) return ~((b << 4) | (n - 1));
-            // forced leaf too large for the 4-bit count: split in the middle regardless of cost
-            return make_inner(b, (b + e) / 2, e, depth);
-        }
-        Box cb;
-        for (int i = b; i < e; i++)
-            for (int a = 0; a < 3; a++)
-                cb.lo[a] = std::min(cb.lo[a], items[i].centroid[a]), cb.hi[a] = std::max(cb.hi[a], items[i].centroid[a]);
-        int axis = 0;
-        float ext = cb.hi[0] - cb.lo[0];
-        for (int a = 1; a < 3; a++)
-            if (cb.hi[a] - cb.lo[a] > ext) axis = a, ext = cb.hi[a] - cb.lo[a];
-        int mid = -1;
-        if (ext > 0.f) {
-            constexpr int kBins = 16;
-            Box bins[kBins];
-            int counts[kBins] = {0};
-            float scale = kBins / ext;
-            auto bin_of = [&](const BuildItem& it) {
-                int k = (int)((it.centroid[axis] - cb.lo[axis]) * scale);
-                return std::min(std::max(k, 0), kBins - 1);
-            };
-            for (int i = b; i < e; i++) {
-                int k = bin_of(items[i]);
-                bins[k].grow(items[i].box);
-                counts[k]++;
-            }
-            float right_area[kBins];
-            int right_count[kBins];
-            Box acc;
-            int cnt = 0;
-            for (int k = kBins - 1; k > 0; k--) {
-                acc.grow(bins[k]);
-                cnt += counts[k];
-                right_area[k] = acc.area();
-                right_count[k] = cnt;
-            }
-            Box left;
-            int lcnt = 0, best_k = -1;
-            float best_cost = INFINITY;
-            for (int k = 0; k < kBins - 1; k++) {
-                left.grow(bins[k]);
-                lcnt += counts[k];
-                if (lcnt == 0 || right_count[k + 1] == 0) continue;
-                float cost = left.area() * lcnt + right_area[k + 1] * right_count[k + 1];
-                if (cost < best_cost) best_cost = cost, best_k = k;
-            }
-            if (best_k >= 0) {
-                auto it = std::partition(items.begin() + b, items.begin() + e,
-                                         [&](const BuildItem& x) { return bin_of(x) <= best_k; });
-                mid = (int)(it - items.begin());
-            }
-        }
-        if (mid <= b || mid >= e) {  // degenerate: equal centroids — split by count
-            mid = (b + e) / 2;
-            std::nth_element(items.begin() + b, items.begin() + mid, items.begin() + e,
-                             [&](const BuildItem& x, const BuildItem& y) { return x.centroid[axis] < y.centroid[axis]; });
-        }
-        return make_inner(b, mid, e, depth);
-    }
-    // Subtrees of the top `par_depth` levels are built by separate threads into their own node arrays (the ranges of
-    // `items` they partition are disjoint) and appended afterwards with their inner links shifted.
-    int par_depth = 0;
-    static void append(std::vector<DevBvhNode>& dst, std::vector<DevBvhNode>& sub, int& link) {
-        const int off = (int)dst.size();
-        for (DevBvhNode& n : sub) {
-            if (n.d.x >= 0) n.d.x += off;
-            if (n.d.y >= 0) n.d.y += off;
-        }
-        if (link >= 0) link += off;
-        dst.insert(dst.end(), sub.begin(), sub.end());
-    }
-    int make_inner(int b, int mid, int e, int depth) {
-        int idx = (int)nodes.size();
-        nodes.emplace_back();
-        Box b0, b1;
-        for (int i = b; i < mid; i++) b0.grow(items[i].box);
-        for (int i = mid; i < e; i++) b1.grow(items[i].box);
-        int c0, c1;
-        if (depth < par_depth && e - b > 4096) {
-            std::vector<DevBvhNode> left_nodes, right_nodes;
-            Builder left{items, left_nodes, leaf_size}, right{items, right_nodes, leaf_size};
-            left.par_depth = right.par_depth = par_depth;
-            auto task = std::async(std::launch::async, [&] { return left.build(b, mid, depth + 1); });
-            c1 = right.build(mid, e, depth + 1);
-            c0 = task.get();
-            append(nodes, left_nodes, c0);
-            append(nodes, right_nodes, c1);
-        } else {
-            c0 = build(b, mid, depth + 1);
-            c1 = build(mid, e, depth + 1);
-        }
-        DevBvhNode& n = nodes[idx];
-        n.a = make_float4(b0.lo[0], b0.lo[1], b0.lo[2], b0.hi[0]);
-        n.b = make_float4(b0.hi[1], b0.hi[2], b1.lo[0], b1.lo[1]);
-        n.c = make_float4(b1.lo[2], b1.hi[0], b1.hi[1], b1.hi[2]);
-        // d.z bit i: child i holds closed primitives only (find_containers may cull it with a point-in-box test)
-        bool closed0 = true, closed1 = true;
-        for (int i = b; i < mid; i++) closed0 = closed0 && items[i].closed;
-        for (int i = mid; i < e; i++) closed1 = closed1 && items[i].closed;
-        n.d = make_int4(c0, c1, (closed0 ? 1 : 0) | (closed1 ? 2 : 0), 0);
-        return idx;
-    }
-};
-
-// worst-case number of intersections a leaf kind can emit (cone: 2 walls + 2 caps)
-int max_hits(int type) {
-    switch (type) {
-        case RTC_SPHERE: return 2;
-        case RTC_PLANE: return 1;
-        case RTC_CUBE: return 2;
-        case RTC_CYLINDER: return 3;
-        case RTC_CONE: return 4;
-        default: return 1;
-    }
-}
-
-struct Flattened {
-    std::vector<int4> head;  // 2 * n_pos entries: [pos] main, [n_pos + pos] {cull-chain parent node, api prim, 0, 0}
-    std::vector<float4> xform, tri, bound, rec;
-    std::vector<DevBvhNode> bvh;
-    std::vector<int> linear;
-    std::vector<DevNode> nodes;
-    std::vector<DevCsgOp> ops;
-    std::vector<DevMaterial> materials;
-    std::vector<DevPattern> patterns;
-    std::vector<DevUvPattern> uvs;
-    std::vector<float4> texels;
-    int leaf_size = 0;  // the BVH leaf size used
-    std::vector<float4> samples;
-    SmallScene small{};
-    int bvh_root = -1;
-    int n_pos = 0;
-    int all_cast_shadow = 1;
-};
-
-int flatten(RtcScene* s, Flattened& f) {
-    const int np = (int)s->prims.size(), nn = (int)s->nodes.size();
-    const bool timing = getenv("RTC_TIMING") != nullptr;  // tuning aid: phase times of the host half on stderr
-    auto t_last = std::chrono::steady_clock::now();
-    auto lap = [&](const char* what) {
-        if (!timing) return;
-        const auto now = std::chrono::steady_clock::now();
-        fprintf(stderr, "[rtc commit] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(now - t_last).count());
-        t_last = now;
-    };
-    // ---- validate references
-    for (int i = 0; i < np; i++) {
-        const RtcPrim& p = s->prims[i];
-        if (p.type < RTC_SPHERE || p.type > RTC_TRIANGLE) return fail(RTC_ERR_INVALID, "primitive " + std::to_string(i) + ": bad type");
-        if (p.material < 0 || p.material >= (int)s->materials.size())
-            return fail(RTC_ERR_INVALID, "primitive " + std::to_string(i) + ": bad material index");
-        if (p.parent < -1 || p.parent >= nn) return fail(RTC_ERR_INVALID, "primitive " + std::to_string(i) + ": bad parent");
-    }
-    for (int i = 0; i < nn; i++) {
-        const RtcNode& n = s->nodes[i];
-        if (n.kind != RTC_NODE_GROUP && n.kind != RTC_NODE_CSG) return fail(RTC_ERR_INVALID, "node: bad kind");
-        if (n.parent < -1 || n.parent >= nn || n.parent == i) return fail(RTC_ERR_INVALID, "node: bad parent");
-        if (n.child_begin < 0 || n.child_count < 0 || n.child_begin + n.child_count > (int)s->refs.size())
-            return fail(RTC_ERR_INVALID, "node: bad child range");
-        if (n.kind == RTC_NODE_CSG && (n.child_count != 2 || n.op < 0 || n.op > 2)) return fail(RTC_ERR_INVALID, "csg node: needs 2 children and a valid operator");
-        for (int c = 0; c < n.child_count; c++) {
-            int r = s->refs[n.child_begin + c];
-            if (r >= np || (r < 0 && ~r >= nn)) return fail(RTC_ERR_INVALID, "node: bad child reference");
-        }
-    }
-    for (const RtcMaterial& m : s->materials)
-        if (m.pattern < -1 || m.pattern >= (int)s->patterns.size()) return fail(RTC_ERR_INVALID, "material: bad pattern index");
-    for (const RtcPattern& p : s->patterns) {
-        if (p.kind < RTC_PAT_STRIPES || p.kind > RTC_PAT_CUBIC_MAP) return fail(RTC_ERR_INVALID, "pattern: bad kind");
-        int need = p.kind == RTC_PAT_TEXTURE_MAP ? 1 : (p.kind == RTC_PAT_CUBIC_MAP ? 6 : 0);
-        for (int i = 0; i < need; i++)
-            if (p.uv[i] < 0 || p.uv[i] >= (int)s->uvs.size()) return fail(RTC_ERR_INVALID, "pattern: bad uv pattern index");
-    }
-
-    // ---- which CSG (if any) is the outermost CSG ancestor of each node / primitive
-    std::vector<int> top_csg_of_node(nn, -1);
-    auto resolve = [&](int node) {
-        int top = -1, guard = 0;
-        for (int a = node; a >= 0; a = s->nodes[a].parent) {
-            if (s->nodes[a].kind == RTC_NODE_CSG) top = a;
-            if (++guard > nn) return -2;
-        }
-        return top;
-    };
-    for (int i = 0; i < nn; i++) {
-        top_csg_of_node[i] = resolve(i);
-        if (top_csg_of_node[i] == -2) return fail(RTC_ERR_INVALID, "node parents form a cycle");
-    }
-    std::vector<int> prim_top_csg(np, -1);
-    for (int i = 0; i < np; i++) prim_top_csg[i] = s->prims[i].parent >= 0 ? top_csg_of_node[s->prims[i].parent] : -1;
-
-    // ---- top-level items: free primitives and outermost CSG nodes
-    struct Item {
-        int prim;  // >= 0 primitive, else ~csg node
-        Box box;
-    };
-    std::vector<Item> bounded, unbounded;
-    auto add_item = [&](int ref, const float* lo, const float* hi) {
-        Item it;
-        it.prim = ref;
-        for (int a = 0; a < 3; a++) it.box.lo[a] = lo[a], it.box.hi[a] = hi[a];
-        (it.box.finite() ? bounded : unbounded).push_back(it);
-    };
-    for (int i = 0; i < np; i++)
-        if (prim_top_csg[i] < 0) add_item(i, s->prims[i].bbox_min, s->prims[i].bbox_max);
-    for (int i = 0; i < nn; i++)
-        if (s->nodes[i].kind == RTC_NODE_CSG && top_csg_of_node[i] == i) add_item(~i, s->nodes[i].world_bbox_min, s->nodes[i].world_bbox_max);
-    if ((int)bounded.size() < s->bvh_min_prims) {  // tiny scene: test everything for every ray, no tree
-        unbounded.insert(unbounded.end(), bounded.begin(), bounded.end());
-        bounded.clear();
-        // group the linear list by (shadow casters first, kind) — the small-scene kernels loop over runs of one
-        // kind; depth-first order inside a run (ties are broken by the stored order field, not by position)
-        std::stable_sort(unbounded.begin(), unbounded.end(), [&](const Item& a, const Item& b) {
-            auto key = [&](const Item& it) {
-                int dfs = it.prim >= 0 ? it.prim : np + ~it.prim;
-                int caster = it.prim >= 0 ? (s->prims[it.prim].casts_shadow ? 0 : 1) : 0;
-                int type = it.prim >= 0 ? s->prims[it.prim].type : 99;
-                int bucket = type == RTC_SPHERE ? 0 : type == RTC_PLANE ? 1 : type == RTC_CUBE ? 2 : 3;
-                return std::make_tuple(caster, bucket, dfs);
-            };
-            return key(a) < key(b);
-        });
-    }
-
-    lap("validate + item lists");
-    // ---- BVH
-    std::vector<BuildItem> build_items(bounded.size());
-    for (size_t i = 0; i < bounded.size(); i++) {
-        BuildItem& b = build_items[i];
-        b.box = bounded[i].box;
-        b.item = (int)i;
-        b.closed = bounded[i].prim >= 0 && (s->prims[bounded[i].prim].type == RTC_SPHERE || s->prims[bounded[i].prim].type == RTC_CUBE);
-        for (int a = 0; a < 3; a++) {
-            // pad: the tree must never reject a hit the reference would report (it is only an accelerator)
-            float ext = b.box.hi[a] - b.box.lo[a];
-            float pad = 1e-4f * ext + 1e-5f * std::max(std::fabs(b.box.lo[a]), std::fabs(b.box.hi[a])) + 1e-6f;
-            b.box.lo[a] -= pad;
-            b.box.hi[a] += pad;
-            b.centroid[a] = 0.5f * (b.box.lo[a] + b.box.hi[a]);
-        }
-    }
-    if (!build_items.empty()) {
-        // Leaf size: a mesh's triangles share one transform (the object-space ray is cached), so a few per leaf cost
-        // less than the extra boxes; every other primitive pays its own ray transform, and one per leaf wins
-        // (measured on B200: 102 k triangles 0.50 ms at 4 vs 0.58 at 1; 100 k spheres 38.7 ms at 1 vs 51.7 at 4).
-        size_t n_triangles = 0;
-        for (const Item& it : bounded) n_triangles += it.prim >= 0 && s->prims[it.prim].type == RTC_TRIANGLE;
-        int leaf = s->leaf_size > 0 ? s->leaf_size : (2 * n_triangles > bounded.size() ? 4 : 1);
-        if (const char* env = getenv("RTC_BVH_LEAF")) leaf = atoi(env);  // tuning aid
-        f.leaf_size = std::min(std::max(leaf, 1), 16);
-        Builder builder{build_items, f.bvh, f.leaf_size};
-        const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
-        while ((1u << builder.par_depth) < hw && builder.par_depth < 5) builder.par_depth++;  // up to 32 subtree tasks
-        f.bvh.reserve(build_items.size());
-        int root = builder.build(0, (int)build_items.size(), 0);
-        if (root < 0) {  // a single leaf: wrap it so the traversal always starts at an inner node
-            DevBvhNode n;
-            Box b;
-            for (auto& it : build_items) b.grow(it.box);
-            n.a = make_float4(b.lo[0], b.lo[1], b.lo[2], b.hi[0]);
-            n.b = make_float4(b.hi[1], b.hi[2], NAN, NAN);  // second child: a NaN box never passes the slab test
-            n.c = make_float4(NAN, NAN, NAN, NAN);
-            n.d = make_int4(root, root, 0, 0);
-            f.bvh.push_back(n);
-            root = (int)f.bvh.size() - 1;
-        }
-        f.bvh_root = root;
-    }
-
-    lap("bvh build");
-    // ---- device positions: BVH order, then the linear list, then CSG-internal primitives
-    std::vector<int> item_refs;
-    for (const BuildItem& b : build_items) item_refs.push_back(bounded[b.item].prim);
-    const int n_tree = (int)item_refs.size();
-    for (const Item& it : unbounded) item_refs.push_back(it.prim);
-    const int n_items = (int)item_refs.size();
-    std::vector<int> prim_pos(np, -1), csg_pos(nn, -1);
-    for (int i = 0; i < n_items; i++) {
-        if (item_refs[i] >= 0)
-            prim_pos[item_refs[i]] = i;
-        else
-            csg_pos[~item_refs[i]] = i;
-    }
-    int next = n_items;
-    for (int i = 0; i < np; i++)
-        if (prim_top_csg[i] >= 0) prim_pos[i] = next++;
-    f.n_pos = next;
-    for (int i = n_tree; i < n_items; i++) f.linear.push_back(i);
-
-    // ---- transforms (deduplicated bitwise), triangle and bound tables, heads
-    struct XfKey {
-        uint32_t w[12];
-        bool operator==(const XfKey& o) const { return memcmp(w, o.w, sizeof(w)) == 0; }
-    };
-    struct XfHash {
-        size_t operator()(const XfKey& k) const {  // FNV-1a over the 12 words
-            uint64_t h = 1469598103934665603ull;
-            for (uint32_t v : k.w) h = (h ^ v) * 1099511628211ull;
-            return (size_t)h;
-        }
-    };
-    std::unordered_map<XfKey, int, XfHash> xf_ids;
-    f.xform.reserve(3 * (size_t)np);
-    XfKey last_key{};
-    int last_id = -1;
-    // only a mesh's triangles share transforms in practice (and only they profit: the object-space ray is cached by
-    // transform id), so every other primitive gets its own slot without a lookup
-    auto xform_id = [&](const float m[16], bool dedup) {
-        if (!dedup) {
-            float4 r[3];
-            rows3(m, r);
-            f.xform.insert(f.xform.end(), r, r + 3);
-            return (int)f.xform.size() / 3 - 1;
-        }
-        XfKey key;
-        memcpy(key.w, m, sizeof(key.w));
-        if (last_id >= 0 && key == last_key) return last_id;  // a mesh's triangles share one transform
-        last_key = key;
-        auto it = xf_ids.find(key);
-        if (it != xf_ids.end()) return last_id = it->second;
-        int id = (int)f.xform.size() / 3;
-        float4 r[3];
-        rows3(m, r);
-        f.xform.insert(f.xform.end(), r, r + 3);
-        xf_ids.emplace(key, id);
-        return last_id = id;
-    };
-    f.head.assign(2 * (size_t)f.n_pos, make_int4(0, 0, 0, 0));
-    s->pos_to_prim.assign(f.n_pos, -1);
-    f.tri.reserve(3 * (size_t)np);
-    for (int i = 0; i < np; i++) {
-        const RtcPrim& p = s->prims[i];
-        int pos = prim_pos[i];
-        int aux = 0;
-        if (p.type == RTC_TRIANGLE) {
-            aux = (int)f.tri.size() / 3;
-            const float* q = p.params;  // p1, e1, e2, normal
-            f.tri.push_back(make_float4(q[0], q[1], q[2], q[3]));
-            f.tri.push_back(make_float4(q[4], q[5], q[6], q[7]));
-            f.tri.push_back(make_float4(q[8], q[9], q[10], q[11]));
-        } else if (p.type == RTC_CYLINDER || p.type == RTC_CONE) {
-            aux = (int)f.bound.size();
-            f.bound.push_back(make_float4(p.params[0], p.params[1], p.params[2] != 0.f ? 1.f : 0.f, 0.f));
-        }
-        int flags = p.casts_shadow ? kFlagCastsShadow : 0;
-        if (!p.casts_shadow) f.all_cast_shadow = 0;
-        bool in_linear = pos >= n_tree && pos < n_items;
-        if (in_linear && p.parent >= 0) flags |= kFlagHasParent;
-        f.head[pos] = make_int4(p.type | (flags << 4) | (p.material << 8), xform_id(p.inv, p.type == RTC_TRIANGLE), aux, i);
-        f.head[f.n_pos + pos] = make_int4(prim_top_csg[i] < 0 ? p.parent : -1, i, 0, 0);
-        s->pos_to_prim[pos] = i;
-    }
-
-    lap("positions, transforms, heads");
-    // ---- reference shape-tree nodes
-    f.nodes.resize(nn);
-    for (int i = 0; i < nn; i++) {
-        const RtcNode& n = s->nodes[i];
-        DevNode& d = f.nodes[i];
-        rows3(n.inv, d.inv);
-        for (int a = 0; a < 3; a++) d.bmin[a] = n.bbox_min[a], d.bmax[a] = n.bbox_max[a];
-        d.kind = n.kind;
-        d.parent = n.parent;
-        d.op = n.op;
-        d.pad = 0;
-    }
-
-    // ---- CSG programs
-    struct Emit {
-        RtcScene* s;
-        Flattened& f;
-        std::vector<int>& prim_pos;
-        int worst_hits = 0, max_depth = 0;
-        int emit(int ref, int csg_depth) {  // returns worst-case hit count of the subtree
-            if (ref >= 0) {
-                f.ops.push_back(DevCsgOp{OP_PRIM, prim_pos[ref], 0, 0});
-                return max_hits(s->prims[ref].type);
-            }
-            int node = ~ref;
-            const RtcNode& n = s->nodes[node];
-            int total = 0;
-            if (n.kind == RTC_NODE_GROUP) {
-                size_t idx = f.ops.size();
-                f.ops.push_back(DevCsgOp{OP_GROUP, node, 0, 0});
-                for (int c = 0; c < n.child_count; c++) total += emit(s->refs[n.child_begin + c], csg_depth);
-                f.ops[idx].skip = (int)f.ops.size();
-            } else {
-                max_depth = std::max(max_depth, csg_depth + 1);
-                size_t idx = f.ops.size();
-                f.ops.push_back(DevCsgOp{OP_CSG_ENTER, node, 0, 0});
-                total += emit(s->refs[n.child_begin], csg_depth + 1);
-                f.ops.push_back(DevCsgOp{OP_CSG_MID, node, 0, 0});
-                total += emit(s->refs[n.child_begin + 1], csg_depth + 1);
-                f.ops.push_back(DevCsgOp{OP_CSG_EXIT, node, 0, 0});
-                f.ops[idx].skip = (int)f.ops.size();
-            }
-            worst_hits = std::max(worst_hits, total);
-            return total;
-        }
-    } emitter{s, f, prim_pos};
-    for (int i = 0; i < nn; i++) {
-        if (csg_pos[i] < 0) continue;
-        int start = (int)f.ops.size();
-        emitter.emit(~i, 0);
-        int pos = csg_pos[i];
-        // order: depth-first index of the CSG's first leaf (ties are resolved with the leaves' own orders)
-        f.head[pos] = make_int4(T_CSG | (kFlagCastsShadow << 4), 0, start, 0);
-        f.head[f.n_pos + pos] = make_int4(s->nodes[i].parent, -1, 0, 0);
-    }
-    if (emitter.worst_hits > kCsgHitCap)
-        return fail(RTC_ERR_CAPACITY, "a CSG subtree can produce " + std::to_string(emitter.worst_hits) +
-                                          " intersections on one ray; the device hit buffer holds " + std::to_string(kCsgHitCap));
-    if (emitter.max_depth > kCsgRayDepth - 1)
-        return fail(RTC_ERR_CAPACITY, "CSG nesting depth " + std::to_string(emitter.max_depth) + " exceeds " + std::to_string(kCsgRayDepth - 1));
-
-    lap("nodes + csg programs");
-    // ---- traversal records: head + the rows the intersection test needs, one 64 B fetch per primitive
-    f.rec.assign(4 * (size_t)f.n_pos, make_float4(0.f, 0.f, 0.f, 0.f));
-    for (int pos = 0; pos < f.n_pos; pos++) {
-        int4 h = f.head[pos];
-        memcpy(&f.rec[4 * (size_t)pos], &h, sizeof(h));
-        int type = h.x & 15;
-        if (type == T_CSG) continue;
-        const float4* src = (type == T_TRIANGLE) ? &f.tri[3 * (size_t)h.z] : &f.xform[3 * (size_t)h.y];
-        for (int r = 0; r < 3; r++) f.rec[4 * (size_t)pos + 1 + r] = src[r];
-    }
-
-    // ---- shading tables
-    s->has_branching_materials = false;
-    for (const RtcMaterial& m : s->materials) {
-        if (m.reflective != 0.0f && m.transparency != 0.0f) s->has_branching_materials = true;
-        DevMaterial d{};
-        memcpy(d.color, m.color, sizeof(d.color));
-        d.ambient = m.ambient, d.diffuse = m.diffuse, d.specular = m.specular, d.shininess = m.shininess;
-        d.reflective = m.reflective, d.transparency = m.transparency, d.refractive_index = m.refractive_index;
-        d.pattern = m.pattern;
-        f.materials.push_back(d);
-    }
-    for (const RtcPattern& p : s->patterns) {
-        DevPattern d{};
-        rows3(p.inv, d.inv);
-        memcpy(d.a, p.a, sizeof(d.a));
-        memcpy(d.b, p.b, sizeof(d.b));
-        d.kind = p.kind, d.mapping = p.mapping;
-        memcpy(d.uv, p.uv, sizeof(d.uv));
-        f.patterns.push_back(d);
-    }
-    std::vector<size_t> texel_base;
-    for (const RtcScene::Texture& t : s->textures) {
-        texel_base.push_back(f.texels.size());
-        for (size_t i = 0; i < (size_t)t.width * t.height; i++)
-            f.texels.push_back(make_float4(t.rgb[3 * i], t.rgb[3 * i + 1], t.rgb[3 * i + 2], 0.f));
-    }
-    if (f.texels.size() >= (1u << 30)) return fail(RTC_ERR_CAPACITY, "image textures exceed 2^30 pixels");
-    for (const RtcUvPattern& u : s->uvs) {
-        DevUvPattern d{};
-        d.kind = u.kind;
-        memcpy(d.p, u.params, sizeof(d.p));
-        if (u.kind == RTC_UV_IMAGE) {  // {first texel, width, height} as integers
-            const int t = (int)u.params[0];
-            if (t < 0 || t >= (int)s->textures.size() || (float)t != u.params[0]) return fail(RTC_ERR_INVALID, "uv image: bad texture index");
-            const int base = (int)texel_base[t], w = (int)s->textures[t].width, h = (int)s->textures[t].height;
-            if (w < 1 || h < 1) return fail(RTC_ERR_INVALID, "uv image: empty canvas");
-            memcpy(&d.p[0], &base, 4), memcpy(&d.p[1], &w, 4), memcpy(&d.p[2], &h, 4);
-        }
-        f.uvs.push_back(d);
-    }
-    // ---- table-mode light samples: point_on_light (rectangle_light.rs:60-66) is the same for every shade
-    if (s->light_is_rect && !s->jitter.empty()) {
-        size_t cursor = 0, L = s->jitter.size();
-        for (int v = 0; v < s->v_steps; v++)
-            for (int u = 0; u < s->u_steps; u++) {
-                float j1 = s->jitter[cursor % L], j2 = s->jitter[(cursor + 1) % L];
-                cursor += 2;
-                float su = (float)u + j1, sv = (float)v + j2;
-                float p[3];
-                for (int a = 0; a < 3; a++) {
-                    volatile float t1 = s->u_cell[a] * su;  // volatile: no host-side contraction / reassociation
-                    volatile float t2 = s->corner[a] + t1;
-                    volatile float t3 = s->v_cell[a] * sv;
-                    p[a] = t2 + t3;
-                }
-                f.samples.push_back(make_float4(p[0], p[1], p[2], 0.f));
-            }
-    }
-    // ---- small-scene table (kernel parameter block): no tree, every item in the linear list, few enough of them
-    memset(&f.small, 0, sizeof(f.small));
-    if (f.bvh_root < 0 && n_items > 0 && n_items <= kSmallCap) {
-        f.small.n = n_items;
-        f.small.two_pass_shadows = 1;
-        int ends[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        for (int i = 0; i < n_items; i++) {
-            SmallPrim& sp = f.small.p[i];
-            int4 h = f.head[i];
-            sp.head = make_int4(h.x, f.head[f.n_pos + i].x, h.z, h.w);
-            int type = h.x & 15;
-            bool caster = type == T_CSG || ((h.x >> 4) & kFlagCastsShadow);
-            int bucket = (caster ? 0 : 4) + (type == T_SPHERE ? 0 : type == T_PLANE ? 1 : type == T_CUBE ? 2 : 3);
-            for (int b = bucket; b < 8; b++) ends[b] = i + 1;
-            if ((h.x >> 4) & kFlagHasParent) f.small.has_cull_chain = 1;
-            sp.ball = make_float4(NAN, NAN, NAN, NAN);  // a NaN ball never rejects
-            if (type == T_CSG) {
-                f.small.two_pass_shadows = 0;
-                sp.r0 = sp.r1 = sp.r2 = sp.bound = make_float4(0.f, 0.f, 0.f, 0.f);
-                continue;
-            }
-            sp.r0 = f.xform[3 * (size_t)h.y], sp.r1 = f.xform[3 * (size_t)h.y + 1], sp.r2 = f.xform[3 * (size_t)h.y + 2];
-            sp.bound = (type == T_CYLINDER || type == T_CONE) ? f.bound[h.z] : make_float4(0.f, 0.f, 0.f, 0.f);
-            // ---- world-space bounding ball (rtc_device.cuh: ball_missed, bundle_misses).  Sphere / cube: centre =
-            // forward transform of the origin, radius = the largest stretch of the forward 3x3 (bounded by
-            // sqrt(|T|_1 |T|_inf)), times sqrt(3) for a cube's corners; other bounded shapes: the ball around their
-            // world box.  bound.w = 2^-17 cond^2 / radius is the rate at which the tested radius grows with the squared
-            // distance of the ray origin: beyond that clearance no f32 intersection test of the reference reports a hit.
-            {
-                const double m[3][4] = {{sp.r0.x, sp.r0.y, sp.r0.z, sp.r0.w}, {sp.r1.x, sp.r1.y, sp.r1.z, sp.r1.w}, {sp.r2.x, sp.r2.y, sp.r2.z, sp.r2.w}};
-                const double det = m[0][0] * (m[1][1] * m[2][2] - m[1][2] * m[2][1]) - m[0][1] * (m[1][0] * m[2][2] - m[1][2] * m[2][0]) +
-                                   m[0][2] * (m[1][0] * m[2][1] - m[1][1] * m[2][0]);
-                double t[3][3], n1 = 0.0, ninf = 0.0, mi = 0.0;  // t = forward 3x3 = inverse of m's 3x3
-                for (int a = 0; a < 3; a++)
-                    for (int b = 0; b < 3; b++) {
-                        const int a1 = (a + 1) % 3, a2 = (a + 2) % 3, b1 = (b + 1) % 3, b2 = (b + 2) % 3;
-                        t[a][b] = (m[b1][a1] * m[b2][a2] - m[b1][a2] * m[b2][a1]) / det;
-                    }
-                for (int a = 0; a < 3; a++) {
-                    n1 = std::max(n1, std::fabs(t[0][a]) + std::fabs(t[1][a]) + std::fabs(t[2][a]));
-                    ninf = std::max(ninf, std::fabs(t[a][0]) + std::fabs(t[a][1]) + std::fabs(t[a][2]));
-                    mi = std::max(mi, std::fabs(m[a][0]) + std::fabs(m[a][1]) + std::fabs(m[a][2]));
-                }
-                const double cond = std::max(1.0, mi * ninf);
-                double c[3], radius;
-                if (type == T_SPHERE || type == T_CUBE) {
-                    radius = std::sqrt(n1 * ninf) * (type == T_CUBE ? std::sqrt(3.0) : 1.0);
-                    for (int a = 0; a < 3; a++) c[a] = -(t[a][0] * m[0][3] + t[a][1] * m[1][3] + t[a][2] * m[2][3]);
-                } else {
-                    const RtcPrim& pr = s->prims[h.w];
-                    double d2 = 0.0;
-                    for (int a = 0; a < 3; a++) {
-                        c[a] = 0.5 * ((double)pr.bbox_min[a] + pr.bbox_max[a]);
-                        d2 += 0.25 * ((double)pr.bbox_max[a] - pr.bbox_min[a]) * ((double)pr.bbox_max[a] - pr.bbox_min[a]);
-                    }
-                    radius = std::sqrt(d2);
-                }
-                if (std::isfinite(radius) && std::isfinite(c[0]) && std::isfinite(c[1]) && std::isfinite(c[2]) && radius > 0.0 &&
-                    std::isfinite(cond)) {
-                    sp.ball = make_float4((float)c[0], (float)c[1], (float)c[2], (float)(radius * 1.001 + 1e-6));
-                    sp.bound.w = (float)(std::ldexp(1.0, -17) * cond * cond / radius);
-                }
-            }
-        }
-        f.small.caster_end = make_int4(ends[0], ends[1], ends[2], ends[3]);
-        f.small.other_end = make_int4(ends[4], ends[5], ends[6], ends[7]);
-        // ---- shadow-filter eligibility (rtc_device.cuh: shadow_filter): spheres whose transform is well conditioned
-        // (the filter's error bound scales with the condition number), planes (term-wise bound: any transform),
-        // cubes whose inverse has a diagonal 3x3 part (every direction component is a single product)
-        bool ok = f.small.two_pass_shadows && !f.small.has_cull_chain && ends[2] == ends[3] && ends[6] == ends[7];
-        double worst = 1.0;
-        for (int i = 0; i < n_items && ok; i++) {
-            const SmallPrim& sp = f.small.p[i];
-            const int type = sp.head.x & 15;
-            const double m[3][3] = {{sp.r0.x, sp.r0.y, sp.r0.z}, {sp.r1.x, sp.r1.y, sp.r1.z}, {sp.r2.x, sp.r2.y, sp.r2.z}};
-            for (int a = 0; a < 3; a++)
-                for (int b = 0; b < 3; b++) ok = ok && std::isfinite(m[a][b]);
-            if (type == T_CUBE) {
-                for (int a = 0; a < 3; a++)
-                    for (int b = 0; b < 3; b++) ok = ok && (a == b ? m[a][b] != 0.0 : m[a][b] == 0.0);
-            } else if (type == T_SPHERE) {
-                const double det = m[0][0] * (m[1][1] * m[2][2] - m[1][2] * m[2][1]) - m[0][1] * (m[1][0] * m[2][2] - m[1][2] * m[2][0]) +
-                                   m[0][2] * (m[1][0] * m[2][1] - m[1][1] * m[2][0]);
-                double norm_m = 0.0, norm_i = 0.0;
-                for (int a = 0; a < 3; a++) {
-                    double row_m = 0.0, row_i = 0.0;
-                    for (int b = 0; b < 3; b++) {
-                        const int a1 = (a + 1) % 3, a2 = (a + 2) % 3, b1 = (b + 1) % 3, b2 = (b + 2) % 3;
-                        row_m += std::fabs(m[a][b]);
-                        row_i += std::fabs((m[b1][a1] * m[b2][a2] - m[b1][a2] * m[b2][a1]) / det);  // inverse = adjugate / det
-                    }
-                    norm_m = std::max(norm_m, row_m), norm_i = std::max(norm_i, row_i);
-                }
-                const double cond = norm_m * norm_i;
-                ok = ok && std::isfinite(cond) && cond <= 64.0;
-                if (ok) worst = std::max(worst, cond);
-            }
-        }
-        f.small.filter_ok = ok ? 1 : 0;
-        // cell-mask path: a table-mode light whose samples fit the staging area, or the counter-mode generator
-        const bool table_light = s->light_is_rect && !f.samples.empty() && f.samples.size() <= (size_t)kSampleCap;
-        const bool counter_light = s->light_is_rect && s->jitter.empty() && s->u_steps > 0 && s->v_steps > 0;
-        f.small.cell_masks = ok && (table_light || counter_light);
-        if (f.small.cell_masks) {
-            // the bundle reject (rtc_device.cuh: bundle_misses): a ball around the light samples, and for every sphere /
-            // cube its world-space bounding ball — centre = forward transform of the origin, radius = the largest
-            // stretch of the forward 3x3 (bounded by sqrt(|T|_1 |T|_inf)), times sqrt(3) for a cube's corners
-            // the light's possible sample points: the table's, or (counter mode: jitter in (0, 1]) the whole rectangle
-            std::vector<float4> pts = f.samples;
-            if (pts.empty())
-                for (int cu = 0; cu < 2; cu++)
-                    for (int cv = 0; cv < 2; cv++)
-                        pts.push_back(make_float4(s->corner[0] + s->u_cell[0] * (cu * s->u_steps) + s->v_cell[0] * (cv * s->v_steps),
-                                                  s->corner[1] + s->u_cell[1] * (cu * s->u_steps) + s->v_cell[1] * (cv * s->v_steps),
-                                                  s->corner[2] + s->u_cell[2] * (cu * s->u_steps) + s->v_cell[2] * (cv * s->v_steps), 0.f));
-            double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
-            for (const float4& q : pts) {
-                const double v[3] = {q.x, q.y, q.z};
-                for (int a = 0; a < 3; a++) lo[a] = std::min(lo[a], v[a]), hi[a] = std::max(hi[a], v[a]);
-            }
-            const double lc[3] = {0.5 * (lo[0] + hi[0]), 0.5 * (lo[1] + hi[1]), 0.5 * (lo[2] + hi[2])};
-            double rl = 0.0;
-            for (const float4& q : pts)
-                rl = std::max(rl, std::sqrt((q.x - lc[0]) * (q.x - lc[0]) + (q.y - lc[1]) * (q.y - lc[1]) + (q.z - lc[2]) * (q.z - lc[2])));
-            f.small.light_ball = make_float4((float)lc[0], (float)lc[1], (float)lc[2], (float)(rl * 1.001 + 1e-6));
-            const int n_planes = ends[1] - ends[0];
-            f.small.plane_cells = table_light && n_planes > 0 && (size_t)n_planes * f.samples.size() <= (size_t)kPlaneCellCap;
-            // bounds of the per-(plane, cell) constants over all cells (rtc_device.cuh: plane_cell_constants), padded
-            // beyond the f32 rounding of the device's own evaluation: lets a shade settle the plane for every cell at once
-            for (int q = 0; q < 2; q++) {
-                f.small.plane_bundle[q] = make_float4(NAN, NAN, NAN, NAN);  // NaN: the bundle test never decides
-                if (!f.small.plane_cells || q >= n_planes) continue;
-                const float4 r1 = f.small.p[ends[0] + q].r1;
-                double lo = 1e300, hi = -1e300, e_max = 0.0, l1_max = 0.0;
-                for (const float4& L : f.samples) {
-                    const double px = (double)r1.x * L.x, py = (double)r1.y * L.y, pz = (double)r1.z * L.z;
-                    const double a = std::fabs(px) + std::fabs(py) + std::fabs(pz);
-                    lo = std::min(lo, px + py + pz - 1e-6 * a), hi = std::max(hi, px + py + pz + 1e-6 * a);
-                    e_max = std::max(e_max, 3.814697265625e-06 * a * 1.000001);
-                    l1_max = std::max(l1_max, 1.1920929e-3 * (1.0 + 7.7e-6) * (std::fabs(L.x) + std::fabs(L.y) + std::fabs(L.z)) * 1.000001);
-                }
-                f.small.plane_bundle[q] = make_float4((float)lo, (float)hi, (float)e_max, (float)l1_max);
-                // round outwards
-                f.small.plane_bundle[q].x = std::nextafter(f.small.plane_bundle[q].x, -INFINITY);
-                f.small.plane_bundle[q].y = std::nextafter(f.small.plane_bundle[q].y, INFINITY);
-                f.small.plane_bundle[q].z = std::nextafter(f.small.plane_bundle[q].z, INFINITY);
-                f.small.plane_bundle[q].w = std::nextafter(f.small.plane_bundle[q].w, INFINITY);
-            }
-        }
-        f.small.tol_sphere = (float)(std::ldexp(1.0, -24) * 64.0 * (worst + 1.0));
-    }
-    lap("records, tables, small scene");
-    s->n_bvh_nodes = (int)f.bvh.size();
-    s->n_linear = (int)f.linear.size();
-    s->n_xforms = (int)f.xform.size() / 3;
-    return 0;
-}
 
 int upload_replica(RtcScene* s, const Flattened& f, Replica& r, int device) {
     int rc;

@@ -1,0 +1,139 @@
+// rtc_internal.h — structures shared by the two host translation units of librtc_b200.so: rtc_api.cu (C ABI, device
+// resources, upload, render) and rtc_commit.cu (the host half of a commit: validation, BVH, CSG programs, tables).
+#pragma once
+#include <cmath>
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/rtc_b200.h"
+#include "rtc_types.h"
+
+namespace rtc {
+
+// records the message for rtc_last_error() (thread-local) and returns `code`
+int fail(int code, const std::string& msg);
+
+// the first three rows of a row-major 4x4 (an affine inverse transform) as the device keeps them
+inline void rows3(const float m[16], float4 out[3]) {
+    for (int r = 0; r < 3; r++) out[r] = make_float4(m[r * 4], m[r * 4 + 1], m[r * 4 + 2], m[r * 4 + 3]);
+}
+
+struct Box {
+    float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    void grow(const Box& o) {
+        for (int a = 0; a < 3; a++) lo[a] = std::min(lo[a], o.lo[a]), hi[a] = std::max(hi[a], o.hi[a]);
+    }
+    float area() const {
+        float dx = hi[0] - lo[0], dy = hi[1] - lo[1], dz = hi[2] - lo[2];
+        if (dx < 0 || dy < 0 || dz < 0) return 0.f;
+        return 2.f * (dx * dy + dy * dz + dz * dx);
+    }
+    bool finite() const {
+        for (int a = 0; a < 3; a++)
+            if (!std::isfinite(lo[a]) || !std::isfinite(hi[a]) || lo[a] > hi[a]) return false;
+        return true;
+    }
+};
+
+// Device-side resources that outlive a scene: creating streams / events and allocating the frame and scene
+// buffers costs more than rendering a small frame, so they are pooled per device and leased to a scene at
+// commit (Camera::render_b200 commits a fresh scene on every call, like the reference's render takes its
+// World by value).
+struct DeviceSlot {
+    int device = -1;
+    cudaStream_t stream = nullptr;       // kernels
+    cudaStream_t copy_stream = nullptr;  // device-to-host copies, overlapped with the kernels of later slices
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::vector<cudaEvent_t> slice_done;
+    float* d_rgb = nullptr;
+    unsigned char* d_u8 = nullptr;
+    size_t frame_px = 0;
+    DevCounters* d_counters = nullptr;
+    unsigned* d_tile_cost = nullptr;  // clock cycles per frame tile, recorded by the render that learns the order
+    int* d_tile_order = nullptr;      // launch order of this shard's tiles
+    int tile_capacity = 0;
+    int sm_count = 148;
+    char* arena = nullptr;  // scene arrays, one allocation
+    size_t arena_bytes = 0;
+    char* staging = nullptr;  // pinned host mirror of the arena for one asynchronous upload
+    size_t staging_bytes = 0;
+    void* d_flush = nullptr;
+    size_t flush_bytes = 0;
+};
+
+// One committed replica of the scene on one device.
+struct Replica {
+    DeviceSlot* slot = nullptr;
+    DevScene scene{};
+    SmallScene small{};
+    int cell_masks_eligible = 0, plane_cells_eligible = 0;
+    int filter_eligible = 0;  // SmallScene::filter_ok as computed at commit (RTC_OPT_SHADOW_FILTER masks it per render)
+    // Longest-first launch order learnt from the previous render of the same shard (see render_impl)
+    int order_shard = -1, order_n_shards = -1, order_depth = -1, order_filter = -1;  // what d_tile_order was learnt for
+    bool learning = false;  // this render records the tile costs
+};
+
+// Everything rtc_scene_commit derives from the scene on the host, ready for upload (rtc_commit.cu: flatten).
+struct Flattened {
+    std::vector<int4> head;  // 2 * n_pos entries: [pos] main, [n_pos + pos] {cull-chain parent node, api prim, 0, 0}
+    std::vector<float4> xform, tri, bound, rec;
+    std::vector<DevBvhNode> bvh;
+    std::vector<int> linear;
+    std::vector<DevNode> nodes;
+    std::vector<DevCsgOp> ops;
+    std::vector<DevMaterial> materials;
+    std::vector<DevPattern> patterns;
+    std::vector<DevUvPattern> uvs;
+    std::vector<float4> texels;
+    int leaf_size = 0;  // the BVH leaf size used
+    std::vector<float4> samples;
+    SmallScene small{};
+    int bvh_root = -1;
+    int n_pos = 0;
+    int all_cast_shadow = 1;
+};
+
+}  // namespace rtc
+
+struct RtcScene {
+    bool have_camera = false, have_light = false, committed = false;
+    uint32_t width = 0, height = 0;
+    float half_w = 0, half_h = 0, pixel_size = 0;
+    float cam_inv[16];
+    std::vector<RtcPrim> prims;
+    std::vector<RtcNode> nodes;
+    std::vector<int32_t> refs;
+    std::vector<RtcMaterial> materials;
+    std::vector<RtcPattern> patterns;
+    std::vector<RtcUvPattern> uvs;
+    struct Texture {
+        uint32_t width, height;
+        std::vector<float> rgb;
+    };
+    std::vector<Texture> textures;
+    bool light_is_rect = false;
+    float light_pos[3], light_rgb[3], corner[3], u_cell[3], v_cell[3];
+    int u_steps = 1, v_steps = 1;
+    std::vector<float> jitter;
+    uint64_t seed = 0;
+    int strict_fp = 1, leaf_size = 0 /* automatic */, bvh_min_prims = rtc::kSmallCap + 1;
+    int render_slices = 6;  // kernel / copy pipeline depth when rendering into host memory
+    int adaptive_order = 1;  // launch a shard's bands longest-first, learnt from the previous render
+    int shadow_filter = 1;   // RTC_OPT_SHADOW_FILTER
+    int converge = -1;         // color_at warp vote: -1 automatic (branching ray trees), 0 / 1 forced (RTC_CONVERGE)
+    bool has_branching_materials = false;  // some material is reflective AND transparent (set at commit)
+    int order_max_waves = 24;  // longest-first order only for launches shorter than this many waves of blocks
+    std::vector<rtc::Replica> replicas;
+    std::vector<int> replica_devices;
+    std::vector<int> pos_to_prim;  // device position -> API primitive index (-1 for CSG pseudo-primitives)
+    // commit statistics
+    int n_bvh_nodes = 0, n_linear = 0, n_xforms = 0;
+};
+
+namespace rtc {
+// The host half of a commit: fills `f` from the scene (and the scene's commit statistics); no device calls.
+int flatten(RtcScene* s, Flattened& f);
+}  // namespace rtc
