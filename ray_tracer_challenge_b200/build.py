@@ -46,7 +46,7 @@ def _run(cmd: list[str]) -> None:
 
 def build(force: bool = False, verbose: bool = False) -> None:
     os.makedirs(BUILD, exist_ok=True)
-    headers = [os.path.join(CSRC, h) for h in ("rtc_types.h", "rtc_device.cuh", "rtc_launch.h", "rtc_internal.h")]
+    headers = [os.path.join(CSRC, h) for h in sorted(os.listdir(CSRC)) if h.endswith((".h", ".cuh"))]
     headers.append(os.path.join(ROOT, "include", "rtc_b200.h"))
     kernels = os.path.join(CSRC, "rtc_kernels.cu")
     api = os.path.join(CSRC, "rtc_api.cu")
