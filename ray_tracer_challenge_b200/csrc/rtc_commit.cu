@@ -153,7 +153,7 @@ int max_hits(int type) {
 
 // The small-scene table of the kernel parameter block (every demo scene: no tree, at most kSmallCap items in the
 // linear list) and the plan of its shadow filter: per-item bounding balls, filter eligibility, the cell-mask loops
-// of an area light, the ball around the light's samples and the per-plane bundle constants (rtc_device.cuh: shadow
+// of an area light, the ball around the light's samples and the per-plane bundle constants (dev_shadow.cuh: shadow
 // filter, intensity_cells, bundle_misses, ball_missed).
 void plan_small_scene(const RtcScene* s, Flattened& f, int n_items) {
     // ---- small-scene table (kernel parameter block): no tree, every item in the linear list, few enough of them
@@ -179,7 +179,7 @@ void plan_small_scene(const RtcScene* s, Flattened& f, int n_items) {
             }
             sp.r0 = f.xform[3 * (size_t)h.y], sp.r1 = f.xform[3 * (size_t)h.y + 1], sp.r2 = f.xform[3 * (size_t)h.y + 2];
             sp.bound = (type == T_CYLINDER || type == T_CONE) ? f.bound[h.z] : make_float4(0.f, 0.f, 0.f, 0.f);
-            // ---- world-space bounding ball (rtc_device.cuh: ball_missed, bundle_misses).  Sphere / cube: centre =
+            // ---- world-space bounding ball (dev_small.cuh: ball_missed, dev_shadow.cuh: bundle_misses).  Sphere / cube: centre =
             // forward transform of the origin, radius = the largest stretch of the forward 3x3 (bounded by
             // sqrt(|T|_1 |T|_inf)), times sqrt(3) for a cube's corners; other bounded shapes: the ball around their
             // world box.  bound.w = 2^-17 cond^2 / radius is the rate at which the tested radius grows with the squared
@@ -222,7 +222,7 @@ void plan_small_scene(const RtcScene* s, Flattened& f, int n_items) {
         }
         f.small.caster_end = make_int4(ends[0], ends[1], ends[2], ends[3]);
         f.small.other_end = make_int4(ends[4], ends[5], ends[6], ends[7]);
-        // ---- shadow-filter eligibility (rtc_device.cuh: shadow_filter): spheres whose transform is well conditioned
+        // ---- shadow-filter eligibility (dev_shadow.cuh: shadow_filter): spheres whose transform is well conditioned
         // (the filter's error bound scales with the condition number), planes (term-wise bound: any transform),
         // cubes whose inverse has a diagonal 3x3 part (every direction component is a single product)
         bool ok = f.small.two_pass_shadows && !f.small.has_cull_chain && ends[2] == ends[3] && ends[6] == ends[7];
@@ -260,7 +260,7 @@ void plan_small_scene(const RtcScene* s, Flattened& f, int n_items) {
         const bool counter_light = s->light_is_rect && s->jitter.empty() && s->u_steps > 0 && s->v_steps > 0;
         f.small.cell_masks = ok && (table_light || counter_light);
         if (f.small.cell_masks) {
-            // the bundle reject (rtc_device.cuh: bundle_misses): a ball around the light samples, and for every sphere /
+            // the bundle reject (dev_shadow.cuh: bundle_misses): a ball around the light samples, and for every sphere /
             // cube its world-space bounding ball — centre = forward transform of the origin, radius = the largest
             // stretch of the forward 3x3 (bounded by sqrt(|T|_1 |T|_inf)), times sqrt(3) for a cube's corners
             // the light's possible sample points: the table's, or (counter mode: jitter in (0, 1]) the whole rectangle
@@ -283,7 +283,7 @@ void plan_small_scene(const RtcScene* s, Flattened& f, int n_items) {
             f.small.light_ball = make_float4((float)lc[0], (float)lc[1], (float)lc[2], (float)(rl * 1.001 + 1e-6));
             const int n_planes = ends[1] - ends[0];
             f.small.plane_cells = table_light && n_planes > 0 && (size_t)n_planes * f.samples.size() <= (size_t)kPlaneCellCap;
-            // bounds of the per-(plane, cell) constants over all cells (rtc_device.cuh: plane_cell_constants), padded
+            // bounds of the per-(plane, cell) constants over all cells (dev_small.cuh: plane_cell_constants), padded
             // beyond the f32 rounding of the device's own evaluation: lets a shade settle the plane for every cell at once
             for (int q = 0; q < 2; q++) {
                 f.small.plane_bundle[q] = make_float4(NAN, NAN, NAN, NAN);  // NaN: the bundle test never decides

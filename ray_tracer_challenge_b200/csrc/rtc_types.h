@@ -56,7 +56,7 @@ struct DevNode {  // group / CSG node of the reference shape tree (cull chain + 
     int kind, parent, op, pad;
 };
 
-// One instruction of a flattened CSG tree (post-order), see csg_eval in rtc_device.cuh.
+// One instruction of a flattened CSG tree (post-order), see csg_eval in dev_bvh.cuh.
 enum : int { OP_CSG_ENTER = 0, OP_CSG_MID = 1, OP_CSG_EXIT = 2, OP_GROUP = 3, OP_PRIM = 4 };
 struct DevCsgOp {
     int op;    // OP_*
