@@ -175,8 +175,8 @@ enum {
     RTC_OPT_RENDER_SLICES = 4, /* kernel launches a frame is cut into when it is copied to host memory, so the
                                   copy of one slice overlaps the kernel of the next (default 6) */
     RTC_OPT_ADAPTIVE_ORDER = 5, /* default 1: a repeated render of the same shard launches its 16x8-pixel tiles
-                                  most-expensive-first (clock cycles per tile recorded by the first render); used
-                                  for launches short enough to have a tail (a shard of a frame); changes no pixel */
+                                  most-expensive-first (clock cycles per tile recorded by an earlier render) when a
+                                  timed trial render shows that order to be faster; changes no pixel */
     RTC_OPT_SHADOW_FILTER = 6   /* default 1: in small scenes of spheres, planes and axis-aligned cubes a shadow ray is
                                   first decided on the un-normalised point->light segment with error bounds; only
                                   undecided rays run the reference's arithmetic.  Changes no pixel (0 = always run

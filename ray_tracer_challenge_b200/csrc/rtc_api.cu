@@ -291,9 +291,10 @@ int render_impl(RtcScene* s, int depth, int shard0, int n_shards_ext, float* rgb
         // only 53 % of the launch).  The first render of a (shard, depth) configuration runs in natural order and
         // records how many clock cycles every tile's block took; later renders launch the shard's tiles
         // most-expensive-first from a list kept on the device.  The order changes no pixel.  It needs one
-        // copy-free launch, so it is used when the frame stays on the device or is copied in one piece — and only
-        // for launches of fewer than `order_max_waves` waves of blocks (a whole 4K frame, 73 waves, has no tail to
-        // speak of and runs a few percent faster in natural order: neighbouring tiles share their cache lines).
+        // copy-free launch, so it is used when the frame stays on the device or is copied in one piece.  Whether it
+        // pays depends on the frame, not on its size alone (c3: 1/8 of the 4K frame 13 % faster, 1/4 of it 2 %
+        // slower, the whole frame 7 % slower; the whole 1080p mesh frame c4 25 % faster), so the second render is a
+        // trial: the learnt order is kept only if that render beats the natural-order one by more than 2 %.
         const int n_slices = copy_out ? std::max(1, std::min(s->render_slices, nb)) : 1;
         const int tiles_x = ((int)s->width + kTileW - 1) / kTileW;
         int rc0;
@@ -303,8 +304,9 @@ int render_impl(RtcScene* s, int depth, int shard0, int n_shards_ext, float* rgb
                                   launch_blocks < (long long)s->order_max_waves * 5 * slot->sm_count;
         const bool learnt = r.order_shard == shard && r.order_n_shards == n_shards && r.order_depth == depth &&
                             r.order_filter == s->shadow_filter;
-        const bool use_order = order_wanted && learnt;
-        r.learning = order_wanted && !learnt;
+        const bool use_order = order_wanted && learnt && r.order_verdict >= 0;
+        r.learning = order_wanted && !learnt && r.renders_done > 0;
+        r.order_on_trial = use_order && r.order_verdict == 0 && !detailed;
         if (r.learning) CUDA_TRY(cudaMemsetAsync(slot->d_tile_cost, 0, (size_t)total_bands * tiles_x * sizeof(unsigned), slot->stream));
         // With a host destination the frame is rendered in a few slices so that the device-to-host copy of one
         // slice overlaps the kernel of the next (the 4K canvases are 124 MB: ~2.3 ms of PCIe against ~2 ms of
@@ -348,6 +350,11 @@ int render_impl(RtcScene* s, int depth, int shard0, int n_shards_ext, float* rgb
         CUDA_TRY(cudaMemcpy(&c, slot->d_counters, sizeof(c), cudaMemcpyDeviceToHost));
         add_counters(st, c);
         Replica& r = s->replicas[i];
+        r.renders_done++;
+        if (r.order_on_trial) {
+            r.order_verdict = ms < 0.98f * r.natural_ms ? 1 : -1;
+            r.order_on_trial = false;
+        }
         if (r.learning) {  // sort this shard's tiles by the cycles their blocks took: the launch order from now on
             const int shard = external ? shard0 : i;
             const int tiles_x = ((int)s->width + kTileW - 1) / kTileW;
@@ -365,6 +372,7 @@ int render_impl(RtcScene* s, int depth, int shard0, int n_shards_ext, float* rgb
             }
             CUDA_TRY(cudaMemcpy(slot->d_tile_order, order.data(), order.size() * sizeof(int), cudaMemcpyHostToDevice));
             r.order_shard = shard, r.order_n_shards = n_shards, r.order_depth = depth, r.order_filter = s->shadow_filter;
+            r.order_verdict = 0, r.natural_ms = ms;
             r.learning = false;
         }
     }

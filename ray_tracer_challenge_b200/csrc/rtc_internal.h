@@ -73,6 +73,12 @@ struct Replica {
     int filter_eligible = 0;  // SmallScene::filter_ok as computed at commit (RTC_OPT_SHADOW_FILTER masks it per render)
     // Longest-first launch order learnt from the previous render of the same shard (see render_impl)
     int order_shard = -1, order_n_shards = -1, order_depth = -1, order_filter = -1;  // what d_tile_order was learnt for
+    // 0: the learnt order is on trial (its first render is timed against the natural-order render that recorded the
+    // costs), 1: it won and is used, -1: it lost (natural order is kept)
+    int order_verdict = 0;
+    bool order_on_trial = false;  // this render is the trial
+    float natural_ms = 0.f;
+    int renders_done = 0;  // the first render of a replica is cold (module load, caches): its time is not compared
     bool learning = false;  // this render records the tile costs
 };
 
@@ -125,7 +131,7 @@ struct RtcScene {
     int shadow_filter = 1;   // RTC_OPT_SHADOW_FILTER
     int converge = -1;         // color_at warp vote: -1 automatic (branching ray trees), 0 / 1 forced (RTC_CONVERGE)
     bool has_branching_materials = false;  // some material is reflective AND transparent (set at commit)
-    int order_max_waves = 16;  // longest-first order only for launches shorter than this many waves of blocks (measured: 1/8 of a 4K frame, 11 waves, 13 % faster; 1/4, 22 waves, 2 % slower)
+    int order_max_waves = 128;  // the longest-first order is not even tried for launches longer than this many waves
     std::vector<rtc::Replica> replicas;
     std::vector<int> replica_devices;
     std::vector<int> pos_to_prim;  // device position -> API primitive index (-1 for CSG pseudo-primitives)
