@@ -304,9 +304,10 @@ int render_impl(RtcScene* s, int depth, int shard0, int n_shards_ext, float* rgb
                                   launch_blocks < (long long)s->order_max_waves * 5 * slot->sm_count;
         const bool learnt = r.order_shard == shard && r.order_n_shards == n_shards && r.order_depth == depth &&
                             r.order_filter == s->shadow_filter;
-        const bool use_order = order_wanted && learnt && r.order_verdict >= 0;
         r.learning = order_wanted && !learnt && r.renders_done > 0;
-        r.order_on_trial = use_order && r.order_verdict == 0 && !detailed;
+        // undecided: stage 1 = natural order again, stages 2 and 3 = the learnt order; decided: by the verdict
+        r.order_timed = order_wanted && learnt && r.order_verdict == 0 && !detailed;
+        const bool use_order = order_wanted && learnt && (r.order_verdict > 0 || (r.order_verdict == 0 && r.order_stage >= 2));
         if (r.learning) CUDA_TRY(cudaMemsetAsync(slot->d_tile_cost, 0, (size_t)total_bands * tiles_x * sizeof(unsigned), slot->stream));
         // With a host destination the frame is rendered in a few slices so that the device-to-host copy of one
         // slice overlaps the kernel of the next (the 4K canvases are 124 MB: ~2.3 ms of PCIe against ~2 ms of
@@ -351,9 +352,12 @@ int render_impl(RtcScene* s, int depth, int shard0, int n_shards_ext, float* rgb
         add_counters(st, c);
         Replica& r = s->replicas[i];
         r.renders_done++;
-        if (r.order_on_trial) {
-            r.order_verdict = ms < 0.98f * r.natural_ms ? 1 : -1;
-            r.order_on_trial = false;
+        if (r.order_timed) {
+            if (r.order_stage == 1) r.natural_ms = std::min(r.natural_ms, ms);
+            if (r.order_stage == 2) r.ordered_ms = ms;
+            if (r.order_stage == 3) r.order_verdict = std::min(r.ordered_ms, ms) < 0.98f * r.natural_ms ? 1 : -1;
+            r.order_stage++;
+            r.order_timed = false;
         }
         if (r.learning) {  // sort this shard's tiles by the cycles their blocks took: the launch order from now on
             const int shard = external ? shard0 : i;
@@ -372,7 +376,7 @@ int render_impl(RtcScene* s, int depth, int shard0, int n_shards_ext, float* rgb
             }
             CUDA_TRY(cudaMemcpy(slot->d_tile_order, order.data(), order.size() * sizeof(int), cudaMemcpyHostToDevice));
             r.order_shard = shard, r.order_n_shards = n_shards, r.order_depth = depth, r.order_filter = s->shadow_filter;
-            r.order_verdict = 0, r.natural_ms = ms;
+            r.order_verdict = 0, r.order_stage = 1, r.natural_ms = ms;
             r.learning = false;
         }
     }

@@ -73,11 +73,12 @@ struct Replica {
     int filter_eligible = 0;  // SmallScene::filter_ok as computed at commit (RTC_OPT_SHADOW_FILTER masks it per render)
     // Longest-first launch order learnt from the previous render of the same shard (see render_impl)
     int order_shard = -1, order_n_shards = -1, order_depth = -1, order_filter = -1;  // what d_tile_order was learnt for
-    // 0: the learnt order is on trial (its first render is timed against the natural-order render that recorded the
-    // costs), 1: it won and is used, -1: it lost (natural order is kept)
-    int order_verdict = 0;
-    bool order_on_trial = false;  // this render is the trial
-    float natural_ms = 0.f;
+    // The learnt order is kept only if it wins a timed trial: after the render that records the costs, one more in
+    // natural order and two in the learnt order are timed (stages 1..3) and the minima compared.
+    // order_verdict: 0 undecided, 1 the learnt order won and is used, -1 it lost (natural order is kept)
+    int order_verdict = 0, order_stage = 0;
+    bool order_timed = false;  // this render is one of the timed trial renders
+    float natural_ms = 0.f, ordered_ms = 0.f;
     int renders_done = 0;  // the first render of a replica is cold (module load, caches): its time is not compared
     bool learning = false;  // this render records the tile costs
 };

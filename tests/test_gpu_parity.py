@@ -139,9 +139,9 @@ def test_longest_first_band_order_changes_no_pixel(gpu):
             p.set_option(5, 0)
             ref = p.render(5, shard=shard, n_shards=n_shards)
             p.set_option(5, 1)
-            first = p.render(5, shard=shard, n_shards=n_shards)   # natural order, learns the cost
-            second = p.render(5, shard=shard, n_shards=n_shards)  # longest-first
-            for got in (first, second):
+            # natural order recording the costs, natural again, two trial renders in the learnt order, the decided one
+            frames = [p.render(5, shard=shard, n_shards=n_shards) for _ in range(5)]
+            for got in frames:
                 assert np.array_equal(got.data.view(np.uint32), ref.data.view(np.uint32))
                 assert np.array_equal(got.to_u8(), ref.to_u8())
     finally:
