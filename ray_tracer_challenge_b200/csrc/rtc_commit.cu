@@ -151,6 +151,104 @@ int max_hits(int type) {
     }
 }
 
+// Every index the flattened scene carries must point inside its table (the reference cannot express a dangling
+// reference; a foreign host can).
+int validate_scene(const RtcScene* s) {
+    const int np = (int)s->prims.size(), nn = (int)s->nodes.size();
+    // ---- validate references
+    for (int i = 0; i < np; i++) {
+        const RtcPrim& p = s->prims[i];
+        if (p.type < RTC_SPHERE || p.type > RTC_TRIANGLE) return fail(RTC_ERR_INVALID, "primitive " + std::to_string(i) + ": bad type");
+        if (p.material < 0 || p.material >= (int)s->materials.size())
+            return fail(RTC_ERR_INVALID, "primitive " + std::to_string(i) + ": bad material index");
+        if (p.parent < -1 || p.parent >= nn) return fail(RTC_ERR_INVALID, "primitive " + std::to_string(i) + ": bad parent");
+    }
+    for (int i = 0; i < nn; i++) {
+        const RtcNode& n = s->nodes[i];
+        if (n.kind != RTC_NODE_GROUP && n.kind != RTC_NODE_CSG) return fail(RTC_ERR_INVALID, "node: bad kind");
+        if (n.parent < -1 || n.parent >= nn || n.parent == i) return fail(RTC_ERR_INVALID, "node: bad parent");
+        if (n.child_begin < 0 || n.child_count < 0 || n.child_begin + n.child_count > (int)s->refs.size())
+            return fail(RTC_ERR_INVALID, "node: bad child range");
+        if (n.kind == RTC_NODE_CSG && (n.child_count != 2 || n.op < 0 || n.op > 2)) return fail(RTC_ERR_INVALID, "csg node: needs 2 children and a valid operator");
+        for (int c = 0; c < n.child_count; c++) {
+            int r = s->refs[n.child_begin + c];
+            if (r >= np || (r < 0 && ~r >= nn)) return fail(RTC_ERR_INVALID, "node: bad child reference");
+        }
+    }
+    for (const RtcMaterial& m : s->materials)
+        if (m.pattern < -1 || m.pattern >= (int)s->patterns.size()) return fail(RTC_ERR_INVALID, "material: bad pattern index");
+    for (const RtcPattern& p : s->patterns) {
+        if (p.kind < RTC_PAT_STRIPES || p.kind > RTC_PAT_CUBIC_MAP) return fail(RTC_ERR_INVALID, "pattern: bad kind");
+        int need = p.kind == RTC_PAT_TEXTURE_MAP ? 1 : (p.kind == RTC_PAT_CUBIC_MAP ? 6 : 0);
+        for (int i = 0; i < need; i++)
+            if (p.uv[i] < 0 || p.uv[i] >= (int)s->uvs.size()) return fail(RTC_ERR_INVALID, "pattern: bad uv pattern index");
+    }
+    return 0;
+}
+
+// Materials, patterns, UV patterns and image texels in their device layout, and the table-mode light samples.
+int build_shading_tables(RtcScene* s, Flattened& f) {
+    // ---- shading tables
+    s->has_branching_materials = false;
+    for (const RtcMaterial& m : s->materials) {
+        if (m.reflective != 0.0f && m.transparency != 0.0f) s->has_branching_materials = true;
+        DevMaterial d{};
+        memcpy(d.color, m.color, sizeof(d.color));
+        d.ambient = m.ambient, d.diffuse = m.diffuse, d.specular = m.specular, d.shininess = m.shininess;
+        d.reflective = m.reflective, d.transparency = m.transparency, d.refractive_index = m.refractive_index;
+        d.pattern = m.pattern;
+        f.materials.push_back(d);
+    }
+    for (const RtcPattern& p : s->patterns) {
+        DevPattern d{};
+        rows3(p.inv, d.inv);
+        memcpy(d.a, p.a, sizeof(d.a));
+        memcpy(d.b, p.b, sizeof(d.b));
+        d.kind = p.kind, d.mapping = p.mapping;
+        memcpy(d.uv, p.uv, sizeof(d.uv));
+        f.patterns.push_back(d);
+    }
+    std::vector<size_t> texel_base;
+    for (const RtcScene::Texture& t : s->textures) {
+        texel_base.push_back(f.texels.size());
+        for (size_t i = 0; i < (size_t)t.width * t.height; i++)
+            f.texels.push_back(make_float4(t.rgb[3 * i], t.rgb[3 * i + 1], t.rgb[3 * i + 2], 0.f));
+    }
+    if (f.texels.size() >= (1u << 30)) return fail(RTC_ERR_CAPACITY, "image textures exceed 2^30 pixels");
+    for (const RtcUvPattern& u : s->uvs) {
+        DevUvPattern d{};
+        d.kind = u.kind;
+        memcpy(d.p, u.params, sizeof(d.p));
+        if (u.kind == RTC_UV_IMAGE) {  // {first texel, width, height} as integers
+            const int t = (int)u.params[0];
+            if (t < 0 || t >= (int)s->textures.size() || (float)t != u.params[0]) return fail(RTC_ERR_INVALID, "uv image: bad texture index");
+            const int base = (int)texel_base[t], w = (int)s->textures[t].width, h = (int)s->textures[t].height;
+            if (w < 1 || h < 1) return fail(RTC_ERR_INVALID, "uv image: empty canvas");
+            memcpy(&d.p[0], &base, 4), memcpy(&d.p[1], &w, 4), memcpy(&d.p[2], &h, 4);
+        }
+        f.uvs.push_back(d);
+    }
+    // ---- table-mode light samples: point_on_light (rectangle_light.rs:60-66) is the same for every shade
+    if (s->light_is_rect && !s->jitter.empty()) {
+        size_t cursor = 0, L = s->jitter.size();
+        for (int v = 0; v < s->v_steps; v++)
+            for (int u = 0; u < s->u_steps; u++) {
+                float j1 = s->jitter[cursor % L], j2 = s->jitter[(cursor + 1) % L];
+                cursor += 2;
+                float su = (float)u + j1, sv = (float)v + j2;
+                float p[3];
+                for (int a = 0; a < 3; a++) {
+                    volatile float t1 = s->u_cell[a] * su;  // volatile: no host-side contraction / reassociation
+                    volatile float t2 = s->corner[a] + t1;
+                    volatile float t3 = s->v_cell[a] * sv;
+                    p[a] = t2 + t3;
+                }
+                f.samples.push_back(make_float4(p[0], p[1], p[2], 0.f));
+            }
+    }
+    return 0;
+}
+
 // The small-scene table of the kernel parameter block (every demo scene: no tree, at most kSmallCap items in the
 // linear list) and the plan of its shadow filter: per-item bounding balls, filter eligibility, the cell-mask loops
 // of an area light, the ball around the light's samples and the per-plane bundle constants (dev_shadow.cuh: shadow
@@ -321,34 +419,7 @@ int flatten(RtcScene* s, Flattened& f) {
         fprintf(stderr, "[rtc commit] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(now - t_last).count());
         t_last = now;
     };
-    // ---- validate references
-    for (int i = 0; i < np; i++) {
-        const RtcPrim& p = s->prims[i];
-        if (p.type < RTC_SPHERE || p.type > RTC_TRIANGLE) return fail(RTC_ERR_INVALID, "primitive " + std::to_string(i) + ": bad type");
-        if (p.material < 0 || p.material >= (int)s->materials.size())
-            return fail(RTC_ERR_INVALID, "primitive " + std::to_string(i) + ": bad material index");
-        if (p.parent < -1 || p.parent >= nn) return fail(RTC_ERR_INVALID, "primitive " + std::to_string(i) + ": bad parent");
-    }
-    for (int i = 0; i < nn; i++) {
-        const RtcNode& n = s->nodes[i];
-        if (n.kind != RTC_NODE_GROUP && n.kind != RTC_NODE_CSG) return fail(RTC_ERR_INVALID, "node: bad kind");
-        if (n.parent < -1 || n.parent >= nn || n.parent == i) return fail(RTC_ERR_INVALID, "node: bad parent");
-        if (n.child_begin < 0 || n.child_count < 0 || n.child_begin + n.child_count > (int)s->refs.size())
-            return fail(RTC_ERR_INVALID, "node: bad child range");
-        if (n.kind == RTC_NODE_CSG && (n.child_count != 2 || n.op < 0 || n.op > 2)) return fail(RTC_ERR_INVALID, "csg node: needs 2 children and a valid operator");
-        for (int c = 0; c < n.child_count; c++) {
-            int r = s->refs[n.child_begin + c];
-            if (r >= np || (r < 0 && ~r >= nn)) return fail(RTC_ERR_INVALID, "node: bad child reference");
-        }
-    }
-    for (const RtcMaterial& m : s->materials)
-        if (m.pattern < -1 || m.pattern >= (int)s->patterns.size()) return fail(RTC_ERR_INVALID, "material: bad pattern index");
-    for (const RtcPattern& p : s->patterns) {
-        if (p.kind < RTC_PAT_STRIPES || p.kind > RTC_PAT_CUBIC_MAP) return fail(RTC_ERR_INVALID, "pattern: bad kind");
-        int need = p.kind == RTC_PAT_TEXTURE_MAP ? 1 : (p.kind == RTC_PAT_CUBIC_MAP ? 6 : 0);
-        for (int i = 0; i < need; i++)
-            if (p.uv[i] < 0 || p.uv[i] >= (int)s->uvs.size()) return fail(RTC_ERR_INVALID, "pattern: bad uv pattern index");
-    }
+    if (int rc = validate_scene(s)) return rc;
 
     // ---- which CSG (if any) is the outermost CSG ancestor of each node / primitive
     std::vector<int> top_csg_of_node(nn, -1);
@@ -603,64 +674,7 @@ int flatten(RtcScene* s, Flattened& f) {
         for (int r = 0; r < 3; r++) f.rec[4 * (size_t)pos + 1 + r] = src[r];
     }
 
-    // ---- shading tables
-    s->has_branching_materials = false;
-    for (const RtcMaterial& m : s->materials) {
-        if (m.reflective != 0.0f && m.transparency != 0.0f) s->has_branching_materials = true;
-        DevMaterial d{};
-        memcpy(d.color, m.color, sizeof(d.color));
-        d.ambient = m.ambient, d.diffuse = m.diffuse, d.specular = m.specular, d.shininess = m.shininess;
-        d.reflective = m.reflective, d.transparency = m.transparency, d.refractive_index = m.refractive_index;
-        d.pattern = m.pattern;
-        f.materials.push_back(d);
-    }
-    for (const RtcPattern& p : s->patterns) {
-        DevPattern d{};
-        rows3(p.inv, d.inv);
-        memcpy(d.a, p.a, sizeof(d.a));
-        memcpy(d.b, p.b, sizeof(d.b));
-        d.kind = p.kind, d.mapping = p.mapping;
-        memcpy(d.uv, p.uv, sizeof(d.uv));
-        f.patterns.push_back(d);
-    }
-    std::vector<size_t> texel_base;
-    for (const RtcScene::Texture& t : s->textures) {
-        texel_base.push_back(f.texels.size());
-        for (size_t i = 0; i < (size_t)t.width * t.height; i++)
-            f.texels.push_back(make_float4(t.rgb[3 * i], t.rgb[3 * i + 1], t.rgb[3 * i + 2], 0.f));
-    }
-    if (f.texels.size() >= (1u << 30)) return fail(RTC_ERR_CAPACITY, "image textures exceed 2^30 pixels");
-    for (const RtcUvPattern& u : s->uvs) {
-        DevUvPattern d{};
-        d.kind = u.kind;
-        memcpy(d.p, u.params, sizeof(d.p));
-        if (u.kind == RTC_UV_IMAGE) {  // {first texel, width, height} as integers
-            const int t = (int)u.params[0];
-            if (t < 0 || t >= (int)s->textures.size() || (float)t != u.params[0]) return fail(RTC_ERR_INVALID, "uv image: bad texture index");
-            const int base = (int)texel_base[t], w = (int)s->textures[t].width, h = (int)s->textures[t].height;
-            if (w < 1 || h < 1) return fail(RTC_ERR_INVALID, "uv image: empty canvas");
-            memcpy(&d.p[0], &base, 4), memcpy(&d.p[1], &w, 4), memcpy(&d.p[2], &h, 4);
-        }
-        f.uvs.push_back(d);
-    }
-    // ---- table-mode light samples: point_on_light (rectangle_light.rs:60-66) is the same for every shade
-    if (s->light_is_rect && !s->jitter.empty()) {
-        size_t cursor = 0, L = s->jitter.size();
-        for (int v = 0; v < s->v_steps; v++)
-            for (int u = 0; u < s->u_steps; u++) {
-                float j1 = s->jitter[cursor % L], j2 = s->jitter[(cursor + 1) % L];
-                cursor += 2;
-                float su = (float)u + j1, sv = (float)v + j2;
-                float p[3];
-                for (int a = 0; a < 3; a++) {
-                    volatile float t1 = s->u_cell[a] * su;  // volatile: no host-side contraction / reassociation
-                    volatile float t2 = s->corner[a] + t1;
-                    volatile float t3 = s->v_cell[a] * sv;
-                    p[a] = t2 + t3;
-                }
-                f.samples.push_back(make_float4(p[0], p[1], p[2], 0.f));
-            }
-    }
+    if (int rc = build_shading_tables(s, f)) return rc;
     plan_small_scene(s, f, n_items);
     lap("records, tables, small scene");
     s->n_bvh_nodes = (int)f.bvh.size();
