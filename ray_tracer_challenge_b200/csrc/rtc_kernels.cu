@@ -23,6 +23,9 @@
 #ifndef RTC_SMALL_CONVERGE_MINBLOCKS
 #define RTC_SMALL_CONVERGE_MINBLOCKS 3  // the converging small-scene build keeps more state live: 3 blocks (168 regs) win
 #endif
+#ifndef RTC_BVH_CONVERGE_MINBLOCKS
+#define RTC_BVH_CONVERGE_MINBLOCKS 6  // the converging BVH build (branching ray trees) gains from more warps (80 regs)
+#endif
 #ifndef RTC_BVH_MINBLOCKS
 #define RTC_BVH_MINBLOCKS 5
 #endif
@@ -66,7 +69,8 @@ __device__ __forceinline__ void flush_counters<true>(const Rays& r, const Ctr<tr
 }
 
 template <bool STATS, bool SMALL, bool CONVERGE, bool DRAWN>
-__global__ void __launch_bounds__(128, SMALL ? (CONVERGE ? RTC_SMALL_CONVERGE_MINBLOCKS : RTC_SMALL_MINBLOCKS) : RTC_BVH_MINBLOCKS)
+__global__ void __launch_bounds__(128, SMALL ? (CONVERGE ? RTC_SMALL_CONVERGE_MINBLOCKS : RTC_SMALL_MINBLOCKS)
+                                             : (CONVERGE ? RTC_BVH_CONVERGE_MINBLOCKS : RTC_BVH_MINBLOCKS))
     render_tiles(const __grid_constant__ DevScene S, const __grid_constant__ SmallScene SS,
                                                     const DevFrame F, DevCounters* counters) {
     // small scenes: primitive table + per-thread shadow-origin cache in dynamic shared memory (kSmallSmemBytes)
