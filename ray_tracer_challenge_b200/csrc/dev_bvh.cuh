@@ -153,6 +153,12 @@ __device__ __noinline__ int csg_eval(const DevScene& S, int pc, V3 wo, V3 wd, fl
     return n;
 }
 
+// nearest_t for the tree's non-mesh primitives, out of line: one copy of the sphere / cube / cylinder / cone tests
+// in the kernel instead of one per inlined traversal loop.
+__device__ __noinline__ float nearest_t_general(const DevScene& S, int type, int aux, float4 bd, V3 o, V3 d) {
+    return nearest_t(S, type, aux, bd, o, d);
+}
+
 // Test one stored primitive against the world ray for the nearest-hit search.
 template <bool STATS>
 __device__ __forceinline__ void test_prim(const DevScene& S, int pos, V3 o, V3 d, ObjRay& cache, Hit& best, Ctr<STATS>& k) {
@@ -186,7 +192,7 @@ __device__ __forceinline__ void test_prim(const DevScene& S, int pos, V3 o, V3 d
     } else {
         Xf m = load_xf(rec + 1);  // the primitive's own inverse transform travels in its record
         k.xform();
-        tn = nearest_t(S, type, h.z, load_bound(S, type, h.z), xf_point(m, o), xf_vec(m, d));
+        tn = nearest_t_general(S, type, h.z, load_bound(S, type, h.z), xf_point(m, o), xf_vec(m, d));
     }
     if (!(tn >= 0.0f)) return;
     if (((h.x >> 4) & kFlagHasParent) && !ancestors_pass(S, __ldg(&S.head[pos + S.n_prims]).x, o, d)) return;
