@@ -153,17 +153,13 @@ __device__ __noinline__ int csg_eval(const DevScene& S, int pc, V3 wo, V3 wd, fl
     return n;
 }
 
-// nearest_t for the tree's non-mesh primitives, out of line: one copy of the sphere / cube / cylinder / cone tests
-// in the kernel instead of one per inlined traversal loop.
-__device__ __noinline__ float nearest_t_general(const DevScene& S, int type, int aux, float4 bd, V3 o, V3 d) {
-    return nearest_t(S, type, aux, bd, o, d);
-}
-
-// Test one stored primitive against the world ray for the nearest-hit search.
+// Test one stored primitive against the world ray for the nearest-hit search: test_prim, below, does a mesh triangle
+// itself and sends the rest here.
+// Everything but a mesh triangle: CSG trees and the analytic shapes.  Out of line: the traversal loop then holds only
+// the slab tests and the triangle test, which is what keeps it inside the instruction cache (profiles/README.md).
 template <bool STATS>
-__device__ __forceinline__ void test_prim(const DevScene& S, int pos, V3 o, V3 d, ObjRay& cache, Hit& best, Ctr<STATS>& k) {
+__device__ __noinline__ void test_prim_other(const DevScene& S, int pos, int4 h, V3 o, V3 d, Hit& best, Ctr<STATS>& k) {
     const float4* rec = S.rec + 4 * (size_t)pos;
-    int4 h = __ldg(reinterpret_cast<const int4*>(rec));
     int type = h.x & 15;
     if (type == T_CSG) {
         float ht[kCsgHitCap];
@@ -177,23 +173,33 @@ __device__ __forceinline__ void test_prim(const DevScene& S, int pos, V3 o, V3 d
         }
         return;
     }
-    float tn;
     k.prim(type);
-    if (type == T_TRIANGLE) {
-        // a mesh's triangles share one transform: the object-space ray is kept across primitives (shape.rs:60-70)
-        if (h.y != cache.xf_id) {
-            Xf m = load_xf(S.xform + 3 * (size_t)h.y);
-            cache.o = xf_point(m, o);
-            cache.d = xf_vec(m, d);
-            cache.xf_id = h.y;
-            k.xform();
-        }
-        tn = nearest_t(S, T_TRIANGLE, h.z, make_float4(0.f, 0.f, 0.f, 0.f), cache.o, cache.d, rec + 1);
-    } else {
-        Xf m = load_xf(rec + 1);  // the primitive's own inverse transform travels in its record
-        k.xform();
-        tn = nearest_t_general(S, type, h.z, load_bound(S, type, h.z), xf_point(m, o), xf_vec(m, d));
+    Xf m = load_xf(rec + 1);  // the primitive's own inverse transform travels in its record
+    k.xform();
+    float tn = nearest_t(S, type, h.z, load_bound(S, type, h.z), xf_point(m, o), xf_vec(m, d));
+    if (!(tn >= 0.0f)) return;
+    if (((h.x >> 4) & kFlagHasParent) && !ancestors_pass(S, __ldg(&S.head[pos + S.n_prims]).x, o, d)) return;
+    consider(best, tn, pos, h.w);
+}
+
+template <bool STATS>
+__device__ __forceinline__ void test_prim(const DevScene& S, int pos, V3 o, V3 d, ObjRay& cache, Hit& best, Ctr<STATS>& k) {
+    const float4* rec = S.rec + 4 * (size_t)pos;
+    int4 h = __ldg(reinterpret_cast<const int4*>(rec));
+    if ((h.x & 15) != T_TRIANGLE) {
+        test_prim_other<STATS>(S, pos, h, o, d, best, k);
+        return;
     }
+    k.prim(T_TRIANGLE);
+    // a mesh's triangles share one transform: the object-space ray is kept across primitives (shape.rs:60-70)
+    if (h.y != cache.xf_id) {
+        Xf m = load_xf(S.xform + 3 * (size_t)h.y);
+        cache.o = xf_point(m, o);
+        cache.d = xf_vec(m, d);
+        cache.xf_id = h.y;
+        k.xform();
+    }
+    float tn = nearest_t(S, T_TRIANGLE, h.z, make_float4(0.f, 0.f, 0.f, 0.f), cache.o, cache.d, rec + 1);
     if (!(tn >= 0.0f)) return;
     if (((h.x >> 4) & kFlagHasParent) && !ancestors_pass(S, __ldg(&S.head[pos + S.n_prims]).x, o, d)) return;
     consider(best, tn, pos, h.w);
