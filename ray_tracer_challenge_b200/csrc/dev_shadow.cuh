@@ -138,12 +138,14 @@ __device__ __forceinline__ int filter_scan(const Env& E, bool cached, int begin,
         return true;
     };
     int i = begin;
+#pragma unroll 1
     for (; i < ends.x; i++) {
         Xf m{tab[i * kSmallStride + 1], tab[i * kSmallStride + 2], tab[i * kSmallStride + 3]};
         k.xform();
         k.prim(T_SPHERE);
         if (take(filter_sphere(m, small_origin(cached, i, m, p), v, tol))) return result;
     }
+#pragma unroll 1
     for (; i < ends.y; i++) {
         float4 r1 = tab[i * kSmallStride + 2];
         float oy;
@@ -155,6 +157,7 @@ __device__ __forceinline__ int filter_scan(const Env& E, bool cached, int begin,
         k.prim(T_PLANE);
         if (take(filter_plane<MODE != 0>(r1, oy, v, len))) return result;
     }
+#pragma unroll 1
     for (; i < ends.z; i++) {
         Xf m{tab[i * kSmallStride + 1], tab[i * kSmallStride + 2], tab[i * kSmallStride + 3]};
         k.xform();
@@ -196,15 +199,24 @@ __device__ __forceinline__ bool shadow_exact_small(const Env& E, bool cached, V3
     // order -1: a hit AT the light distance is never accepted (`<`, world.rs:116)
     Hit best{distance, -1, -1};
     if (!SS.two_pass_shadows || SS.has_cull_chain) {  // a CSG root or a cull chain: plain nearest-hit search
+#pragma unroll 1
         for (int i = 0; i < SS.n; i++) test_small<STATS>(E, i, cached, p, direction, best, k);
         return best.pos >= 0 && ((__ldg(&S.head[best.pos]).x >> 4) & kFlagCastsShadow);
     }
     if (S.all_cast_shadow)  // every object casts: any hit in [0, distance) shadows the point
         return scan_small<STATS, true>(E, cached, 0, SS.caster_end, p, direction, best, k);
-    scan_small<STATS, false>(E, cached, 0, SS.caster_end, p, direction, best, k);
-    if (best.pos < 0) return false;
-    const int caster = best.pos;
-    scan_small<STATS, false>(E, cached, SS.caster_end.w, SS.other_end, p, direction, best, k);
+    int begin = 0, caster = -1;
+    int4 ends = SS.caster_end;
+#pragma unroll 1
+    for (int seg = 0; seg < 2; seg++) {  // casters, then non-casters: one copy of the loops
+        scan_small<STATS, false>(E, cached, begin, ends, p, direction, best, k);
+        if (seg == 0) {
+            if (best.pos < 0) return false;
+            caster = best.pos;
+        }
+        begin = ends.w;
+        ends = SS.other_end;
+    }
     return best.pos == caster;
 }
 // One shadow ray of a small scene, out of line (ONE copy of the filter and of the exact test in the kernel: the
@@ -325,6 +337,7 @@ __device__ __forceinline__ float intensity_cells(const Env& E, V3 p, unsigned pi
         unsigned hit = 0u, unsure = 0u;
         float far_hit = 0.0f;  // no caster hit of this chunk is farther from p than this (bounding balls)
         int i = 0;
+#pragma unroll 1
         for (; i < ends.x && (hit | unsure) != full; i++) {  // caster spheres
             if (bundle_misses(tab[i * kSmallStride + 5], tab[i * kSmallStride + 4].w, SS.light_ball, p)) continue;
             const unsigned hit_before = hit;
@@ -357,6 +370,7 @@ __device__ __forceinline__ float intensity_cells(const Env& E, V3 p, unsigned pi
             }
             if (hit != hit_before) far_hit = fmaxf(far_hit, ball_reach(tab[i * kSmallStride + 5], p));
         }
+#pragma unroll 1
         for (i = ends.x; i < ends.y && (hit | unsure) != full; i++) {  // caster planes
             const unsigned hit_before = hit;
             const float4 r1 = tab[i * kSmallStride + 2];
@@ -403,6 +417,7 @@ __device__ __forceinline__ float intensity_cells(const Env& E, V3 p, unsigned pi
             }
             if (hit != hit_before) far_hit = kInfF;
         }
+#pragma unroll 1
         for (i = ends.y; i < ends.z && (hit | unsure) != full; i++) {  // caster cubes
             if (bundle_misses(tab[i * kSmallStride + 5], tab[i * kSmallStride + 4].w, SS.light_ball, p)) continue;
             const unsigned hit_before = hit;
@@ -428,6 +443,7 @@ __device__ __forceinline__ float intensity_cells(const Env& E, V3 p, unsigned pi
         bool hits_final = S.all_cast_shadow != 0;
         if (!hits_final && (hit & ~unsure) != 0u) {
             float near_other = kInfF;
+#pragma unroll 1
             for (int q = ends.w; q < SS.other_end.z; q++) {
                 const float4 ball = tab[q * kSmallStride + 5];
                 const bool has_ball = q < SS.other_end.x || q >= SS.other_end.y;  // spheres and cubes; planes have none

@@ -135,11 +135,12 @@ __device__ __noinline__ void test_small(const Env& E, int i, bool cached, V3 o, 
 // Nearest hit among the items [begin, ends.w) of a small scene, which are runs of spheres, planes, cubes and
 // "everything else" ending at ends.x / .y / .z / .w: one tight loop per kind, no per-item dispatch.
 // ANY: return true as soon as some item is hit in [0, best.t) (shadow rays when every object casts a shadow).
-template <bool STATS, bool ANY>
-__device__ __forceinline__ bool scan_small(const Env& E, bool cached, int begin, int4 ends, V3 o, V3 d, Hit& best, Ctr<STATS>& k) {
-    constexpr bool any = ANY;
+template <bool STATS>
+__device__ __forceinline__ bool scan_small_impl(const Env& E, bool cached, const bool any, int begin, int4 ends, V3 o, V3 d, Hit& best,
+                                                Ctr<STATS>& k) {
     const float4* tab = small_tab();
     int i = begin;
+#pragma unroll 1
     for (; i < ends.x; i++) {  // spheres — sphere.rs:47-70
         if (ball_missed(tab[i * kSmallStride + 5], tab[i * kSmallStride + 4].w, o, d)) continue;
         Xf m{tab[i * kSmallStride + 1], tab[i * kSmallStride + 2], tab[i * kSmallStride + 3]};
@@ -151,6 +152,7 @@ __device__ __forceinline__ bool scan_small(const Env& E, bool cached, int begin,
         if (any && t >= 0.0f && t < best.t) return true;
         consider(best, t, i, __float_as_int(tab[i * kSmallStride].w));
     }
+#pragma unroll 1
     for (; i < ends.y; i++) {  // planes — plane.rs:45-56 only reads the y components of the object-space ray
         float4 r1 = tab[i * kSmallStride + 2];
         float oy;
@@ -165,6 +167,7 @@ __device__ __forceinline__ bool scan_small(const Env& E, bool cached, int begin,
         if (any && t >= 0.0f && t < best.t) return true;
         consider(best, t, i, __float_as_int(tab[i * kSmallStride].w));
     }
+#pragma unroll 1
     for (; i < ends.z; i++) {  // cubes — cube.rs:55-63
         if (ball_missed(tab[i * kSmallStride + 5], tab[i * kSmallStride + 4].w, o, d)) continue;
         Xf m{tab[i * kSmallStride + 1], tab[i * kSmallStride + 2], tab[i * kSmallStride + 3]};
@@ -176,6 +179,7 @@ __device__ __forceinline__ bool scan_small(const Env& E, bool cached, int begin,
         if (any && t >= 0.0f && t < best.t) return true;
         consider(best, t, i, __float_as_int(tab[i * kSmallStride].w));
     }
+#pragma unroll 1
     for (; i < ends.w; i++) {  // cylinders, cones, triangles, CSG roots
         if (ball_missed(tab[i * kSmallStride + 5], tab[i * kSmallStride + 4].w, o, d)) continue;
         const int before = best.pos;
@@ -184,6 +188,28 @@ __device__ __forceinline__ bool scan_small(const Env& E, bool cached, int begin,
     }
     return false;
 }
+#ifdef RTC_SHARED_SCAN
+// One out-of-line copy of the four loops for every caller (nearest hit, both shadow passes); `any` at run time.
+template <bool STATS>
+__device__ __noinline__ Hit scan_small_shared(const Env& E, bool cached, bool any, int begin, int4 ends, V3 o, V3 d, Hit best, Ctr<STATS>& k) {
+    if (scan_small_impl<STATS>(E, cached, any, begin, ends, o, d, best, k)) best.pos = -2;  // any: found
+    return best;
+}
+template <bool STATS, bool ANY>
+__device__ __forceinline__ bool scan_small(const Env& E, bool cached, int begin, int4 ends, V3 o, V3 d, Hit& best, Ctr<STATS>& k) {
+    best = scan_small_shared<STATS>(E, cached, ANY, begin, ends, o, d, best, k);
+    if (ANY && best.pos == -2) {
+        best.pos = -1;
+        return true;
+    }
+    return false;
+}
+#else
+template <bool STATS, bool ANY>
+__device__ __forceinline__ bool scan_small(const Env& E, bool cached, int begin, int4 ends, V3 o, V3 d, Hit& best, Ctr<STATS>& k) {
+    return scan_small_impl<STATS>(E, cached, ANY, begin, ends, o, d, best, k);
+}
+#endif
 
 // World::intersect + Intersection::hit for the nearest hit, general (BVH) or small-scene form.
 template <bool STATS, bool SMALL>
@@ -191,6 +217,7 @@ __device__ __forceinline__ void find_hit(const Env& E, V3 o, V3 d, Hit& best, Ct
     if (SMALL) {
         const SmallScene& SS = E.SS;
         if (SS.has_cull_chain) {
+#pragma unroll 1
             for (int i = 0; i < SS.n; i++) test_small<STATS>(E, i, false, o, d, best, k);
         } else {
             int begin = 0;
