@@ -227,6 +227,7 @@ __device__ __forceinline__ bool slab(V3 o, V3 inv, float lx, float ly, float lz,
 template <bool STATS, bool ANY>
 __device__ __noinline__ void nearest_hit(const DevScene& S, V3 o, V3 d, Hit& best, Ctr<STATS>& k) {
     ObjRay cache;
+#pragma unroll 1
     for (int i = 0; i < S.n_linear; i++) {
         test_prim<STATS>(S, __ldg(&S.linear[i]), o, d, cache, best, k);
         if (ANY && best.pos >= 0) return;
@@ -304,31 +305,39 @@ __device__ __forceinline__ void container_add(Containers& c, int hit_pos, float 
         c.best_pos = pos;
     }
 }
+// The CSG case of container_prim, out of line (one copy for both of its call sites; rarely taken).
+template <bool STATS>
+__device__ __noinline__ void container_csg(const DevScene& S, int pc, V3 o, V3 d, int hit_pos, Containers& c, Ctr<STATS>& k) {
+    float ht[kCsgHitCap];
+    int hp[kCsgHitCap];
+    int n = csg_eval<STATS>(S, pc, o, d, ht, hp, k);
+    // per leaf: parity and last negative hit among the filtered hits
+#pragma unroll 1
+    for (int i = 0; i < n; i++) {
+        if (!(ht[i] < 0.0f)) break;
+        int p = hp[i];
+        bool seen = false;
+#pragma unroll 1
+        for (int j = 0; j < i; j++) seen |= (hp[j] == p);
+        if (seen) continue;
+        int cnt = 0;
+        float last = 0.f;
+#pragma unroll 1
+        for (int j = i; j < n && ht[j] < 0.0f; j++)
+            if (hp[j] == p) {
+                cnt++;
+                last = ht[j];
+            }
+        if (cnt & 1) container_add(c, hit_pos, last, p, __ldg(&S.head[p]).w);
+    }
+}
 template <bool STATS>
 __device__ __forceinline__ void container_prim(const DevScene& S, int pos, V3 o, V3 d, ObjRay& cache, int hit_pos, Containers& c,
                                                Ctr<STATS>& k) {
     int4 h = __ldg(&S.head[pos]);
     int type = h.x & 15;
     if (type == T_CSG) {
-        float ht[kCsgHitCap];
-        int hp[kCsgHitCap];
-        int n = csg_eval<STATS>(S, h.z, o, d, ht, hp, k);
-        // per leaf: parity and last negative hit among the filtered hits
-        for (int i = 0; i < n; i++) {
-            if (!(ht[i] < 0.0f)) break;
-            int p = hp[i];
-            bool seen = false;
-            for (int j = 0; j < i; j++) seen |= (hp[j] == p);
-            if (seen) continue;
-            int cnt = 0;
-            float last = 0.f;
-            for (int j = i; j < n && ht[j] < 0.0f; j++)
-                if (hp[j] == p) {
-                    cnt++;
-                    last = ht[j];
-                }
-            if (cnt & 1) container_add(c, hit_pos, last, p, __ldg(&S.head[p]).w);
-        }
+        container_csg<STATS>(S, h.z, o, d, hit_pos, c, k);
         return;
     }
     if (h.y != cache.xf_id) {
@@ -358,6 +367,7 @@ template <bool STATS>
 __device__ __noinline__ void find_containers(const DevScene& S, V3 o, V3 d, int hit_pos, float& n1, float& n2, Ctr<STATS>& k) {
     Containers c;
     ObjRay cache;
+#pragma unroll 1
     for (int i = 0; i < S.n_linear; i++) container_prim<STATS>(S, __ldg(&S.linear[i]), o, d, cache, hit_pos, c, k);
     if (S.bvh_root >= 0) {
         // walk the backward half-line: the forward half-line of the reversed ray
@@ -403,6 +413,7 @@ __device__ __noinline__ void find_containers(const DevScene& S, V3 o, V3 d, int 
             {
                 int code = ~node;
                 int first = code >> 4, count = (code & 15) + 1;
+#pragma unroll 1
                 for (int i = 0; i < count; i++) container_prim<STATS>(S, first + i, o, d, cache, hit_pos, c, k);
             }
             if (sp == 0) break;
