@@ -201,6 +201,9 @@ typedef struct RtcCommitInfo {
     float tol_sphere;        /* the filter's relative error bound for spheres */
     float light_ball[4];     /* ball around the light's sample points (cell_masks) */
     double host_ms;          /* time the host half took */
+    uint64_t digest;         /* FNV-1a over the arrays a commit would upload for intersection (primitive heads and
+                              * records, transforms, triangles, bounds, tree nodes, linear list): equal digests mean
+                              * the device would trace the same geometry through the same tree */
 } RtcCommitInfo;
 int rtc_scene_inspect(RtcScene*, RtcCommitInfo* out);
 

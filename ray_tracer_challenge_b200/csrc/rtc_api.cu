@@ -541,6 +541,18 @@ int rtc_scene_inspect(RtcScene* s, RtcCommitInfo* out) {
     out->tol_sphere = f.small.tol_sphere;
     out->light_ball[0] = f.small.light_ball.x, out->light_ball[1] = f.small.light_ball.y;
     out->light_ball[2] = f.small.light_ball.z, out->light_ball[3] = f.small.light_ball.w;
+    // FNV-1a over the padding-free geometry arrays (the tree's two unused link lanes are skipped)
+    uint64_t h = 1469598103934665603ull;
+    auto mix = [&h](const void* p, size_t bytes) {
+        const unsigned char* b = static_cast<const unsigned char*>(p);
+        for (size_t i = 0; i < bytes; i++) h = (h ^ b[i]) * 1099511628211ull;
+    };
+    auto mix_vec = [&](const auto& v) { mix(v.data(), v.size() * sizeof(v[0])); };
+    mix_vec(f.head), mix_vec(f.xform), mix_vec(f.tri), mix_vec(f.bound), mix_vec(f.rec), mix_vec(f.linear);
+    for (const DevBvhNode& n : f.bvh) mix(&n, offsetof(DevBvhNode, d) + 3 * sizeof(int));
+    const int tail[3] = {f.n_pos, f.bvh_root, f.leaf_size};
+    mix(tail, sizeof(tail));
+    out->digest = h;
     return 0;
 }
 

@@ -171,5 +171,8 @@ def test_parallel_tree_build_is_deterministic(host):
     """The BVH's top levels are built by several threads; the tree (node count, and so the render) does not depend on
     their timing."""
     cam, world = scenes.stress(host, width=64, height=36, n_spheres=20000, n_each=4, n_csg=2)
-    seen = {(p["n_bvh_nodes"], p["n_positions"], p["n_xforms"]) for p in (host.inspect(cam, world) for _ in range(4))}
-    assert len(seen) == 1, seen
+    seen = {(p["n_bvh_nodes"], p["n_positions"], p["n_xforms"], p["digest"]) for p in (host.inspect(cam, world) for _ in range(4))}
+    assert len(seen) == 1, seen  # digest: every byte of the heads, records, transforms and tree nodes
+    # the digest does see geometry: the same field with one sphere fewer hashes differently
+    cam2, world2 = scenes.stress(host, width=64, height=36, n_spheres=19999, n_each=4, n_csg=2)
+    assert host.inspect(cam2, world2)["digest"] not in {s[3] for s in seen}
