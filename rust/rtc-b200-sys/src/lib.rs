@@ -127,6 +127,26 @@ pub struct RtcStats {
     pub reserved: i32,
 }
 
+/// What `rtc_scene_commit` would build, computed without a device (`rtc_scene_inspect`).
+#[repr(C)]
+#[derive(Clone, Copy, Default)]
+pub struct RtcCommitInfo {
+    pub n_positions: i32,
+    pub n_bvh_nodes: i32,
+    pub n_linear: i32,
+    pub n_xforms: i32,
+    pub bvh_leaf_size: i32,
+    pub small_n: i32,
+    pub filter_ok: i32,
+    pub cell_masks: i32,
+    pub plane_cells: i32,
+    pub converge: i32,
+    pub tol_sphere: f32,
+    pub light_ball: [f32; 4],
+    pub host_ms: f64,
+    pub digest: u64,
+}
+
 extern "C" {
     pub fn rtc_last_error() -> *const c_char;
     pub fn rtc_device_count() -> c_int;
@@ -144,6 +164,7 @@ extern "C" {
                               u_steps: i32, v_cell: *const f32, v_steps: i32, position: *const f32,
                               jitter_table: *const f32, table_len: u32, seed: u64) -> c_int;
     pub fn rtc_set_option(scene: *mut RtcScene, option: i32, value: i64) -> c_int;
+    pub fn rtc_scene_inspect(scene: *mut RtcScene, out: *mut RtcCommitInfo) -> c_int;
     pub fn rtc_scene_commit(scene: *mut RtcScene, n_devices: i32, device_ids: *const i32) -> c_int;
     pub fn rtc_render(scene: *mut RtcScene, depth: i32, rgb_f32: *mut f32, rgb_u8: *mut u8, stats: *mut RtcStats) -> c_int;
     pub fn rtc_render_shard(scene: *mut RtcScene, depth: i32, shard: i32, n_shards: i32, rgb_f32: *mut f32,

@@ -151,3 +151,41 @@ def test_raw_c_abi_validates_scenes_without_a_device():
     if lib.rtc_device_count() == 0:
         assert lib.rtc_scene_commit(scene, 1, None) < 0 and b"no CPU fallback" in lib.rtc_last_error()
     lib.rtc_scene_destroy(scene)
+
+
+def test_ctypes_mirrors_have_the_layout_of_the_header(tmp_path):
+    """Every ctypes structure that crosses the C ABI has the size and the field offsets gcc gives the header's struct
+    (the Rust `#[repr(C)]` mirrors in rust/rtc-b200-sys follow the same field lists)."""
+    import shutil
+    import subprocess
+
+    import ray_tracer_challenge_b200 as rt
+
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    mirrors = [getattr(rt, n) for n in ("RtcStats", "RtcCommitInfo", "RtcPrim", "RtcNode", "RtcMaterial", "RtcPattern",
+                                        "RtcUvPattern", "RtcTexture") if hasattr(rt, n)]
+    assert len(mirrors) >= 4
+    from ray_tracer_challenge_b200.api import SgStats
+
+    c_names = {m: m.__name__ for m in mirrors}
+    mirrors.append(SgStats)  # include/rtc_scene.h
+    c_names[SgStats] = "sg_stats"
+    lines = []
+    for m in mirrors:
+        lines.append(f'printf("{m.__name__} %zu", sizeof({c_names[m]}));')
+        for field, _ in m._fields_:
+            c_field = "type" if field == "type_" else field
+            lines.append(f'printf(" %zu", offsetof({c_names[m]}, {c_field}));')
+        lines.append('printf("\\n");')
+    src = tmp_path / "layout.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "rtc_b200.h"\n#include "rtc_scene.h"\nint main(void) {\n'
+                   + "\n".join(lines) + "\nreturn 0;\n}\n")
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split("\n")
+    for m, line in zip(mirrors, out):
+        name, size, *offsets = line.split()
+        assert name == m.__name__
+        assert int(size) == C.sizeof(m), (name, size, C.sizeof(m))
+        assert [int(o) for o in offsets] == [getattr(m, f).offset for f, _ in m._fields_], name
