@@ -176,3 +176,20 @@ def test_parallel_tree_build_is_deterministic(host):
     # the digest does see geometry: the same field with one sphere fewer hashes differently
     cam2, world2 = scenes.stress(host, width=64, height=36, n_spheres=19999, n_each=4, n_csg=2)
     assert host.inspect(cam2, world2)["digest"] not in {s[3] for s in seen}
+
+
+def test_empty_worlds_commit_and_render_black(host, oracle):
+    """Edge cases of World::objects: no objects at all, and only an empty group (group.rs:199-206 — an empty group has
+    no intersections).  The host half of the commit accepts both (nothing to trace: no tree, no table), and the oracle's
+    frame is the reference's black canvas."""
+    from ray_tracer_challenge_b200.scenes import PI
+
+    for make in (lambda api: [], lambda api: [api.GroupShape()]):
+        cam = host.Camera(16, 8, PI / 2.0, host.view_transform((0, 0, -5), (0, 0, 0), (0, 1, 0)))
+        world = host.World(make(host), host.PointLight((-10, 10, -10), (1, 1, 1)))
+        p = host.inspect(cam, world)
+        assert (p["n_positions"], p["n_bvh_nodes"], p["n_linear"], p["small_n"]) == (0, 0, 0, 0), p
+        ocam = oracle.Camera(16, 8, PI / 2.0, oracle.view_transform((0, 0, -5), (0, 0, 0), (0, 1, 0)))
+        oworld = oracle.World(make(oracle), oracle.PointLight((-10, 10, -10), (1, 1, 1)))
+        frame = ocam.render(oworld, 5)
+        assert not frame.data.any()
