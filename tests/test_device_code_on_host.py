@@ -1,0 +1,128 @@
+"""The device code of the tree path, compiled for the HOST (tests/emu/emu_nearest.cpp: dev_math / dev_shapes / dev_bvh
+.cuh behind a shim of the CUDA intrinsics they use) and run over the arrays the host half of rtc_scene_commit builds —
+the primitive tests, the CSG programs, the group cull chains and the BVH walk checked against the oracle's
+World::intersect + Intersection::hit (world.rs:52-60, intersection.rs:30-35) on a machine without a GPU.  Test
+infrastructure only: nothing here is a render path, and the product never loads it."""
+import ctypes as C
+import os
+import shutil
+import subprocess
+
+import numpy as np
+import pytest
+
+from ray_tracer_challenge_b200 import scenes
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CUDA_INCLUDE = "/usr/local/cuda/include"
+
+
+@pytest.fixture(scope="module")
+def emu(tmp_path_factory):
+    import ray_tracer_challenge_b200 as rt
+
+    if shutil.which("g++") is None or not os.path.isdir(CUDA_INCLUDE):
+        pytest.skip("needs g++ and the CUDA headers")
+    out = tmp_path_factory.mktemp("emu") / "libemu_nearest.so"
+    lib_dir = os.path.dirname(rt.LIB_DEVICE)
+    subprocess.run(["g++", "-std=c++17", "-O1", "-ffp-contract=off", "-fPIC", "-shared", "-I", CUDA_INCLUDE,
+                    "-I", os.path.join(ROOT, "ray_tracer_challenge_b200", "csrc"), os.path.join(ROOT, "tests", "emu", "emu_nearest.cpp"),
+                    "-o", str(out), "-L", lib_dir, "-lrtc_b200", f"-Wl,-rpath,{lib_dir}"], check=True)
+    device = rt.device_library()  # the raw C ABI; RTLD_GLOBAL, so the harness binds rtc::flatten from it
+    device.rtc_last_error.restype = C.c_char_p
+    lib = C.CDLL(str(out))
+    lib.emu_nearest.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float),
+                                C.POINTER(C.c_int32)]
+    return device, lib
+
+
+@pytest.fixture(scope="module")
+def host():
+    import ray_tracer_challenge_b200 as rt
+
+    return rt.new_session()
+
+
+class _Material(C.Structure):  # include/rtc_b200.h: RtcMaterial
+    _fields_ = [("color", C.c_float * 3), ("v", C.c_float * 7), ("pattern", C.c_int32)]
+
+
+def _raw_scene(device, host, world):
+    """An RtcScene with the world's flattened geometry (materials are placeholders: a nearest-hit search reads none)."""
+    prims, nodes, refs, _, _ = host.flatten(world)
+    scene = C.c_void_p()
+    assert device.rtc_scene_create(C.byref(scene)) == 0
+    ident = (C.c_float * 16)(1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1)
+    device.rtc_set_camera.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_float, C.c_float, C.c_float, C.POINTER(C.c_float)]
+    assert device.rtc_set_camera(scene, 8, 8, 1.0, 1.0, 0.25, ident) == 0
+    assert device.rtc_set_point_light(scene, (C.c_float * 3)(-10, 10, -10), (C.c_float * 3)(1, 1, 1)) == 0
+    import ray_tracer_challenge_b200 as rt
+
+    parr = (rt.RtcPrim * max(len(prims), 1))(*prims)
+    narr = (rt.RtcNode * max(len(nodes), 1))(*nodes)
+    rarr = (C.c_int32 * max(len(refs), 1))(*refs)
+    n_mat = max([p.material for p in prims] + [0]) + 1
+    marr = (_Material * n_mat)()
+    for m in marr:
+        m.pattern = -1
+    assert device.rtc_set_primitives(scene, len(prims), parr) == 0, device.rtc_last_error()
+    assert device.rtc_set_nodes(scene, len(nodes), narr, len(refs), rarr) == 0, device.rtc_last_error()
+    assert device.rtc_set_materials(scene, n_mat, marr) == 0, device.rtc_last_error()
+    return scene
+
+
+def _rays(camera_api, cam, n, seed):
+    """Primary rays of random pixels plus rays between random points of the scene's volume (secondary-ray-like)."""
+    rng = np.random.default_rng(seed)
+    o = np.zeros((n, 3), np.float32)
+    d = np.zeros((n, 3), np.float32)
+    for i in range(n // 2):
+        ro, rd = camera_api.probe.camera_ray(cam, int(rng.integers(0, cam.width_pixels - 1)), int(rng.integers(0, cam.height_pixels - 1)))
+        o[i], d[i] = ro[:3], rd[:3]
+    a = rng.uniform(-6, 6, (n - n // 2, 3)).astype(np.float32)
+    b = rng.uniform(-6, 6, (n - n // 2, 3)).astype(np.float32)
+    v = b - a
+    o[n // 2:] = a
+    d[n // 2:] = v / np.linalg.norm(v, axis=1, keepdims=True).astype(np.float32)
+    return o, d
+
+
+SCENES = {
+    # tree over spheres, cylinders, cones, cubes and CSG roots (one primitive per leaf)
+    "sphere_field": (scenes.stress, dict(width=64, height=36, n_spheres=1500, n_each=6, n_csg=6)),
+    # triangle mesh in divided groups (four triangles per leaf, shared transform) + display case + pedestal
+    "mesh": (scenes.dragon_element, dict(width=64, height=36, n_u=24, n_v=12)),
+    # every CSG operator, nested, with transformed children
+    "csg": (scenes.csg_gallery, dict(width=64, height=40)),
+    # small scenes run through the same general functions here (linear list, no tree)
+    "zoo": (scenes.shapes_zoo, dict(width=64, height=40)),
+}
+
+
+@pytest.mark.parametrize("name", sorted(SCENES))
+def test_tree_path_nearest_hit_matches_oracle(name, emu, host, oracle):
+    device, lib = emu
+    make, kw = SCENES[name]
+    cam, world = make(host, **kw)
+    ocam, oworld = make(oracle, **kw)
+    scene = _raw_scene(device, host, world)
+    try:
+        n = 600
+        o, d = _rays(oracle, ocam, n, seed=7)
+        t = np.zeros(n, np.float32)
+        prim = np.zeros(n, np.int32)
+        fp = lambda a: a.ctypes.data_as(C.POINTER(C.c_float))  # noqa: E731
+        rc = lib.emu_nearest(scene, n, fp(o), fp(d), fp(t), prim.ctypes.data_as(C.POINTER(C.c_int32)))
+        assert rc == 0, device.rtc_last_error()
+        hits = 0
+        for i in range(n):
+            ts, _ = oracle.probe.world_intersect(oworld, o[i], d[i], cap=256)
+            h = oracle.probe.hit_index(ts)
+            want = np.float32(ts[h]) if h >= 0 else np.float32(-1.0)
+            assert t[i] == want, (name, i, float(t[i]), float(want), o[i], d[i])  # bit-exact: same IEEE expression order
+            hits += h >= 0
+        print(name, "hits", hits, "of", n)
+        assert hits > n // 10, (name, hits)  # the rays do exercise the scene
+    finally:
+        device.rtc_scene_destroy.argtypes = [C.c_void_p]
+        device.rtc_scene_destroy(scene)
