@@ -86,6 +86,7 @@ _HOST_EXTRAS = {
     "sg_last_rtc_stats": (_I, [_V, C.POINTER(RtcStats)]),
     "sg_prepare": (_I, [_V, _I, _I]),
     "sg_inspect": (_I, [_V, _I, _I, C.c_void_p, C.POINTER(C.c_double)]),
+    "sg_export_scene": (_I, [_V, _I, _I, C.POINTER(C.c_void_p)]),
     "sg_release_prepared": (_I, [_V, _I]),
     "sg_render_prepared": (_I, [_V, _I, _I, _I, _I, _I, _I, _FP, _U8P, C.POINTER(SgStats)]),
     "sg_flush_l2": (_I, [_V, _I]),
@@ -186,6 +187,13 @@ class HostApi(_api.Api):
         out = info.as_dict()
         out["flatten_ms"] = flatten_ms.value
         return out
+
+    def export_scene(self, camera, world) -> C.c_void_p:
+        """The flattened (camera, world) as a raw RtcScene handle of include/rtc_b200.h; the caller destroys it with
+        rtc_scene_destroy of device_library()."""
+        scene = C.c_void_p()
+        self.check(self.lib.sg_export_scene(self.ctx, camera.handle, world.handle, C.byref(scene)))
+        return scene
 
     def flatten(self, world):
         """The flattener's output (no device needed): (prims, nodes, refs, prim_shape_handles, counts)."""

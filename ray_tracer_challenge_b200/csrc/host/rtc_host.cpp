@@ -444,6 +444,26 @@ int sg_inspect(sg_ctx* c, int cam, int w, void* info, double* flatten_ms) {
     return rc;
 }
 
+// The flattened (camera, world) as an RtcScene of include/rtc_b200.h that the CALLER owns (rtc_scene_destroy): for a
+// host that drives the C ABI itself from here on — rtc_scene_inspect, rtc_scene_commit on devices of its choice,
+// rtc_trace_rays — and for the test harness that runs the device code on the host (tests/emu).
+int sg_export_scene(sg_ctx* c, int cam, int w, void** out_scene) {
+    if (!out_scene) return fail("null out pointer");
+    if (cam < 0 || cam >= (int)c->cameras.size()) return fail("bad camera handle");
+    if (w < 0 || w >= (int)c->worlds.size()) return fail("bad world handle");
+    RtcScene* scene = nullptr;
+    if (rtc_scene_create(&scene)) return fail(rtc_last_error());
+    try {
+        FlatScene flat;
+        fill_scene(scene, c->graph, c->worlds[w], c->cameras[cam], flat);
+    } catch (const std::exception& e) {
+        rtc_scene_destroy(scene);
+        return fail(e.what());
+    }
+    *out_scene = scene;
+    return 0;
+}
+
 // Keep a committed scene resident on the device(s) for repeated renders (animation / benchmarking).
 int sg_prepare(sg_ctx* c, int cam, int w) {
     if (cam < 0 || cam >= (int)c->cameras.size()) return fail("bad camera handle");

@@ -17,22 +17,36 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CUDA_INCLUDE = "/usr/local/cuda/include"
 
 
-@pytest.fixture(scope="module")
-def emu(tmp_path_factory):
+def _build(tmp_path_factory, source):
     import ray_tracer_challenge_b200 as rt
 
     if shutil.which("g++") is None or not os.path.isdir(CUDA_INCLUDE):
         pytest.skip("needs g++ and the CUDA headers")
-    out = tmp_path_factory.mktemp("emu") / "libemu_nearest.so"
+    out = tmp_path_factory.mktemp("emu") / ("lib" + source.replace(".cpp", ".so"))
     lib_dir = os.path.dirname(rt.LIB_DEVICE)
     subprocess.run(["g++", "-std=c++17", "-O1", "-ffp-contract=off", "-fPIC", "-shared", "-I", CUDA_INCLUDE,
-                    "-I", os.path.join(ROOT, "ray_tracer_challenge_b200", "csrc"), os.path.join(ROOT, "tests", "emu", "emu_nearest.cpp"),
+                    "-I", os.path.join(ROOT, "ray_tracer_challenge_b200", "csrc"), os.path.join(ROOT, "tests", "emu", source),
                     "-o", str(out), "-L", lib_dir, "-lrtc_b200", f"-Wl,-rpath,{lib_dir}"], check=True)
     device = rt.device_library()  # the raw C ABI; RTLD_GLOBAL, so the harness binds rtc::flatten from it
     device.rtc_last_error.restype = C.c_char_p
-    lib = C.CDLL(str(out))
-    lib.emu_nearest.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float),
-                                C.POINTER(C.c_int32)]
+    device.rtc_scene_destroy.argtypes = [C.c_void_p]
+    return device, C.CDLL(str(out))
+
+
+FP = C.POINTER(C.c_float)
+
+
+@pytest.fixture(scope="module")
+def emu(tmp_path_factory):
+    device, lib = _build(tmp_path_factory, "emu_nearest.cpp")
+    lib.emu_nearest.argtypes = [C.c_void_p, C.c_uint32, FP, FP, FP, C.POINTER(C.c_int32)]
+    return device, lib
+
+
+@pytest.fixture(scope="module")
+def emu_color(tmp_path_factory):
+    device, lib = _build(tmp_path_factory, "emu_color.cpp")
+    lib.emu_color_at.argtypes = [C.c_void_p, C.c_uint32, FP, FP, C.c_int, C.c_int, C.c_int, FP, FP, C.POINTER(C.c_int32)]
     return device, lib
 
 
@@ -125,4 +139,53 @@ def test_tree_path_nearest_hit_matches_oracle(name, emu, host, oracle):
         assert hits > n // 10, (name, hits)  # the rays do exercise the scene
     finally:
         device.rtc_scene_destroy.argtypes = [C.c_void_p]
+        device.rtc_scene_destroy(scene)
+
+
+# name -> (scene, arguments, take the small-scene path when the scene qualifies)
+COLOR_CASES = {
+    "sphere_field": (scenes.stress, dict(width=64, height=36, n_spheres=1500, n_each=6, n_csg=6), False),
+    "mesh": (scenes.dragon_element, dict(width=64, height=36, n_u=24, n_v=12), False),
+    "csg": (scenes.csg_gallery, dict(width=64, height=40), False),
+    "zoo_general_path": (scenes.shapes_zoo, dict(width=64, height=40), False),
+    "zoo": (scenes.shapes_zoo, dict(width=64, height=40), True),
+    "zoo_area_light": (scenes.shapes_zoo, dict(width=64, height=40, area_light=True), True),
+    "soft_shadows_table": (scenes.soft_shadows, dict(width=64, height=32, u_steps=4, v_steps=4), True),  # cell masks, plane cells
+    "soft_shadows_100_cells": (scenes.soft_shadows, dict(width=64, height=32), True),
+    "reflect_refract": (scenes.reflect_refract, dict(width=64, height=32), True),  # exact shadow test, n1 / n2, Schlick
+    "reflect_refract_csg": (scenes.reflect_refract, dict(width=64, height=32, with_csg=True), True),
+    "filter_zoo_table": (scenes.filter_zoo, dict(width=64, height=40, jitter="table"), True),
+    "filter_zoo_point": (scenes.filter_zoo, dict(width=64, height=40, area_light=False), True),
+    "textured": (scenes.textured, dict(width=64, height=40), True),
+    "hexagons": (scenes.hexagons, dict(width=64, height=32), True),
+}
+
+
+@pytest.mark.parametrize("name", sorted(COLOR_CASES))
+def test_color_at_of_the_device_code_matches_oracle_bit_for_bit(name, emu_color, host, oracle):
+    """World::color_at (world.rs:88-101) with everything under it — hit record, patterns, Phong, shadow rays and area
+    lights, reflect / refract stack — through the device code on the host: the tree path and the small-scene path, the
+    latter with the shadow filter and the cell-mask loops on and off.  f32 results equal the oracle's bit for bit (host
+    libm on both sides, IEEE expression order), so in particular the filter changes no value."""
+    device, lib = emu_color
+    make, kw, small = COLOR_CASES[name]
+    cam, world = make(host, **kw)
+    ocam, oworld = make(oracle, **kw)
+    scene = host.export_scene(cam, world)
+    try:
+        n = 240
+        o, d = _rays(oracle, ocam, n, seed=11)
+        want = np.array([oracle.probe.color_at(oworld, o[i], d[i], 5) for i in range(n)], np.float32)
+        assert np.abs(want).sum() > 0
+        fp = lambda a: a.ctypes.data_as(FP)  # noqa: E731
+        for use_filter in ((0, 1) if small else (0,)):
+            rgb = np.zeros((n, 3), np.float32)
+            path = C.c_int32(-1)
+            rc = lib.emu_color_at(scene, n, fp(o), fp(d), 5, int(small), use_filter, fp(rgb), None, C.byref(path))
+            assert rc == 0, device.rtc_last_error()
+            if small:
+                assert path.value == 1, "the scene was meant to take the small-scene path"
+            same = (rgb.view(np.uint32) == want.view(np.uint32)).all(axis=1)
+            assert same.all(), (name, use_filter, int((~same).sum()), rgb[~same][:3], want[~same][:3])
+    finally:
         device.rtc_scene_destroy(scene)
