@@ -189,3 +189,24 @@ def test_color_at_of_the_device_code_matches_oracle_bit_for_bit(name, emu_color,
             assert same.all(), (name, use_filter, int((~same).sum()), rgb[~same][:3], want[~same][:3])
     finally:
         device.rtc_scene_destroy(scene)
+
+
+def test_empty_world_is_black_through_the_device_code(emu_color, host):
+    """No objects at all, and only an empty group: every ray misses, color_at returns black (world.rs:98-100)."""
+    device, lib = emu_color
+    from ray_tracer_challenge_b200.scenes import PI
+
+    for objects in ([], [host.GroupShape()]):
+        cam = host.Camera(16, 8, PI / 2.0, host.view_transform((0, 0, -5), (0, 0, 0), (0, 1, 0)))
+        world = host.World(objects, host.PointLight((-10, 10, -10), (1, 1, 1)))
+        scene = host.export_scene(cam, world)
+        try:
+            o = np.zeros((8, 3), np.float32)
+            o[:, 2] = -5
+            d = np.tile(np.array([0, 0, 1], np.float32), (8, 1))
+            rgb = np.ones((8, 3), np.float32)
+            fp = lambda a: a.ctypes.data_as(FP)  # noqa: E731
+            assert lib.emu_color_at(scene, 8, fp(o), fp(d), 5, 1, 1, fp(rgb), None, None) == 0, device.rtc_last_error()
+            assert not rgb.any()
+        finally:
+            device.rtc_scene_destroy(scene)
