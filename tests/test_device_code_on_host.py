@@ -210,3 +210,72 @@ def test_empty_world_is_black_through_the_device_code(emu_color, host):
             assert not rgb.any()
         finally:
             device.rtc_scene_destroy(scene)
+
+
+@pytest.mark.parametrize("name,make,kw", [
+    ("soft_shadows_as_shipped", scenes.soft_shadows, dict(width=40, height=16, u_steps=10, v_steps=10, jitter=None, seed=3)),
+    ("filter_zoo_drawn", scenes.filter_zoo, dict(width=40, height=24)),
+    ("first_textures_drawn", scenes.first_textures, dict(width=40, height=20, u_steps=4, v_steps=4)),
+])
+def test_counter_mode_jitter_frame_matches_oracle(name, make, kw, emu_color, host, oracle):
+    """Area lights with `jitter_fn = None` draw their samples from the counter-based generator keyed by (seed, pixel,
+    path, index): ray i of the harness is pixel i of the frame, so a whole small frame traced through the device code
+    (drawn-sample cell masks where the scene is filter-eligible) equals the oracle's Camera::render bit for bit."""
+    device, lib = emu_color
+    cam, world = make(host, **kw)
+    ocam, oworld = make(oracle, **kw)
+    want = ocam.render(oworld, 5).data
+    w, h = ocam.width_pixels, ocam.height_pixels
+    o = np.zeros((w * h, 3), np.float32)
+    d = np.zeros((w * h, 3), np.float32)
+    d[:, 2] = 1.0
+    for y in range(h - 1):
+        for x in range(w - 1):
+            ro, rd = oracle.probe.camera_ray(ocam, x, y)
+            o[y * w + x], d[y * w + x] = ro[:3], rd[:3]
+    scene = host.export_scene(cam, world)
+    try:
+        fp = lambda a: a.ctypes.data_as(FP)  # noqa: E731
+        for use_filter in (0, 1):
+            rgb = np.zeros((w * h, 3), np.float32)
+            assert lib.emu_color_at(scene, w * h, fp(o), fp(d), 5, 1, use_filter, fp(rgb), None, None) == 0, device.rtc_last_error()
+            got = rgb.reshape(h, w, 3)[: h - 1, : w - 1]
+            ref = np.asarray(want, np.float32)[: h - 1, : w - 1]
+            same = (got.view(np.uint32) == ref.view(np.uint32)).all(axis=2)
+            assert same.all(), (name, use_filter, int((~same).sum()), got[~same][:2], ref[~same][:2])
+    finally:
+        device.rtc_scene_destroy(scene)
+
+
+def test_shadow_filter_fuzz_through_the_device_code(emu_color, host, oracle):
+    """Random filter-eligible scenes (sheared / squashed spheres, tilted planes, boxes, touching and interpenetrating,
+    area or point light, table or counter jitter): whole small frames through the device code with the filter and the
+    cell-mask loops ON equal the oracle's render bit for bit — the CPU twin of test_gpu_parity's on-device fuzz, on other seeds."""
+    device, lib = emu_color
+    fp = lambda a: a.ctypes.data_as(FP)  # noqa: E731
+    eligible = 0
+    for seed in range(100, 116):
+        kw = dict(width=28, height=18)
+        cam, world = scenes.random_filter_scene(host, seed, **kw)
+        ocam, oworld = scenes.random_filter_scene(oracle, seed, **kw)
+        eligible += host.inspect(cam, world)["filter_ok"]
+        want = np.asarray(ocam.render(oworld, 5).data, np.float32)
+        w, h = ocam.width_pixels, ocam.height_pixels
+        o = np.zeros((w * h, 3), np.float32)
+        d = np.zeros((w * h, 3), np.float32)
+        d[:, 2] = 1.0
+        for y in range(h - 1):
+            for x in range(w - 1):
+                ro, rd = oracle.probe.camera_ray(ocam, x, y)
+                o[y * w + x], d[y * w + x] = ro[:3], rd[:3]
+        scene = host.export_scene(cam, world)
+        try:
+            rgb = np.zeros((w * h, 3), np.float32)
+            assert lib.emu_color_at(scene, w * h, fp(o), fp(d), 5, 1, 1, fp(rgb), None, None) == 0, device.rtc_last_error()
+            got = rgb.reshape(h, w, 3)[: h - 1, : w - 1]
+            ref = want[: h - 1, : w - 1]
+            same = (got.view(np.uint32) == ref.view(np.uint32)).all(axis=2)
+            assert same.all(), (seed, int((~same).sum()), got[~same][:2], ref[~same][:2])
+        finally:
+            device.rtc_scene_destroy(scene)
+    assert eligible >= 12, eligible
