@@ -104,6 +104,10 @@ void host_scene(const RtcScene* s, const rtc::Flattened& f, rtc::DevScene& d) {
 }
 }  // namespace
 
+static int g_converge = 0;
+// 1: the converging build of color_at (a warp vote before every ray; here a warp of one lane)
+extern "C" void emu_set_converge(int on) { g_converge = on; }
+
 // World::color_at for n rays.  use_small: take the small-scene path when the scene qualifies (as the kernels do);
 // use_filter: with the shadow filter and the cell-mask loops where eligible.  out_path: 0 tree / linear path, 1 small.
 extern "C" int emu_color_at(RtcScene* s, uint32_t n, const float* origins, const float* directions, int depth, int use_small,
@@ -129,11 +133,14 @@ extern "C" int emu_color_at(RtcScene* s, uint32_t n, const float* origins, const
         int pos = -1;
         emu::V3 c;
         if (drawn)
-            c = emu::color_at<false, true, false, true>(E, true, o, d, depth, i, r, k, &t, &pos);
+            c = g_converge ? emu::color_at<false, true, true, true>(E, true, o, d, depth, i, r, k, &t, &pos)
+                           : emu::color_at<false, true, false, true>(E, true, o, d, depth, i, r, k, &t, &pos);
         else if (small)
-            c = emu::color_at<false, true, false, false>(E, true, o, d, depth, i, r, k, &t, &pos);
+            c = g_converge ? emu::color_at<false, true, true, false>(E, true, o, d, depth, i, r, k, &t, &pos)
+                           : emu::color_at<false, true, false, false>(E, true, o, d, depth, i, r, k, &t, &pos);
         else
-            c = emu::color_at<false, false, false, false>(E, true, o, d, depth, i, r, k, &t, &pos);
+            c = g_converge ? emu::color_at<false, false, true, false>(E, true, o, d, depth, i, r, k, &t, &pos)
+                           : emu::color_at<false, false, false, false>(E, true, o, d, depth, i, r, k, &t, &pos);
         out_rgb[3 * (size_t)i] = c.x, out_rgb[3 * (size_t)i + 1] = c.y, out_rgb[3 * (size_t)i + 2] = c.z;
         if (out_t) out_t[i] = t;
     }

@@ -178,7 +178,8 @@ def test_color_at_of_the_device_code_matches_oracle_bit_for_bit(name, emu_color,
         want = np.array([oracle.probe.color_at(oworld, o[i], d[i], 5) for i in range(n)], np.float32)
         assert np.abs(want).sum() > 0
         fp = lambda a: a.ctypes.data_as(FP)  # noqa: E731
-        for use_filter in ((0, 1) if small else (0,)):
+        for use_filter, converge in (((0, 0), (1, 0), (1, 1)) if small else ((0, 0), (0, 1))):
+            lib.emu_set_converge(converge)  # the converging build of color_at (single lane: the vote is the predicate)
             rgb = np.zeros((n, 3), np.float32)
             path = C.c_int32(-1)
             rc = lib.emu_color_at(scene, n, fp(o), fp(d), 5, int(small), use_filter, fp(rgb), None, C.byref(path))
@@ -186,8 +187,9 @@ def test_color_at_of_the_device_code_matches_oracle_bit_for_bit(name, emu_color,
             if small:
                 assert path.value == 1, "the scene was meant to take the small-scene path"
             same = (rgb.view(np.uint32) == want.view(np.uint32)).all(axis=1)
-            assert same.all(), (name, use_filter, int((~same).sum()), rgb[~same][:3], want[~same][:3])
+            assert same.all(), (name, use_filter, converge, int((~same).sum()), rgb[~same][:3], want[~same][:3])
     finally:
+        lib.emu_set_converge(0)
         device.rtc_scene_destroy(scene)
 
 
