@@ -104,6 +104,8 @@ void host_scene(const RtcScene* s, const rtc::Flattened& f, rtc::DevScene& d) {
 }
 }  // namespace
 
+static unsigned long long g_rays[4];  // primary, secondary, shadow rays and shades of the last emu_color_at call
+extern "C" void emu_last_rays(unsigned long long out[4]) { memcpy(out, g_rays, sizeof(g_rays)); }
 static int g_converge = 0;
 // 1: the converging build of color_at (a warp vote before every ray; here a warp of one lane)
 extern "C" void emu_set_converge(int on) { g_converge = on; }
@@ -124,6 +126,7 @@ extern "C" int emu_color_at(RtcScene* s, uint32_t n, const float* origins, const
     const bool drawn = small && SS.cell_masks && S.jitter_len == 0;
     if (out_path) *out_path = small ? 1 : 0;
     const emu::Env E{S, SS};
+    memset(g_rays, 0, sizeof(g_rays));
     for (uint32_t i = 0; i < n; i++) {
         if (small) emu::stage_small_scene(S, SS);  // one thread per block: it stages the whole table
         emu::V3 o = emu::ld3(origins + 3 * (size_t)i), d = emu::ld3(directions + 3 * (size_t)i);
@@ -141,6 +144,7 @@ extern "C" int emu_color_at(RtcScene* s, uint32_t n, const float* origins, const
         else
             c = g_converge ? emu::color_at<false, false, true, false>(E, true, o, d, depth, i, r, k, &t, &pos)
                            : emu::color_at<false, false, false, false>(E, true, o, d, depth, i, r, k, &t, &pos);
+        g_rays[0] += r.primary, g_rays[1] += r.secondary, g_rays[2] += r.shadow, g_rays[3] += r.shades;
         out_rgb[3 * (size_t)i] = c.x, out_rgb[3 * (size_t)i + 1] = c.y, out_rgb[3 * (size_t)i + 2] = c.z;
         if (out_t) out_t[i] = t;
     }

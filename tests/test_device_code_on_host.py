@@ -230,7 +230,7 @@ def test_counter_mode_jitter_frame_matches_oracle(name, make, kw, emu_color, hos
     w, h = ocam.width_pixels, ocam.height_pixels
     o = np.zeros((w * h, 3), np.float32)
     d = np.zeros((w * h, 3), np.float32)
-    d[:, 2] = 1.0
+    o[:, 1], d[:, 1] = 1.0e6, 1.0
     for y in range(h - 1):
         for x in range(w - 1):
             ro, rd = oracle.probe.camera_ray(ocam, x, y)
@@ -245,6 +245,12 @@ def test_counter_mode_jitter_frame_matches_oracle(name, make, kw, emu_color, hos
             ref = np.asarray(want, np.float32)[: h - 1, : w - 1]
             same = (got.view(np.uint32) == ref.view(np.uint32)).all(axis=2)
             assert same.all(), (name, use_filter, int((~same).sum()), got[~same][:2], ref[~same][:2])
+            # the ray counters of the device code against the oracle's for the same frame (the never-rendered border
+            # of the harness' w x h grid holds rays that start far above the scene and point away: they trace nothing)
+            rays = (C.c_ulonglong * 4)()
+            lib.emu_last_rays(rays)
+            st = ocam.last_stats
+            assert (rays[1], rays[2], rays[3]) == (st.secondary_rays, st.shadow_rays, st.shades), (list(rays), st.as_dict())
     finally:
         device.rtc_scene_destroy(scene)
 
