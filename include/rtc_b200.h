@@ -29,9 +29,11 @@ typedef struct RtcScene RtcScene;
 typedef enum RtcStatus {
     RTC_OK = 0,
     RTC_ERR_INVALID = -1,   /* bad argument / inconsistent scene */
-    RTC_ERR_NO_DEVICE = -2, /* no CUDA device, or CUDA call failed */
+    RTC_ERR_NO_DEVICE = -2, /* no CUDA device is visible (there is no CPU fallback) */
     RTC_ERR_CAPACITY = -3,  /* a documented device-side capacity was exceeded (depth, CSG size) */
-    RTC_ERR_STATE = -4      /* call sequence error (render before commit, ...) */
+    RTC_ERR_STATE = -4,     /* call sequence error (render before commit, ...) */
+    RTC_ERR_CUDA = -5       /* a CUDA runtime call failed on a visible device (out of memory, launch failure, ...);
+                               rtc_last_error() names the call */
 } RtcStatus;
 
 /* Leaf primitive kinds — lib/src/shape/{sphere,plane,cube,cylinder,cone,triangle}.rs.  SmoothTriangle
@@ -155,9 +157,13 @@ int rtc_set_textures(RtcScene*, uint32_t n, const RtcTexture* textures);
 int rtc_set_point_light(RtcScene*, const float position[3], const float intensity[3]);
 /* RectangleLight after construction (rectangle_light.rs:48-58): u_cell / v_cell are the per-cell edges,
  * `position` the rectangle centre used by phong_lighting (phong_lighting.rs:36).  Jitter: a cyclic table
- * consumed `for v { for u { j_u, j_v } }` from index 0 at every intensity_at (rectangle_light.rs:60-88), or,
- * with table_len == 0, the counter-based generator seeded by `seed` (stand-in for thread_rng,
- * rectangle_light.rs:46). */
+ * consumed `for v { for u { j_u, j_v } }` (rectangle_light.rs:60-88), or, with table_len == 0, the counter-based
+ * generator seeded by `seed` (stand-in for thread_rng, rectangle_light.rs:46).
+ * DEVIATION: the reference's table closure (test/utils.rs `hardcoded_jitter`) is ONE stateful cyclic iterator whose
+ * cursor carries over from one intensity_at call to the next, in the serial order of the render loop.  Here every
+ * intensity_at starts at index 0 (pixels are shaded in parallel; there is no call order).  The two coincide exactly
+ * when table_len divides 2 * u_steps * v_steps (every call consumes whole cycles), so any other table_len is
+ * REJECTED with RTC_ERR_INVALID rather than rendered with different shadows. */
 int rtc_set_rect_light(RtcScene*, const float intensity[3], const float corner[3], const float u_cell[3],
                        int32_t u_steps, const float v_cell[3], int32_t v_steps, const float position[3],
                        const float* jitter_table, uint32_t table_len, uint64_t seed);
@@ -200,6 +206,8 @@ typedef struct RtcCommitInfo {
     int32_t converge;        /* some material is reflective and transparent: the converging kernel build */
     float tol_sphere;        /* the filter's relative error bound for spheres */
     float light_ball[4];     /* ball around the light's sample points (cell_masks) */
+    int32_t bvh_depth;       /* levels of inner nodes on the longest root-to-leaf path (0: no tree); the builder keeps
+                                it below the traversal stack's capacity for every scene */
     double host_ms;          /* time the host half took */
     uint64_t digest;         /* FNV-1a over the arrays a commit would upload for intersection (primitive heads and
                               * records, transforms, triangles, bounds, tree nodes, linear list): equal digests mean

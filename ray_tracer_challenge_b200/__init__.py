@@ -61,7 +61,7 @@ class RtcCommitInfo(C.Structure):
         ("n_positions", C.c_int32), ("n_bvh_nodes", C.c_int32), ("n_linear", C.c_int32), ("n_xforms", C.c_int32),
         ("bvh_leaf_size", C.c_int32), ("small_n", C.c_int32), ("filter_ok", C.c_int32), ("cell_masks", C.c_int32),
         ("plane_cells", C.c_int32), ("converge", C.c_int32), ("tol_sphere", C.c_float), ("light_ball", C.c_float * 4),
-        ("host_ms", C.c_double), ("digest", C.c_uint64),
+        ("bvh_depth", C.c_int32), ("host_ms", C.c_double), ("digest", C.c_uint64),
     ]
 
     def as_dict(self) -> dict:
@@ -85,6 +85,7 @@ _HOST_EXTRAS = {
     "sg_set_render_options": (_I, [_V, _I, _IP, _I, _I]),
     "sg_last_rtc_stats": (_I, [_V, C.POINTER(RtcStats)]),
     "sg_prepare": (_I, [_V, _I, _I]),
+    "sg_camera_render_shard": (_I, [_V, _I, _I, _I, _I, _I, _FP, _U8P, C.POINTER(SgStats)]),
     "sg_inspect": (_I, [_V, _I, _I, C.c_void_p, C.POINTER(C.c_double)]),
     "sg_export_scene": (_I, [_V, _I, _I, C.POINTER(C.c_void_p)]),
     "sg_release_prepared": (_I, [_V, _I]),

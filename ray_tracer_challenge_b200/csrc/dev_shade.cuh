@@ -10,22 +10,31 @@ __device__ __forceinline__ float powi5(float x) {  // llvm.powi with a constant 
     return x * (x2 * x2);
 }
 
-// One pending shade_hit whose children are still being traced (world.rs:62-86).
+// One pending shade_hit whose children are still being traced (world.rs:62-86).  The reference adds its three terms
+// left to right, `(surface + reflected * R) + refracted * (1 - R)` (world.rs:80-85), so a frame holds ONE colour: the
+// surface colour while the reflection subtree is traced, then the first partial sum while the refraction subtree is.
+// Only the fields a frame's children need are written (a mirror's frame: acc, reflective, reflectance, path, flags —
+// the refraction ray and the transparency are stored for frames that refract); `remaining` is not stored at all: the
+// frame at stack index i was pushed by a ray with remaining = depth - i.
 struct Frame {
-    V3 surface;
-    V3 refl;          // reflected_color once known
-    V3 refr_o, refr_d;
-    float reflective, transparency;
+    V3 acc;             // stage 1: surface; stage 2: surface + reflected * R (or surface + reflected)
+    float reflective;
     float reflectance;  // Schlick R, or < 0 when the plain sum applies (world.rs:80-85)
-    int remaining;
     unsigned path;
-    int stage;  // 1: waiting for the reflection subtree, 2: waiting for the refraction subtree
-    int has_refr;
+    int flags;          // bit 0: waiting for the refraction subtree (stage 2); bit 1: a refraction ray is pending
+    float transparency;
+    V3 refr_o, refr_d;
 };
 
+// world.rs:80-85, first and second addition
+__device__ __forceinline__ V3 add_reflected(V3 surface, V3 reflected, float reflectance) {
+    return reflectance >= 0.0f ? surface + reflected * reflectance : surface + reflected;
+}
+__device__ __forceinline__ V3 add_refracted(V3 partial, V3 refracted, float reflectance) {
+    return reflectance >= 0.0f ? partial + refracted * (1.0f - reflectance) : partial + refracted;
+}
 __device__ __forceinline__ V3 combine(V3 surface, V3 reflected, V3 refracted, float reflectance) {
-    if (reflectance >= 0.0f) return surface + reflected * reflectance + refracted * (1.0f - reflectance);
-    return surface + reflected + refracted;
+    return add_refracted(add_reflected(surface, reflected, reflectance), refracted, reflectance);
 }
 
 // World::color_at (world.rs:88-101) with the recursion of reflected_color / refracted_color replaced by an
@@ -147,26 +156,26 @@ __device__ __forceinline__ V3 color_at(const Env& E, bool active, V3 ro, V3 rd, 
             }
             if ((want_refl || want_refr) && sp < kMaxFrames) {
                 Frame& f = stack[sp++];
-                f.surface = surface;
-                f.refl = mk(0.f, 0.f, 0.f);
-                f.refr_o = point - n * kAcne;  // under_point
-                f.refr_d = refr_d;
-                f.reflective = mat.reflective;
-                f.transparency = mat.transparency;
                 f.reflectance = reflectance;
-                f.remaining = remaining;
                 f.path = path;
-                f.has_refr = want_refr;
                 r.secondary++;
                 remaining = remaining - 1;
+                if (want_refr) {
+                    f.transparency = mat.transparency;
+                    f.refr_o = point - n * kAcne;  // under_point
+                    f.refr_d = refr_d;
+                }
                 if (want_refl) {
-                    f.stage = 1;
+                    f.acc = surface;
+                    f.reflective = mat.reflective;
+                    f.flags = want_refr ? 2 : 0;
                     ro = over_point;
                     rd = reflectv;
                     path = path * 3u + 1u;
-                } else {
-                    f.stage = 2;
-                    ro = f.refr_o;
+                } else {  // no reflection: reflected_color is black (world.rs:126-128)
+                    f.acc = add_reflected(surface, mk(0.f, 0.f, 0.f), reflectance);
+                    f.flags = 1;
+                    ro = point - n * kAcne;
                     rd = refr_d;
                     path = path * 3u + 2u;
                 }
@@ -183,20 +192,23 @@ __device__ __forceinline__ V3 color_at(const Env& E, bool active, V3 ro, V3 rd, 
                 break;
             }
             Frame& f = stack[sp - 1];
-            if (f.stage == 1) {
-                f.refl = c * f.reflective;  // world.rs:131
-                if (f.has_refr) {
-                    f.stage = 2;
+            const int flags = f.flags;
+            const float reflectance = f.reflectance;
+            if (!(flags & 1)) {                        // the reflection subtree is done
+                const V3 reflected = c * f.reflective;  // world.rs:131
+                if (flags & 2) {                        // its refraction sibling is next
+                    f.acc = add_reflected(f.acc, reflected, reflectance);
+                    f.flags = 1;
                     ro = f.refr_o;
                     rd = f.refr_d;
-                    remaining = f.remaining - 1;
+                    remaining = depth - sp;  // the frame's ray had depth - (sp - 1)
                     path = f.path * 3u + 2u;
                     r.secondary++;
                     break;
                 }
-                c = combine(f.surface, f.refl, mk(0.f, 0.f, 0.f), f.reflectance);
+                c = combine(f.acc, reflected, mk(0.f, 0.f, 0.f), reflectance);
             } else {
-                c = combine(f.surface, f.refl, c * f.transparency, f.reflectance);  // world.rs:159-160
+                c = add_refracted(f.acc, c * f.transparency, reflectance);  // world.rs:159-160
             }
             sp--;
         }

@@ -397,8 +397,12 @@ int sg_last_rtc_stats(sg_ctx* c, RtcStats* out) {
     return 0;
 }
 
-// Camera::render_b200 — one call: flatten, commit, render, copy back, release.
-int sg_camera_render(sg_ctx* c, int cam, int w, int depth, float* out_rgb, uint8_t* out_u8, sg_stats* stats) {
+// Camera::render_b200 — one call: flatten, commit, render, copy back, release.  With n_shards > 1 the call renders
+// and copies only the bands of `shard` (one process per GPU, every process making the same one-shot call on its own
+// device for one shared frame); either plane may be null (not copied: the reference's demos only ever serialise the
+// 8-bit values, canvas.rs:58-96).
+static int camera_render(sg_ctx* c, int cam, int w, int depth, int shard, int n_shards, float* out_rgb, uint8_t* out_u8,
+                         sg_stats* stats) {
     if (cam < 0 || cam >= (int)c->cameras.size()) return fail("bad camera handle");
     if (w < 0 || w >= (int)c->worlds.size()) return fail("bad world handle");
     RtcScene* scene = nullptr;
@@ -410,8 +414,11 @@ int sg_camera_render(sg_ctx* c, int cam, int w, int depth, float* out_rgb, uint8
         fill_scene(scene, c->graph, c->worlds[w], c->cameras[cam], flat);
         rc = commit(c, scene);
         if (!rc) {
-            rc = c->options.detailed ? rtc_render_detailed(scene, depth, out_rgb, out_u8, &c->last_stats)
-                                     : rtc_render(scene, depth, out_rgb, out_u8, &c->last_stats);
+            if (n_shards > 1)
+                rc = rtc_render_shard(scene, depth, shard, n_shards, out_rgb, out_u8, &c->last_stats);
+            else
+                rc = c->options.detailed ? rtc_render_detailed(scene, depth, out_rgb, out_u8, &c->last_stats)
+                                         : rtc_render(scene, depth, out_rgb, out_u8, &c->last_stats);
             if (rc) fail(rtc_last_error());
         }
         c->last_stats.total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
@@ -421,6 +428,14 @@ int sg_camera_render(sg_ctx* c, int cam, int w, int depth, float* out_rgb, uint8
     }
     rtc_scene_destroy(scene);
     return rc ? -1 : 0;
+}
+int sg_camera_render(sg_ctx* c, int cam, int w, int depth, float* out_rgb, uint8_t* out_u8, sg_stats* stats) {
+    return camera_render(c, cam, w, depth, 0, 1, out_rgb, out_u8, stats);
+}
+int sg_camera_render_shard(sg_ctx* c, int cam, int w, int depth, int shard, int n_shards, float* out_rgb, uint8_t* out_u8,
+                           sg_stats* stats) {
+    if (n_shards < 1 || shard < 0 || shard >= n_shards) return fail("bad shard index");
+    return camera_render(c, cam, w, depth, shard, n_shards, out_rgb, out_u8, stats);
 }
 
 // rtc_scene_inspect for (camera, world): flatten + the host half of the commit, no device needed.  `info` is an

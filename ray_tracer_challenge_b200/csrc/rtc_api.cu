@@ -36,11 +36,29 @@ int fail(int code, const std::string& msg) {
 }
 }  // namespace rtc
 namespace {
+// no usable device -> RTC_ERR_NO_DEVICE (the "no CPU fallback" contract); anything else a visible device reports
+// (out of memory, launch failure, bad argument) -> RTC_ERR_CUDA
+int cuda_status(cudaError_t e) {
+    switch (e) {
+        case cudaErrorNoDevice:
+        case cudaErrorInsufficientDriver:
+        case cudaErrorInvalidDevice:
+        case cudaErrorDevicesUnavailable:
+        case cudaErrorInitializationError:
+        case cudaErrorSystemNotReady:
+        case cudaErrorSystemDriverMismatch:
+        case cudaErrorCompatNotSupportedOnDevice:
+        case cudaErrorStubLibrary:
+        case cudaErrorNoKernelImageForDevice:  // not an sm_100a part: this library has kernels for nothing else
+            return RTC_ERR_NO_DEVICE;
+        default: return RTC_ERR_CUDA;
+    }
+}
 #define CUDA_TRY(expr)                                                                                          \
     do {                                                                                                        \
         cudaError_t _e = (expr);                                                                                \
         if (_e != cudaSuccess)                                                                                  \
-            return fail(RTC_ERR_NO_DEVICE, std::string(#expr) + ": " + cudaGetErrorString(_e));                  \
+            return fail(cuda_status(_e), std::string(#expr) + ": " + cudaGetErrorString(_e));                    \
     } while (0)
 
 
@@ -484,6 +502,13 @@ int rtc_set_rect_light(RtcScene* s, const float intensity[3], const float corner
     if (!s || !intensity || !corner || !u_cell || !v_cell || !position || (table_len && !table))
         return fail(RTC_ERR_INVALID, "null argument");
     if (u_steps < 1 || v_steps < 1 || (int64_t)u_steps * v_steps > (1 << 20)) return fail(RTC_ERR_INVALID, "bad light steps");
+    // every intensity_at restarts the table (see the header): identical to the reference's carried-over cursor only
+    // when each call consumes whole cycles
+    if (table_len && (2 * (int64_t)u_steps * v_steps) % table_len != 0)
+        return fail(RTC_ERR_INVALID, "jitter table length " + std::to_string(table_len) + " does not divide 2 * u_steps * v_steps = " +
+                                         std::to_string(2 * (int64_t)u_steps * v_steps) +
+                                         ": the reference's cyclic table would carry its cursor from one intensity_at to the next "
+                                         "in render order, which a parallel render cannot reproduce");
     s->light_is_rect = true;
     memcpy(s->light_rgb, intensity, 12);
     memcpy(s->corner, corner, 12);
@@ -535,7 +560,7 @@ int rtc_scene_inspect(RtcScene* s, RtcCommitInfo* out) {
     memset(out, 0, sizeof(*out));
     out->host_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     out->n_positions = f.n_pos, out->n_bvh_nodes = (int)f.bvh.size(), out->n_linear = (int)f.linear.size();
-    out->n_xforms = (int)f.xform.size() / 3, out->bvh_leaf_size = f.leaf_size;
+    out->n_xforms = (int)f.xform.size() / 3, out->bvh_leaf_size = f.leaf_size, out->bvh_depth = f.bvh_depth;
     out->small_n = f.small.n, out->filter_ok = f.small.filter_ok, out->cell_masks = f.small.cell_masks;
     out->plane_cells = f.small.plane_cells, out->converge = s->has_branching_materials ? 1 : 0;
     out->tol_sphere = f.small.tol_sphere;
@@ -625,30 +650,32 @@ int rtc_trace_rays(RtcScene* s, uint32_t n, const float* origins, const float* d
         SmallScene& small;
     } r{rep.slot->device, rep.slot->stream, rep.slot->d_counters, rep.scene, rep.small};
     CUDA_TRY(cudaSetDevice(r.device));
-    float *d_o = nullptr, *d_d = nullptr, *d_rgb = nullptr, *d_t = nullptr;
-    int* d_pos = nullptr;
+    struct Buffers {  // freed on every exit path
+        float *o = nullptr, *d = nullptr, *rgb = nullptr, *t = nullptr;
+        int* pos = nullptr;
+        ~Buffers() { cudaFree(o), cudaFree(d), cudaFree(rgb), cudaFree(t), cudaFree(pos); }
+    } b;
     size_t b3 = (size_t)n * 3 * sizeof(float);
-    CUDA_TRY(cudaMalloc(&d_o, b3));
-    CUDA_TRY(cudaMalloc(&d_d, b3));
-    CUDA_TRY(cudaMalloc(&d_rgb, b3));
-    CUDA_TRY(cudaMalloc(&d_t, (size_t)n * sizeof(float)));
-    CUDA_TRY(cudaMalloc(&d_pos, (size_t)n * sizeof(int)));
-    CUDA_TRY(cudaMemcpyAsync(d_o, origins, b3, cudaMemcpyHostToDevice, r.stream));
-    CUDA_TRY(cudaMemcpyAsync(d_d, directions, b3, cudaMemcpyHostToDevice, r.stream));
+    CUDA_TRY(cudaMalloc(&b.o, b3));
+    CUDA_TRY(cudaMalloc(&b.d, b3));
+    CUDA_TRY(cudaMalloc(&b.rgb, b3));
+    CUDA_TRY(cudaMalloc(&b.t, (size_t)n * sizeof(float)));
+    CUDA_TRY(cudaMalloc(&b.pos, (size_t)n * sizeof(int)));
+    CUDA_TRY(cudaMemcpyAsync(b.o, origins, b3, cudaMemcpyHostToDevice, r.stream));
+    CUDA_TRY(cudaMemcpyAsync(b.d, directions, b3, cudaMemcpyHostToDevice, r.stream));
     CUDA_TRY(cudaMemsetAsync(r.d_counters, 0, sizeof(DevCounters), r.stream));
     if (s->strict_fp)
-        strict::launch_trace(r.scene, r.small, (int)n, d_o, d_d, depth, d_rgb, d_t, d_pos, r.d_counters, r.stream);
+        strict::launch_trace(r.scene, r.small, (int)n, b.o, b.d, depth, b.rgb, b.t, b.pos, r.d_counters, r.stream);
     else
-        fast::launch_trace(r.scene, r.small, (int)n, d_o, d_d, depth, d_rgb, d_t, d_pos, r.d_counters, r.stream);
+        fast::launch_trace(r.scene, r.small, (int)n, b.o, b.d, depth, b.rgb, b.t, b.pos, r.d_counters, r.stream);
     CUDA_TRY(cudaGetLastError());
     std::vector<int> pos(n);
-    CUDA_TRY(cudaMemcpyAsync(out_rgb, d_rgb, b3, cudaMemcpyDeviceToHost, r.stream));
-    if (out_t) CUDA_TRY(cudaMemcpyAsync(out_t, d_t, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, r.stream));
-    CUDA_TRY(cudaMemcpyAsync(pos.data(), d_pos, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, r.stream));
+    CUDA_TRY(cudaMemcpyAsync(out_rgb, b.rgb, b3, cudaMemcpyDeviceToHost, r.stream));
+    if (out_t) CUDA_TRY(cudaMemcpyAsync(out_t, b.t, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, r.stream));
+    CUDA_TRY(cudaMemcpyAsync(pos.data(), b.pos, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, r.stream));
     CUDA_TRY(cudaStreamSynchronize(r.stream));
     if (out_prim)
         for (uint32_t i = 0; i < n; i++) out_prim[i] = pos[i] >= 0 ? s->pos_to_prim[pos[i]] : -1;
-    cudaFree(d_o), cudaFree(d_d), cudaFree(d_rgb), cudaFree(d_t), cudaFree(d_pos);
     return 0;
 }
 

@@ -31,12 +31,34 @@ struct Builder {
     std::vector<DevBvhNode>& nodes;
     int leaf_size;
     // returns the link for the range [b, e): >= 0 inner node, < 0 leaf code
+    // The traversal stack holds one deferred child per level (kBvhStack entries, dev_bvh.cuh) and a full stack must
+    // never drop a subtree, so the tree's depth is bounded HERE: SAH splits are free to be lopsided only while
+    // `depth + ceil(log2 n)` leaves room; past that every split is the balanced median (depth grows by exactly
+    // ceil(log2 n) from there), so no path is longer than kBvhDepthCap whatever the scene (10^5 coincident centroids
+    // included).  max_depth records what was built; flatten() refuses a tree that exceeds the cap.
+    static constexpr int kBvhDepthCap = kBvhStack - 2;
+    int max_depth = 0;
+    static int ceil_log2(int n) {
+        int l = 0;
+        while ((1 << l) < n) l++;
+        return l;
+    }
     int build(int b, int e, int depth) {
         int n = e - b;
-        if (n <= leaf_size || depth > 40) {
-            if (n <= 16) return ~((b << 4) | (n - 1));
-            // forced leaf too large for the 4-bit count: split in the middle regardless of cost
-            return make_inner(b, (b + e) / 2, e, depth);
+        max_depth = std::max(max_depth, depth);
+        if (n <= leaf_size) return ~((b << 4) | (n - 1));
+        if (depth + ceil_log2(n) + 1 >= kBvhDepthCap) {  // balanced from here on
+            int mid = (b + e) / 2;
+            Box cb;
+            for (int i = b; i < e; i++)
+                for (int a = 0; a < 3; a++)
+                    cb.lo[a] = std::min(cb.lo[a], items[i].centroid[a]), cb.hi[a] = std::max(cb.hi[a], items[i].centroid[a]);
+            int axis = 0;
+            for (int a = 1; a < 3; a++)
+                if (cb.hi[a] - cb.lo[a] > cb.hi[axis] - cb.lo[axis]) axis = a;
+            std::nth_element(items.begin() + b, items.begin() + mid, items.begin() + e,
+                             [&](const BuildItem& x, const BuildItem& y) { return x.centroid[axis] < y.centroid[axis]; });
+            return make_inner(b, mid, e, depth);
         }
         Box cb;
         for (int i = b; i < e; i++)
@@ -120,6 +142,7 @@ struct Builder {
             auto task = std::async(std::launch::async, [&] { return left.build(b, mid, depth + 1); });
             c1 = right.build(mid, e, depth + 1);
             c0 = task.get();
+            max_depth = std::max(max_depth, std::max(left.max_depth, right.max_depth));
             append(nodes, left_nodes, c0);
             append(nodes, right_nodes, c1);
         } else {
@@ -174,6 +197,31 @@ int validate_scene(const RtcScene* s) {
             int r = s->refs[n.child_begin + c];
             if (r >= np || (r < 0 && ~r >= nn)) return fail(RTC_ERR_INVALID, "node: bad child reference");
         }
+    }
+    // ---- the node graph must be a forest whose parent and child links agree (the reference's Box<dyn Shape> tree
+    // cannot be anything else; a foreign host's arrays can): every child reference names an item whose `parent` is the
+    // referring node, no item is referenced twice, every item with a parent is in that parent's list, and parent chains
+    // end.  A parent cycle would spin the device's cull-chain walk forever; a reference cycle would recurse the CSG
+    // emitter without bound.
+    std::vector<char> prim_seen(np, 0), node_seen(nn, 0);
+    for (int i = 0; i < nn; i++) {
+        const RtcNode& n = s->nodes[i];
+        for (int c = 0; c < n.child_count; c++) {
+            const int r = s->refs[n.child_begin + c];
+            char& seen = r >= 0 ? prim_seen[r] : node_seen[~r];
+            const int claimed = r >= 0 ? s->prims[r].parent : s->nodes[~r].parent;
+            if (seen) return fail(RTC_ERR_INVALID, "node " + std::to_string(i) + ": a child is referenced twice");
+            if (claimed != i) return fail(RTC_ERR_INVALID, "node " + std::to_string(i) + ": child's parent field does not point back");
+            seen = 1;
+        }
+    }
+    for (int i = 0; i < np; i++)
+        if (s->prims[i].parent >= 0 && !prim_seen[i]) return fail(RTC_ERR_INVALID, "primitive " + std::to_string(i) + ": not in its parent's child list");
+    for (int i = 0; i < nn; i++) {
+        if (s->nodes[i].parent >= 0 && !node_seen[i]) return fail(RTC_ERR_INVALID, "node " + std::to_string(i) + ": not in its parent's child list");
+        int steps = 0;
+        for (int a = s->nodes[i].parent; a >= 0; a = s->nodes[a].parent)
+            if (++steps > nn) return fail(RTC_ERR_INVALID, "node parents form a cycle");
     }
     for (const RtcMaterial& m : s->materials)
         if (m.pattern < -1 || m.pattern >= (int)s->patterns.size()) return fail(RTC_ERR_INVALID, "material: bad pattern index");
@@ -502,6 +550,10 @@ int flatten(RtcScene* s, Flattened& f) {
         while ((1u << builder.par_depth) < hw && builder.par_depth < 5) builder.par_depth++;  // up to 32 subtree tasks
         f.bvh.reserve(build_items.size());
         int root = builder.build(0, (int)build_items.size(), 0);
+        f.bvh_depth = builder.max_depth + 1;
+        if (f.bvh_depth > kBvhStack - 1)  // cannot happen (Builder::build balances before the cap); never silent if it does
+            return fail(RTC_ERR_CAPACITY, "BVH depth " + std::to_string(f.bvh_depth) + " exceeds the traversal stack (" +
+                                              std::to_string(kBvhStack) + ")");
         if (root < 0) {  // a single leaf: wrap it so the traversal always starts at an inner node
             DevBvhNode n;
             Box b;

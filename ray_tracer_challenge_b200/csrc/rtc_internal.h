@@ -96,6 +96,7 @@ struct Flattened {
     std::vector<DevUvPattern> uvs;
     std::vector<float4> texels;
     int leaf_size = 0;  // the BVH leaf size used
+    int bvh_depth = 0;  // inner-node levels of the tree (<= kBvhStack - 1, enforced by the builder)
     std::vector<float4> samples;
     SmallScene small{};
     int bvh_root = -1;

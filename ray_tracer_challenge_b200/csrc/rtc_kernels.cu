@@ -101,7 +101,30 @@ __global__ void __launch_bounds__(128, SMALL ? (CONVERGE ? RTC_SMALL_CONVERGE_MI
     }
     if (CONVERGE || rendered)
         c = color_at<STATS, SMALL, CONVERGE, DRAWN>(E, rendered, o, d, F.depth, (unsigned)(y * S.width + x), r, k, nullptr, nullptr);
-    if (inside) {
+    // Canvas::write_pixel + scale_color (canvas.rs:26-43).  A tile that lies wholly inside a frame whose width is a
+    // multiple of the tile width is staged in shared memory as the 16x8 RGB block it is in the canvas (8 rows of
+    // 192 B f32 / 48 B u8, every row 16-byte aligned in global memory) and written with 16-byte streaming stores: 96
+    // STG.128 for the f32 plane and 24 for the 8-bit plane per block, instead of 6 scalar stores per thread at
+    // 12- / 3-byte strides.  Other tiles (ragged right / bottom edge, odd widths) keep the per-pixel stores.
+    __shared__ __align__(16) float s_rgb[kTileH * kTileW * 3];
+    __shared__ __align__(16) unsigned char s_u8[kTileH * kTileW * 3];
+    const bool whole_tile = (S.width % kTileW) == 0 && band * kBandRows + kTileH <= S.height;  // block-uniform
+    if (whole_tile) {
+        const int local = (((warp >> 1) * 4 + (lane >> 3)) * kTileW + (warp & 1) * 8 + (lane & 7)) * 3;
+        s_rgb[local] = c.x, s_rgb[local + 1] = c.y, s_rgb[local + 2] = c.z;
+        s_u8[local] = scale_color(c.x), s_u8[local + 1] = scale_color(c.y), s_u8[local + 2] = scale_color(c.z);
+        __syncthreads();
+        const int t = threadIdx.x;
+        const size_t px0 = (size_t)band * kBandRows * S.width + (size_t)bx * kTileW;  // the tile's first pixel
+        if (F.rgb && t < kTileH * 12) {  // 12 float4 per tile row
+            const int row = t / 12, q = t - row * 12;
+            __stcs(reinterpret_cast<float4*>(F.rgb + (px0 + (size_t)row * S.width) * 3) + q, reinterpret_cast<const float4*>(s_rgb)[t]);
+        }
+        if (F.u8 && t >= 128 - kTileH * 3) {  // 3 uint4 per tile row: the last 24 threads (another warp than most f32 stores)
+            const int u = t - (128 - kTileH * 3), row = u / 3, q = u - row * 3;
+            __stcs(reinterpret_cast<uint4*>(F.u8 + (px0 + (size_t)row * S.width) * 3) + q, reinterpret_cast<const uint4*>(s_u8)[u]);
+        }
+    } else if (inside) {
         size_t idx = ((size_t)y * S.width + x) * 3;
         if (F.rgb) {
             F.rgb[idx] = c.x;
@@ -119,7 +142,9 @@ __global__ void __launch_bounds__(128, SMALL ? (CONVERGE ? RTC_SMALL_CONVERGE_MI
         atomicMax(&F.tile_cost[band * gridDim.x + bx], (unsigned)min(clock64() - t_start, 0xffffffffLL));
 }
 
-template <bool SMALL>
+// DRAWN: as in render_tiles — a small scene whose area light draws its jitter (`jitter_fn = None`) takes the
+// drawn-sample cell loop; without it intensity_cells would read light samples nobody staged.
+template <bool SMALL, bool DRAWN>
 __global__ void __launch_bounds__(128) trace_rays(const __grid_constant__ DevScene S, const __grid_constant__ SmallScene SS, int n,
                                                   const float* origins, const float* directions, int depth, float* out_rgb,
                                                   float* out_t, int* out_pos, DevCounters* counters) {
@@ -133,7 +158,7 @@ __global__ void __launch_bounds__(128) trace_rays(const __grid_constant__ DevSce
     if (active) o = ld3(origins + 3 * (size_t)i), d = ld3(directions + 3 * (size_t)i);
     float t = -1.0f;
     int pos = -1;
-    const V3 c = color_at<false, SMALL, true>(E, active, o, d, depth, (unsigned)i, r, k, &t, &pos);
+    const V3 c = color_at<false, SMALL, true, DRAWN>(E, active, o, d, depth, (unsigned)i, r, k, &t, &pos);
     if (active) {
         out_rgb[3 * (size_t)i] = c.x;
         out_rgb[3 * (size_t)i + 1] = c.y;
@@ -180,10 +205,14 @@ void launch_render(const DevScene& S, const SmallScene& SS, const DevFrame& F, D
 void launch_trace(const DevScene& S, const SmallScene& SS, int n, const float* origins, const float* directions, int depth,
                   float* out_rgb, float* out_t, int* out_pos, DevCounters* counters, cudaStream_t stream) {
     if (n <= 0) return;
-    if (SS.n > 0)
-        trace_rays<true><<<(n + 127) / 128, 128, kSmallSmemBytes, stream>>>(S, SS, n, origins, directions, depth, out_rgb, out_t, out_pos, counters);
+    const bool small = SS.n > 0;
+    const bool drawn = small && SS.cell_masks && S.jitter_len == 0;  // the predicate of launch_render
+    if (drawn)
+        trace_rays<true, true><<<(n + 127) / 128, 128, kSmallSmemBytes, stream>>>(S, SS, n, origins, directions, depth, out_rgb, out_t, out_pos, counters);
+    else if (small)
+        trace_rays<true, false><<<(n + 127) / 128, 128, kSmallSmemBytes, stream>>>(S, SS, n, origins, directions, depth, out_rgb, out_t, out_pos, counters);
     else
-        trace_rays<false><<<(n + 127) / 128, 128, 0, stream>>>(S, SS, n, origins, directions, depth, out_rgb, out_t, out_pos, counters);
+        trace_rays<false, false><<<(n + 127) / 128, 128, 0, stream>>>(S, SS, n, origins, directions, depth, out_rgb, out_t, out_pos, counters);
 }
 
 #ifndef RTC_STRICT

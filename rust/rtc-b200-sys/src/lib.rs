@@ -14,6 +14,7 @@ pub const RTC_ERR_INVALID: c_int = -1;
 pub const RTC_ERR_NO_DEVICE: c_int = -2;
 pub const RTC_ERR_CAPACITY: c_int = -3;
 pub const RTC_ERR_STATE: c_int = -4;
+pub const RTC_ERR_CUDA: c_int = -5;
 
 pub const RTC_SPHERE: i32 = 0;
 pub const RTC_PLANE: i32 = 1;
@@ -23,6 +24,24 @@ pub const RTC_CONE: i32 = 4;
 pub const RTC_TRIANGLE: i32 = 5;
 pub const RTC_NODE_GROUP: i32 = 0;
 pub const RTC_NODE_CSG: i32 = 1;
+pub const RTC_CSG_UNION: i32 = 0;
+pub const RTC_CSG_INTERSECTION: i32 = 1;
+pub const RTC_CSG_DIFFERENCE: i32 = 2;
+pub const RTC_PAT_STRIPES: i32 = 0;
+pub const RTC_PAT_GRADIENT: i32 = 1;
+pub const RTC_PAT_RINGS: i32 = 2;
+pub const RTC_PAT_CHECKERS: i32 = 3;
+pub const RTC_PAT_SINE2D: i32 = 4;
+pub const RTC_PAT_TEST: i32 = 5;
+pub const RTC_PAT_TEXTURE_MAP: i32 = 6;
+pub const RTC_PAT_CUBIC_MAP: i32 = 7;
+pub const RTC_UV_CHECKERS: i32 = 0;
+pub const RTC_UV_ALIGN_CHECK: i32 = 1;
+pub const RTC_UV_IMAGE: i32 = 2;
+pub const RTC_MAP_SPHERICAL: i32 = 0;
+pub const RTC_MAP_PLANAR: i32 = 1;
+pub const RTC_MAP_CYLINDRICAL: i32 = 2;
+pub const RTC_BAND_ROWS: u32 = 8;
 pub const RTC_OPT_FMA_CONTRACTION: i32 = 1;
 pub const RTC_OPT_BVH_LEAF_SIZE: i32 = 2;
 pub const RTC_OPT_BVH_MIN_PRIMS: i32 = 3;
@@ -143,6 +162,7 @@ pub struct RtcCommitInfo {
     pub converge: i32,
     pub tol_sphere: f32,
     pub light_ball: [f32; 4],
+    pub bvh_depth: i32,
     pub host_ms: f64,
     pub digest: u64,
 }

@@ -189,3 +189,179 @@ def test_ctypes_mirrors_have_the_layout_of_the_header(tmp_path):
         assert name == m.__name__
         assert int(size) == C.sizeof(m), (name, size, C.sizeof(m))
         assert [int(o) for o in offsets] == [getattr(m, f).offset for f, _ in m._fields_], name
+
+
+def _raw_scene(lib, rt):
+    """A scene handle with a camera, a point light and one default material — through the raw C ABI."""
+    ident = (C.c_float * 16)(1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1)
+    lib.rtc_last_error.restype = C.c_char_p
+    lib.rtc_set_camera.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_float, C.c_float, C.c_float, C.POINTER(C.c_float)]
+    scene = C.c_void_p()
+    assert lib.rtc_scene_create(C.byref(scene)) == 0
+    assert lib.rtc_set_camera(scene, 64, 32, 1.0, 0.5, 2.0 / 64, ident) == 0
+    pos, rgb = (C.c_float * 3)(-10, 10, -10), (C.c_float * 3)(1, 1, 1)
+    assert lib.rtc_set_point_light(scene, pos, rgb) == 0
+
+    class RtcMaterial(C.Structure):
+        _fields_ = [("color", C.c_float * 3), ("v", C.c_float * 7), ("pattern", C.c_int32)]
+
+    mat = RtcMaterial()
+    mat.color[:], mat.v[:], mat.pattern = [1, 1, 1], [0.1, 0.9, 0.9, 200.0, 0.0, 0.0, 1.0], -1
+    assert lib.rtc_set_materials(scene, 1, C.byref(mat)) == 0
+    return scene, ident
+
+
+def _sphere(rt, ident, centre=(0.0, 0.0, 0.0), parent=-1):
+    p = rt.RtcPrim()
+    p.type, p.material, p.casts_shadow, p.parent = 0, 0, 1, parent
+    p.inv[:] = list(ident)
+    p.inv[3], p.inv[7], p.inv[11] = -centre[0], -centre[1], -centre[2]
+    p.bbox_min[:] = [c - 1 for c in centre]
+    p.bbox_max[:] = [c + 1 for c in centre]
+    return p
+
+
+def test_node_graph_must_be_a_forest():
+    """parent cycles (A -> B -> A) would spin the device's cull-chain walk, reference cycles would recurse
+    the CSG emitter; links that disagree are rejected too.  All without a device (rtc_scene_inspect)."""
+    import ray_tracer_challenge_b200 as rt
+
+    lib = C.CDLL(rt.LIB_DEVICE)
+    scene, ident = _raw_scene(lib, rt)
+    info = rt.RtcCommitInfo()
+    lib.rtc_set_nodes.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(rt.RtcNode), C.c_uint32, C.POINTER(C.c_int32)]
+
+    def group(parent, begin, count):
+        n = rt.RtcNode()
+        n.kind, n.parent, n.op, n.child_begin, n.child_count = 0, parent, 0, begin, count
+        n.inv[:] = list(ident)
+        n.bbox_min[:], n.bbox_max[:] = [-1, -1, -1], [1, 1, 1]
+        n.world_bbox_min[:], n.world_bbox_max[:] = [-1, -1, -1], [1, 1, 1]
+        return n
+
+    def inspect(prims, nodes, refs):
+        pa = (rt.RtcPrim * len(prims))(*prims)
+        na = (rt.RtcNode * len(nodes))(*nodes)
+        ra = (C.c_int32 * max(len(refs), 1))(*refs)
+        assert lib.rtc_set_primitives(scene, len(prims), pa) == 0
+        assert lib.rtc_set_nodes(scene, len(nodes), na, len(refs), ra) == 0
+        rc = lib.rtc_scene_inspect(scene, C.byref(info))
+        return rc, lib.rtc_last_error()
+
+    # a well-formed group of one sphere
+    rc, _ = inspect([_sphere(rt, ident, parent=0)], [group(-1, 0, 1)], [0])
+    assert rc == 0
+    # A's parent is B and B's parent is A; each lists the other as its child
+    rc, msg = inspect([_sphere(rt, ident)], [group(1, 0, 1), group(0, 1, 1)], [~1, ~0])
+    assert rc == -1 and b"cycle" in msg
+    # the sphere says its parent is node 0, but node 0 does not list it
+    rc, msg = inspect([_sphere(rt, ident, parent=0)], [group(-1, 0, 0)], [])
+    assert rc == -1 and b"child list" in msg
+    # node 0 lists the sphere, but the sphere claims no parent
+    rc, msg = inspect([_sphere(rt, ident, parent=-1)], [group(-1, 0, 1)], [0])
+    assert rc == -1 and b"point back" in msg
+    # the same child twice
+    rc, msg = inspect([_sphere(rt, ident, parent=0)], [group(-1, 0, 2)], [0, 0])
+    assert rc == -1 and b"twice" in msg
+    lib.rtc_scene_destroy(scene)
+
+
+def test_jitter_table_that_does_not_divide_the_draws_is_rejected():
+    """the reference's table closure carries its cursor across intensity_at calls (test/utils.rs); restarting
+    it per call is the same thing only when the table length divides 2 * u_steps * v_steps."""
+    import ray_tracer_challenge_b200 as rt
+
+    lib = C.CDLL(rt.LIB_DEVICE)
+    scene, _ = _raw_scene(lib, rt)
+    v3 = lambda *a: (C.c_float * 3)(*a)
+    lib.rtc_set_rect_light.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_int32,
+                                       C.POINTER(C.c_float), C.c_int32, C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_uint32,
+                                       C.c_uint64]
+    table5 = (C.c_float * 5)(0.7, 0.3, 0.9, 0.1, 0.5)
+    args = (v3(1, 1, 1), v3(0, 0, 0), v3(1, 0, 0))
+    # 2 * 4 * 4 = 32 draws: 5 does not divide them, 4 and 32 do; 10 x 10 cells = 200 draws: 5 does
+    assert lib.rtc_set_rect_light(scene, *args, 4, v3(0, 1, 0), 4, v3(0.5, 0.5, 0), table5, 5, 0) == -1
+    assert b"does not divide" in lib.rtc_last_error()
+    assert lib.rtc_set_rect_light(scene, *args, 4, v3(0, 1, 0), 4, v3(0.5, 0.5, 0), table5, 4, 0) == 0
+    assert lib.rtc_set_rect_light(scene, *args, 10, v3(0, 1, 0), 10, v3(0.5, 0.5, 0), table5, 5, 0) == 0
+    assert lib.rtc_set_rect_light(scene, *args, 4, v3(0, 1, 0), 4, v3(0.5, 0.5, 0), None, 0, 7) == 0  # counter mode
+    lib.rtc_scene_destroy(scene)
+
+
+@pytest.mark.parametrize("layout", ["coincident", "geometric", "line"])
+def test_bvh_depth_is_bounded_for_degenerate_scenes(layout):
+    """the traversal stack (48 entries) must never be asked to hold more than the builder allows.
+    10^5 spheres with one centroid, with geometrically shrinking spacing (SAH peels one sphere per level) and on a line:
+    the tree stays below the cap, without a device."""
+    import numpy as np
+
+    import ray_tracer_challenge_b200 as rt
+
+    lib = C.CDLL(rt.LIB_DEVICE)
+    scene, ident = _raw_scene(lib, rt)
+    n = 100_000
+    prims = (rt.RtcPrim * n)()
+    base = _sphere(rt, ident)
+    for i in range(n):
+        C.memmove(C.byref(prims[i]), C.byref(base), C.sizeof(rt.RtcPrim))
+    if layout != "coincident":
+        xs = np.cumsum(2.0 ** -np.arange(n, dtype=np.float64).clip(max=100)) * 1e3 if layout == "geometric" else np.arange(n) * 2.5
+        arr = np.ctypeslib.as_array(C.cast(prims, C.POINTER(C.c_float)), shape=(n, C.sizeof(rt.RtcPrim) // 4))
+        inv_off, lo_off, hi_off = rt.RtcPrim.inv.offset // 4, rt.RtcPrim.bbox_min.offset // 4, rt.RtcPrim.bbox_max.offset // 4
+        arr[:, inv_off + 3] = -xs
+        arr[:, lo_off] = xs - 1
+        arr[:, hi_off] = xs + 1
+    assert lib.rtc_set_primitives(scene, n, prims) == 0
+    info = rt.RtcCommitInfo()
+    assert lib.rtc_scene_inspect(scene, C.byref(info)) == 0, lib.rtc_last_error()
+    assert info.n_bvh_nodes >= n // 16 and 17 <= info.bvh_depth <= 47, info.bvh_depth
+    lib.rtc_scene_destroy(scene)
+
+
+def test_rust_sys_crate_mirrors_the_header(tmp_path):
+    """The `#[repr(C)]` structs of rust/rtc-b200-sys/src/lib.rs (not compilable here: no Rust toolchain) declare the same
+    fields, in the same order, with the same element types and array lengths, as include/rtc_b200.h — and every
+    `rtc_*` function of the header is declared in the crate's `extern "C"` block."""
+    header = open(os.path.join(ROOT, "include", "rtc_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    rust = open(os.path.join(ROOT, "rust", "rtc-b200-sys", "src", "lib.rs")).read()
+    rust = re.sub(r"//[^\n]*", "", rust)
+    c_to_rust = {"int32_t": "i32", "uint32_t": "u32", "uint64_t": "u64", "int64_t": "i64", "float": "f32", "double": "f64",
+                 "const float*": "*const f32"}
+
+    def c_fields(body):
+        out = []
+        for decl in body.split(";"):
+            decl = " ".join(decl.split())
+            if not decl:
+                continue
+            m = re.match(r"(const float\s*\*|\w+)\s*(.*)", decl)
+            ctype = "const float*" if m.group(1).startswith("const") else m.group(1)
+            for name in m.group(2).split(","):
+                name = name.strip()
+                arr = re.match(r"(\w+)\[(\d+)\]", name)
+                out.append((arr.group(1), f"[{c_to_rust[ctype]}; {arr.group(2)}]") if arr else (name, c_to_rust[ctype]))
+        return out
+
+    def rust_fields(body):
+        out = []
+        for name, ty in re.findall(r"pub\s+(\w+)\s*:\s*([^,\n]+)", body):
+            out.append((name[2:] if name.startswith("r#") else name, ty.strip()))
+        return out
+
+    structs = re.findall(r"typedef struct (\w+) \{(.*?)\} \1;", header, flags=re.S)
+    assert {n for n, _ in structs} >= {"RtcPrim", "RtcNode", "RtcMaterial", "RtcPattern", "RtcUvPattern", "RtcTexture", "RtcStats",
+                                      "RtcCommitInfo"}
+    for name, body in structs:
+        m = re.search(r"#\[repr\(C\)\][^{]*pub struct " + name + r"\s*\{(.*?)\n\}", rust, flags=re.S)
+        assert m, f"rtc-b200-sys lacks #[repr(C)] struct {name}"
+        want, got = c_fields(body), rust_fields(m.group(1))
+        want = [("type_" if f == "type" else f, t) for f, t in want]
+        got = [("type_" if f in ("type", "type_", "kind_") and False else f, t) for f, t in got]
+        assert [t for _, t in got] == [t for _, t in want], (name, got, want)
+        assert [f.rstrip("_") for f, _ in got] == [f.rstrip("_") for f, _ in want], (name, got, want)
+    for fn in declared("rtc_b200.h", "rtc_"):
+        assert re.search(r"pub fn " + fn + r"\s*\(", rust), f"rtc-b200-sys lacks `{fn}`"
+    for const in re.findall(r"\b(RTC_[A-Z0-9_]+)\s*=\s*(-?\d+)", header):
+        m = re.search(r"pub const " + const[0] + r"\s*:\s*\w+\s*=\s*(-?\d+)", rust)
+        assert m and m.group(1) == const[1], f"rtc-b200-sys: constant {const[0]} missing or different"

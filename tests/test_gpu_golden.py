@@ -195,3 +195,34 @@ def test_uv_image_on_gpu_matches_golden_table(gpu, oracle):
     want = np.asarray([oracle.probe.color_at(ow, o, (0, -1, 0), 0) for o in origins], np.float32)
     p.release()
     assert_abs_diff_eq(rgb, want, epsilon=0)
+
+
+def test_trace_rays_with_generated_jitter_matches_render_and_oracle(gpu, oracle):
+    """a small, filter-eligible scene whose area light DRAWS its jitter (`jitter_fn = None`,
+    rectangle_light.rs:46 -> the counter-based generator) takes the cell-mask path; rtc_trace_rays must run the
+    drawn-sample build of it like rtc_render does (it used to read light samples nobody had staged).  Ray i of a
+    trace is keyed as pixel i, so (a) tracing the camera's own rays reproduces the rendered frame bit for bit and
+    (b) a one-ray trace (pixel 0) equals the oracle's World::color_at, whose default path context is pixel 0."""
+    from ray_tracer_challenge_b200 import scenes
+
+    w, h = 48, 24
+    cam, world = scenes.soft_shadows(gpu, width=w, height=h, u_steps=4, v_steps=4, jitter=None, seed=5)
+    ocam, oworld = scenes.soft_shadows(oracle, width=w, height=h, u_steps=4, v_steps=4, jitter=None, seed=5)
+    plan = gpu.inspect(cam, world)
+    assert plan["small_n"] > 0 and plan["filter_ok"] and plan["cell_masks"], plan
+    rays = [oracle.probe.camera_ray(ocam, x, y) for y in range(h) for x in range(w)]
+    origins = np.asarray([o for o, _ in rays], np.float32)
+    dirs = np.asarray([d for _, d in rays], np.float32)
+    p = cam.prepare(world)
+    try:
+        frame = p.render(5).data
+        rgb, _, _ = p.trace_rays(origins, dirs, 5)
+        got = rgb.reshape(h, w, 3)[: h - 1, : w - 1]
+        assert np.array_equal(got, frame[: h - 1, : w - 1]), "trace_rays and render_tiles disagree on a drawn-jitter light"
+        assert len(np.unique(got[..., 0])) > 16, "the frame should show a penumbra"
+        for i in (0, 7 * w + 11, 13 * w + 30, 20 * w + 5, 22 * w + 40):
+            one, _, _ = p.trace_rays(origins[i:i + 1], dirs[i:i + 1], 5)
+            want = oracle.probe.color_at(oworld, origins[i], dirs[i], 5)
+            assert_abs_diff_eq(one[0], want, epsilon=EPS_STRICT, msg=f"ray {i}")
+    finally:
+        p.release()
