@@ -1167,14 +1167,24 @@ inline Color Pattern::color_at_object(Tuple world_point, const Shape& object) co
 struct World;
 
 // Counter-based stand-in for thread_rng().sample(OpenClosed01) (rectangle_light.rs:46): 24 random bits
-// mapped to (k+1)*2^-24 in (0,1].  Shared bit-for-bit with the device path (rtc_jitter.h semantics).
+// mapped to (k+1)*2^-24 in (0,1].  Shared bit-for-bit with the device path (dev_patterns.cuh: jitter_key / jitter_value).
+// 32-bit arithmetic throughout (two rounds of a multiply-xorshift finaliser per draw): a shade of a 4x4 light draws 32
+// values, and 64-bit multiplies cost a GPU six instructions each.  One key per (seed, pixel, path) — i.e. per
+// intensity_at call — then value i = mix(key + i * golden ratio).
+inline uint32_t jitter_mix32(uint32_t x) {
+    x ^= x >> 16;
+    x *= 0x7feb352du;
+    x ^= x >> 15;
+    x *= 0x846ca68bu;
+    x ^= x >> 16;
+    return x;
+}
+inline uint32_t jitter_key(uint64_t seed, uint32_t pixel, uint32_t path) {
+    uint32_t k = jitter_mix32((uint32_t)seed ^ pixel);
+    return jitter_mix32(k ^ (uint32_t)(seed >> 32) ^ (path * 0x9E3779B9u));
+}
 inline uint32_t jitter_hash(uint64_t seed, uint32_t pixel, uint32_t path, uint32_t index) {
-    uint64_t z = seed + 0x9E3779B97F4A7C15ull * (uint64_t)(pixel + 1u);
-    z ^= ((uint64_t)path << 32) | index;
-    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-    z = z ^ (z >> 31);
-    return (uint32_t)(z >> 32);
+    return jitter_mix32(jitter_key(seed, pixel, path) + index * 0x9E3779B9u);
 }
 inline float jitter_open_closed01(uint32_t bits) { return (float)((bits >> 8) + 1u) * 5.9604644775390625e-08f; }
 

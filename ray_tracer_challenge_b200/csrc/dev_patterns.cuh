@@ -111,15 +111,23 @@ __device__ __noinline__ V3 pattern_color(const DevScene& S, int pid, V3 object_p
 }
 
 // ---------------------------------------------------------------------------------------------------
-// Counter-based stand-in for thread_rng().sample(OpenClosed01) (rectangle_light.rs:46): identical to the
-// oracle's jitter_hash / jitter_open_closed01.
-__device__ __forceinline__ float jitter_value(unsigned long long seed, unsigned pixel, unsigned path, unsigned index) {
-    unsigned long long z = seed + 0x9E3779B97F4A7C15ull * (unsigned long long)(pixel + 1u);
-    z ^= ((unsigned long long)path << 32) | index;
-    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-    z = z ^ (z >> 31);
-    unsigned bits = (unsigned)(z >> 32);
+// Counter-based stand-in for thread_rng().sample(OpenClosed01) (rectangle_light.rs:46): identical to the oracle's
+// jitter_key / jitter_hash / jitter_open_closed01.  32-bit arithmetic only: one key per intensity_at call (seed, pixel,
+// path), then two IMADs and three shift-xors per drawn value.
+__device__ __forceinline__ unsigned jitter_mix32(unsigned x) {
+    x ^= x >> 16;
+    x *= 0x7feb352du;
+    x ^= x >> 15;
+    x *= 0x846ca68bu;
+    x ^= x >> 16;
+    return x;
+}
+__device__ __forceinline__ unsigned jitter_key(unsigned long long seed, unsigned pixel, unsigned path) {
+    const unsigned k = jitter_mix32((unsigned)seed ^ pixel);
+    return jitter_mix32(k ^ (unsigned)(seed >> 32) ^ (path * 0x9E3779B9u));
+}
+__device__ __forceinline__ float jitter_value(unsigned key, unsigned index) {
+    const unsigned bits = jitter_mix32(key + index * 0x9E3779B9u);
     return (float)((bits >> 8) + 1u) * 5.9604644775390625e-08f;
 }
 

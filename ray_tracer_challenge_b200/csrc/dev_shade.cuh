@@ -75,24 +75,28 @@ __device__ __forceinline__ V3 color_at(const Env& E, bool active, V3 ro, V3 rd, 
         if (best.pos >= 0) {
             // ---- precompute_values (world.rs:212-283)
             r.shades++;
-            int4 h = __ldg(&S.head[best.pos]);
-            int type = h.x & 15;
+            const int4 h = __ldg(&S.head[best.pos]);
             const DevMaterial& mat = S.materials[h.x >> 8];
-            Xf m = load_xf(S.xform + 3 * (size_t)h.y);
-            V3 point = ro + rd * best.t;
-            V3 object_point = xf_point(m, point);
-            V3 n = norm(xf_normal(m, local_normal(S, type, h.z, object_point)));  // shape.rs:148-154,130-145
-            V3 eye = -rd;
-            V3 reflectv = reflect(rd, n);
-            if (dot(n, eye) < 0.0f) n = -n;
-            V3 over_point = point + n * kAcne;
-            // ---- shade_hit (world.rs:62-86): light intensity first, then Phong (phong_lighting.rs:12-63)
-            float li = intensity_at<STATS, SMALL, DRAWN>(E, over_point, pixel, path, r, k);
-            V3 material_color = ld3(mat.color);
-            if (mat.pattern >= 0) {
-                k.pattern();
-                material_color = pattern_color(S, mat.pattern, xf_point(m, over_point));  // pattern.rs:15-19 at over_point (Q4)
+            V3 n, over_point, material_color;
+            {
+                // everything that needs the hit primitive's transform happens here, BEFORE the light loop, so the
+                // twelve registers of `m` (and the hit point) are dead while intensity_at runs; the pattern colour
+                // (pattern.rs:15-19, evaluated at over_point, Q4) does not depend on the light
+                const Xf m = load_xf(S.xform + 3 * (size_t)h.y);
+                const V3 point = ro + rd * best.t;
+                const V3 object_point = xf_point(m, point);
+                n = norm(xf_normal(m, local_normal(S, h.x & 15, h.z, object_point)));  // shape.rs:148-154,130-145
+                if (dot(n, -rd) < 0.0f) n = -n;
+                over_point = point + n * kAcne;
+                material_color = ld3(mat.color);
+                if (mat.pattern >= 0) {
+                    k.pattern();
+                    material_color = pattern_color(S, mat.pattern, xf_point(m, over_point));
+                }
             }
+            // ---- shade_hit (world.rs:62-86): light intensity first, then Phong (phong_lighting.rs:12-63)
+            const float li = intensity_at<STATS, SMALL, DRAWN>(E, over_point, pixel, path, r, k);
+            const V3 eye = -rd;
             V3 light_rgb = ld3(S.light_rgb);
             V3 effective = material_color * light_rgb;
             V3 ambient = effective * mat.ambient;
@@ -160,22 +164,27 @@ __device__ __forceinline__ V3 color_at(const Env& E, bool active, V3 ro, V3 rd, 
                 f.path = path;
                 r.secondary++;
                 remaining = remaining - 1;
+                V3 under_point = over_point;
                 if (want_refr) {
+                    under_point = (ro + rd * best.t) - n * kAcne;  // `point` again: the same expression, the same bits
                     f.transparency = mat.transparency;
-                    f.refr_o = point - n * kAcne;  // under_point
+                    f.refr_o = under_point;
                     f.refr_d = refr_d;
                 }
                 if (want_refl) {
                     f.acc = surface;
                     f.reflective = mat.reflective;
                     f.flags = want_refr ? 2 : 0;
+                    // reflect(rd, n) (world.rs:225) is bit-for-bit the same for n and -n — every product and every sum
+                    // changes sign twice — so it is evaluated here from the flipped normal instead of being kept live
+                    // across the light loop
                     ro = over_point;
-                    rd = reflectv;
+                    rd = reflect(rd, n);
                     path = path * 3u + 1u;
                 } else {  // no reflection: reflected_color is black (world.rs:126-128)
                     f.acc = add_reflected(surface, mk(0.f, 0.f, 0.f), reflectance);
                     f.flags = 1;
-                    ro = point - n * kAcne;
+                    ro = under_point;
                     rd = refr_d;
                     path = path * 3u + 2u;
                 }
@@ -215,6 +224,9 @@ __device__ __forceinline__ V3 color_at(const Env& E, bool active, V3 ro, V3 rd, 
     }
     return result;
 }
+
+// is_shadowed calls of a thread's shades (see Rays)
+__device__ __forceinline__ void finish_rays(const DevScene& S, Rays& r) { r.shadow = r.shades * (unsigned)(S.light_is_rect ? S.cells : 1); }
 
 // Camera::ray_for_pixel (camera.rs:60-74)
 __device__ __forceinline__ void ray_for_pixel(const DevScene& S, int x, int y, V3& o, V3& d) {

@@ -150,7 +150,7 @@ __device__ __forceinline__ int filter_scan(const Env& E, bool cached, int begin,
         float4 r1 = tab[i * kSmallStride + 2];
         float oy;
         if (cached && i < kOrgCache)
-            oy = small_org()[(i * 3 + 1) * 128];
+            oy = small_org()[(i * 3 + 1) * kBlockThreads];
         else
             oy = r1.x * p.x + r1.y * p.y + r1.z * p.z + r1.w;
         k.xform();
@@ -195,7 +195,7 @@ __device__ __forceinline__ bool shadow_exact_small(const Env& E, bool cached, V3
     const SmallScene& SS = E.SS;
     V3 v = light_position - p;
     float distance = magnitude(v);
-    V3 direction = mk(v.x / distance, v.y / distance, v.z / distance);
+    V3 direction = div3(v, distance);
     // order -1: a hit AT the light distance is never accepted (`<`, world.rs:116)
     Hit best{distance, -1, -1};
     if (!SS.two_pass_shadows || SS.has_cull_chain) {  // a CSG root or a cull chain: plain nearest-hit search
@@ -233,12 +233,11 @@ __device__ __noinline__ bool shadow_query_small(const Env& E, bool cached, bool 
 }
 template <bool STATS, bool SMALL, bool CACHED>
 __device__ __forceinline__ bool is_shadowed(const Env& E, V3 light_position, V3 p, Rays& r, Ctr<STATS>& k) {
-    r.shadow++;
     if (SMALL) return shadow_query_small<STATS>(E, CACHED, false, light_position, p, k);
     const DevScene& S = E.S;
     V3 v = light_position - p;
     float distance = magnitude(v);
-    V3 direction = mk(v.x / distance, v.y / distance, v.z / distance);
+    V3 direction = div3(v, distance);
     Hit best{distance, -1, -1};  // order -1: a hit AT the light distance is never accepted (`<`, world.rs:116)
     if (S.all_cast_shadow) {
         nearest_hit<STATS, true>(S, p, direction, best, k);
@@ -316,7 +315,6 @@ __device__ __forceinline__ float intensity_cells(const Env& E, V3 p, unsigned pi
     const int cells = S.cells;
     const float tol = SS.tol_sphere;
     const int4 ends = SS.caster_end;
-    r.shadow += cells;
     int lit = 0;
     float4 drawn[TABLE ? 1 : 32];
     for (int c0 = 0; c0 < cells; c0 += 32) {
@@ -324,11 +322,12 @@ __device__ __forceinline__ float intensity_cells(const Env& E, V3 p, unsigned pi
         const unsigned full = nc == 32 ? 0xffffffffu : ((1u << nc) - 1u);
         if (!TABLE) {
             const V3 corner = ld3(S.corner), u_vec = ld3(S.u_vec), v_vec = ld3(S.v_vec);
+            const unsigned key = jitter_key(S.seed, pixel, path);
             for (int j = 0; j < nc; j++) {
                 const unsigned cell = (unsigned)(c0 + j);
                 const int v = (int)cell / S.u_steps, u = (int)cell - v * S.u_steps;
-                const float j1 = jitter_value(S.seed, pixel, path, 2u * cell);
-                const float j2 = jitter_value(S.seed, pixel, path, 2u * cell + 1u);
+                const float j1 = jitter_value(key, 2u * cell);
+                const float j2 = jitter_value(key, 2u * cell + 1u);
                 const V3 lp = corner + u_vec * ((float)u + j1) + v_vec * ((float)v + j2);
                 drawn[j] = make_float4(lp.x, lp.y, lp.z, 0.f);
             }
@@ -472,6 +471,7 @@ __device__ __forceinline__ float intensity_at(const Env& E, V3 p, unsigned pixel
     if (SMALL && E.SS.cell_masks)
         return DRAWN ? intensity_cells<STATS, false>(E, p, pixel, path, r, k) : intensity_cells<STATS, true>(E, p, pixel, path, r, k);
     if (SMALL) cache_origins(E, p);
+    const unsigned key = S.jitter_len > 0 ? 0u : jitter_key(S.seed, pixel, path);
     float total = 0.f;
     int cell = 0;
     for (int v = 0; v < S.v_steps; v++) {
@@ -482,8 +482,8 @@ __device__ __forceinline__ float intensity_at(const Env& E, V3 p, unsigned pixel
                 float4 s = __ldg(&S.samples[cell]);  // table mode: point_on_light is the same for every shade
                 lp = mk(s.x, s.y, s.z);
             } else {
-                float j1 = jitter_value(S.seed, pixel, path, 2u * cell);
-                float j2 = jitter_value(S.seed, pixel, path, 2u * cell + 1u);
+                float j1 = jitter_value(key, 2u * cell);
+                float j2 = jitter_value(key, 2u * cell + 1u);
                 // rectangle_light.rs:60-66
                 lp = ld3(S.corner) + ld3(S.u_vec) * ((float)u + j1) + ld3(S.v_vec) * ((float)v + j2);
             }

@@ -13,52 +13,41 @@ struct Env {
 };
 
 // Small scenes keep these in (dynamic) shared memory, kSmallSmemBytes in all:
-//   tab     : the primitive table, kSmallStride x float4 per primitive {head, row0, row1, row2, bound, ball}, copied
-//             from the parameter block by stage_small_scene — every thread of a warp reads the same entry, so a row
-//             is one broadcast LDS.128 with an immediate offset;
-//   org     : per thread, the object-space origin of the current shade's shadow rays for the first kOrgCache
-//             primitives (element (i, c) of thread t at org[(i * 3 + c) * 128 + t]) — the per-cell shadow loop;
+//   tab     : the primitive table, kSmallStride x float4 per primitive {head, row0, row1, row2, bound, ball} — every
+//             thread of a warp reads the same entry, so a row is one broadcast LDS.128 with an immediate offset;
 //   samples : table-mode area light: the `cells` sample points (cell-mask loops, intensity_cells);
-//   plane cells : per (caster plane, cell) the constants of filter_plane_cell.
+//   plane cells : per (caster plane, cell) the constants of filter_plane_cell (rtc_types.h: plane_cell_constants);
+//   org     : per thread, the object-space origin of the current shade's shadow rays for the first kOrgCache
+//             primitives (element (i, c) of thread t at org[(i * 3 + c) * kBlockThreads + t]) — the per-cell shadow loop.
+// The first three are the same for every block: stage_small_scene copies them from the scene's image.
 __device__ __forceinline__ const float4* small_tab() {
     extern __shared__ float4 rtc_smem[];
     return rtc_smem;
 }
 __device__ __forceinline__ float* small_org() {
     extern __shared__ float4 rtc_smem[];
-    return reinterpret_cast<float*>(rtc_smem + kSmallCap * kSmallStride) + threadIdx.x;
-}
-// Shadow filter, plane test with the light sample folded in (SmallScene::plane_cells): for light point L and shading
-// point p the object-space direction's y is r1.L - r1.p, so everything that depends on L alone is staged once per
-// block: {r1.L, tol * sum|r1_k L_k|, EPSILON' * |L|_1}.  See filter_plane_cell.
-constexpr float kTolP = 3.814697265625e-06f;  // 2^-18 = 64 ulp: planes and cubes (bounds are term-wise, no conditioning)
-__device__ __forceinline__ float4 plane_cell_constants(float4 r1, float4 L) {
-    const float px = r1.x * L.x, py = r1.y * L.y, pz = r1.z * L.z;
-    return make_float4(px + py + pz, kTolP * (fabsf(px) + fabsf(py) + fabsf(pz)),
-                       (1.1920929e-3f * (1.0f + 2.0f * kTolP)) * (fabsf(L.x) + fabsf(L.y) + fabsf(L.z)), 0.0f);
+    return reinterpret_cast<float*>(rtc_smem + kSmemOrg) + threadIdx.x;
 }
 __device__ __forceinline__ const float4* small_plane_cells() {
     extern __shared__ float4 rtc_smem[];
-    return rtc_smem + kSmallCap * kSmallStride + kOrgCache * 3 * 128 / 4 + kSampleCap;
+    return rtc_smem + kSmemPlaneCells;
 }
 __device__ __forceinline__ const float4* small_samples() {  // table-mode light samples (SmallScene::cell_masks)
     extern __shared__ float4 rtc_smem[];
-    return rtc_smem + kSmallCap * kSmallStride + kOrgCache * 3 * 128 / 4;
+    return rtc_smem + kSmemSamples;
 }
+// A block's staging: three coalesced copies out of the scene's image (L2 / L1 resident after the first blocks), each
+// started by a different warp so that no warp does all of it while the others wait at the barrier.
 __device__ __forceinline__ void stage_small_scene(const DevScene& S, const SmallScene& SS) {
     extern __shared__ float4 rtc_smem[];
-    const float4* src = reinterpret_cast<const float4*>(SS.p);
-    for (int i = threadIdx.x; i < SS.n * kSmallStride; i += blockDim.x) rtc_smem[i] = src[i];
+    const float4* img = S.small_image;
+    const int t = threadIdx.x, nt = blockDim.x;
+    for (int i = t; i < SS.n * kSmallStride; i += nt) rtc_smem[i] = __ldg(img + i);
     if (SS.cell_masks && S.jitter_len > 0) {
-        float4* dst = rtc_smem + kSmallCap * kSmallStride + kOrgCache * 3 * 128 / 4;
-        for (int i = threadIdx.x; i < S.cells; i += blockDim.x) dst[i] = __ldg(&S.samples[i]);
-        if (SS.plane_cells) {  // see plane_cell_constants
-            const int n_planes = SS.caster_end.y - SS.caster_end.x;
-            for (int i = threadIdx.x; i < n_planes * S.cells; i += blockDim.x) {
-                const float4 r1 = SS.p[SS.caster_end.x + i / S.cells].r1;
-                const float4 L = __ldg(&S.samples[i % S.cells]);
-                dst[kSampleCap + i] = plane_cell_constants(r1, L);
-            }
+        for (int i = (t + nt - 32) % nt; i < S.cells; i += nt) rtc_smem[kSmemSamples + i] = __ldg(img + kSmemSamples + i);
+        if (SS.plane_cells) {
+            const int n = (SS.caster_end.y - SS.caster_end.x) * S.cells;
+            for (int i = (t + nt - 64) % nt; i < n; i += nt) rtc_smem[kSmemPlaneCells + i] = __ldg(img + kSmemPlaneCells + i);
         }
     }
     __syncthreads();
@@ -70,7 +59,7 @@ __device__ __forceinline__ void stage_small_scene(const DevScene& S, const Small
 __device__ __forceinline__ V3 small_origin(bool cached, int i, const Xf& m, V3 o) {
     if (cached && i < kOrgCache) {
         const float* org = small_org();
-        return mk(org[(i * 3 + 0) * 128], org[(i * 3 + 1) * 128], org[(i * 3 + 2) * 128]);
+        return mk(org[(i * 3 + 0) * kBlockThreads], org[(i * 3 + 1) * kBlockThreads], org[(i * 3 + 2) * kBlockThreads]);
     }
     return xf_point(m, o);
 }
@@ -82,9 +71,9 @@ __device__ __forceinline__ void cache_origins(const Env& E, V3 o) {
     for (int i = 0; i < n; i++) {
         Xf m{tab[i * kSmallStride + 1], tab[i * kSmallStride + 2], tab[i * kSmallStride + 3]};
         V3 o2 = xf_point(m, o);
-        org[(i * 3 + 0) * 128] = o2.x;
-        org[(i * 3 + 1) * 128] = o2.y;
-        org[(i * 3 + 2) * 128] = o2.z;
+        org[(i * 3 + 0) * kBlockThreads] = o2.x;
+        org[(i * 3 + 1) * kBlockThreads] = o2.y;
+        org[(i * 3 + 2) * kBlockThreads] = o2.z;
     }
 }
 
@@ -157,7 +146,7 @@ __device__ __forceinline__ bool scan_small_impl(const Env& E, bool cached, const
         float4 r1 = tab[i * kSmallStride + 2];
         float oy;
         if (cached && i < kOrgCache)
-            oy = small_org()[(i * 3 + 1) * 128];
+            oy = small_org()[(i * 3 + 1) * kBlockThreads];
         else
             oy = r1.x * o.x + r1.y * o.y + r1.z * o.z + r1.w;
         float dy = r1.x * d.x + r1.y * d.y + r1.z * d.z;

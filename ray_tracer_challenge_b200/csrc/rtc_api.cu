@@ -199,7 +199,7 @@ int upload_replica(RtcScene* s, const Flattened& f, Replica& r, int device) {
     size_t o_jitter = w.add(s->jitter), o_samples = w.add(f.samples), o_head = w.add(f.head), o_rec = w.add(f.rec);
     size_t o_xform = w.add(f.xform), o_tri = w.add(f.tri), o_bound = w.add(f.bound), o_bvh = w.add(f.bvh);
     size_t o_linear = w.add(f.linear), o_nodes = w.add(f.nodes), o_ops = w.add(f.ops), o_mat = w.add(f.materials);
-    size_t o_pat = w.add(f.patterns), o_uv = w.add(f.uvs), o_tex = w.add(f.texels);
+    size_t o_pat = w.add(f.patterns), o_uv = w.add(f.uvs), o_tex = w.add(f.texels), o_img = w.add(f.small_image);
     if ((rc = ensure_arena(slot, std::max<size_t>(w.bytes, 256)))) return rc;
     for (const auto& p : w.parts) memcpy(slot->staging + p.off, p.src, p.n);
     if (w.bytes) CUDA_TRY(cudaMemcpyAsync(slot->arena, slot->staging, w.bytes, cudaMemcpyHostToDevice, slot->stream));
@@ -219,6 +219,7 @@ int upload_replica(RtcScene* s, const Flattened& f, Replica& r, int device) {
     d.patterns = (const DevPattern*)at(o_pat, !f.patterns.empty());
     d.uvs = (const DevUvPattern*)at(o_uv, !f.uvs.empty());
     d.texels = (const float4*)at(o_tex, !f.texels.empty());
+    d.small_image = (const float4*)at(o_img, !f.small_image.empty());
     d.n_linear = (int)f.linear.size();
     d.bvh_root = f.bvh_root;
     d.n_prims = f.n_pos;
@@ -240,8 +241,10 @@ double flops_of(const RtcStats& st, uint64_t pixels) {
     return f;
 }
 
-void add_counters(RtcStats& st, const DevCounters& c) {
-    st.primary_rays += c.primary, st.secondary_rays += c.secondary, st.shadow_rays += c.shadow, st.shades += c.shades;
+// The device accumulates the secondary rays and the shades; `primary` is what the host knows the launch rendered, and
+// every shade_hit casts one shadow ray per light cell (point light: one) — rectangle_light.rs:76-88, point_light.rs:28-34.
+void add_counters(RtcStats& st, const DevCounters& c, uint64_t primary, uint64_t shadow_per_shade) {
+    st.primary_rays += primary, st.secondary_rays += c.secondary, st.shadow_rays += c.shades * shadow_per_shade, st.shades += c.shades;
     st.node_visits += c.node_visits;
     for (int i = 0; i < 8; i++) st.prim_tests[i] += c.prim_tests[i];
     st.xforms += c.xforms, st.patterns += c.patterns, st.cells += c.cells, st.schlicks += c.schlicks;
@@ -367,7 +370,14 @@ int render_impl(RtcScene* s, int depth, int shard0, int n_shards_ext, float* rgb
         st.kernel_ms = std::max(st.kernel_ms, (double)ms);
         DevCounters c;
         CUDA_TRY(cudaMemcpy(&c, slot->d_counters, sizeof(c), cudaMemcpyDeviceToHost));
-        add_counters(st, c);
+        {
+            // camera.rs:80-81: rows y < h - 1 and columns x < w - 1 of this shard's bands
+            const int shard = external ? shard0 : i;
+            uint64_t rows = 0;
+            for (int b = shard; b < total_bands; b += n_shards)
+                rows += (uint64_t)std::max(0, std::min<int>((int)s->height - 1, (b + 1) * kBandRows) - b * kBandRows);
+            add_counters(st, c, rows * (uint64_t)(s->width - 1), s->light_is_rect ? (uint64_t)s->u_steps * s->v_steps : 1);
+        }
         Replica& r = s->replicas[i];
         r.renders_done++;
         if (r.order_timed) {

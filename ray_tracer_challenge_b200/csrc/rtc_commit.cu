@@ -452,6 +452,18 @@ void plan_small_scene(const RtcScene* s, Flattened& f, int n_items) {
             }
         }
         f.small.tol_sphere = (float)(std::ldexp(1.0, -24) * 64.0 * (worst + 1.0));
+        // ---- the image every block stages into shared memory (dev_small.cuh: stage_small_scene)
+        f.small_image.assign(kSmemOrg, make_float4(0.f, 0.f, 0.f, 0.f));
+        memcpy(f.small_image.data(), f.small.p, (size_t)n_items * sizeof(SmallPrim));
+        static_assert(sizeof(SmallPrim) == kSmallStride * sizeof(float4), "table entry layout");
+        if (table_light) {
+            std::copy(f.samples.begin(), f.samples.end(), f.small_image.begin() + kSmemSamples);
+            if (f.small.plane_cells)
+                for (int q = 0; q < ends[1] - ends[0]; q++)
+                    for (size_t c = 0; c < f.samples.size(); c++)
+                        f.small_image[kSmemPlaneCells + (size_t)q * f.samples.size() + c] =
+                            plane_cell_constants(f.small.p[ends[0] + q].r1, f.samples[c]);
+        }
     }
 }
 

@@ -98,6 +98,7 @@ struct Flattened {
     int leaf_size = 0;  // the BVH leaf size used
     int bvh_depth = 0;  // inner-node levels of the tree (<= kBvhStack - 1, enforced by the builder)
     std::vector<float4> samples;
+    std::vector<float4> small_image;  // small scenes: what every block stages (rtc_types.h: kSmemOrg float4)
     SmallScene small{};
     int bvh_root = -1;
     int n_pos = 0;

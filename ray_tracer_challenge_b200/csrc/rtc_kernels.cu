@@ -40,10 +40,10 @@ __device__ __forceinline__ void warp_add(unsigned long long* dst, unsigned v) {
     unsigned s = __reduce_add_sync(0xffffffffu, v);
     if ((threadIdx.x & 31) == 0 && s) atomicAdd(dst, (unsigned long long)s);
 }
+// primary and shadow are not accumulated: the host knows how many pixels a launch renders, and every shade casts
+// exactly cells-of-the-light shadow rays (rtc_api.cu: add_counters)
 __device__ __forceinline__ void flush_rays(const Rays& r, DevCounters* out) {
-    warp_add(&out->primary, r.primary);
     warp_add(&out->secondary, r.secondary);
-    warp_add(&out->shadow, r.shadow);
     warp_add(&out->shades, r.shades);
 }
 __device__ __forceinline__ void warp_add_u32(unsigned* dst, unsigned v) {
@@ -68,9 +68,12 @@ __device__ __forceinline__ void flush_counters<true>(const Rays& r, const Ctr<tr
     warp_add(&out->prim_tests[7], k.refilters);  // shadow-filter fallbacks to the exact test
 }
 
+// the RTC_*_MINBLOCKS figures are resident blocks of 128 threads: the same warps per SM for any tile width
+constexpr int min_blocks(int of_128_threads) { return of_128_threads * 128 / kBlockThreads > 0 ? of_128_threads * 128 / kBlockThreads : 1; }
+
 template <bool STATS, bool SMALL, bool CONVERGE, bool DRAWN>
-__global__ void __launch_bounds__(128, SMALL ? (CONVERGE ? RTC_SMALL_CONVERGE_MINBLOCKS : RTC_SMALL_MINBLOCKS)
-                                             : (CONVERGE ? RTC_BVH_CONVERGE_MINBLOCKS : RTC_BVH_MINBLOCKS))
+__global__ void __launch_bounds__(kBlockThreads, min_blocks(SMALL ? (CONVERGE ? RTC_SMALL_CONVERGE_MINBLOCKS : RTC_SMALL_MINBLOCKS)
+                                                                       : (CONVERGE ? RTC_BVH_CONVERGE_MINBLOCKS : RTC_BVH_MINBLOCKS)))
     render_tiles(const __grid_constant__ DevScene S, const __grid_constant__ SmallScene SS,
                                                     const DevFrame F, DevCounters* counters) {
     // small scenes: primitive table + per-thread shadow-origin cache in dynamic shared memory (kSmallSmemBytes)
@@ -86,8 +89,8 @@ __global__ void __launch_bounds__(128, SMALL ? (CONVERGE ? RTC_SMALL_CONVERGE_MI
         band = id / (int)gridDim.x;
         bx = id - band * (int)gridDim.x;
     }
-    const int x = bx * kTileW + (warp & 1) * 8 + (lane & 7);
-    const int y = band * kBandRows + (warp >> 1) * 4 + (lane >> 3);
+    const int x = bx * kTileW + (warp % kWarpsX) * 8 + (lane & 7);
+    const int y = band * kBandRows + (warp / kWarpsX) * 4 + (lane >> 3);
     Ctr<STATS> k;
     Rays r;
     V3 c = mk(0.f, 0.f, 0.f);
@@ -95,34 +98,31 @@ __global__ void __launch_bounds__(128, SMALL ? (CONVERGE ? RTC_SMALL_CONVERGE_MI
     // camera.rs:80-81 — the last row and the last column are never rendered and stay black (canvas.rs:23)
     const bool rendered = inside && x < S.width - 1 && y < S.height - 1;
     V3 o = mk(0.f, 0.f, 0.f), d = mk(0.f, 0.f, 1.f);
-    if (rendered) {
-        ray_for_pixel(S, x, y, o, d);
-        r.primary++;
-    }
+    if (rendered) ray_for_pixel(S, x, y, o, d);
     if (CONVERGE || rendered)
         c = color_at<STATS, SMALL, CONVERGE, DRAWN>(E, rendered, o, d, F.depth, (unsigned)(y * S.width + x), r, k, nullptr, nullptr);
-    // Canvas::write_pixel + scale_color (canvas.rs:26-43).  A tile that lies wholly inside a frame whose width is a
-    // multiple of the tile width is staged in shared memory as the 16x8 RGB block it is in the canvas (8 rows of
-    // 192 B f32 / 48 B u8, every row 16-byte aligned in global memory) and written with 16-byte streaming stores: 96
-    // STG.128 for the f32 plane and 24 for the 8-bit plane per block, instead of 6 scalar stores per thread at
-    // 12- / 3-byte strides.  Other tiles (ragged right / bottom edge, odd widths) keep the per-pixel stores.
-    __shared__ __align__(16) float s_rgb[kTileH * kTileW * 3];
-    __shared__ __align__(16) unsigned char s_u8[kTileH * kTileW * 3];
-    const bool whole_tile = (S.width % kTileW) == 0 && band * kBandRows + kTileH <= S.height;  // block-uniform
-    if (whole_tile) {
-        const int local = (((warp >> 1) * 4 + (lane >> 3)) * kTileW + (warp & 1) * 8 + (lane & 7)) * 3;
-        s_rgb[local] = c.x, s_rgb[local + 1] = c.y, s_rgb[local + 2] = c.z;
-        s_u8[local] = scale_color(c.x), s_u8[local + 1] = scale_color(c.y), s_u8[local + 2] = scale_color(c.z);
-        __syncthreads();
-        const int t = threadIdx.x;
-        const size_t px0 = (size_t)band * kBandRows * S.width + (size_t)bx * kTileW;  // the tile's first pixel
-        if (F.rgb && t < kTileH * 12) {  // 12 float4 per tile row
-            const int row = t / 12, q = t - row * 12;
-            __stcs(reinterpret_cast<float4*>(F.rgb + (px0 + (size_t)row * S.width) * 3) + q, reinterpret_cast<const float4*>(s_rgb)[t]);
+    // Canvas::write_pixel + scale_color (canvas.rs:26-43).  A warp owns 8x4 pixels: four canvas rows of 96 B (f32) and
+    // 24 B (8-bit).  When the frame's width is a multiple of 8 those row pieces are 16- / 8-byte aligned in global memory,
+    // so the warp transposes its colours through shared memory and writes them as 24 STG.128 + 12 STG.64 streaming
+    // stores instead of six scalar stores per thread at 12- / 3-byte strides.  Warp-private staging: no block barrier,
+    // a warp that has finished its pixels leaves.  Ragged right / bottom edges and odd widths keep the per-pixel stores.
+    __shared__ __align__(16) float s_rgb[kBlockThreads * 3];
+    __shared__ __align__(16) unsigned char s_u8[kBlockThreads * 3];
+    const int wx0 = bx * kTileW + (warp % kWarpsX) * 8, wy0 = band * kBandRows + (warp / kWarpsX) * 4;  // warp-uniform
+    if ((S.width & 7) == 0 && wx0 + 8 <= S.width && wy0 + 4 <= S.height) {
+        float* w_rgb = s_rgb + warp * 96;          // [row 0..3][8 px][rgb]
+        unsigned char* w_u8 = s_u8 + warp * 96;
+        w_rgb[lane * 3] = c.x, w_rgb[lane * 3 + 1] = c.y, w_rgb[lane * 3 + 2] = c.z;
+        w_u8[lane * 3] = scale_color(c.x), w_u8[lane * 3 + 1] = scale_color(c.y), w_u8[lane * 3 + 2] = scale_color(c.z);
+        __syncwarp();
+        const size_t px0 = (size_t)wy0 * S.width + wx0;  // the warp's first pixel
+        if (F.rgb && lane < 24) {  // 6 float4 per row
+            const int row = lane / 6, q = lane - row * 6;
+            __stcs(reinterpret_cast<float4*>(F.rgb + (px0 + (size_t)row * S.width) * 3) + q, reinterpret_cast<const float4*>(w_rgb)[lane]);
         }
-        if (F.u8 && t >= 128 - kTileH * 3) {  // 3 uint4 per tile row: the last 24 threads (another warp than most f32 stores)
-            const int u = t - (128 - kTileH * 3), row = u / 3, q = u - row * 3;
-            __stcs(reinterpret_cast<uint4*>(F.u8 + (px0 + (size_t)row * S.width) * 3) + q, reinterpret_cast<const uint4*>(s_u8)[u]);
+        if (F.u8 && lane >= 20) {  // 3 uint2 per row: lanes 20..31
+            const int u = lane - 20, row = u / 3, q = u - row * 3;
+            __stcs(reinterpret_cast<uint2*>(F.u8 + (px0 + (size_t)row * S.width) * 3) + q, reinterpret_cast<const uint2*>(w_u8)[u]);
         }
     } else if (inside) {
         size_t idx = ((size_t)y * S.width + x) * 3;
@@ -145,7 +145,7 @@ __global__ void __launch_bounds__(128, SMALL ? (CONVERGE ? RTC_SMALL_CONVERGE_MI
 // DRAWN: as in render_tiles — a small scene whose area light draws its jitter (`jitter_fn = None`) takes the
 // drawn-sample cell loop; without it intensity_cells would read light samples nobody staged.
 template <bool SMALL, bool DRAWN>
-__global__ void __launch_bounds__(128) trace_rays(const __grid_constant__ DevScene S, const __grid_constant__ SmallScene SS, int n,
+__global__ void __launch_bounds__(kBlockThreads) trace_rays(const __grid_constant__ DevScene S, const __grid_constant__ SmallScene SS, int n,
                                                   const float* origins, const float* directions, int depth, float* out_rgb,
                                                   float* out_t, int* out_pos, DevCounters* counters) {
     if (SMALL) stage_small_scene(S, SS);
@@ -179,26 +179,26 @@ void launch_render(const DevScene& S, const SmallScene& SS, const DevFrame& F, D
     // the detailed (counting) pass always uses the converging build; the timed kernels pick by DevFrame::converge
     if (drawn) {
         if (detailed)
-            render_tiles<true, true, true, true><<<grid, 128, kSmallSmemBytes, stream>>>(S, SS, F, counters);
+            render_tiles<true, true, true, true><<<grid, kBlockThreads, kSmallSmemBytes, stream>>>(S, SS, F, counters);
         else if (F.converge)
-            render_tiles<false, true, true, true><<<grid, 128, kSmallSmemBytes, stream>>>(S, SS, F, counters);
+            render_tiles<false, true, true, true><<<grid, kBlockThreads, kSmallSmemBytes, stream>>>(S, SS, F, counters);
         else
-            render_tiles<false, true, false, true><<<grid, 128, kSmallSmemBytes, stream>>>(S, SS, F, counters);
+            render_tiles<false, true, false, true><<<grid, kBlockThreads, kSmallSmemBytes, stream>>>(S, SS, F, counters);
     } else if (detailed) {
         if (small)
-            render_tiles<true, true, true, false><<<grid, 128, kSmallSmemBytes, stream>>>(S, SS, F, counters);
+            render_tiles<true, true, true, false><<<grid, kBlockThreads, kSmallSmemBytes, stream>>>(S, SS, F, counters);
         else
-            render_tiles<true, false, true, false><<<grid, 128, 0, stream>>>(S, SS, F, counters);
+            render_tiles<true, false, true, false><<<grid, kBlockThreads, 0, stream>>>(S, SS, F, counters);
     } else if (small) {
         if (F.converge)
-            render_tiles<false, true, true, false><<<grid, 128, kSmallSmemBytes, stream>>>(S, SS, F, counters);
+            render_tiles<false, true, true, false><<<grid, kBlockThreads, kSmallSmemBytes, stream>>>(S, SS, F, counters);
         else
-            render_tiles<false, true, false, false><<<grid, 128, kSmallSmemBytes, stream>>>(S, SS, F, counters);
+            render_tiles<false, true, false, false><<<grid, kBlockThreads, kSmallSmemBytes, stream>>>(S, SS, F, counters);
     } else {
         if (F.converge)
-            render_tiles<false, false, true, false><<<grid, 128, 0, stream>>>(S, SS, F, counters);
+            render_tiles<false, false, true, false><<<grid, kBlockThreads, 0, stream>>>(S, SS, F, counters);
         else
-            render_tiles<false, false, false, false><<<grid, 128, 0, stream>>>(S, SS, F, counters);
+            render_tiles<false, false, false, false><<<grid, kBlockThreads, 0, stream>>>(S, SS, F, counters);
     }
 }
 
@@ -208,11 +208,11 @@ void launch_trace(const DevScene& S, const SmallScene& SS, int n, const float* o
     const bool small = SS.n > 0;
     const bool drawn = small && SS.cell_masks && S.jitter_len == 0;  // the predicate of launch_render
     if (drawn)
-        trace_rays<true, true><<<(n + 127) / 128, 128, kSmallSmemBytes, stream>>>(S, SS, n, origins, directions, depth, out_rgb, out_t, out_pos, counters);
+        trace_rays<true, true><<<(n + kBlockThreads - 1) / kBlockThreads, kBlockThreads, kSmallSmemBytes, stream>>>(S, SS, n, origins, directions, depth, out_rgb, out_t, out_pos, counters);
     else if (small)
-        trace_rays<true, false><<<(n + 127) / 128, 128, kSmallSmemBytes, stream>>>(S, SS, n, origins, directions, depth, out_rgb, out_t, out_pos, counters);
+        trace_rays<true, false><<<(n + kBlockThreads - 1) / kBlockThreads, kBlockThreads, kSmallSmemBytes, stream>>>(S, SS, n, origins, directions, depth, out_rgb, out_t, out_pos, counters);
     else
-        trace_rays<false, false><<<(n + 127) / 128, 128, 0, stream>>>(S, SS, n, origins, directions, depth, out_rgb, out_t, out_pos, counters);
+        trace_rays<false, false><<<(n + kBlockThreads - 1) / kBlockThreads, kBlockThreads, 0, stream>>>(S, SS, n, origins, directions, depth, out_rgb, out_t, out_pos, counters);
 }
 
 #ifndef RTC_STRICT

@@ -18,6 +18,12 @@
 #include <vector_types.h>
 #endif
 
+#if defined(__CUDACC__)
+#define RTC_HD __host__ __device__
+#else
+#define RTC_HD
+#endif
+
 namespace rtc {
 
 enum : int { T_SPHERE = 0, T_PLANE = 1, T_CUBE = 2, T_CYLINDER = 3, T_CONE = 4, T_TRIANGLE = 5, T_CSG = 6 };
@@ -86,6 +92,7 @@ struct DevScene {
     int jitter_len;            // > 0: table mode
     const float* jitter;       // table
     const float4* samples;     // table mode: the `cells` precomputed point_on_light positions
+    const float4* small_image; // small scenes: the first kSmemOrg float4 of a block's shared memory, ready to copy
     unsigned long long seed;   // counter mode
     // geometry
     const int4* head;
@@ -143,7 +150,37 @@ struct SmallScene {
 };
 constexpr int kSampleCap = 128;     // table-mode light samples staged in shared memory
 constexpr int kPlaneCellCap = 256;  // (caster plane, light cell) constants staged in shared memory
-constexpr int kSmallSmemBytes = kSmallCap * kSmallStride * 16 + kOrgCache * 3 * 128 * 4 + kSampleCap * 16 + kPlaneCellCap * 16;
+// A block renders one tile of kTileW x kTileH pixels, one thread per pixel, as 8x4-pixel warps (kTileW / 8 across).
+#ifndef RTC_TILE_W
+#define RTC_TILE_W 16
+#endif
+// Shadow filter, plane test with the light sample folded in (SmallScene::plane_cells, dev_shadow.cuh:
+// filter_plane_cell): for light point L and shading point p the object-space direction's y is r1.L - r1.p, so everything
+// that depends on L alone is computed once per scene, in f32, by the commit: {r1.L, tol * sum|r1_k L_k|, EPSILON' * |L|_1}.
+constexpr float kTolP = 3.814697265625e-06f;  // 2^-18 = 64 ulp: planes and cubes (bounds are term-wise, no conditioning)
+RTC_HD inline float4 plane_cell_constants(float4 r1, float4 L) {
+    const float px = r1.x * L.x, py = r1.y * L.y, pz = r1.z * L.z;
+    const float ax = px < 0.f ? -px : px, ay = py < 0.f ? -py : py, az = pz < 0.f ? -pz : pz;
+    const float lx = L.x < 0.f ? -L.x : L.x, ly = L.y < 0.f ? -L.y : L.y, lz = L.z < 0.f ? -L.z : L.z;
+    float4 q;
+    q.x = px + py + pz;
+    q.y = kTolP * (ax + ay + az);
+    q.z = (1.1920929e-3f * (1.0f + 2.0f * kTolP)) * (lx + ly + lz);
+    q.w = 0.0f;
+    return q;
+}
+
+constexpr int kTileW = RTC_TILE_W, kTileH = 8;
+constexpr int kBlockThreads = kTileW * kTileH;
+constexpr int kWarpsX = kTileW / 8;
+static_assert(kTileW % 16 == 0 && kBlockThreads <= 1024, "tile width: a multiple of 16 (16-byte rows of the 8-bit canvas)");
+// Dynamic shared memory of the small-scene kernels, in float4 units: [table | light samples | (plane, cell) constants |
+// per-thread shadow-origin cache].  Everything before the cache is the same for every block of a scene: the commit lays
+// it out once (Flattened::small_image -> DevScene::small_image) and a block's staging is a plain coalesced copy.
+constexpr int kSmemSamples = kSmallCap * kSmallStride;
+constexpr int kSmemPlaneCells = kSmemSamples + kSampleCap;
+constexpr int kSmemOrg = kSmemPlaneCells + kPlaneCellCap;
+constexpr int kSmallSmemBytes = kSmemOrg * 16 + kOrgCache * 3 * kBlockThreads * 4;
 
 struct DevFrame {  // where a render writes
     float* rgb;            // width*height*3 f32 or null
@@ -157,7 +194,6 @@ struct DevFrame {  // where a render writes
     int converge;          // color_at: all lanes of a warp meet at a vote before every ray (see color_at)
 };
 
-constexpr int kTileW = 16, kTileH = 8;  // pixels per 128-thread block: 4 warps of 8x4
 constexpr int kBandRows = kTileH;
 
 struct DevCounters {  // accumulated with one atomic per warp

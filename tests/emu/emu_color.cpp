@@ -100,6 +100,7 @@ void host_scene(const RtcScene* s, const rtc::Flattened& f, rtc::DevScene& d) {
     d.jitter = at(s->jitter), d.samples = at(f.samples), d.head = at(f.head), d.rec = at(f.rec), d.xform = at(f.xform);
     d.tri = at(f.tri), d.bound = at(f.bound), d.bvh = at(f.bvh), d.linear = at(f.linear), d.nodes = at(f.nodes);
     d.csg_ops = at(f.ops), d.materials = at(f.materials), d.patterns = at(f.patterns), d.uvs = at(f.uvs), d.texels = at(f.texels);
+    d.small_image = at(f.small_image);
     d.n_linear = (int)f.linear.size(), d.bvh_root = f.bvh_root, d.n_prims = f.n_pos, d.all_cast_shadow = f.all_cast_shadow;
 }
 }  // namespace
@@ -144,6 +145,7 @@ extern "C" int emu_color_at(RtcScene* s, uint32_t n, const float* origins, const
         else
             c = g_converge ? emu::color_at<false, false, true, false>(E, true, o, d, depth, i, r, k, &t, &pos)
                            : emu::color_at<false, false, false, false>(E, true, o, d, depth, i, r, k, &t, &pos);
+        emu::finish_rays(S, r);
         g_rays[0] += r.primary, g_rays[1] += r.secondary, g_rays[2] += r.shadow, g_rays[3] += r.shades;
         out_rgb[3 * (size_t)i] = c.x, out_rgb[3 * (size_t)i + 1] = c.y, out_rgb[3 * (size_t)i + 2] = c.z;
         if (out_t) out_t[i] = t;

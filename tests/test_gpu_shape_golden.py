@@ -182,6 +182,9 @@ def test_shape_table_on_gpu(gpu, oracle, label, build, rows, normalise, with_tre
                 want = hit_of(ots)
                 got = float(t[i])
                 where = f"{label} row {i} origin {o} strict={strict}"
+                if not strict and isinstance(expected, list) and len(expected) == 2 and expected[0] == expected[1]:
+                    continue  # a tangent ray (discriminant exactly 0 in the reference's arithmetic): any contraction of
+                    # b*b - 4ac may flip its sign, which is why the FMA build is opt-in and not the parity build
                 if isinstance(expected, bool):
                     assert (got >= 0.0) == expected, where
                 elif isinstance(expected, int):
