@@ -258,11 +258,19 @@ def textured(rt, width=320, height=200):
     return camera, world
 
 
-def random_filter_scene(rt, seed, width=160, height=100):
+def random_filter_scene(rt, seed, width=160, height=100, extreme=None):
     """A random filter-eligible scene (spheres with random rotations / shears / squashes, tilted planes, axis-aligned
     boxes, some touching or interpenetrating, some not casting shadows) under a random area or point light: fuzzing
-    input for the shadow filter's on / off equality test."""
+    input for the shadow filter's on / off equality test.
+
+    extreme: None, or one of the regimes the filter's RELATIVE error bounds must survive —
+      "millimetre" / "kilometre"  every length of the scene (objects, light, camera) times 1e-3 / 1e3;
+      "far light"                 the light 1e4 units away along its own direction from the scene;
+      "tiny spheres"              radius-1e-3 spheres on the floor, seen (and shadow-tested) from units away;
+      "stretched"                 ellipsoids near the eligibility limit (condition number ~60);
+      "grazing"                   the light a hair above the floor plane: shadow segments almost parallel to it."""
     rnd = _xorshift64star(0x5EED0000 + seed)
+    S = {"millimetre": 1e-3, "kilometre": 1e3}.get(extreme, 1.0)
 
     def u(a, b):
         return a + (b - a) * rnd()
@@ -293,16 +301,41 @@ def random_filter_scene(rt, seed, width=160, height=100):
         if rnd() < 0.25:
             box.set_casts_shadow(False)
         objects.append(box)
-    if rnd() < 0.7:
+    if extreme == "tiny spheres":
+        for _ in range(4):
+            objects.append(rt.Sphere.build(rt.translation(u(-2, 2), 1e-3, u(-4, 1)) * rt.scaling(1e-3, 1e-3, 1e-3), mat()))
+    if extreme == "stretched":
+        for _ in range(3):
+            r = u(0.4, 1.0)
+            objects.append(rt.Sphere.build(rt.translation(u(-3, 3), u(0.5, 1.5), u(-2, 3)) * rt.rotation_y(u(0, 6.28)) *
+                                           rt.rotation_z(u(0, 1.5)) * rt.scaling(r, r / u(20.0, 28.0), r * u(0.5, 1.0)), mat()))
+    if rnd() < 0.7 or extreme == "grazing":
         us, vs = 1 + int(rnd() * 4), 1 + int(rnd() * 4)
         mode = rnd()
         jitter = jitter_table(2 * us * vs, seed + 11) if mode < 0.4 else ([0.5] if mode < 0.6 else None)
-        light = RectangleLight((1.2, 1.2, 1.2), (u(-4, 0), u(2.5, 6), u(-5, -1)), (u(0.3, 1.0), 0, u(-0.2, 0.2)), us,
-                               (0, u(0.3, 1.0), u(-0.2, 0.2)), vs, jitter, seed)
+        corner, eu, ev = (u(-4, 0), u(2.5, 6), u(-5, -1)), (u(0.3, 1.0), 0, u(-0.2, 0.2)), (0, u(0.3, 1.0), u(-0.2, 0.2))
+        if extreme == "grazing":  # a horizontal strip light just above the floor
+            corner, eu, ev = (u(-6, -4), u(1e-4, 3e-3), u(-5, -1)), (u(0.3, 1.0), 0, u(-0.2, 0.2)), (0, u(1e-4, 1e-3), u(0.3, 1.0))
+        if extreme == "far light":
+            k = 1e4 / math.sqrt(sum(c * c for c in corner))
+            corner = tuple(c * k for c in corner)
+        light = RectangleLight((1.2, 1.2, 1.2), tuple(c * S for c in corner), tuple(c * S for c in eu), us,
+                               tuple(c * S for c in ev), vs, jitter, seed)
     else:
-        light = PointLight((u(-6, 6), u(3, 9), u(-7, -2)), (1, 1, 1))
+        pos = (u(-6, 6), u(3, 9), u(-7, -2))
+        if extreme == "far light":
+            k = 1e4 / math.sqrt(sum(c * c for c in pos))
+            pos = tuple(c * k for c in pos)
+        light = PointLight(tuple(c * S for c in pos), (1, 1, 1))
+    if S != 1.0:  # the whole scene in other units: every object's transform gains a uniform scaling on the left
+        scaled = []
+        for o in objects:
+            o.set_transformation(rt.scaling(S, S, S) * o.transformation())
+            scaled.append(o)
+        objects = scaled
     world = rt.World(objects, light)
-    camera = rt.Camera(width, height, PI / 3.0, rt.view_transform((u(-2, 2), u(1.5, 3.5), u(-8, -6)), (0, 1.0, 0), (0, 1, 0)))
+    frm = (u(-2, 2), u(1.5, 3.5), u(-8, -6))
+    camera = rt.Camera(width, height, PI / 3.0, rt.view_transform(tuple(c * S for c in frm), (0, 1.0 * S, 0), (0, 1, 0)))
     return camera, world
 
 

@@ -24,7 +24,12 @@ def _build(tmp_path_factory, source):
         pytest.skip("needs g++ and the CUDA headers")
     out = tmp_path_factory.mktemp("emu") / ("lib" + source.replace(".cpp", ".so"))
     lib_dir = os.path.dirname(rt.LIB_DEVICE)
-    subprocess.run(["g++", "-std=c++17", "-O1", "-ffp-contract=off", "-fPIC", "-shared", "-I", CUDA_INCLUDE,
+    # RTC_EMU_SANITIZE=1 (set by test_device_code_under_address_sanitizer, which re-runs this module in a process with
+    # libasan preloaded): the device code's shared-memory carving, bounce stack, traversal stack and CSG hit buffers
+    # under AddressSanitizer + UBSan — the memcheck pass a host can give CUDA code
+    sanitize = ["-fsanitize=address,undefined", "-fno-omit-frame-pointer", "-fno-sanitize-recover=undefined"] \
+        if os.environ.get("RTC_EMU_SANITIZE") else []
+    subprocess.run(["g++", "-std=c++17", "-O1", "-ffp-contract=off", "-fPIC", "-shared", *sanitize, "-I", CUDA_INCLUDE,
                     "-I", os.path.join(ROOT, "ray_tracer_challenge_b200", "csrc"), os.path.join(ROOT, "tests", "emu", source),
                     "-o", str(out), "-L", lib_dir, "-lrtc_b200", f"-Wl,-rpath,{lib_dir}"], check=True)
     device = rt.device_library()  # the raw C ABI; RTLD_GLOBAL, so the harness binds rtc::flatten from it
@@ -287,3 +292,65 @@ def test_shadow_filter_fuzz_through_the_device_code(emu_color, host, oracle):
         finally:
             device.rtc_scene_destroy(scene)
     assert eligible >= 12, eligible
+
+
+EXTREMES = ["millimetre", "kilometre", "far light", "tiny spheres", "stretched", "grazing"]
+
+
+@pytest.mark.parametrize("extreme", EXTREMES)
+def test_shadow_filter_at_scale_extremes_through_the_device_code(emu_color, host, oracle, extreme):
+    """the filter's bounds (sphere tolerance, 2^-18 plane / cube bounds, the 0.1 % ball padding, the
+    2^-17 |w|^2 / R bundle padding) were only ever exercised in a +-10-unit world of unit-scale objects.  The same
+    random scenes in millimetres and kilometres, with the light 10^4 units away, with radius-10^-3 spheres, with
+    ellipsoids near the conditioning limit and with a light grazing the floor: whole frames through the device code
+    with the filter ON are the oracle's frames, bit for bit."""
+    device, lib = emu_color
+    fp = lambda a: a.ctypes.data_as(FP)  # noqa: E731
+    eligible = 0
+    for seed in range(200, 206):
+        kw = dict(width=28, height=18, extreme=extreme)
+        cam, world = scenes.random_filter_scene(host, seed, **kw)
+        ocam, oworld = scenes.random_filter_scene(oracle, seed, **kw)
+        eligible += host.inspect(cam, world)["filter_ok"]
+        want = np.asarray(ocam.render(oworld, 5).data, np.float32)
+        w, h = ocam.width_pixels, ocam.height_pixels
+        o = np.zeros((w * h, 3), np.float32)
+        d = np.zeros((w * h, 3), np.float32)
+        d[:, 2] = 1.0
+        for y in range(h - 1):
+            for x in range(w - 1):
+                ro, rd = oracle.probe.camera_ray(ocam, x, y)
+                o[y * w + x], d[y * w + x] = ro[:3], rd[:3]
+        scene = host.export_scene(cam, world)
+        try:
+            rgb = np.zeros((w * h, 3), np.float32)
+            assert lib.emu_color_at(scene, w * h, fp(o), fp(d), 5, 1, 1, fp(rgb), None, None) == 0, device.rtc_last_error()
+            got = rgb.reshape(h, w, 3)[: h - 1, : w - 1]
+            ref = want[: h - 1, : w - 1]
+            same = (got.view(np.uint32) == ref.view(np.uint32)).all(axis=2)
+            assert same.all(), (extreme, seed, int((~same).sum()), got[~same][:2], ref[~same][:2])
+        finally:
+            device.rtc_scene_destroy(scene)
+    assert eligible >= (2 if extreme == "stretched" else 4), (extreme, eligible)
+
+
+def test_device_code_under_address_sanitizer():
+    """compute-sanitizer is not available on the GPU pool, so the memcheck pass runs here: this module's tests again in
+    a child process whose harness is built with -fsanitize=address,undefined (libasan preloaded into python).  The
+    shared-memory block is a global array with red zones, the per-thread stacks are stack arrays: an out-of-bounds
+    index in the table / samples / plane-cell / origin-cache carving, the bounce stack, the BVH stack or the CSG hit
+    buffer aborts the child."""
+    import sys
+
+    if os.environ.get("RTC_EMU_SANITIZE"):
+        pytest.skip("already inside the sanitized run")
+    libasan = subprocess.run(["g++", "-print-file-name=libasan.so"], capture_output=True, text=True).stdout.strip()
+    if not libasan or not os.path.exists(libasan):
+        pytest.skip("no libasan")
+    env = dict(os.environ, RTC_EMU_SANITIZE="1", LD_PRELOAD=libasan, ASAN_OPTIONS="detect_leaks=0:abort_on_error=1",
+               UBSAN_OPTIONS="print_stacktrace=1:halt_on_error=1")
+    proc = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-x", "-q", "-p", "no:cacheprovider"],
+                          cwd=ROOT, env=env, capture_output=True, text=True)
+    tail = (proc.stdout + proc.stderr)[-3000:]
+    assert proc.returncode == 0, tail
+    assert "passed" in proc.stdout and "AddressSanitizer" not in tail and "runtime error" not in tail, tail

@@ -260,3 +260,131 @@ def test_cube_filter_never_contradicts_the_reference(seed):
     wrong = ((got == HIT) & ~want) | ((got == MISS) & want)
     assert not wrong.any(), (int(wrong.sum()), np.flatnonzero(wrong)[:5])
     assert (got != UNSURE)[kind == 3].mean() > 0.99
+
+
+# ---------------------------------------------------------------------------------------------------
+# Scale extremes: everything above lives in a +-10-unit world of unit-scale objects.  The bounds are
+# RELATIVE (see DESIGN.md "Shadow filter: where the bounds come from"), so they must hold for a millimetre world, a
+# kilometre world, a light 10^4 units away, spheres of radius 10^-3 seen from a few units away (the reference's own
+# discriminant is pure cancellation noise there: both must then be UNSURE or agree), and transforms at the eligibility
+# limit (condition number 64).
+REGIMES = {
+    #            world scale, sphere radius range,   far end of the segment, condition range
+    "millimetre": (1e-3, (0.15e-3, 2.5e-3), None, (1.0, 64.0)),
+    "kilometre": (1e3, (0.15e3, 2.5e3), None, (1.0, 64.0)),
+    "far light": (1.0, (0.15, 2.5), 1e4, (1.0, 64.0)),
+    "tiny spheres": (1.0, (1e-3, 1e-2), None, (1.0, 64.0)),
+    "huge spheres": (1.0, (1e2, 1e3), None, (1.0, 64.0)),
+    "condition limit": (1.0, (0.15, 2.5), None, (40.0, 64.0)),
+}
+
+
+def regime_transforms(n, rng, world, radius, cond_range):
+    def rot(axis, ang):
+        c, s = np.cos(ang), np.sin(ang)
+        r = np.tile(np.eye(3), (n, 1, 1))
+        i, j = [(1, 2), (0, 2), (0, 1)][axis]
+        r[:, i, i], r[:, j, j], r[:, i, j], r[:, j, i] = c, c, -s, s
+        return r
+    base = np.exp(rng.uniform(np.log(radius[0]), np.log(radius[1]), size=(n, 1)))
+    aniso = np.exp(rng.uniform(0.0, np.log(cond_range[1]), size=(n, 3)))
+    aniso[:, 0] = 1.0
+    scale = base * aniso / aniso.max(axis=1, keepdims=True)  # the largest semi-axis is `base`
+    fwd = rot(1, rng.uniform(0, 6.28, n)) @ rot(2, rng.uniform(0, 6.28, n)) @ (np.eye(3)[None] * scale[:, None, :])
+    inv = np.linalg.inv(fwd)
+    cond = np.abs(inv).sum(axis=2).max(axis=1) * np.abs(fwd).sum(axis=2).max(axis=1)
+    keep = (cond <= cond_range[1]) & (cond >= cond_range[0])
+    centre = rng.uniform(-4, 4, size=(n, 3)) * world
+    t = -(inv @ centre[:, :, None])[:, :, 0]
+    return inv[keep].astype(F), t[keep].astype(F), fwd[keep], centre[keep], cond[keep]
+
+
+@pytest.mark.parametrize("regime", sorted(REGIMES))
+def test_sphere_filter_at_scale_extremes(regime):
+    world, radius, far, cond_range = REGIMES[regime]
+    rng = np.random.default_rng(sorted(REGIMES).index(regime) + 40)
+    inv, t, fwd, centre, cond = regime_transforms(500_000, rng, world, radius, cond_range)
+    n = len(inv)
+    assert n > 20_000, n
+    tol = F(2.0 ** -24 * 64.0 * (float(cond.max()) + 1.0))
+    u = rng.normal(size=(n, 3))
+    u /= np.linalg.norm(u, axis=1, keepdims=True)
+    w = np.cross(u, rng.normal(size=(n, 3)))
+    w /= np.linalg.norm(w, axis=1, keepdims=True)
+    kind = rng.integers(0, 5, n)
+    eps = 10.0 ** rng.uniform(-9, -1, n) * rng.choice([-1.0, 1.0], n)
+    lift = np.where(kind == 0, 1.0 + eps, 1.0 + np.abs(rng.normal(0, 0.5, n)))
+    a_obj = u * lift[:, None] - w * rng.uniform(0.5, 6, (n, 1))
+    b_obj = u * lift[:, None] + w * rng.uniform(0.5, 6, (n, 1))
+    a_obj = np.where((kind == 1)[:, None], u * (1.0 + eps)[:, None], a_obj)
+    b_obj = np.where((kind == 2)[:, None], u * (1.0 + eps)[:, None], b_obj)
+    p = (fwd @ a_obj[:, :, None])[:, :, 0] + centre
+    light = (fwd @ b_obj[:, :, None])[:, :, 0] + centre
+    rand = kind >= 3  # world-space ends a few world units away: for tiny spheres |w|^2 / R^2 reaches 10^7
+    p[rand] = rng.normal(0, 2.5 * world, (rand.sum(), 3))
+    light[rand] = rng.normal(0, 2.5 * world, (rand.sum(), 3))
+    aim = rand & (rng.random(n) < 0.5)  # ... half of them aimed at the sphere so that hits occur at all
+    light[aim] = (centre + (centre - p) * rng.uniform(0.2, 3.0, (n, 1)) + (fwd @ (u * rng.uniform(0, 1.3, (n, 1)))[:, :, None])[:, :, 0])[aim]
+    if far is not None:
+        d = light - p
+        light = p + d / np.linalg.norm(d, axis=1, keepdims=True) * far * rng.uniform(0.3, 1.0, (n, 1))
+    p, light = p.astype(F), light.astype(F)
+    o = xf_point(inv, t, p)
+    want = reference_sphere(inv, o, p, light)
+    got = filter_sphere(inv, o, p, light, tol, rng)
+    wrong = ((got == HIT) & ~want) | ((got == MISS) & want)
+    assert not wrong.any(), (regime, int(wrong.sum()), np.flatnonzero(wrong)[:5], cond[wrong][:5])
+    assert want[got == HIT].all() and 0.001 < (got == HIT).mean(), (regime, (got == HIT).mean())
+    # decisiveness is a performance property, not a correctness one: every regime draws ellipsoids up to the 64:1
+    # eligibility limit (bound 65 x 64 ulp) and 60 % of the segments are tangent / on-surface cases; a third is decided
+    assert (got != UNSURE).mean() > 0.25, (regime, (got != UNSURE).mean())
+
+
+@pytest.mark.parametrize("world,far", [(1e-3, None), (1e3, None), (1.0, 1e4), (1e3, 1e7)])
+def test_plane_and_cube_filters_at_scale_extremes(world, far):
+    rng = np.random.default_rng(int(abs(np.log10(world)) * 7 + (0 if far is None else 3)) + 50)
+    n = 400_000
+    # ---- planes: grazing segments, origin / light almost on the plane, at the world's scale
+    normal = rng.normal(size=(n, 3))
+    normal /= np.linalg.norm(normal, axis=1, keepdims=True)
+    normal *= np.exp(rng.uniform(np.log(0.1), np.log(10), (n, 1))) / world
+    r1 = np.concatenate([normal, rng.uniform(-3, 3, (n, 1))], axis=1).astype(F)
+    p = rng.normal(0, 3 * world, (n, 3))
+    light = rng.normal(0, 3 * world, (n, 3))
+    kind = rng.integers(0, 4, n)
+    nn = normal / (np.linalg.norm(normal, axis=1, keepdims=True) ** 2)
+    height = lambda q: (q * normal).sum(axis=1) + r1[:, 3]  # noqa: E731
+    eps = 10.0 ** rng.uniform(-9, -2, n) * rng.choice([-1.0, 1.0], n)
+    light = np.where((kind == 0)[:, None], light - nn * (height(light) - eps)[:, None], light)
+    p = np.where((kind == 1)[:, None], p - nn * (height(p) - eps)[:, None], p)
+    para = kind == 2
+    light[para] = (light - nn * (height(light) - height(p) * (1.0 + eps * 50))[:, None])[para]
+    if far is not None:
+        d = light - p
+        light = p + d / np.linalg.norm(d, axis=1, keepdims=True) * far * rng.uniform(0.3, 1.0, (n, 1))
+    pf, lf = p.astype(F), light.astype(F)
+    oy, want = reference_plane(r1, pf, lf)
+    got = filter_plane(r1, oy, pf, lf, rng)
+    wrong = ((got == HIT) & ~want) | ((got == MISS) & want)
+    assert not wrong.any(), ("plane", int(wrong.sum()), np.flatnonzero(wrong)[:5])
+    assert (got != UNSURE)[kind == 3].mean() > 0.98
+    # ---- axis-aligned cubes (slabs down to 100:1) at the world's scale
+    half = np.exp(rng.uniform(np.log(0.01), np.log(3), (n, 3))) * world
+    centre = rng.uniform(-3, 3, (n, 3)) * world
+    scale, t = (1.0 / half).astype(F), (-centre / half).astype(F)
+    p = rng.normal(0, 3 * world, (n, 3))
+    light = rng.normal(0, 3 * world, (n, 3))
+    eps3 = 10.0 ** rng.uniform(-9, -2, (n, 1)) * rng.choice([-1.0, 1.0], (n, 1))
+    face = centre + half * np.where(rng.random((n, 3)) < 0.4, rng.choice([-1.0, 1.0], (n, 3)), rng.uniform(-1, 1, (n, 3)))
+    light = np.where((kind == 0)[:, None], face + eps3 * half, light)
+    p = np.where((kind == 1)[:, None], face + eps3 * half, p)
+    graze = kind == 2
+    light[graze] = (face + (face - p) * rng.uniform(0.1, 2, (n, 1)) + eps3 * half)[graze]
+    if far is not None:
+        d = light - p
+        light = p + d / np.linalg.norm(d, axis=1, keepdims=True) * far * rng.uniform(0.3, 1.0, (n, 1))
+    pf, lf = p.astype(F), light.astype(F)
+    o, want = reference_cube(scale, t, pf, lf)
+    got = filter_cube(scale, o, pf, lf, rng)
+    wrong = ((got == HIT) & ~want) | ((got == MISS) & want)
+    assert not wrong.any(), ("cube", int(wrong.sum()), np.flatnonzero(wrong)[:5])

@@ -210,6 +210,34 @@ def test_shadow_filter_fuzz(gpu, oracle):
     assert checked >= 20
 
 
+@pytest.mark.parametrize("extreme", ["millimetre", "kilometre", "far light", "tiny spheres", "stretched", "grazing"])
+def test_shadow_filter_at_scale_extremes(gpu, oracle, extreme):
+    """The fuzz above in the regimes the filter's relative bounds must survive (scenes.random_filter_scene: whole scene
+    x 1e-3 / x 1e3, light 1e4 away, radius-1e-3 spheres, condition ~60 ellipsoids, a light grazing the floor): on sm_100a
+    the frame is bit-identical with the filter on and off AND equal to the oracle's in every 8-bit channel."""
+    decided = 0
+    for seed in range(300, 310):
+        cam, world = scenes.random_filter_scene(gpu, seed, extreme=extreme)
+        p = cam.prepare(world)
+        try:
+            p.set_option(6, 0)
+            off = p.render(5)
+            rays_off = p.last_stats.rays
+            p.set_option(6, 1)
+            on = p.render(5, detailed=True)
+            st = p.last_stats
+            assert st.rays == rays_off, (extreme, seed)
+            assert np.array_equal(on.data.view(np.uint32), off.data.view(np.uint32)), (extreme, seed)
+            decided += st.prim_tests[7] < st.shadow_rays
+            ocam, oworld = scenes.random_filter_scene(oracle, seed, extreme=extreme)
+            want = ocam.render(oworld, 5)
+            rep = compare_frames(on.to_u8(), want.to_u8(), on.data, want.data)
+            assert rep["exact_u8"] == 1.0 and st.rays == ocam.last_stats.rays, (extreme, seed, rep)
+        finally:
+            p.release()
+    assert decided >= 5, (extreme, decided)
+
+
 def test_depth_semantics(gpu, oracle):
     """remaining-depth guards (world.rs:126,140): depth 0 and 1 frames match the oracle."""
     for depth in (0, 1, 2):
