@@ -205,20 +205,30 @@ __device__ __forceinline__ void test_prim(const DevScene& S, int pos, V3 o, V3 d
     consider(best, tn, pos, h.w);
 }
 
-// Conservative slab test for the acceleration structure (boxes are padded at build time, so this never
-// rejects a primitive the reference would have hit; it is not part of the reference's semantics).
-__device__ __forceinline__ bool slab(V3 o, V3 inv, float lx, float ly, float lz, float hx, float hy, float hz, float tmax,
+// Conservative slab test for the acceleration structure (boxes are padded at build time, so this never rejects a
+// primitive the reference would have hit; it is not part of the reference's semantics).  The distances are formed as
+// fma(plane, 1 / d, -(o / d)) — one FFMA per plane instead of a subtraction and a product, in both kernel builds; the two
+// product roundings are at most 2^-22 of the scene's extent in length, which the builder's padding includes
+// (rtc_commit.cu).  A direction component below 2^-60 in magnitude is replaced by +-2^-60 first (tree_inverse): its
+// reciprocal stays finite, so no inf - inf = NaN can appear — a ray parallel to a slab gets distances of +-1e18 with the
+// right signs: inside the slab no constraint, outside a miss (and it is the padded box the ray has to clear).
+__device__ __forceinline__ bool slab(V3 noi, V3 inv, float lx, float ly, float lz, float hx, float hy, float hz, float tmax,
                                      float& tnear) {
-    float a = (lx - o.x) * inv.x, b = (hx - o.x) * inv.x;
+    float a = fma_(lx, inv.x, noi.x), b = fma_(hx, inv.x, noi.x);
     float lo = fminf(a, b), hi = fmaxf(a, b);
-    a = (ly - o.y) * inv.y, b = (hy - o.y) * inv.y;
+    a = fma_(ly, inv.y, noi.y), b = fma_(hy, inv.y, noi.y);
     lo = fmaxf(lo, fminf(a, b));
     hi = fminf(hi, fmaxf(a, b));
-    a = (lz - o.z) * inv.z, b = (hz - o.z) * inv.z;
+    a = fma_(lz, inv.z, noi.z), b = fma_(hz, inv.z, noi.z);
     lo = fmaxf(lo, fminf(a, b));
     hi = fminf(hi, fmaxf(a, b));
     tnear = lo;
     return hi >= fmaxf(lo, 0.0f) && lo <= tmax;
+}
+
+__device__ __forceinline__ float tree_inverse(float d) {
+    const float tiny = 8.673617379884035e-19f;  // 2^-60
+    return 1.0f / (fabsf(d) < tiny ? copysignf(tiny, d) : d);
 }
 
 // World::intersect + Intersection::hit (world.rs:52-60, intersection.rs:30-35): nearest t >= 0 with the
@@ -233,7 +243,8 @@ __device__ __noinline__ void nearest_hit(const DevScene& S, V3 o, V3 d, Hit& bes
         if (ANY && best.pos >= 0) return;
     }
     if (S.bvh_root < 0) return;
-    V3 inv = mk(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+    const V3 inv = mk(tree_inverse(d.x), tree_inverse(d.y), tree_inverse(d.z));
+    const V3 noi = mk(-(o.x * inv.x), -(o.y * inv.y), -(o.z * inv.z));
     int stack[kBvhStack];
     int sp = 0;
     int node = S.bvh_root;
@@ -249,8 +260,8 @@ __device__ __noinline__ void nearest_hit(const DevScene& S, V3 o, V3 d, Hit& bes
             float t0, t1;
             k.node();
             k.node();
-            bool h0 = slab(o, inv, a.x, a.y, a.z, a.w, b.x, b.y, best.t, t0);
-            bool h1 = slab(o, inv, b.z, b.w, c.x, c.y, c.z, c.w, best.t, t1);
+            bool h0 = slab(noi, inv, a.x, a.y, a.z, a.w, b.x, b.y, best.t, t0);
+            bool h1 = slab(noi, inv, b.z, b.w, c.x, c.y, c.z, c.w, best.t, t1);
             if (h0 && h1) {
                 int near = link.x, far = link.y;
                 if (t1 < t0) {
@@ -371,7 +382,8 @@ __device__ __noinline__ void find_containers(const DevScene& S, V3 o, V3 d, int 
     for (int i = 0; i < S.n_linear; i++) container_prim<STATS>(S, __ldg(&S.linear[i]), o, d, cache, hit_pos, c, k);
     if (S.bvh_root >= 0) {
         // walk the backward half-line: the forward half-line of the reversed ray
-        V3 inv = mk(-1.0f / d.x, -1.0f / d.y, -1.0f / d.z);
+        const V3 inv = mk(tree_inverse(-d.x), tree_inverse(-d.y), tree_inverse(-d.z));
+        const V3 noi = mk(-(o.x * inv.x), -(o.y * inv.y), -(o.z * inv.z));
         int stack[kBvhStack];
         int sp = 0;
         int node = S.bvh_root;
@@ -393,11 +405,11 @@ __device__ __noinline__ void find_containers(const DevScene& S, V3 o, V3 d, int 
                 if (link.z & 1)
                     h0 = o.x >= a.x && o.x <= a.w && o.y >= a.y && o.y <= b.x && o.z >= a.z && o.z <= b.y;
                 else
-                    h0 = slab(o, inv, a.x, a.y, a.z, a.w, b.x, b.y, kInfF, t0);
+                    h0 = slab(noi, inv, a.x, a.y, a.z, a.w, b.x, b.y, kInfF, t0);
                 if (link.z & 2)
                     h1 = o.x >= b.z && o.x <= cc.y && o.y >= b.w && o.y <= cc.z && o.z >= cc.x && o.z <= cc.w;
                 else
-                    h1 = slab(o, inv, b.z, b.w, cc.x, cc.y, cc.z, cc.w, kInfF, t1);
+                    h1 = slab(noi, inv, b.z, b.w, cc.x, cc.y, cc.z, cc.w, kInfF, t1);
                 if (h0 && h1) {
                     if (sp < kBvhStack) stack[sp++] = link.y;
                     node = link.x;

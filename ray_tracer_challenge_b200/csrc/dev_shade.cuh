@@ -37,6 +37,68 @@ __device__ __forceinline__ V3 combine(V3 surface, V3 reflected, V3 refracted, fl
     return add_refracted(add_reflected(surface, reflected, reflectance), refracted, reflectance);
 }
 
+// Where a lane's rays come from.  OnePixel: the caller's ray, one per thread (render_tiles, trace_rays).  PixelStream:
+// a lane whose ray tree is finished stores its pixel and draws the next pixel of the launch from a global counter at
+// the converged top of the loop — in scenes whose ray trees differ wildly from pixel to pixel (mirrors and glass among
+// 100 k spheres: one pixel traces 2 rays, its neighbour 60) a warp otherwise runs until its deepest tree is done with
+// the other lanes idle (ncu, c5: 8 of 32 lanes active per instruction).
+struct OnePixel {
+    static constexpr bool kStream = false;
+    __device__ __forceinline__ bool exhausted() const { return true; }
+    __device__ __forceinline__ bool refill(bool&, V3&, V3&, unsigned&) { return false; }
+    __device__ __forceinline__ void finish(unsigned, V3) {}
+};
+
+__device__ __forceinline__ unsigned char scale_color(float c);
+__device__ __forceinline__ void ray_for_pixel(const DevScene& S, int x, int y, V3& o, V3& d);
+
+// Pixels of a launch in stream order: 32 consecutive indices are one 8x4 block (so a warp that refills all its lanes at
+// once gets coherent primary rays), blocks run along a band (kBandRows rows: two block rows), bands in the order of
+// the shard's band list.
+struct PixelStream {
+    static constexpr bool kStream = true;
+    const DevScene& S;
+    const DevFrame& F;
+    unsigned* counter;  // next unclaimed stream index of this launch
+    unsigned total;     // stream indices of this launch
+    int blocks_x;       // 8-pixel blocks across the frame
+    bool done = false;  // warp-uniform: the counter has run past the end
+    __device__ __forceinline__ bool exhausted() const { return done; }
+    // Warp-collective, called converged.  Idle lanes draw new pixels when at least kRefillLanes of them are idle (one
+    // atomic per refill); returns true for a lane that starts a new pixel.
+    __device__ __forceinline__ bool refill(bool& running, V3& ro, V3& rd, unsigned& pixel) {
+        const unsigned idle = __ballot_sync(0xffffffffu, !running);
+        if (done || (__popc(idle) < kRefillLanes && idle != 0xffffffffu)) return false;
+        const int lane = threadIdx.x & 31, leader = __ffs(idle) - 1;
+        unsigned base = 0;
+        if (lane == leader) base = atomicAdd(counter, (unsigned)__popc(idle));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (base + (unsigned)__popc(idle) >= total) done = true;
+        if (running) return false;
+        const unsigned idx = base + (unsigned)__popc(idle & ((1u << lane) - 1u));
+        if (idx >= total) return false;
+        const unsigned block = idx >> 5, within = idx & 31u;
+        const unsigned per_band = (unsigned)blocks_x * 2u;
+        const unsigned band_i = block / per_band, b = block - band_i * per_band;
+        const int band = F.shard + (F.band_begin + (int)band_i) * F.n_shards;
+        const int x = (int)(b >> 1) * 8 + (int)(within & 7u), y = band * kBandRows + (int)(b & 1u) * 4 + (int)(within >> 3);
+        if (x >= S.width || y >= S.height) return false;
+        pixel = (unsigned)(y * S.width + x);
+        if (x >= S.width - 1 || y >= S.height - 1) {  // camera.rs:80-81: never rendered, stays black (canvas.rs:23)
+            finish(pixel, mk(0.f, 0.f, 0.f));
+            return false;
+        }
+        ray_for_pixel(S, x, y, ro, rd);
+        running = true;
+        return true;
+    }
+    __device__ __forceinline__ void finish(unsigned pixel, V3 c) {  // Canvas::write_pixel + scale_color (canvas.rs:26-43)
+        const size_t i = (size_t)pixel * 3;
+        if (F.rgb) F.rgb[i] = c.x, F.rgb[i + 1] = c.y, F.rgb[i + 2] = c.z;
+        if (F.u8) F.u8[i] = scale_color(c.x), F.u8[i + 1] = scale_color(c.y), F.u8[i + 2] = scale_color(c.z);
+    }
+};
+
 // World::color_at (world.rs:88-101) with the recursion of reflected_color / refracted_color replaced by an
 // explicit stack of at most depth+1 frames, evaluated in the reference's order (surface, then the whole
 // reflection subtree, then the whole refraction subtree) and combined bottom-up with the same arithmetic.
@@ -49,9 +111,10 @@ __device__ __forceinline__ V3 combine(V3 surface, V3 reflected, V3 refracted, fl
 // Without the vote the compiler's reconvergence points leave lanes that took different exits of the body running
 // their iterations one after the other (c5: 5 of 32 lanes active in the traversal code; 126 -> 64 ms with it).  Scenes
 // whose trees are chains run ~5 % faster without it.
-template <bool STATS, bool SMALL, bool CONVERGE, bool DRAWN = false>
+template <bool STATS, bool SMALL, bool CONVERGE, bool DRAWN = false, class Source = OnePixel>
 __device__ __forceinline__ V3 color_at(const Env& E, bool active, V3 ro, V3 rd, int depth, unsigned pixel, Rays& r, Ctr<STATS>& k,
-                                       float* out_t, int* out_pos) {
+                                       float* out_t, int* out_pos, Source src = Source()) {
+    static_assert(!Source::kStream || CONVERGE, "a pixel stream refills at the converged top of the loop");
     const DevScene& S = E.S;
     Frame stack[kMaxFrames];
     int sp = 0;
@@ -61,7 +124,15 @@ __device__ __forceinline__ V3 color_at(const Env& E, bool active, V3 ro, V3 rd, 
     V3 result = mk(0.f, 0.f, 0.f);
     for (;;) {
         if (CONVERGE) {
-            if (!__any_sync(0xffffffffu, running)) break;
+            if (Source::kStream && src.refill(running, ro, rd, pixel)) sp = 0, remaining = depth, path = 1u;
+            if (!__any_sync(0xffffffffu, running)) {
+                if (src.exhausted()) break;
+                continue;
+            }
+#ifdef RTC_DIAG_LANES
+            k.schlick();                 // diagnostic build: lane-iterations of the ray loop ...
+            if (running) k.pattern();    // ... and how many of them trace a ray
+#endif
             if (!running) continue;
         }
         Hit best{kInfF, -1, 0x7fffffff};
@@ -196,6 +267,7 @@ __device__ __forceinline__ V3 color_at(const Env& E, bool active, V3 ro, V3 rd, 
         for (;;) {
             if (sp == 0) {
                 if (!CONVERGE) return c;
+                if (Source::kStream) src.finish(pixel, c);
                 result = c;
                 running = false;
                 break;

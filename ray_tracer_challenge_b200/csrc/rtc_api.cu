@@ -84,6 +84,7 @@ int lease_slot(int device, DeviceSlot** out) {
     CUDA_TRY(cudaEventCreate(&d->ev0));
     CUDA_TRY(cudaEventCreate(&d->ev1));
     CUDA_TRY(cudaMalloc(&d->d_counters, sizeof(DevCounters)));
+    CUDA_TRY(cudaMalloc(&d->d_stream_counter, 64 * sizeof(unsigned)));  // RTC_OPT_RENDER_SLICES <= 64
     CUDA_TRY(cudaDeviceGetAttribute(&d->sm_count, cudaDevAttrMultiProcessorCount, device));
     // the kernels keep their bounce and traversal stacks in local memory
     size_t have = 0;
@@ -321,7 +322,8 @@ int render_impl(RtcScene* s, int depth, int shard0, int n_shards_ext, float* rgb
         int rc0;
         if ((rc0 = ensure_tiles(slot, total_bands * tiles_x))) return rc0;
         const long long launch_blocks = (long long)nb * tiles_x;
-        const bool order_wanted = s->adaptive_order && n_slices == 1 && nb > 0 &&
+        const bool stream_scene = r.small.n == 0 && (s->stream < 0 ? s->has_branching_materials : s->stream != 0);
+        const bool order_wanted = !stream_scene && s->adaptive_order && n_slices == 1 && nb > 0 &&
                                   launch_blocks < (long long)s->order_max_waves * 5 * slot->sm_count;
         const bool learnt = r.order_shard == shard && r.order_n_shards == n_shards && r.order_depth == depth &&
                             r.order_filter == s->shadow_filter;
@@ -338,12 +340,21 @@ int render_impl(RtcScene* s, int depth, int shard0, int n_shards_ext, float* rgb
             CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
             slot->slice_done.push_back(e);
         }
+        // tree scenes whose ray trees branch: the streaming kernel (lanes draw pixels from a per-slice counter)
+        const bool use_stream = r.small.n == 0 && (s->stream < 0 ? s->has_branching_materials : s->stream != 0);
+        if (use_stream) CUDA_TRY(cudaMemsetAsync(slot->d_stream_counter, 0, 64 * sizeof(unsigned), slot->stream));
         CUDA_TRY(cudaEventRecord(slot->ev0, slot->stream));
         for (int k = 0; k < n_slices; k++) {
             const int b0 = (int)((int64_t)nb * k / n_slices), b1 = (int)((int64_t)nb * (k + 1) / n_slices);
             if (b1 <= b0) continue;
             DevFrame F{slot->d_rgb, slot->d_u8, shard, n_shards, depth, b1 - b0, b0, use_order ? slot->d_tile_order : nullptr,
-                       r.learning ? slot->d_tile_cost : nullptr, s->converge < 0 ? (int)s->has_branching_materials : s->converge};
+                       r.learning ? slot->d_tile_cost : nullptr, s->converge < 0 ? (int)s->has_branching_materials : s->converge,
+                       nullptr, 0};
+            if (use_stream) {
+                F.stream_counter = slot->d_stream_counter + k;
+                F.stream_blocks = slot->sm_count * 6;
+                F.tile_order = nullptr, F.tile_cost = nullptr;
+            }
             if (s->strict_fp)
                 strict::launch_render(r.scene, r.small, F, slot->d_counters, detailed, slot->stream);
             else
@@ -436,6 +447,7 @@ int rtc_scene_create(RtcScene** out) {
     if (const char* env = getenv("RTC_SHADOW_FILTER")) (*out)->shadow_filter = atoi(env) != 0;
     if (const char* env = getenv("RTC_ORDER_MAX_WAVES")) (*out)->order_max_waves = atoi(env);
     if (const char* env = getenv("RTC_CONVERGE")) (*out)->converge = atoi(env);
+    if (const char* env = getenv("RTC_STREAM")) (*out)->stream = atoi(env);
     return 0;
 }
 void rtc_scene_destroy(RtcScene* s) {

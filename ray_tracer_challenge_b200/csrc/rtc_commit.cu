@@ -533,6 +533,22 @@ int flatten(RtcScene* s, Flattened& f) {
 
     lap("validate + item lists");
     // ---- BVH
+    // the largest coordinate a ray of this scene starts from or aims at: the bounded items, the camera, the light
+    float extent = 0.f;
+    for (const Item& it : bounded)
+        for (int a = 0; a < 3; a++) extent = std::max(extent, std::max(std::fabs(it.box.lo[a]), std::fabs(it.box.hi[a])));
+    {
+        float m[16], cam[3] = {0.f, 0.f, 0.f};
+        memcpy(m, s->cam_inv, sizeof(m));  // the camera's origin = inverse * (0, 0, 0): the translation column
+        for (int a = 0; a < 3; a++) cam[a] = m[a * 4 + 3];
+        for (int a = 0; a < 3; a++) {
+            extent = std::max(extent, std::fabs(cam[a]));
+            float l = std::fabs(s->light_pos[a]);
+            if (s->light_is_rect)
+                l = std::max(l, std::fabs(s->corner[a]) + std::fabs(s->u_cell[a]) * s->u_steps + std::fabs(s->v_cell[a]) * s->v_steps);
+            if (std::isfinite(l)) extent = std::max(extent, l);
+        }
+    }
     std::vector<BuildItem> build_items(bounded.size());
     for (size_t i = 0; i < bounded.size(); i++) {
         BuildItem& b = build_items[i];
@@ -540,9 +556,12 @@ int flatten(RtcScene* s, Flattened& f) {
         b.item = (int)i;
         b.closed = bounded[i].prim >= 0 && (s->prims[bounded[i].prim].type == RTC_SPHERE || s->prims[bounded[i].prim].type == RTC_CUBE);
         for (int a = 0; a < 3; a++) {
-            // pad: the tree must never reject a hit the reference would report (it is only an accelerator)
+            // pad: the tree must never reject a hit the reference would report (it is only an accelerator).  The last
+            // term covers the traversal's own arithmetic: slab distances are formed as fma(plane, 1/d, -(o * 1/d)), two
+            // roundings of products as large as the ray origin's coordinate, and 1/d is rounded once — together below 2^-21 of
+            // the scene's extent in length; 2^-20 is added
             float ext = b.box.hi[a] - b.box.lo[a];
-            float pad = 1e-4f * ext + 1e-5f * std::max(std::fabs(b.box.lo[a]), std::fabs(b.box.hi[a])) + 1e-6f;
+            float pad = 1e-4f * ext + 1e-5f * std::max(std::fabs(b.box.lo[a]), std::fabs(b.box.hi[a])) + 1e-6f + 9.54e-7f * extent;
             b.box.lo[a] -= pad;
             b.box.hi[a] += pad;
             b.centroid[a] = 0.5f * (b.box.lo[a] + b.box.hi[a]);
@@ -569,11 +588,12 @@ int flatten(RtcScene* s, Flattened& f) {
         if (root < 0) {  // a single leaf: wrap it so the traversal always starts at an inner node
             DevBvhNode n;
             Box b;
-            for (auto& it : build_items) b.grow(it.box);
+            bool closed = true;
+            for (auto& it : build_items) b.grow(it.box), closed = closed && it.closed;
             n.a = make_float4(b.lo[0], b.lo[1], b.lo[2], b.hi[0]);
             n.b = make_float4(b.hi[1], b.hi[2], NAN, NAN);  // second child: a NaN box never passes the slab test
             n.c = make_float4(NAN, NAN, NAN, NAN);
-            n.d = make_int4(root, root, 0, 0);
+            n.d = make_int4(root, root, closed ? 1 : 0, 0);
             f.bvh.push_back(n);
             root = (int)f.bvh.size() - 1;
         }

@@ -60,6 +60,7 @@ struct DeviceSlot {
     size_t arena_bytes = 0;
     char* staging = nullptr;  // pinned host mirror of the arena for one asynchronous upload
     size_t staging_bytes = 0;
+    unsigned* d_stream_counter = nullptr;  // render_stream's pixel counters, one per slice of a render
     void* d_flush = nullptr;
     size_t flush_bytes = 0;
 };
@@ -132,6 +133,8 @@ struct RtcScene {
     int render_slices = 6;  // kernel / copy pipeline depth when rendering into host memory
     int adaptive_order = 1;  // launch a shard's bands longest-first, learnt from the previous render
     int shadow_filter = 1;   // RTC_OPT_SHADOW_FILTER
+    int stream = -1;           // tree scenes: lanes draw pixels from a counter (render_stream): -1 automatic (branching ray
+                               // trees), 0 / 1 forced (RTC_STREAM)
     int converge = -1;         // color_at warp vote: -1 automatic (branching ray trees), 0 / 1 forced (RTC_CONVERGE)
     bool has_branching_materials = false;  // some material is reflective AND transparent (set at commit)
     int order_max_waves = 128;  // the longest-first order is not even tried for launches longer than this many waves

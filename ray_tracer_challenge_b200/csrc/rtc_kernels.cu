@@ -142,6 +142,23 @@ __global__ void __launch_bounds__(kBlockThreads, min_blocks(SMALL ? (CONVERGE ? 
         atomicMax(&F.tile_cost[band * gridDim.x + bx], (unsigned)min(clock64() - t_start, 0xffffffffLL));
 }
 
+// K1b render_stream: Camera::render for tree scenes with branching ray trees — a persistent grid whose lanes draw
+// pixels from a counter as their ray trees finish (dev_shade.cuh: PixelStream) instead of owning one pixel each.
+#ifndef RTC_STREAM_MINBLOCKS
+#define RTC_STREAM_MINBLOCKS 6
+#endif
+template <bool STATS>
+__global__ void __launch_bounds__(kBlockThreads, min_blocks(RTC_STREAM_MINBLOCKS))
+    render_stream(const __grid_constant__ DevScene S, const __grid_constant__ SmallScene SS, const DevFrame F, DevCounters* counters) {
+    const Env E{S, SS};
+    const int blocks_x = (S.width + 7) / 8;
+    PixelStream src{S, F, F.stream_counter, (unsigned)F.n_bands * (unsigned)blocks_x * 2u * 32u, blocks_x};
+    Ctr<STATS> k;
+    Rays r;
+    color_at<STATS, false, true, false, PixelStream>(E, false, mk(0.f, 0.f, 0.f), mk(0.f, 0.f, 1.f), F.depth, 0u, r, k, nullptr, nullptr, src);
+    flush_counters<STATS>(r, k, counters);
+}
+
 // DRAWN: as in render_tiles — a small scene whose area light draws its jitter (`jitter_fn = None`) takes the
 // drawn-sample cell loop; without it intensity_cells would read light samples nobody staged.
 template <bool SMALL, bool DRAWN>
@@ -174,6 +191,13 @@ void launch_render(const DevScene& S, const SmallScene& SS, const DevFrame& F, D
     dim3 grid((S.width + kTileW - 1) / kTileW, F.n_bands);
     if (grid.x == 0 || grid.y == 0) return;
     const bool small = SS.n > 0;
+    if (!small && F.stream_counter) {  // the host zeroed the counter on this stream
+        if (detailed)
+            render_stream<true><<<F.stream_blocks, kBlockThreads, 0, stream>>>(S, SS, F, counters);
+        else
+            render_stream<false><<<F.stream_blocks, kBlockThreads, 0, stream>>>(S, SS, F, counters);
+        return;
+    }
     // small scenes whose area light draws its samples (jitter None) need the build with the drawn-sample cell loop
     const bool drawn = small && SS.cell_masks && S.jitter_len == 0;
     // the detailed (counting) pass always uses the converging build; the timed kernels pick by DevFrame::converge

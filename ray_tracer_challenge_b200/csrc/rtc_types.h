@@ -33,7 +33,7 @@ constexpr int kFlagHasParent = 2;     // has an enclosing group / CSG whose cull
 constexpr int kMaxFrames = 24;        // explicit reflect/refract stack: depth + 1 frames (depth <= 23)
 constexpr int kCsgHitCap = 32;        // hits a CSG evaluation may hold at once
 constexpr int kCsgRayDepth = 6;       // nested CSG transforms
-constexpr int kBvhStack = 48;
+constexpr int kBvhStack = 48;  // traversal stack entries per thread: one deferred child per level (the builder bounds the depth)
 
 struct DevMaterial {  // 48 B
     float color[3];
@@ -75,7 +75,8 @@ struct DevBvhNode {  // 64 B
     float4 a;  // lo0.xyz, hi0.x
     float4 b;  // hi0.yz, lo1.xy
     float4 c;  // lo1.z, hi1.xyz
-    int4 d;    // child0, child1 (>= 0 inner node; < 0 leaf: ~((first << 4) | (count - 1))), unused, unused
+    int4 d;    // child0, child1 (>= 0 inner node; < 0 leaf: ~((first << 4) | (count - 1))); z: bit i = child i holds closed
+               // primitives only (find_containers culls it with a point-in-box test); w unused
 };
 
 struct DevScene {
@@ -192,7 +193,13 @@ struct DevFrame {  // where a render writes
     const int* tile_order; // this shard's tiles (band * tiles_x + tile column) in launch order, or null: natural order
     unsigned* tile_cost;   // per frame tile: clock cycles its block ran (learns the launch order), or null
     int converge;          // color_at: all lanes of a warp meet at a vote before every ray (see color_at)
+    unsigned* stream_counter;  // render_stream: next unclaimed pixel of the launch (zeroed by the host), or null
+    int stream_blocks;         // render_stream: resident blocks to launch (a persistent grid)
 };
+#ifndef RTC_REFILL_LANES
+#define RTC_REFILL_LANES 8
+#endif
+constexpr int kRefillLanes = RTC_REFILL_LANES;  // render_stream: idle lanes of a warp that trigger a refill
 
 constexpr int kBandRows = kTileH;
 

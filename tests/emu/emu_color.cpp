@@ -8,6 +8,7 @@
 #include <string.h>
 
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include "rtc_internal.h"  // Flattened, RtcScene, rtc::flatten (exported by librtc_b200.so)
@@ -59,10 +60,21 @@ static inline float __uint_as_float(unsigned i) {
 static inline int __float2int_rz(float f) { return (int)f; }
 static inline unsigned __float2uint_rz(float f) { return f > 0.0f ? (unsigned)f : 0u; }
 static inline int min(int a, int b) { return a < b ? a : b; }
+static inline unsigned min(unsigned a, unsigned b) { return a < b ? a : b; }
+static inline unsigned max(unsigned a, unsigned b) { return a > b ? a : b; }
+[[noreturn]] static inline void __trap() { abort(); }
 static inline int max(int a, int b) { return a > b ? a : b; }
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 static inline int __ffs(int v) { return __builtin_ffs(v); }
 static inline int __any_sync(unsigned, int p) { return p; }
+// PixelStream (dev_shade.cuh) is compiled but never run here: one lane per "warp"
+static inline unsigned __ballot_sync(unsigned, int p) { return p ? 1u : 0u; }
+static inline unsigned __shfl_sync(unsigned, unsigned v, int) { return v; }
+static inline unsigned atomicAdd(unsigned* p, unsigned v) {
+    unsigned old = *p;
+    *p += v;
+    return old;
+}
 static inline void __syncthreads() {}
 
 namespace rtc {
