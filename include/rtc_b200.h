@@ -183,6 +183,11 @@ enum {
     RTC_OPT_ADAPTIVE_ORDER = 5, /* default 1: a repeated render of the same shard launches its 16x8-pixel tiles
                                   most-expensive-first (clock cycles per tile recorded by an earlier render) when a
                                   timed trial render shows that order to be faster; changes no pixel */
+    RTC_OPT_BVH_BUILDER = 7,   /* 0 (default): the host's binned-SAH builder — the better tree, 25-30 ms for 10^5 primitives;
+                                  1: the device builder (Morton codes, sort, Karras topology, refit: K3 lbvh_build) for
+                                  scenes of >= 1024 bounded items — a millisecond, a tree that costs more visits per ray:
+                                  the choice for a one-shot render, where the build is most of the frame.  Same pixels
+                                  either way (the tree only selects which primitives get the exact test).  Before commit */
     RTC_OPT_SHADOW_FILTER = 6   /* default 1: in small scenes of spheres, planes and axis-aligned cubes a shadow ray is
                                   first decided on the un-normalised point->light segment with error bounds; only
                                   undecided rays run the reference's arithmetic.  Changes no pixel (0 = always run

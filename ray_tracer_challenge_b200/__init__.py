@@ -84,6 +84,7 @@ _V, _I, _FP, _IP, _U8P = C.c_void_p, C.c_int, _api.FP, _api.IP, _api.U8P
 _HOST_EXTRAS = {
     "sg_set_render_options": (_I, [_V, _I, _IP, _I, _I]),
     "sg_last_rtc_stats": (_I, [_V, C.POINTER(RtcStats)]),
+    "sg_set_bvh_builder": (_I, [_V, _I]),
     "sg_prepare": (_I, [_V, _I, _I]),
     "sg_camera_render_shard": (_I, [_V, _I, _I, _I, _I, _I, _FP, _U8P, C.POINTER(SgStats)]),
     "sg_inspect": (_I, [_V, _I, _I, C.c_void_p, C.POINTER(C.c_double)]),
@@ -174,6 +175,11 @@ class HostApi(_api.Api):
             ids = (C.c_int * len(device_ids))(*device_ids)
             n_devices = len(device_ids)
         self.check(self.lib.sg_set_render_options(self.ctx, int(n_devices), ids, int(fma), int(detailed)))
+
+    def set_bvh_builder(self, mode: int = -1):
+        """RTC_OPT_BVH_BUILDER policy of this session: -1 automatic (device LBVH for one-shot renders of >= 10 000
+        primitives, the host's binned SAH for prepared scenes), 0 always host, 1 always device."""
+        self.check(self.lib.sg_set_bvh_builder(self.ctx, int(mode)))
 
     def last_rtc_stats(self) -> RtcStats:
         st = RtcStats()

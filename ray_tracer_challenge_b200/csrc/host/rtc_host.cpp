@@ -163,9 +163,14 @@ static void to_sg_stats(const RtcStats& r, sg_stats* s) {
     s->shades = r.shades, s->flops = r.flops, s->ms = r.kernel_ms, s->ms_total = r.total_ms;
 }
 
-static int commit(sg_ctx* c, RtcScene* scene) {
+// one_shot: the scene is rendered once and dropped (Camera::render_b200: the reference's render consumes its World,
+// camera.rs:76) — for a big scene the tree is then built on the device (RTC_OPT_BVH_BUILDER), where a millisecond buys a
+// tree a little worse than the host's 25-30 ms binned SAH; a scene kept resident (sg_prepare) gets the better tree.
+static int commit(sg_ctx* c, RtcScene* scene, bool one_shot, size_t n_prims) {
     const RenderOptions& o = c->options;
     if (rtc_set_option(scene, RTC_OPT_FMA_CONTRACTION, o.fma ? 1 : 0)) return fail(rtc_last_error());
+    const bool device_tree = o.bvh_builder < 0 ? (one_shot && n_prims >= 10000) : o.bvh_builder != 0;
+    if (rtc_set_option(scene, RTC_OPT_BVH_BUILDER, device_tree ? 1 : 0)) return fail(rtc_last_error());
     const int32_t* ids = o.device_ids.empty() ? nullptr : o.device_ids.data();
     int n = o.device_ids.empty() ? o.n_devices : (int)o.device_ids.size();
     if (rtc_scene_commit(scene, n, ids)) return fail(rtc_last_error());
@@ -392,6 +397,11 @@ int sg_set_render_options(sg_ctx* c, int n_devices, const int* device_ids, int f
     c->options.detailed = detailed != 0;
     return 0;
 }
+// -1 (default): automatic — the device builder for one-shot renders of >= 10 000 primitives; 0 / 1: always host / device
+int sg_set_bvh_builder(sg_ctx* c, int mode) {
+    c->options.bvh_builder = mode < 0 ? -1 : (mode != 0);
+    return 0;
+}
 int sg_last_rtc_stats(sg_ctx* c, RtcStats* out) {
     *out = c->last_stats;
     return 0;
@@ -412,7 +422,7 @@ static int camera_render(sg_ctx* c, int cam, int w, int depth, int shard, int n_
         auto t0 = std::chrono::steady_clock::now();
         FlatScene flat;
         fill_scene(scene, c->graph, c->worlds[w], c->cameras[cam], flat);
-        rc = commit(c, scene);
+        rc = commit(c, scene, true, flat.prims.size());
         if (!rc) {
             if (n_shards > 1)
                 rc = rtc_render_shard(scene, depth, shard, n_shards, out_rgb, out_u8, &c->last_stats);
@@ -491,7 +501,7 @@ int sg_prepare(sg_ctx* c, int cam, int w) {
         rtc_scene_destroy(p->scene);
         return fail(e.what());
     }
-    if (commit(c, p->scene)) {
+    if (commit(c, p->scene, false, p->flat.prims.size())) {
         rtc_scene_destroy(p->scene);
         return -1;
     }

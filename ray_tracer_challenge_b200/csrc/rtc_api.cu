@@ -448,6 +448,7 @@ int rtc_scene_create(RtcScene** out) {
     if (const char* env = getenv("RTC_ORDER_MAX_WAVES")) (*out)->order_max_waves = atoi(env);
     if (const char* env = getenv("RTC_CONVERGE")) (*out)->converge = atoi(env);
     if (const char* env = getenv("RTC_STREAM")) (*out)->stream = atoi(env);
+    if (const char* env = getenv("RTC_BVH_BUILDER")) (*out)->bvh_builder = atoi(env) != 0;
     return 0;
 }
 void rtc_scene_destroy(RtcScene* s) {
@@ -563,6 +564,11 @@ int rtc_set_option(RtcScene* s, int32_t option, int64_t value) {
             if (value < 1 || value > 64) return fail(RTC_ERR_INVALID, "render slices must be in [1,64]");
             s->render_slices = (int)value;
             return 0;
+        case RTC_OPT_BVH_BUILDER:
+            if (value != 0 && value != 1) return fail(RTC_ERR_INVALID, "bvh builder: 0 (host binned SAH) or 1 (device LBVH)");
+            s->bvh_builder = (int)value;
+            s->committed = false;
+            return 0;
         case RTC_OPT_BVH_MIN_PRIMS:
             s->bvh_min_prims = (int)std::max<int64_t>(0, value);
             s->committed = false;
@@ -614,7 +620,18 @@ int rtc_scene_commit(RtcScene* s, int32_t n_devices, const int32_t* device_ids) 
     if (n_devices < 0 || n_devices > visible) return fail(RTC_ERR_INVALID, "bad device count");
     release(s);
     Flattened f;
-    int rc = flatten(s, f);
+    int rc;
+    if (s->bvh_builder == 1) {  // the tree of a big scene is built on the first device of the commit
+        const int dev0 = device_ids ? device_ids[0] : 0;
+        if (dev0 < 0 || dev0 >= visible) return fail(RTC_ERR_INVALID, "bad device id");
+        DeviceSlot* slot = nullptr;
+        if ((rc = lease_slot(dev0, &slot))) return rc;
+        CUDA_TRY(cudaSetDevice(dev0));
+        rc = flatten(s, f, lbvh_build, slot->stream);
+        return_slot(slot);
+    } else {
+        rc = flatten(s, f);
+    }
     if (rc) return rc;
     s->replicas.resize(n_devices);
     s->replica_devices.resize(n_devices);

@@ -469,7 +469,7 @@ void plan_small_scene(const RtcScene* s, Flattened& f, int n_items) {
 
 }  // namespace
 
-int flatten(RtcScene* s, Flattened& f) {
+int flatten(RtcScene* s, Flattened& f, TreeBuilderFn tree_builder, void* tree_builder_ctx) {
     const int np = (int)s->prims.size(), nn = (int)s->nodes.size();
     const bool timing = getenv("RTC_TIMING") != nullptr;  // tuning aid: phase times of the host half on stderr
     auto t_last = std::chrono::steady_clock::now();
@@ -576,12 +576,34 @@ int flatten(RtcScene* s, Flattened& f) {
         int leaf = s->leaf_size > 0 ? s->leaf_size : (2 * n_triangles > bounded.size() ? 4 : 1);
         if (const char* env = getenv("RTC_BVH_LEAF")) leaf = atoi(env);  // tuning aid
         f.leaf_size = std::min(std::max(leaf, 1), 16);
-        Builder builder{build_items, f.bvh, f.leaf_size};
-        const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
-        while ((1u << builder.par_depth) < hw && builder.par_depth < 5) builder.par_depth++;  // up to 32 subtree tasks
-        f.bvh.reserve(build_items.size());
-        int root = builder.build(0, (int)build_items.size(), 0);
-        f.bvh_depth = builder.max_depth + 1;
+        int root = 0;
+        s->built_on_device = 0;
+        if (tree_builder && build_items.size() >= 1024) {  // the device builder: the same padded boxes, Morton order
+            std::vector<float> boxes(6 * build_items.size());
+            std::vector<unsigned char> closed(build_items.size());
+            for (size_t i = 0; i < build_items.size(); i++) {
+                for (int a = 0; a < 3; a++) boxes[6 * i + a] = build_items[i].box.lo[a], boxes[6 * i + 3 + a] = build_items[i].box.hi[a];
+                closed[i] = build_items[i].closed;
+            }
+            TreeBuildOutput out;
+            if (tree_builder(tree_builder_ctx, TreeBuildInput{boxes.data(), closed.data(), (int)build_items.size(), f.leaf_size}, out) == 0) {
+                std::vector<BuildItem> sorted(build_items.size());
+                for (size_t i = 0; i < sorted.size(); i++) sorted[i] = build_items[out.order[i]];
+                build_items.swap(sorted);
+                f.bvh.swap(out.nodes);
+                root = out.root;
+                f.bvh_depth = out.depth;
+                s->built_on_device = 1;
+            }
+        }
+        if (!s->built_on_device) {
+            Builder builder{build_items, f.bvh, f.leaf_size};
+            const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+            while ((1u << builder.par_depth) < hw && builder.par_depth < 5) builder.par_depth++;  // up to 32 subtree tasks
+            f.bvh.reserve(build_items.size());
+            root = builder.build(0, (int)build_items.size(), 0);
+            f.bvh_depth = builder.max_depth + 1;
+        }
         if (f.bvh_depth > kBvhStack - 1)  // cannot happen (Builder::build balances before the cap); never silent if it does
             return fail(RTC_ERR_CAPACITY, "BVH depth " + std::to_string(f.bvh_depth) + " exceeds the traversal stack (" +
                                               std::to_string(kBvhStack) + ")");

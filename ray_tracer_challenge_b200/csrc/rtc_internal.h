@@ -130,6 +130,8 @@ struct RtcScene {
     std::vector<float> jitter;
     uint64_t seed = 0;
     int strict_fp = 1, leaf_size = 0 /* automatic */, bvh_min_prims = rtc::kSmallCap + 1;
+    int bvh_builder = 0;       // RTC_OPT_BVH_BUILDER: 0 host binned SAH, 1 device LBVH (scenes of >= kLbvhMinItems bounded items)
+    int built_on_device = 0;   // the last commit's tree came from the device builder
     int render_slices = 6;  // kernel / copy pipeline depth when rendering into host memory
     int adaptive_order = 1;  // launch a shard's bands longest-first, learnt from the previous render
     int shadow_filter = 1;   // RTC_OPT_SHADOW_FILTER
@@ -146,6 +148,24 @@ struct RtcScene {
 };
 
 namespace rtc {
-// The host half of a commit: fills `f` from the scene (and the scene's commit statistics); no device calls.
-int flatten(RtcScene* s, Flattened& f);
+// A tree builder other than the host's binned SAH (rtc_lbvh.cu: the device LBVH).  In: the padded boxes of the bounded
+// items (6 floats each: lo.xyz, hi.xyz), their "closed primitive" flags, the leaf size.  Out: the items' leaf order, the
+// binary nodes, the root link (>= 0 node, < 0 a leaf code: the whole tree is one leaf) and the tree's depth.  A non-zero
+// return means "not built": flatten() then uses the host builder.
+struct TreeBuildInput {
+    const float* boxes;
+    const unsigned char* closed;
+    int n, leaf_size;
+};
+struct TreeBuildOutput {
+    std::vector<int> order;
+    std::vector<DevBvhNode> nodes;
+    int root = -1, depth = 0;
+};
+using TreeBuilderFn = int (*)(void* ctx, const TreeBuildInput&, TreeBuildOutput&);
+int lbvh_build(void* ctx, const TreeBuildInput& in, TreeBuildOutput& out);  // ctx: the cudaStream_t to build on
+
+// The host half of a commit: fills `f` from the scene (and the scene's commit statistics).  No device calls of its own:
+// rtc_scene_inspect runs it without a GPU; rtc_scene_commit may pass the device tree builder.
+int flatten(RtcScene* s, Flattened& f, TreeBuilderFn tree_builder = nullptr, void* tree_builder_ctx = nullptr);
 }  // namespace rtc

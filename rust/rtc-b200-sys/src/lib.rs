@@ -48,6 +48,7 @@ pub const RTC_OPT_BVH_MIN_PRIMS: i32 = 3;
 pub const RTC_OPT_RENDER_SLICES: i32 = 4;
 pub const RTC_OPT_ADAPTIVE_ORDER: i32 = 5;
 pub const RTC_OPT_SHADOW_FILTER: i32 = 6;
+pub const RTC_OPT_BVH_BUILDER: i32 = 7;
 
 #[repr(C)]
 #[derive(Clone, Copy)]
