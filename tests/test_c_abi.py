@@ -365,3 +365,45 @@ def test_rust_sys_crate_mirrors_the_header(tmp_path):
     for const in re.findall(r"\b(RTC_[A-Z0-9_]+)\s*=\s*(-?\d+)", header):
         m = re.search(r"pub const " + const[0] + r"\s*:\s*\w+\s*=\s*(-?\d+)", rust)
         assert m and m.group(1) == const[1], f"rtc-b200-sys: constant {const[0]} missing or different"
+
+
+def test_rust_glue_covers_every_implementer_and_only_uses_what_the_sys_crate_declares():
+    """rust/lib_patch/render_b200.rs (not compilable here) lowers EVERY Shape / Pattern / UVPattern / UVMapping / Light
+    implementer of the reference, and every `sys::` item it names is declared by rust/rtc-b200-sys.  When the reference
+    checkout is present (this container, not the GPU box) the implementer lists are re-derived from its sources."""
+    glue = open(os.path.join(ROOT, "rust", "lib_patch", "render_b200.rs")).read()
+    sys_crate = open(os.path.join(ROOT, "rust", "rtc-b200-sys", "src", "lib.rs")).read()
+    expected = {
+        "flatten": {"Sphere", "Plane", "Cube", "Cylinder", "Cone", "Triangle", "SmoothTriangle", "GroupShape", "CSG", "TestShape", "BaseShape"},
+        "lower": {"Stripes", "Gradient", "Rings", "Checkers", "Sine2D", "TestPattern", "TextureMap", "CubicMap", "BasePattern",
+                  "PointLight", "RectangleLight"},
+        "lower_uv": {"UVCheckers", "AlignCheck", "UVImage"},
+        "mapping_id": {"SphericalMap", "PlanarMap", "CylindricalMap"},
+    }
+    ref = "/root/reference/lib/src"
+    if os.path.isdir(ref):
+        found = {"Shape": set(), "Pattern": set(), "UVPattern": set(), "UVMapping": set(), "Light": set()}
+        for dirpath, _, files in os.walk(ref):
+            for f in files:
+                if f.endswith(".rs"):
+                    for trait, name in re.findall(r"impl(?:<[^>]*>)?\s+(Shape|Pattern|UVPattern|UVMapping|Light)\s+for\s+(\w+)",
+                                                  open(os.path.join(dirpath, f)).read()):
+                        found[trait].add(name)
+        assert found["Shape"] == expected["flatten"], found["Shape"] ^ expected["flatten"]
+        assert found["Pattern"] | found["Light"] == expected["lower"], (found["Pattern"] | found["Light"]) ^ expected["lower"]
+        assert found["UVPattern"] == expected["lower_uv"] and found["UVMapping"] == expected["mapping_id"]
+    for method, types in expected.items():
+        for t in types:
+            body = re.search(r"impl " + t + r"(?:<'_>)? \{(.*?)\n\}", glue, flags=re.S)
+            assert body and re.search(r"fn " + method + r"\(", body.group(1)), f"render_b200.rs: `{t}` lacks `{method}`"
+    declared_names = set(re.findall(r"pub (?:const|fn|struct) (\w+)", sys_crate))
+    used = set(re.findall(r"\bsys::(\w+)", glue))
+    assert used and used <= declared_names, used - declared_names
+    # field names used in struct literals exist in the sys crate's structs
+    for struct, body in re.findall(r"sys::(Rtc\w+) \{(.*?)\}", glue, flags=re.S):
+        decl = re.search(r"pub struct " + struct + r"\s*\{(.*?)\n\}", sys_crate, flags=re.S).group(1)
+        fields = set(re.findall(r"pub (\w+)\s*:", decl))
+        for name in re.findall(r"(?:^|,|\{)\s*(\w+)\s*(?::|,|$)", body):
+            if name in ("if", "else", "sys", "self", "unsafe"):
+                continue
+            assert name in fields or not name.islower() or name in ("w", "h", "px"), (struct, name, fields)
