@@ -317,12 +317,15 @@ int render_impl(RtcScene* s, int depth, int shard0, int n_shards_ext, float* rgb
         // pays depends on the frame, not on its size alone (c3: 1/8 of the 4K frame 13 % faster, 1/4 of it 2 %
         // slower, the whole frame 7 % slower; the whole 1080p mesh frame c4 25 % faster), so the second render is a
         // trial: the learnt order is kept only if that render beats the natural-order one by more than 2 %.
-        const int n_slices = copy_out ? std::max(1, std::min(s->render_slices, nb)) : 1;
+        // tree scenes whose ray trees branch: the streaming kernel (lanes draw pixels from a per-launch counter).  A
+        // persistent launch pays its tail once per launch and such frames take far longer than their copy, so they
+        // are not sliced
+        const bool stream_scene = r.small.n == 0 && (s->stream < 0 ? s->has_branching_materials : s->stream != 0);
+        const int n_slices = copy_out && !stream_scene ? std::max(1, std::min(s->render_slices, nb)) : 1;
         const int tiles_x = ((int)s->width + kTileW - 1) / kTileW;
         int rc0;
         if ((rc0 = ensure_tiles(slot, total_bands * tiles_x))) return rc0;
         const long long launch_blocks = (long long)nb * tiles_x;
-        const bool stream_scene = r.small.n == 0 && (s->stream < 0 ? s->has_branching_materials : s->stream != 0);
         const bool order_wanted = !stream_scene && s->adaptive_order && n_slices == 1 && nb > 0 &&
                                   launch_blocks < (long long)s->order_max_waves * 5 * slot->sm_count;
         const bool learnt = r.order_shard == shard && r.order_n_shards == n_shards && r.order_depth == depth &&
@@ -340,8 +343,7 @@ int render_impl(RtcScene* s, int depth, int shard0, int n_shards_ext, float* rgb
             CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
             slot->slice_done.push_back(e);
         }
-        // tree scenes whose ray trees branch: the streaming kernel (lanes draw pixels from a per-slice counter)
-        const bool use_stream = r.small.n == 0 && (s->stream < 0 ? s->has_branching_materials : s->stream != 0);
+        const bool use_stream = stream_scene;
         if (use_stream) CUDA_TRY(cudaMemsetAsync(slot->d_stream_counter, 0, 64 * sizeof(unsigned), slot->stream));
         CUDA_TRY(cudaEventRecord(slot->ev0, slot->stream));
         for (int k = 0; k < n_slices; k++) {
@@ -627,7 +629,8 @@ int rtc_scene_commit(RtcScene* s, int32_t n_devices, const int32_t* device_ids) 
         DeviceSlot* slot = nullptr;
         if ((rc = lease_slot(dev0, &slot))) return rc;
         CUDA_TRY(cudaSetDevice(dev0));
-        rc = flatten(s, f, lbvh_build, slot->stream);
+        LbvhContext ctx{slot->stream, &slot->lbvh_scratch, &slot->lbvh_scratch_bytes, &slot->lbvh_pinned, &slot->lbvh_pinned_bytes};
+        rc = flatten(s, f, lbvh_build, &ctx);
         return_slot(slot);
     } else {
         rc = flatten(s, f);

@@ -60,6 +60,10 @@ struct DeviceSlot {
     size_t arena_bytes = 0;
     char* staging = nullptr;  // pinned host mirror of the arena for one asynchronous upload
     size_t staging_bytes = 0;
+    char* lbvh_scratch = nullptr;  // the device tree builder's buffers (grow-only, kept with the slot)
+    size_t lbvh_scratch_bytes = 0;
+    char* lbvh_pinned = nullptr;   // ... and its pinned staging (boxes up, order and nodes down)
+    size_t lbvh_pinned_bytes = 0;
     unsigned* d_stream_counter = nullptr;  // render_stream's pixel counters, one per slice of a render
     void* d_flush = nullptr;
     size_t flush_bytes = 0;
@@ -163,7 +167,14 @@ struct TreeBuildOutput {
     int root = -1, depth = 0;
 };
 using TreeBuilderFn = int (*)(void* ctx, const TreeBuildInput&, TreeBuildOutput&);
-int lbvh_build(void* ctx, const TreeBuildInput& in, TreeBuildOutput& out);  // ctx: the cudaStream_t to build on
+struct LbvhContext {  // lbvh_build's ctx: the stream to build on and the slot's grow-only scratch buffers
+    cudaStream_t stream;
+    char** scratch;
+    size_t* scratch_bytes;
+    char** pinned;
+    size_t* pinned_bytes;
+};
+int lbvh_build(void* ctx, const TreeBuildInput& in, TreeBuildOutput& out);
 
 // The host half of a commit: fills `f` from the scene (and the scene's commit statistics).  No device calls of its own:
 // rtc_scene_inspect runs it without a GPU; rtc_scene_commit may pass the device tree builder.

@@ -5,7 +5,9 @@
 // padded boxes of the bounded items and returns the same two things the host builder produces — the items' leaf order
 // and the array of binary nodes (rtc_types.h: DevBvhNode) — in four small launches:
 //
-//   lbvh_codes    63-bit Morton code of every box centre (21 bits per axis inside the scene's bounds)
+//   lbvh_codes    Morton code of every box centre inside the scene's bounds, `bits` bits per axis with
+//                 3 * bits + ceil(log2 n) <= kBvhStack - 4: the tree's depth is at most the number of code bits plus the
+//                 depth of the balanced position-split subtrees among equal codes, so it always fits the traversal stack
 //   lbvh_sort     bitonic sort of (code, item) pairs, padded to a power of two (hand-written: log^2 n passes of n / 2
 //                 compare-exchanges; 10^5 items: 153 launches, ~0.5 ms)
 //   lbvh_topology Karras 2012: node i's range, split and children from the common prefixes of neighbouring codes
@@ -21,6 +23,7 @@
 // in either: primitives arrive here already flattened in depth-first order.
 #include <cfloat>
 #include <cstdint>
+#include <cstring>
 #include <vector>
 
 #include <cuda_runtime.h>
@@ -44,7 +47,8 @@ __device__ __forceinline__ unsigned long long spread21(unsigned v) {  // 21 bits
     return x;
 }
 
-__global__ void lbvh_codes(const LbvhBox* boxes, int n, int padded, float3 lo, float3 scale, unsigned long long* keys, int* items) {
+__global__ void lbvh_codes(const LbvhBox* boxes, int n, int padded, float3 lo, float3 scale, float qmax, unsigned long long* keys,
+                           int* items) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= padded) return;
     if (i >= n) {  // padding sorts last
@@ -54,9 +58,9 @@ __global__ void lbvh_codes(const LbvhBox* boxes, int n, int padded, float3 lo, f
     }
     const LbvhBox b = boxes[i];
     const float cx = 0.5f * (b.lo[0] + b.hi[0]), cy = 0.5f * (b.lo[1] + b.hi[1]), cz = 0.5f * (b.lo[2] + b.hi[2]);
-    const unsigned qx = (unsigned)fminf(fmaxf((cx - lo.x) * scale.x, 0.0f), 2097151.0f);
-    const unsigned qy = (unsigned)fminf(fmaxf((cy - lo.y) * scale.y, 0.0f), 2097151.0f);
-    const unsigned qz = (unsigned)fminf(fmaxf((cz - lo.z) * scale.z, 0.0f), 2097151.0f);
+    const unsigned qx = (unsigned)fminf(fmaxf((cx - lo.x) * scale.x, 0.0f), qmax);
+    const unsigned qy = (unsigned)fminf(fmaxf((cy - lo.y) * scale.y, 0.0f), qmax);
+    const unsigned qz = (unsigned)fminf(fmaxf((cz - lo.z) * scale.z, 0.0f), qmax);
     keys[i] = spread21(qx) << 2 | spread21(qy) << 1 | spread21(qz);
     items[i] = i;
 }
@@ -189,39 +193,49 @@ __global__ void lbvh_depth(const LbvhNode* nodes, const int* leaf_parent, int n,
         }                                                                      \
     } while (0)
 
-struct DeviceBuffers {  // freed on every exit path
-    std::vector<void*> ptrs;
+// carves 256-byte aligned pieces out of one buffer
+struct Carver {
+    char* base;
+    size_t used = 0;
     template <class T>
-    cudaError_t alloc(T** p, size_t count) {
-        cudaError_t e = cudaMalloc((void**)p, std::max<size_t>(count, 1) * sizeof(T));
-        if (e == cudaSuccess) ptrs.push_back(*p);
-        return e;
-    }
-    ~DeviceBuffers() {
-        for (void* p : ptrs) cudaFree(p);
+    T* take(size_t count) {
+        T* p = reinterpret_cast<T*>(base + used);
+        used = (used + std::max<size_t>(count, 1) * sizeof(T) + 255) & ~size_t(255);
+        return p;
     }
 };
 
 }  // namespace
 
-// TreeBuilderFn (rtc_internal.h).  ctx: the cudaStream_t to build on (the current device is the scene's first replica).
-// Returns 0 and fills `out`, or non-zero: the caller builds on the host instead (too few items, tree too deep, CUDA error).
-int lbvh_build(void* ctx, const TreeBuildInput& in, TreeBuildOutput& out) {
+// TreeBuilderFn (rtc_internal.h).  ctx: an LbvhContext (the current device is the scene's first replica).
+// Returns 0 and fills `out`, or non-zero: the caller builds on the host instead (too few items, CUDA error).
+int lbvh_build(void* ctx_, const TreeBuildInput& in, TreeBuildOutput& out) {
     const int n = in.n;
     if (n < 2) return 1;
-    cudaStream_t stream = static_cast<cudaStream_t>(ctx);
-    int padded = 1;
-    while (padded < n) padded <<= 1;
+    LbvhContext& ctx = *static_cast<LbvhContext*>(ctx_);
+    cudaStream_t stream = ctx.stream;
+    int padded = 1, log2n = 0;
+    while (padded < n) padded <<= 1, log2n++;
+    // depth <= 3 * bits (code bits) + log2n (position bits among equal codes): keep it inside the traversal stack
+    const int bits = std::max(1, std::min(21, (kBvhStack - 4 - log2n) / 3));
     float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
     for (int i = 0; i < n; i++)
         for (int a = 0; a < 3; a++) {
             const float c = 0.5f * (in.boxes[6 * (size_t)i + a] + in.boxes[6 * (size_t)i + 3 + a]);
             lo[a] = std::min(lo[a], c), hi[a] = std::max(hi[a], c);
         }
+    const float cells = (float)(1u << bits);
     float scale[3];
-    for (int a = 0; a < 3; a++) scale[a] = hi[a] > lo[a] ? 2097152.0f / (hi[a] - lo[a]) : 0.0f;
+    for (int a = 0; a < 3; a++) scale[a] = hi[a] > lo[a] ? cells / (hi[a] - lo[a]) : 0.0f;
 
-    DeviceBuffers dev;
+    // ---- buffers: one device block and one pinned block, kept with the device slot between builds
+    static_assert(sizeof(LbvhBox) == 6 * sizeof(float), "boxes arrive as 6 floats per item");
+    auto layout = [&](Carver& c, LbvhBox*& boxes, unsigned char*& closed, unsigned long long*& keys, int*& items, int*& leaf_parent,
+                      int*& arrivals, int*& depth, LbvhNode*& nodes, LbvhBounds*& bounds, DevBvhNode*& outn) {
+        boxes = c.take<LbvhBox>(n), closed = c.take<unsigned char>(n), keys = c.take<unsigned long long>(padded);
+        items = c.take<int>(padded), leaf_parent = c.take<int>(n), arrivals = c.take<int>(n), depth = c.take<int>(1);
+        nodes = c.take<LbvhNode>(n), bounds = c.take<LbvhBounds>(n), outn = c.take<DevBvhNode>(n);
+    };
     LbvhBox* d_boxes;
     unsigned char* d_closed;
     unsigned long long* d_keys;
@@ -229,25 +243,38 @@ int lbvh_build(void* ctx, const TreeBuildInput& in, TreeBuildOutput& out) {
     LbvhNode* d_nodes;
     LbvhBounds* d_bounds;
     DevBvhNode* d_out;
-    LBVH_TRY(dev.alloc(&d_boxes, n));
-    LBVH_TRY(dev.alloc(&d_closed, n));
-    LBVH_TRY(dev.alloc(&d_keys, padded));
-    LBVH_TRY(dev.alloc(&d_items, padded));
-    LBVH_TRY(dev.alloc(&d_leaf_parent, n));
-    LBVH_TRY(dev.alloc(&d_arrivals, n));
-    LBVH_TRY(dev.alloc(&d_depth, 1));
-    LBVH_TRY(dev.alloc(&d_nodes, n));
-    LBVH_TRY(dev.alloc(&d_bounds, n));
-    LBVH_TRY(dev.alloc(&d_out, n));
-    static_assert(sizeof(LbvhBox) == 6 * sizeof(float), "boxes arrive as 6 floats per item");
-    LBVH_TRY(cudaMemcpyAsync(d_boxes, in.boxes, (size_t)n * sizeof(LbvhBox), cudaMemcpyHostToDevice, stream));
-    LBVH_TRY(cudaMemcpyAsync(d_closed, in.closed, (size_t)n, cudaMemcpyHostToDevice, stream));
+    Carver sizing{nullptr};
+    layout(sizing, d_boxes, d_closed, d_keys, d_items, d_leaf_parent, d_arrivals, d_depth, d_nodes, d_bounds, d_out);
+    if (sizing.used > *ctx.scratch_bytes) {
+        if (*ctx.scratch) cudaFree(*ctx.scratch);
+        *ctx.scratch = nullptr, *ctx.scratch_bytes = 0;
+        LBVH_TRY(cudaMalloc(ctx.scratch, sizing.used + sizing.used / 4));
+        *ctx.scratch_bytes = sizing.used + sizing.used / 4;
+    }
+    Carver dev{*ctx.scratch};
+    layout(dev, d_boxes, d_closed, d_keys, d_items, d_leaf_parent, d_arrivals, d_depth, d_nodes, d_bounds, d_out);
+    // pinned staging: [boxes | closed] up, [order | nodes | depth] down
+    const size_t up_bytes = ((size_t)n * sizeof(LbvhBox) + n + 255) & ~size_t(255);
+    const size_t down_bytes = (size_t)n * sizeof(int) + (size_t)n * sizeof(DevBvhNode) + 256;
+    if (up_bytes + down_bytes > *ctx.pinned_bytes) {
+        if (*ctx.pinned) cudaFreeHost(*ctx.pinned);
+        *ctx.pinned = nullptr, *ctx.pinned_bytes = 0;
+        LBVH_TRY(cudaHostAlloc(ctx.pinned, (up_bytes + down_bytes) * 5 / 4, cudaHostAllocDefault));
+        *ctx.pinned_bytes = (up_bytes + down_bytes) * 5 / 4;
+    }
+    char* h_up = *ctx.pinned;
+    char* h_down = *ctx.pinned + up_bytes;
+    memcpy(h_up, in.boxes, (size_t)n * sizeof(LbvhBox));
+    memcpy(h_up + (size_t)n * sizeof(LbvhBox), in.closed, n);
+    LBVH_TRY(cudaMemcpyAsync(d_boxes, h_up, (size_t)n * sizeof(LbvhBox), cudaMemcpyHostToDevice, stream));
+    LBVH_TRY(cudaMemcpyAsync(d_closed, h_up + (size_t)n * sizeof(LbvhBox), (size_t)n, cudaMemcpyHostToDevice, stream));
     LBVH_TRY(cudaMemsetAsync(d_arrivals, 0, (size_t)n * sizeof(int), stream));
     LBVH_TRY(cudaMemsetAsync(d_depth, 0, sizeof(int), stream));
     LBVH_TRY(cudaMemsetAsync(d_out, 0, (size_t)n * sizeof(DevBvhNode), stream));
     const int threads = 256;
     lbvh_codes<<<(padded + threads - 1) / threads, threads, 0, stream>>>(d_boxes, n, padded, make_float3(lo[0], lo[1], lo[2]),
-                                                                         make_float3(scale[0], scale[1], scale[2]), d_keys, d_items);
+                                                                         make_float3(scale[0], scale[1], scale[2]), cells - 1.0f, d_keys,
+                                                                         d_items);
     for (int k = 2; k <= padded; k <<= 1)
         for (int j = k >> 1; j > 0; j >>= 1) lbvh_sort<<<(padded + threads - 1) / threads, threads, 0, stream>>>(d_keys, d_items, padded, j, k);
     lbvh_topology<<<(n + threads - 1) / threads, threads, 0, stream>>>(d_keys, n, d_nodes, d_leaf_parent);
@@ -255,15 +282,17 @@ int lbvh_build(void* ctx, const TreeBuildInput& in, TreeBuildOutput& out) {
                                                                    d_bounds, d_arrivals, d_out);
     lbvh_depth<<<(n + threads - 1) / threads, threads, 0, stream>>>(d_nodes, d_leaf_parent, n, in.leaf_size, d_depth);
     LBVH_TRY(cudaGetLastError());
-    int depth = 0;
-    out.order.resize(n);
-    out.nodes.resize(n - 1);
-    LBVH_TRY(cudaMemcpyAsync(&depth, d_depth, sizeof(int), cudaMemcpyDeviceToHost, stream));
-    LBVH_TRY(cudaMemcpyAsync(out.order.data(), d_items, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, stream));
-    LBVH_TRY(cudaMemcpyAsync(out.nodes.data(), d_out, (size_t)(n - 1) * sizeof(DevBvhNode), cudaMemcpyDeviceToHost, stream));
+    int* h_order = reinterpret_cast<int*>(h_down);
+    DevBvhNode* h_nodes = reinterpret_cast<DevBvhNode*>(h_down + (((size_t)n * sizeof(int) + 63) & ~size_t(63)));
+    int* h_depth = reinterpret_cast<int*>(reinterpret_cast<char*>(h_nodes) + (size_t)n * sizeof(DevBvhNode));
+    LBVH_TRY(cudaMemcpyAsync(h_depth, d_depth, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    LBVH_TRY(cudaMemcpyAsync(h_order, d_items, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, stream));
+    LBVH_TRY(cudaMemcpyAsync(h_nodes, d_out, (size_t)(n - 1) * sizeof(DevBvhNode), cudaMemcpyDeviceToHost, stream));
     LBVH_TRY(cudaStreamSynchronize(stream));
-    if (depth > kBvhStack - 2) return 1;  // deeper than the traversal stack: the host builder balances instead
-    out.depth = depth;
+    if (*h_depth > kBvhStack - 2) return 1;  // cannot happen (the bit budget above); refused rather than truncated if it does
+    out.depth = *h_depth;
+    out.order.assign(h_order, h_order + n);
+    out.nodes.assign(h_nodes, h_nodes + (n - 1));
     // the whole tree fits one leaf: the caller wraps it (as it does for the host builder)
     out.root = n <= in.leaf_size ? ~((0 << 4) | (n - 1)) : 0;
     return 0;
