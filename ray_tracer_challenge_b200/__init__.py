@@ -38,7 +38,7 @@ class RtcStats(C.Structure):
         ("shades", C.c_uint64), ("node_visits", C.c_uint64), ("prim_tests", C.c_uint64 * 8), ("xforms", C.c_uint64),
         ("patterns", C.c_uint64), ("cells", C.c_uint64), ("schlicks", C.c_uint64), ("refr_dirs", C.c_uint64),
         ("capacity_overflows", C.c_uint64), ("flops", C.c_double), ("kernel_ms", C.c_double), ("total_ms", C.c_double),
-        ("n_devices", C.c_int32), ("detailed", C.c_int32), ("launches", C.c_int32), ("reserved", C.c_int32),
+        ("n_devices", C.c_int32), ("detailed", C.c_int32), ("launches", C.c_int32), ("wave_overflows", C.c_int32),
     ]
 
     @property

@@ -280,6 +280,30 @@ int copy_bands(DeviceSlot* slot, const RtcScene* s, int shard, int n_shards, int
     return 0;
 }
 
+// The wavefront renderer's chunking: about a million pixels of the shard at a time (whole bands).
+int wave_chunk_bands(int width, int nb) {
+    const int per_band = std::max(1, width) * kBandRows;
+    int bands = std::max(1, (1 << 20) / per_band);
+    while ((nb + bands - 1) / bands > kWaveMaxChunks) bands *= 2;
+    return std::min(bands, std::max(nb, 1));
+}
+int ensure_wave_pool(DeviceSlot* d, int width, int nb) {
+    const int chunk_px = wave_chunk_bands(width, nb) * kBandRows * ((width + 7) / 8 * 8);
+    const long long want = (long long)chunk_px * d->wave_rays_per_pixel;
+    if (want > 0x7fffffffLL / 2) return fail(RTC_ERR_CAPACITY, "wavefront ray pool too large");
+    CUDA_TRY(cudaSetDevice(d->device));
+    if (!d->d_wave_ints) CUDA_TRY(cudaMalloc(&d->d_wave_ints, kWaveInts * sizeof(int) + 3 * kWaveMaxChunks * sizeof(unsigned long long) + 64));
+    if ((int)want > d->wave_capacity) {
+        if (d->d_wave_rays) cudaFree(d->d_wave_rays);
+        if (d->d_wave_nodes) cudaFree(d->d_wave_nodes);
+        d->d_wave_rays = d->d_wave_nodes = nullptr, d->wave_capacity = 0;
+        CUDA_TRY(cudaMalloc(&d->d_wave_rays, (size_t)want * 96));
+        CUDA_TRY(cudaMalloc(&d->d_wave_nodes, (size_t)want * 64));
+        d->wave_capacity = (int)want;
+    }
+    return 0;
+}
+
 int render_impl(RtcScene* s, int depth, int shard0, int n_shards_ext, float* rgb, uint8_t* u8, RtcStats* stats, bool detailed) {
     if (!s) return fail(RTC_ERR_INVALID, "null scene");
     if (!s->committed) return fail(RTC_ERR_STATE, "rtc_render before rtc_scene_commit");
@@ -322,6 +346,7 @@ int render_impl(RtcScene* s, int depth, int shard0, int n_shards_ext, float* rgb
         // are not sliced
         const bool stream_scene = r.small.n == 0 && (s->stream < 0 ? s->has_branching_materials : s->stream != 0);
         const int n_slices = copy_out && !stream_scene ? std::max(1, std::min(s->render_slices, nb)) : 1;
+        const bool use_wave = stream_scene && !detailed && !s->light_is_rect && s->wavefront != 0 && nb > 0;
         const int tiles_x = ((int)s->width + kTileW - 1) / kTileW;
         int rc0;
         if ((rc0 = ensure_tiles(slot, total_bands * tiles_x))) return rc0;
@@ -346,7 +371,39 @@ int render_impl(RtcScene* s, int depth, int shard0, int n_shards_ext, float* rgb
         const bool use_stream = stream_scene;
         if (use_stream) CUDA_TRY(cudaMemsetAsync(slot->d_stream_counter, 0, 64 * sizeof(unsigned), slot->stream));
         CUDA_TRY(cudaEventRecord(slot->ev0, slot->stream));
-        for (int k = 0; k < n_slices; k++) {
+        // The wavefront renderer (dev_wave.cuh): tree scenes with branching ray trees under a point light.  The shard's
+        // bands are rendered chunk by chunk through one ray pool; a chunk is also the unit of the device-to-host copy.
+        r.wave_chunks = 0;
+        if (use_wave) {
+            int rc;
+            if ((rc = ensure_wave_pool(slot, (int)s->width, nb))) return rc;
+            const int chunk_bands = wave_chunk_bands((int)s->width, nb);
+            for (int b0 = 0, k = 0; b0 < nb; b0 += chunk_bands, k++) {
+                const int b1 = std::min(nb, b0 + chunk_bands);
+                DevFrame F{slot->d_rgb, slot->d_u8, shard, n_shards, depth, b1 - b0, b0, nullptr, nullptr, 1, nullptr, 0};
+                WavePoolRaw pool{slot->d_wave_rays, slot->d_wave_nodes, slot->wave_capacity, slot->d_wave_ints,
+                                 reinterpret_cast<unsigned long long*>(slot->d_wave_ints + kWaveInts) + 3 * k};
+                if (s->strict_fp)
+                    strict::launch_wave(r.scene, r.small, F, pool, slot->d_counters, slot->sm_count * 8, slot->stream);
+                else
+                    fast::launch_wave(r.scene, r.small, F, pool, slot->d_counters, slot->sm_count * 8, slot->stream);
+                CUDA_TRY(cudaGetLastError());
+                st.launches += 2 + 5 * (depth + 1) + (depth + 1);
+                r.wave_chunks = k + 1;
+                if (copy_out) {
+                    while ((int)slot->slice_done.size() <= k) {
+                        cudaEvent_t e;
+                        CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+                        slot->slice_done.push_back(e);
+                    }
+                    CUDA_TRY(cudaEventRecord(slot->slice_done[k], slot->stream));
+                    CUDA_TRY(cudaStreamWaitEvent(slot->copy_stream, slot->slice_done[k], 0));
+                    if (rgb && (rc = copy_bands(slot, s, shard, n_shards, b0, b1, slot->d_rgb, rgb, 3 * sizeof(float)))) return rc;
+                    if (u8 && (rc = copy_bands(slot, s, shard, n_shards, b0, b1, slot->d_u8, u8, 3))) return rc;
+                }
+            }
+        }
+        for (int k = 0; k < n_slices && !use_wave; k++) {
             const int b0 = (int)((int64_t)nb * k / n_slices), b1 = (int)((int64_t)nb * (k + 1) / n_slices);
             if (b1 <= b0) continue;
             DevFrame F{slot->d_rgb, slot->d_u8, shard, n_shards, depth, b1 - b0, b0, use_order ? slot->d_tile_order : nullptr,
@@ -381,6 +438,47 @@ int render_impl(RtcScene* s, int depth, int shard0, int n_shards_ext, float* rgb
         float ms = 0.f;
         CUDA_TRY(cudaEventElapsedTime(&ms, slot->ev0, slot->ev1));
         st.kernel_ms = std::max(st.kernel_ms, (double)ms);
+        Replica& rw = s->replicas[i];
+        if (rw.wave_chunks > 0) {
+            // the chunks' records: rays that did not fit the pool (the chunk is rendered again, by render_stream — never a
+            // silently truncated ray tree), secondary rays, shades
+            const int shard = external ? shard0 : i;
+            const int nb = shard < total_bands ? (total_bands - shard + n_shards - 1) / n_shards : 0;
+            std::vector<unsigned long long> rec(3 * (size_t)rw.wave_chunks);
+            CUDA_TRY(cudaMemcpy(rec.data(), reinterpret_cast<unsigned long long*>(slot->d_wave_ints + kWaveInts), rec.size() * 8,
+                                cudaMemcpyDeviceToHost));
+            const int chunk_bands = wave_chunk_bands((int)s->width, nb);
+            DevCounters extra{};
+            bool again = false;
+            for (int k = 0; k < rw.wave_chunks; k++) {
+                if (rec[3 * k] == 0) {
+                    extra.secondary += rec[3 * k + 1], extra.shades += rec[3 * k + 2];
+                    continue;
+                }
+                again = true;
+                st.wave_overflows++;
+                const int b0 = k * chunk_bands, b1 = std::min(nb, b0 + chunk_bands);
+                DevFrame F{slot->d_rgb, slot->d_u8, shard, n_shards, depth, b1 - b0, b0, nullptr, nullptr, 1, slot->d_stream_counter + (k % 64),
+                           slot->sm_count * 6};
+                CUDA_TRY(cudaMemsetAsync(slot->d_stream_counter + (k % 64), 0, sizeof(unsigned), slot->stream));
+                if (s->strict_fp)
+                    strict::launch_render(rw.scene, rw.small, F, slot->d_counters, false, slot->stream);
+                else
+                    fast::launch_render(rw.scene, rw.small, F, slot->d_counters, false, slot->stream);
+                CUDA_TRY(cudaGetLastError());
+                st.launches++;
+                CUDA_TRY(cudaStreamSynchronize(slot->stream));  // one chunk at a time: they may share a counter slot
+                int rc;
+                if (rgb && (rc = copy_bands(slot, s, shard, n_shards, b0, b1, slot->d_rgb, rgb, 3 * sizeof(float)))) return rc;
+                if (u8 && (rc = copy_bands(slot, s, shard, n_shards, b0, b1, slot->d_u8, u8, 3))) return rc;
+            }
+            if (again) {
+                CUDA_TRY(cudaStreamSynchronize(slot->copy_stream));
+                slot->wave_rays_per_pixel = std::min(64, slot->wave_rays_per_pixel * 2);  // a bigger pool next time
+            }
+            st.secondary_rays += extra.secondary, st.shades += extra.shades;
+            st.shadow_rays += extra.shades * (s->light_is_rect ? (uint64_t)s->u_steps * s->v_steps : 1);
+        }
         DevCounters c;
         CUDA_TRY(cudaMemcpy(&c, slot->d_counters, sizeof(c), cudaMemcpyDeviceToHost));
         {
@@ -450,6 +548,7 @@ int rtc_scene_create(RtcScene** out) {
     if (const char* env = getenv("RTC_ORDER_MAX_WAVES")) (*out)->order_max_waves = atoi(env);
     if (const char* env = getenv("RTC_CONVERGE")) (*out)->converge = atoi(env);
     if (const char* env = getenv("RTC_STREAM")) (*out)->stream = atoi(env);
+    if (const char* env = getenv("RTC_WAVEFRONT")) (*out)->wavefront = atoi(env) != 0;
     if (const char* env = getenv("RTC_BVH_BUILDER")) (*out)->bvh_builder = atoi(env) != 0;
     return 0;
 }
@@ -570,6 +669,9 @@ int rtc_set_option(RtcScene* s, int32_t option, int64_t value) {
             if (value != 0 && value != 1) return fail(RTC_ERR_INVALID, "bvh builder: 0 (host binned SAH) or 1 (device LBVH)");
             s->bvh_builder = (int)value;
             s->committed = false;
+            return 0;
+        case RTC_OPT_WAVEFRONT:  // may change between renders
+            s->wavefront = value != 0;
             return 0;
         case RTC_OPT_BVH_MIN_PRIMS:
             s->bvh_min_prims = (int)std::max<int64_t>(0, value);

@@ -28,3 +28,6 @@
 #include "dev_small.cuh"     // small-scene path: shared-memory table, typed loops, ray-vs-ball pre-test
 #include "dev_shadow.cuh"    // is_shadowed / intensity_at: shadow filter, exact test, cell-mask loops
 #include "dev_shade.cuh"     // color_at (bounded reflect / refract stack), ray_for_pixel, scale_color
+#if defined(__CUDACC__)
+#include "dev_wave.cuh"      // the wavefront renderer of tree scenes: rays as work items, refilled tree walks
+#endif

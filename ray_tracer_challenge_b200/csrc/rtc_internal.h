@@ -64,6 +64,12 @@ struct DeviceSlot {
     size_t lbvh_scratch_bytes = 0;
     char* lbvh_pinned = nullptr;   // ... and its pinned staging (boxes up, order and nodes down)
     size_t lbvh_pinned_bytes = 0;
+    // the wavefront renderer's ray pool (one chunk of a frame at a time) and its per-chunk records
+    void* d_wave_rays = nullptr;
+    void* d_wave_nodes = nullptr;
+    int* d_wave_ints = nullptr;
+    int wave_capacity = 0;
+    int wave_rays_per_pixel = kWaveRaysPerPixel;  // doubled after a chunk overflowed
     unsigned* d_stream_counter = nullptr;  // render_stream's pixel counters, one per slice of a render
     void* d_flush = nullptr;
     size_t flush_bytes = 0;
@@ -86,6 +92,7 @@ struct Replica {
     float natural_ms = 0.f, ordered_ms = 0.f;
     int renders_done = 0;  // the first render of a replica is cold (module load, caches): its time is not compared
     bool learning = false;  // this render records the tile costs
+    int wave_chunks = 0;    // chunks the wavefront renderer launched in this render
 };
 
 // Everything rtc_scene_commit derives from the scene on the host, ready for upload (rtc_commit.cu: flatten).
@@ -139,6 +146,8 @@ struct RtcScene {
     int render_slices = 6;  // kernel / copy pipeline depth when rendering into host memory
     int adaptive_order = 1;  // launch a shard's bands longest-first, learnt from the previous render
     int shadow_filter = 1;   // RTC_OPT_SHADOW_FILTER
+    int wavefront = 0;         // RTC_OPT_WAVEFRONT: tree scenes with branching ray trees and a point light go through the
+                               // wavefront renderer (dev_wave.cuh) instead of render_stream — measured slower on B200, so opt-in
     int stream = -1;           // tree scenes: lanes draw pixels from a counter (render_stream): -1 automatic (branching ray
                                // trees), 0 / 1 forced (RTC_STREAM)
     int converge = -1;         // color_at warp vote: -1 automatic (branching ray trees), 0 / 1 forced (RTC_CONVERGE)

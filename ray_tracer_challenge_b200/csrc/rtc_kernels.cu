@@ -159,6 +159,62 @@ __global__ void __launch_bounds__(kBlockThreads, min_blocks(RTC_STREAM_MINBLOCKS
     flush_counters<STATS>(r, k, counters);
 }
 
+// ---- the wavefront renderer's kernels (dev_wave.cuh) --------------------------------------------------------------------
+#ifndef RTC_WAVE_TRACE_MINBLOCKS
+#define RTC_WAVE_TRACE_MINBLOCKS 8
+#endif
+__device__ __forceinline__ WavePool wave_pool(const WavePoolRaw& raw, DevCounters* counters) {
+    WavePool P;
+    P.rays = static_cast<WaveRay*>(raw.rays), P.nodes = static_cast<WaveNode*>(raw.nodes), P.capacity = raw.capacity;
+    P.base = raw.ints, P.count = raw.ints + kWaveLevels, P.cursor = raw.ints + 2 * kWaveLevels;
+    P.overflow = raw.record, P.secondary = raw.record + 1, P.shades = raw.record + 2;
+    (void)counters;
+    return P;
+}
+__global__ void __launch_bounds__(128) wave_primary_kernel(const __grid_constant__ DevScene S, const DevFrame F, const WavePoolRaw raw,
+                                                          DevCounters* counters) {
+    wave_primary(S, F, wave_pool(raw, counters));
+}
+// the next level starts where this one ends
+__global__ void wave_next_level_kernel(const WavePoolRaw raw, int level) {
+    int* base = raw.ints;
+    int* count = raw.ints + kWaveLevels;
+    base[level + 1] = min(base[level] + count[level], raw.capacity);
+}
+template <bool SHADOW>
+__global__ void __launch_bounds__(128, RTC_WAVE_TRACE_MINBLOCKS) wave_trace_kernel(const __grid_constant__ DevScene S, const WavePoolRaw raw,
+                                                                                 DevCounters* counters, int level) {
+    wave_trace<SHADOW>(S, wave_pool(raw, counters), level);
+}
+__global__ void __launch_bounds__(128) wave_hit_kernel(const __grid_constant__ DevScene S, const WavePoolRaw raw, DevCounters* counters,
+                                                      int level) {
+    wave_hit(S, wave_pool(raw, counters), level);
+}
+__global__ void __launch_bounds__(128) wave_shade_kernel(const __grid_constant__ DevScene S, const WavePoolRaw raw, DevCounters* counters,
+                                                        int level, int depth) {
+    wave_shade(S, wave_pool(raw, counters), level, depth);
+}
+__global__ void __launch_bounds__(128) wave_combine_kernel(const __grid_constant__ DevScene S, const DevFrame F, const WavePoolRaw raw,
+                                                          DevCounters* counters, int level) {
+    wave_combine(S, F, wave_pool(raw, counters), level);
+}
+
+void launch_wave(const DevScene& S, const SmallScene&, const DevFrame& F, const WavePoolRaw& pool, DevCounters* counters, int blocks,
+                 cudaStream_t stream) {
+    cudaMemsetAsync(pool.ints, 0, kWaveInts * sizeof(int), stream);
+    cudaMemsetAsync(pool.record, 0, 3 * sizeof(unsigned long long), stream);
+    const int wide = blocks * 2;  // the one-thread-per-ray kernels: a grid-stride loop over a count only the device knows
+    wave_primary_kernel<<<wide, 128, 0, stream>>>(S, F, pool, counters);
+    for (int level = 0; level <= F.depth; level++) {
+        wave_next_level_kernel<<<1, 1, 0, stream>>>(pool, level);
+        wave_trace_kernel<false><<<blocks, 128, 0, stream>>>(S, pool, counters, level);
+        wave_hit_kernel<<<wide, 128, 0, stream>>>(S, pool, counters, level);
+        wave_trace_kernel<true><<<blocks, 128, 0, stream>>>(S, pool, counters, level);
+        wave_shade_kernel<<<wide, 128, 0, stream>>>(S, pool, counters, level, F.depth);
+    }
+    for (int level = F.depth; level >= 0; level--) wave_combine_kernel<<<wide, 128, 0, stream>>>(S, F, pool, counters, level);
+}
+
 // DRAWN: as in render_tiles — a small scene whose area light draws its jitter (`jitter_fn = None`) takes the
 // drawn-sample cell loop; without it intensity_cells would read light samples nobody staged.
 template <bool SMALL, bool DRAWN>

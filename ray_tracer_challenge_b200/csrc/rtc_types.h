@@ -203,6 +203,20 @@ constexpr int kRefillLanes = RTC_REFILL_LANES;  // render_stream: idle lanes of 
 
 constexpr int kBandRows = kTileH;
 
+// The wavefront renderer's per-chunk ray pool as the host hands it to the launchers (dev_wave.cuh: WavePool holds the
+// same pointers, typed).
+struct WavePoolRaw {
+    void* rays;    // capacity x 96 B
+    void* nodes;   // capacity x 64 B
+    int capacity;
+    int* ints;     // base[L], count[L], cursor[2 L] for L <= kMaxFrames: see rtc_kernels.cu: wave_pool
+    unsigned long long* record;  // this chunk's {rays that did not fit the pool, secondary rays, shades}
+};
+constexpr int kWaveLevels = kMaxFrames + 1;
+constexpr int kWaveInts = 4 * kWaveLevels;
+constexpr int kWaveMaxChunks = 64;         // chunk records per render
+constexpr int kWaveRaysPerPixel = 6;       // pool capacity per pixel of a chunk (a chunk that needs more is re-rendered by render_stream)
+
 struct DevCounters {  // accumulated with one atomic per warp
     unsigned long long primary, secondary, shadow, shades;
     unsigned long long node_visits, prim_tests[8], xforms, patterns, cells, schlicks, refr_dirs, overflows;

@@ -49,6 +49,7 @@ pub const RTC_OPT_RENDER_SLICES: i32 = 4;
 pub const RTC_OPT_ADAPTIVE_ORDER: i32 = 5;
 pub const RTC_OPT_SHADOW_FILTER: i32 = 6;
 pub const RTC_OPT_BVH_BUILDER: i32 = 7;
+pub const RTC_OPT_WAVEFRONT: i32 = 8;
 
 #[repr(C)]
 #[derive(Clone, Copy)]
@@ -144,7 +145,7 @@ pub struct RtcStats {
     pub n_devices: i32,
     pub detailed: i32,
     pub launches: i32,
-    pub reserved: i32,
+    pub wave_overflows: i32,
 }
 
 /// What `rtc_scene_commit` would build, computed without a device (`rtc_scene_inspect`).
