@@ -451,7 +451,11 @@ void plan_small_scene(const RtcScene* s, Flattened& f, int n_items) {
                 f.small.plane_bundle[q].w = std::nextafter(f.small.plane_bundle[q].w, INFINITY);
             }
         }
-        f.small.tol_sphere = (float)(std::ldexp(1.0, -24) * 64.0 * (worst + 1.0));
+        // the sphere filter's relative bound, DESIGN.md "Shadow filter: where the bounds come from": the two discriminants
+        // (reference: normalised direction, no fusing; filter: fused, unnormalised) are each within (4 eps + 14 u) a spread
+        // of the exact one, eps <= 18 k u and <= 9 k u (k = the transforms' worst inf-norm condition number, u = 2^-24):
+        // together (108 k + 28) u; shipped with a margin: (128 k + 32) u
+        f.small.tol_sphere = (float)(std::ldexp(1.0, -24) * (128.0 * worst + 32.0));
         // ---- the image every block stages into shared memory (dev_small.cuh: stage_small_scene)
         f.small_image.assign(kSmemOrg, make_float4(0.f, 0.f, 0.f, 0.f));
         memcpy(f.small_image.data(), f.small.p, (size_t)n_items * sizeof(SmallPrim));
