@@ -85,6 +85,7 @@ _HOST_EXTRAS = {
     "sg_set_render_options": (_I, [_V, _I, _IP, _I, _I]),
     "sg_last_rtc_stats": (_I, [_V, C.POINTER(RtcStats)]),
     "sg_set_bvh_builder": (_I, [_V, _I]),
+    "sg_ppm_from_u8": (C.c_int64, [_V, _I, _I, _U8P, C.c_char_p, C.c_int64]),
     "sg_prepare": (_I, [_V, _I, _I]),
     "sg_camera_render_shard": (_I, [_V, _I, _I, _I, _I, _I, _FP, _U8P, C.POINTER(SgStats)]),
     "sg_inspect": (_I, [_V, _I, _I, C.c_void_p, C.POINTER(C.c_double)]),
@@ -147,6 +148,25 @@ class PreparedScene:
             self.handle = None
 
 
+class CanvasU8:
+    """What `Canvas::to_ppm` (canvas.rs:58-96) needs and nothing more: the frame's 8-bit plane — every channel through
+    `scale_color` (canvas.rs:39-43) on the device.  Returned by Camera.render_b200_u8 (the Rust glue's `CanvasU8`)."""
+
+    def __init__(self, width: int, height: int, u8: np.ndarray, api):
+        self.width, self.height, self._u8, self.api = width, height, u8, api
+
+    def to_u8(self) -> np.ndarray:
+        return self._u8
+
+    def to_ppm(self) -> str:
+        api = self.api
+        u8 = np.ascontiguousarray(self._u8)
+        n = api.check(api.lib.sg_ppm_from_u8(api.ctx, self.width, self.height, u8.ctypes.data_as(_U8P), None, 0))
+        buf = C.create_string_buffer(int(n))
+        api.check(api.lib.sg_ppm_from_u8(api.ctx, self.width, self.height, u8.ctypes.data_as(_U8P), buf, n))
+        return buf.raw[:n].decode("ascii")
+
+
 class HostApi(_api.Api):
     """api.Api bound to librtc_host.so, plus the device-side controls that only the product has."""
 
@@ -165,7 +185,20 @@ class HostApi(_api.Api):
             camera.last_rtc_stats = api.last_rtc_stats()
             return canvas
 
+        def render_b200_u8(camera, world, reflection_recursion_depth=DEFAULT_RAY_RECURSION_DEPTH, out_u8=None):
+            """The demos' flow, `camera.render(world, depth).to_ppm()`, without the f32 plane ever leaving the device:
+            one-shot (flatten, commit, render), 3 bytes per pixel over PCIe instead of 15."""
+            w, h = camera.width_pixels, camera.height_pixels
+            u8 = out_u8 if out_u8 is not None else np.zeros((h, w, 3), np.uint8)
+            stats = SgStats()
+            api.check(api.lib.sg_camera_render_shard(api.ctx, camera.handle, world.handle, int(reflection_recursion_depth), 0, 1,
+                                                     None, u8.ctypes.data_as(_U8P), C.byref(stats)))
+            camera.last_stats = stats
+            camera.last_rtc_stats = api.last_rtc_stats()
+            return CanvasU8(w, h, u8, api)
+
         self.Camera.render_b200 = render_b200
+        self.Camera.render_b200_u8 = render_b200_u8
         self.Camera.render = render_b200
         self.Camera.prepare = lambda camera, world: PreparedScene(api, camera, world)
 

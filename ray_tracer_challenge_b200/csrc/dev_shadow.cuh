@@ -302,6 +302,21 @@ __device__ __forceinline__ bool bundle_misses(float4 ball, float pad_over_r, flo
     return C * A > B * B * 1.0001f;
 }
 
+// point_on_light (rectangle_light.rs:60-66) for the cells [c0, c0 + nc) of a shade with generated jitter: two values per
+// cell in the reference's order `for v { for u { j_u, j_v } }`
+__device__ __forceinline__ void draw_light_samples(const DevScene& S, unsigned pixel, unsigned path, int c0, int nc, float4* drawn) {
+    const V3 corner = ld3(S.corner), u_vec = ld3(S.u_vec), v_vec = ld3(S.v_vec);
+    const unsigned key = jitter_key(S.seed, pixel, path);
+    for (int j = 0; j < nc; j++) {
+        const unsigned cell = (unsigned)(c0 + j);
+        const int v = (int)cell / S.u_steps, u = (int)cell - v * S.u_steps;
+        const float j1 = jitter_value(key, 2u * cell);
+        const float j2 = jitter_value(key, 2u * cell + 1u);
+        const V3 lp = corner + u_vec * ((float)u + j1) + v_vec * ((float)v + j2);
+        drawn[j] = make_float4(lp.x, lp.y, lp.z, 0.f);
+    }
+}
+
 // TABLE: the light samples are the staged table.  Otherwise (jitter `None`, rectangle_light.rs:46: the counter-based
 // generator) a chunk's sample points are drawn first — two jitter values per cell in the reference's order
 // `for v { for u { j_u, j_v } }`, point_on_light's arithmetic (rectangle_light.rs:60-66) — into a per-thread array,
@@ -320,18 +335,17 @@ __device__ __forceinline__ float intensity_cells(const Env& E, V3 p, unsigned pi
     for (int c0 = 0; c0 < cells; c0 += 32) {
         const int nc = min(32, cells - c0);
         const unsigned full = nc == 32 ? 0xffffffffu : ((1u << nc) - 1u);
-        if (!TABLE) {
-            const V3 corner = ld3(S.corner), u_vec = ld3(S.u_vec), v_vec = ld3(S.v_vec);
-            const unsigned key = jitter_key(S.seed, pixel, path);
-            for (int j = 0; j < nc; j++) {
-                const unsigned cell = (unsigned)(c0 + j);
-                const int v = (int)cell / S.u_steps, u = (int)cell - v * S.u_steps;
-                const float j1 = jitter_value(key, 2u * cell);
-                const float j2 = jitter_value(key, 2u * cell + 1u);
-                const V3 lp = corner + u_vec * ((float)u + j1) + v_vec * ((float)v + j2);
-                drawn[j] = make_float4(lp.x, lp.y, lp.z, 0.f);
-            }
-        }
+        // Generated jitter: the chunk's sample points are drawn only when the first caster that the bundle tests cannot
+        // dismiss needs them — most shades of a floor under a light are settled for every cell by those tests alone, and
+        // the points of a cell depend on nothing but (seed, pixel, path, cell), so drawing them late draws the same points.
+        bool have_samples = TABLE;
+#define RTC_DRAW_SAMPLES()                                                   \
+    do {                                                                     \
+        if (!TABLE && !have_samples) {                                       \
+            have_samples = true;                                             \
+            draw_light_samples(S, pixel, path, c0, nc, drawn);               \
+        }                                                                    \
+    } while (0)
         const float4* smp = TABLE ? table + c0 : drawn;
         unsigned hit = 0u, unsure = 0u;
         float far_hit = 0.0f;  // no caster hit of this chunk is farther from p than this (bounding balls)
@@ -340,6 +354,7 @@ __device__ __forceinline__ float intensity_cells(const Env& E, V3 p, unsigned pi
         for (; i < ends.x && (hit | unsure) != full; i++) {  // caster spheres
             if (bundle_misses(tab[i * kSmallStride + 5], tab[i * kSmallStride + 4].w, SS.light_ball, p)) continue;
             const unsigned hit_before = hit;
+            RTC_DRAW_SAMPLES();
             const Xf m{tab[i * kSmallStride + 1], tab[i * kSmallStride + 2], tab[i * kSmallStride + 3]};
             const V3 o = xf_point(m, p);  // the reference's object-space origin (shape.rs:60-70), once per shade
             const float oo = fma_(o.x, o.x, fma_(o.y, o.y, o.z * o.z));
@@ -376,18 +391,19 @@ __device__ __forceinline__ float intensity_cells(const Env& E, V3 p, unsigned pi
             const float tx = r1.x * p.x, ty = r1.y * p.y, tz = r1.z * p.z;
             const float rp = tx + ty + tz;
             const float oy = rp + r1.w;  // the reference's object-space origin.y (shape.rs:60-70)
+            const float erp = kTolP * (fabsf(tx) + fabsf(ty) + fabsf(tz));
+            const float p1 = (kAcne * (1.0f + 2.0f * kTolP)) * (fabsf(p.x) + fabsf(p.y) + fabsf(p.z));
+            if (i - ends.x < 2) {
+                // the whole bundle at once: with the bounds of the cell constants (table mode) or of the light's rectangle
+                // (generated jitter), every cell's direction is clearly steep and points away from the plane's side the
+                // point is on (a floor under a light above it): the per-cell test would answer F_MISS for each of them
+                // (a NaN bound — no bundle data for this plane — fails both comparisons)
+                const float4 pb = SS.plane_bundle[i - ends.x];
+                const float slack = pb.z + erp + pb.w + p1;
+                if ((oy > 0.0f && (pb.x - rp) > slack) || (oy < 0.0f && (rp - pb.y) > slack)) continue;
+            }
             if (SS.plane_cells) {
                 const float4* pc = small_plane_cells() + (i - ends.x) * cells + c0;
-                const float erp = kTolP * (fabsf(tx) + fabsf(ty) + fabsf(tz));
-                const float p1 = (kAcne * (1.0f + 2.0f * kTolP)) * (fabsf(p.x) + fabsf(p.y) + fabsf(p.z));
-                if (i - ends.x < 2) {
-                    // the whole bundle at once: with the bounds of the cell constants, every cell's direction is clearly
-                    // steep and points away from the plane's side the point is on (a floor under a light above it):
-                    // filter_plane_cell would answer F_MISS for each of them
-                    const float4 pb = SS.plane_bundle[i - ends.x];
-                    const float slack = pb.z + erp + pb.w + p1;
-                    if ((oy > 0.0f && (pb.x - rp) > slack) || (oy < 0.0f && (rp - pb.y) > slack)) continue;
-                }
 #pragma unroll 4
                 for (int j = 0; j < nc; j++) {
                     const int code = filter_plane_cell(pc[j], oy, rp, erp, p1);
@@ -401,6 +417,7 @@ __device__ __forceinline__ float intensity_cells(const Env& E, V3 p, unsigned pi
                 if (hit != hit_before) far_hit = kInfF;  // a plane has no bounding ball
                 continue;
             }
+            RTC_DRAW_SAMPLES();
 #pragma unroll 4
             for (int j = 0; j < nc; j++) {
                 const float4 L = smp[j];
@@ -420,6 +437,7 @@ __device__ __forceinline__ float intensity_cells(const Env& E, V3 p, unsigned pi
         for (i = ends.y; i < ends.z && (hit | unsure) != full; i++) {  // caster cubes
             if (bundle_misses(tab[i * kSmallStride + 5], tab[i * kSmallStride + 4].w, SS.light_ball, p)) continue;
             const unsigned hit_before = hit;
+            RTC_DRAW_SAMPLES();
             const Xf m{tab[i * kSmallStride + 1], tab[i * kSmallStride + 2], tab[i * kSmallStride + 3]};
             const V3 o = xf_point(m, p);
 #pragma unroll 2
@@ -452,6 +470,7 @@ __device__ __forceinline__ float intensity_cells(const Env& E, V3 p, unsigned pi
         }
         unsigned todo = hits_final ? unsure : (hit | unsure);
         lit += __popc(full & ~(hit | unsure));
+        if (todo) RTC_DRAW_SAMPLES();
         while (todo) {
             const int j = __ffs(todo) - 1;
             todo &= todo - 1u;
@@ -460,6 +479,7 @@ __device__ __forceinline__ float intensity_cells(const Env& E, V3 p, unsigned pi
         }
     }
     return (float)lit / (float)cells;  // `total += 1.0` per lit cell is exact in f32
+#undef RTC_DRAW_SAMPLES
 }
 
 // Light::intensity_at (point_light.rs:28-34, rectangle_light.rs:76-88).  DRAWN: the kernel build for small scenes whose

@@ -251,6 +251,13 @@ int64_t sg_canvas_to_ppm(sg_ctx* c, int cv, char* out, int64_t capacity) {
              if (out && capacity > 0) memcpy(out, ppm.data(), (size_t)std::min<int64_t>(capacity, (int64_t)ppm.size()));
              return (int64_t)ppm.size();)
 }
+// Canvas::to_ppm (canvas.rs:58-96) from an 8-bit plane (width * height * 3, the device's scale_color values)
+int64_t sg_ppm_from_u8(sg_ctx*, int width, int height, const uint8_t* u8, char* out, int64_t capacity) {
+    if (width < 0 || height < 0 || (!u8 && width * height)) return fail("bad 8-bit canvas");
+    SG_GUARD(std::string ppm = ppm_from_u8(width, height, u8);
+             if (out && capacity > 0) memcpy(out, ppm.data(), (size_t)std::min<int64_t>(capacity, (int64_t)ppm.size()));
+             return (int64_t)ppm.size();)
+}
 int sg_uv_image_new(sg_ctx* c, int cv) {
     if (cv < 0 || cv >= (int)c->graph.canvases.size()) return fail("bad canvas handle");
     if (c->graph.canvases[cv].width < 1 || c->graph.canvases[cv].height < 1) return fail("UVImage needs a non-empty canvas");

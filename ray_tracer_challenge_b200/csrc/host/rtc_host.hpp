@@ -470,7 +470,10 @@ inline unsigned char scale_color(float rgb) {  // canvas.rs:39-43: f32::min / ma
     v = v > 0.0f ? v : 0.0f;
     return (unsigned char)v;
 }
-inline std::string canvas_to_ppm(const CanvasRec& c) {
+// One writer for both sources of 8-bit values: Get(row, i) is channel i of the row through scale_color — computed here
+// from the f32 canvas, or taken from the 8-bit plane the device produced with the same conversion (canvas.rs:39-43).
+template <class Get>
+inline std::string ppm_from(int width, int height, Get get) {
     static const struct Table {
         char text[256][4];
         unsigned char len[256];
@@ -478,14 +481,13 @@ inline std::string canvas_to_ppm(const CanvasRec& c) {
             for (int v = 0; v < 256; v++) len[v] = (unsigned char)snprintf(text[v], 4, "%d", v);
         }
     } table;
-    std::string out = "P3\n" + std::to_string(c.width) + " " + std::to_string(c.height) + "\n255\n";
-    out.reserve(out.size() + (size_t)c.width * c.height * 12 + 16);
-    const size_t n = (size_t)c.width * 3;
-    for (int row = 0; row < c.height; row++) {
-        const float* px = c.rgb.data() + (size_t)row * n;
+    std::string out = "P3\n" + std::to_string(width) + " " + std::to_string(height) + "\n255\n";
+    out.reserve(out.size() + (size_t)width * height * 12 + 16);
+    const size_t n = (size_t)width * 3;
+    for (int row = 0; row < height; row++) {
         size_t line = 0;
         for (size_t i = 0; i < n; i++) {
-            const unsigned v = scale_color(px[i]);
+            const unsigned v = get(row, i);
             out.append(table.text[v], table.len[v]);
             line += table.len[v];
             if (i + 1 == n) break;
@@ -500,6 +502,15 @@ inline std::string canvas_to_ppm(const CanvasRec& c) {
         if (line) out.push_back('\n');
     }
     return out;
+}
+inline std::string canvas_to_ppm(const CanvasRec& c) {
+    const size_t n = (size_t)c.width * 3;
+    return ppm_from(c.width, c.height, [&](int row, size_t i) -> unsigned { return scale_color(c.rgb[(size_t)row * n + i]); });
+}
+// Canvas::to_ppm of a frame of which only the 8-bit plane left the device (Camera::render_b200_u8)
+inline std::string ppm_from_u8(int width, int height, const uint8_t* u8) {
+    const size_t n = (size_t)width * 3;
+    return ppm_from(width, height, [&](int row, size_t i) -> unsigned { return u8[(size_t)row * n + i]; });
 }
 
 // canvas_from_ppm (canvas.rs:119-182) + clean_line (184-200).  Error texts start with the reference's ParseError kind.

@@ -372,7 +372,7 @@ void plan_small_scene(const RtcScene* s, Flattened& f, int n_items) {
         // (the filter's error bound scales with the condition number), planes (term-wise bound: any transform),
         // cubes whose inverse has a diagonal 3x3 part (every direction component is a single product)
         bool ok = f.small.two_pass_shadows && !f.small.has_cull_chain && ends[2] == ends[3] && ends[6] == ends[7];
-        double worst = 1.0;
+        double worst_tol = 64.0;  // in units of u = 2^-24
         for (int i = 0; i < n_items && ok; i++) {
             const SmallPrim& sp = f.small.p[i];
             const int type = sp.head.x & 15;
@@ -397,7 +397,12 @@ void plan_small_scene(const RtcScene* s, Flattened& f, int n_items) {
                 }
                 const double cond = norm_m * norm_i;
                 ok = ok && std::isfinite(cond) && cond <= 64.0;
-                if (ok) worst = std::max(worst, cond);
+                // a diagonal 3x3 part (translation x axis-aligned scaling: every sphere of the demo scenes): each direction
+                // component is ONE product, nothing cancels, and the bound does not grow with the condition number
+                bool diagonal = true;
+                for (int a = 0; a < 3; a++)
+                    for (int b = 0; b < 3; b++) diagonal = diagonal && (a == b || m[a][b] == 0.0);
+                if (ok) worst_tol = std::max(worst_tol, diagonal ? 64.0 : 128.0 * cond + 32.0);
             }
         }
         f.small.filter_ok = ok ? 1 : 0;
@@ -433,10 +438,12 @@ void plan_small_scene(const RtcScene* s, Flattened& f, int n_items) {
             // beyond the f32 rounding of the device's own evaluation: lets a shade settle the plane for every cell at once
             for (int q = 0; q < 2; q++) {
                 f.small.plane_bundle[q] = make_float4(NAN, NAN, NAN, NAN);  // NaN: the bundle test never decides
-                if (!f.small.plane_cells || q >= n_planes) continue;
+                // table mode: over the table's sample points; counter mode (samples drawn per shade): over the corners of
+                // the light's rectangle, which bound every drawn point — r1.L is linear in L, the two error terms convex
+                if (!(f.small.plane_cells || counter_light) || q >= n_planes) continue;
                 const float4 r1 = f.small.p[ends[0] + q].r1;
                 double lo = 1e300, hi = -1e300, e_max = 0.0, l1_max = 0.0;
-                for (const float4& L : f.samples) {
+                for (const float4& L : (f.small.plane_cells ? f.samples : pts)) {
                     const double px = (double)r1.x * L.x, py = (double)r1.y * L.y, pz = (double)r1.z * L.z;
                     const double a = std::fabs(px) + std::fabs(py) + std::fabs(pz);
                     lo = std::min(lo, px + py + pz - 1e-6 * a), hi = std::max(hi, px + py + pz + 1e-6 * a);
@@ -453,9 +460,9 @@ void plan_small_scene(const RtcScene* s, Flattened& f, int n_items) {
         }
         // the sphere filter's relative bound, DESIGN.md "Shadow filter: where the bounds come from": the two discriminants
         // (reference: normalised direction, no fusing; filter: fused, unnormalised) are each within (4 eps + 14 u) a spread
-        // of the exact one, eps <= 18 k u and <= 9 k u (k = the transforms' worst inf-norm condition number, u = 2^-24):
-        // together (108 k + 28) u; shipped with a margin: (128 k + 32) u
-        f.small.tol_sphere = (float)(std::ldexp(1.0, -24) * (128.0 * worst + 32.0));
+        // of the exact one.  General transform: eps <= 18 k u and <= 9 k u (k = inf-norm condition number, u = 2^-24),
+        // together (108 k + 28) u, shipped (128 k + 32) u.  Diagonal 3x3 part: eps <= 4 u and <= u, together 48 u, shipped 64 u.
+        f.small.tol_sphere = (float)(std::ldexp(1.0, -24) * worst_tol);
         // ---- the image every block stages into shared memory (dev_small.cuh: stage_small_scene)
         f.small_image.assign(kSmemOrg, make_float4(0.f, 0.f, 0.f, 0.f));
         memcpy(f.small_image.data(), f.small.p, (size_t)n_items * sizeof(SmallPrim));

@@ -144,7 +144,8 @@ struct SmallScene {
     int plane_cells;            // cell_masks and (caster planes x cells) <= kPlaneCellCap: per-(plane, cell) constants staged
     int pad;
     float4 light_ball;          // cell_masks: ball around the light samples (centre, radius) for the bundle reject
-    float4 plane_bundle[2];     // plane_cells, first two caster planes: over all light cells {min r1.L, max r1.L,
+    float4 plane_bundle[2];     // cell_masks, first two caster planes: over all light cells (table) or the whole light
+                                // rectangle (generated jitter) {min r1.L, max r1.L,
                                 // max tol*|r1||L|, max eps'*|L|_1} (bounds of plane_cell_constants, padded)
     int4 caster_end, other_end;
     SmallPrim p[kSmallCap];

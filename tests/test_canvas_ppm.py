@@ -175,3 +175,23 @@ def test_render_canvas_serialises_natively(oracle):
     assert lines[:3] == ["P3", "11 11", "255"]
     u8 = canvas.to_u8()
     assert [int(v) for v in " ".join(lines[3:]).split()] == [int(v) for v in u8.reshape(-1)]
+
+
+def test_ppm_from_the_8_bit_plane_equals_to_ppm_of_the_f32_canvas():
+    """Camera::render_b200_u8 ships only the 8-bit plane; its PPM must be the bytes Canvas::to_ppm (canvas.rs:58-96) writes
+    for the f32 frame: same header, same 70-column wrap, same scale_color values (canvas.rs:39-43)."""
+    import numpy as np
+
+    import ray_tracer_challenge_b200 as rt
+
+    host = rt.new_session()
+    rng = np.random.default_rng(4)
+    for w, h in ((5, 3), (10, 2), (23, 7), (1, 1)):
+        data = rng.uniform(-0.2, 1.3, size=(h, w, 3)).astype(np.float32)
+        canvas = host.new_canvas(w, h)
+        canvas.data[...] = data
+        want = canvas.to_ppm()
+        u8 = np.clip(np.minimum(data * np.float32(255.0), np.float32(255.0)), 0.0, None).astype(np.uint8)  # scale_color
+        got = rt.CanvasU8(w, h, u8, host).to_ppm()
+        assert got == want, (w, h)
+        assert all(len(line) <= 70 for line in got.splitlines())

@@ -388,3 +388,42 @@ def test_plane_and_cube_filters_at_scale_extremes(world, far):
     got = filter_cube(scale, o, pf, lf, rng)
     wrong = ((got == HIT) & ~want) | ((got == MISS) & want)
     assert not wrong.any(), ("cube", int(wrong.sum()), np.flatnonzero(wrong)[:5])
+
+
+@pytest.mark.parametrize("seed,world", [(61, 1.0), (62, 1e-3), (63, 1e3)])
+def test_sphere_filter_with_diagonal_transforms_at_the_64_ulp_bound(seed, world):
+    """Translation x axis-aligned scaling (every sphere of the reference's demo scenes): each direction component is one
+    product, nothing cancels, and the commit ships tol = 64 u whatever the anisotropy (rtc_commit.cu: plan_small_scene;
+    derivation: 48 u).  Ellipsoids up to 64:1, tangent / on-surface / random segments, three world scales."""
+    rng = np.random.default_rng(seed)
+    n = 500_000
+    scale = np.exp(rng.uniform(np.log(0.05), np.log(3.2), size=(n, 3))) * world
+    iso = rng.random(n) < 0.4
+    scale[iso] = scale[iso, :1]
+    fwd = np.eye(3)[None] * scale[:, None, :]
+    inv = (np.eye(3)[None] / scale[:, None, :]).astype(F)
+    centre = rng.uniform(-4, 4, size=(n, 3)) * world
+    t = (-centre / scale).astype(F)
+    tol = F(2.0 ** -24 * 64.0)
+    u = rng.normal(size=(n, 3))
+    u /= np.linalg.norm(u, axis=1, keepdims=True)
+    w = np.cross(u, rng.normal(size=(n, 3)))
+    w /= np.linalg.norm(w, axis=1, keepdims=True)
+    kind = rng.integers(0, 5, n)
+    eps = 10.0 ** rng.uniform(-9, -1, n) * rng.choice([-1.0, 1.0], n)
+    lift = np.where(kind == 0, 1.0 + eps, 1.0 + np.abs(rng.normal(0, 0.5, n)))
+    a_obj = u * lift[:, None] - w * rng.uniform(0.5, 6, (n, 1))
+    b_obj = u * lift[:, None] + w * rng.uniform(0.5, 6, (n, 1))
+    a_obj = np.where((kind == 1)[:, None], u * (1.0 + eps)[:, None], a_obj)
+    b_obj = np.where((kind == 2)[:, None], u * (1.0 + eps)[:, None], b_obj)
+    rand = kind >= 3
+    a_obj[rand] = rng.normal(0, 2.5, (rand.sum(), 3))
+    b_obj[rand] = rng.normal(0, 2.5, (rand.sum(), 3))
+    p = ((fwd @ a_obj[:, :, None])[:, :, 0] + centre).astype(F)
+    light = ((fwd @ b_obj[:, :, None])[:, :, 0] + centre).astype(F)
+    o = xf_point(inv, t, p)
+    want = reference_sphere(inv, o, p, light)
+    got = filter_sphere(inv, o, p, light, tol, rng)
+    wrong = ((got == HIT) & ~want) | ((got == MISS) & want)
+    assert not wrong.any(), (int(wrong.sum()), np.flatnonzero(wrong)[:5])
+    assert (got != UNSURE)[rand].mean() > 0.97

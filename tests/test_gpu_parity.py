@@ -256,3 +256,14 @@ def test_errors_are_loud(gpu):
         cam.render_b200(world, 24)  # deeper than the device's bounce stack
     with pytest.raises(rt.RtcError):
         cam.render_b200(gpu.World([gpu.Sphere()]), 5)  # "World light should be set" (world.rs:66)
+
+
+def test_render_b200_u8_is_the_8_bit_plane_of_render_b200(gpu, oracle):
+    """The demos' render -> to_ppm flow without the f32 plane leaving the device: same bytes, same PPM."""
+    cam, world = scenes.soft_shadows(gpu, width=160, height=64, u_steps=4, v_steps=4)
+    full = cam.render_b200(world, 5)
+    only_u8 = cam.render_b200_u8(world, 5)
+    assert np.array_equal(only_u8.to_u8(), full.to_u8())
+    assert only_u8.to_ppm() == full.to_ppm()
+    ocam, oworld = scenes.soft_shadows(oracle, width=160, height=64, u_steps=4, v_steps=4)
+    assert only_u8.to_ppm() == ocam.render(oworld, 5).to_ppm()
