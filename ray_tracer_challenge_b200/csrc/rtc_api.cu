@@ -321,6 +321,24 @@ int render_impl(RtcScene* s, int depth, int shard0, int n_shards_ext, float* rgb
     memset(&st, 0, sizeof(st));
     st.n_devices = ndev;
     st.detailed = detailed;
+    // With several devices in one process the copies are queued only after every device has all its kernels: a
+    // device-to-host copy into pageable memory blocks the calling thread, and queued inside the loop it would make the
+    // devices run one after the other.  One device: the copy of a slice is queued right behind its kernel.
+    struct PendingCopy {
+        DeviceSlot* slot;
+        int shard, b0, b1;
+    };
+    std::vector<PendingCopy> pending;
+    auto queue_copy = [&](DeviceSlot* slot, int shard, int b0, int b1) -> int {
+        if (ndev > 1) {
+            pending.push_back({slot, shard, b0, b1});
+            return 0;
+        }
+        int rc;
+        if (rgb && (rc = copy_bands(slot, s, shard, n_shards, b0, b1, slot->d_rgb, rgb, 3 * sizeof(float)))) return rc;
+        if (u8 && (rc = copy_bands(slot, s, shard, n_shards, b0, b1, slot->d_u8, u8, 3))) return rc;
+        return 0;
+    };
     for (int i = 0; i < ndev; i++) {
         Replica& r = s->replicas[i];
         DeviceSlot* slot = r.slot;
@@ -398,8 +416,7 @@ int render_impl(RtcScene* s, int depth, int shard0, int n_shards_ext, float* rgb
                     }
                     CUDA_TRY(cudaEventRecord(slot->slice_done[k], slot->stream));
                     CUDA_TRY(cudaStreamWaitEvent(slot->copy_stream, slot->slice_done[k], 0));
-                    if (rgb && (rc = copy_bands(slot, s, shard, n_shards, b0, b1, slot->d_rgb, rgb, 3 * sizeof(float)))) return rc;
-                    if (u8 && (rc = copy_bands(slot, s, shard, n_shards, b0, b1, slot->d_u8, u8, 3))) return rc;
+                    if ((rc = queue_copy(slot, shard, b0, b1))) return rc;
                 }
             }
         }
@@ -423,12 +440,16 @@ int render_impl(RtcScene* s, int depth, int shard0, int n_shards_ext, float* rgb
             if (copy_out) {
                 CUDA_TRY(cudaEventRecord(slot->slice_done[k], slot->stream));
                 CUDA_TRY(cudaStreamWaitEvent(slot->copy_stream, slot->slice_done[k], 0));
-                int rc;
-                if (rgb && (rc = copy_bands(slot, s, shard, n_shards, b0, b1, slot->d_rgb, rgb, 3 * sizeof(float)))) return rc;
-                if (u8 && (rc = copy_bands(slot, s, shard, n_shards, b0, b1, slot->d_u8, u8, 3))) return rc;
+                if (int rc = queue_copy(slot, shard, b0, b1)) return rc;
             }
         }
         CUDA_TRY(cudaEventRecord(slot->ev1, slot->stream));
+    }
+    for (const PendingCopy& c : pending) {  // the copy stream of each device already waits for the slice's event
+        CUDA_TRY(cudaSetDevice(c.slot->device));
+        int rc;
+        if (rgb && (rc = copy_bands(c.slot, s, c.shard, n_shards, c.b0, c.b1, c.slot->d_rgb, rgb, 3 * sizeof(float)))) return rc;
+        if (u8 && (rc = copy_bands(c.slot, s, c.shard, n_shards, c.b0, c.b1, c.slot->d_u8, u8, 3))) return rc;
     }
     for (int i = 0; i < ndev; i++) {
         DeviceSlot* slot = s->replicas[i].slot;

@@ -267,3 +267,30 @@ def test_render_b200_u8_is_the_8_bit_plane_of_render_b200(gpu, oracle):
     assert only_u8.to_ppm() == full.to_ppm()
     ocam, oworld = scenes.soft_shadows(oracle, width=160, height=64, u_steps=4, v_steps=4)
     assert only_u8.to_ppm() == ocam.render(oworld, 5).to_ppm()
+
+
+def test_in_process_multi_device_render_is_bit_identical(gpu):
+    """rtc_scene_commit(scene, N, ids) + one rtc_render: N replicas in ONE process, bands interleaved over the devices,
+    every device's copies queued after all devices have their kernels.  Needs >= 2 GPUs (skipped on a 1-GPU box; the
+    one-process-per-GPU path is what bench.py and test_band_sharding_is_bit_identical exercise)."""
+    import ctypes as C
+
+    import ray_tracer_challenge_b200 as rt
+
+    n = rt.device_library().rtc_device_count()
+    if n < 2:
+        pytest.skip("one GPU visible")
+    one = rt.new_session()
+    one.set_render_options(device_ids=[0])
+    many = rt.new_session()
+    many.set_render_options(device_ids=list(range(min(n, 4))))
+    for name, kw in (("soft_shadows", dict(width=333, height=123, u_steps=4, v_steps=4)),
+                     ("stress", dict(width=200, height=120, n_spheres=2000, n_each=4, n_csg=2))):
+        cam1, w1 = getattr(scenes, name)(one, **kw)
+        camn, wn = getattr(scenes, name)(many, **kw)
+        a = cam1.render_b200(w1, 5)
+        b = camn.render_b200(wn, 5)
+        assert camn.last_rtc_stats.n_devices == min(n, 4)
+        assert np.array_equal(a.data.view(np.uint32), b.data.view(np.uint32)), name
+        assert np.array_equal(a.to_u8(), b.to_u8()), name
+        assert cam1.last_rtc_stats.rays == camn.last_rtc_stats.rays
