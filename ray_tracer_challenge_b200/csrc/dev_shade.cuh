@@ -129,10 +129,6 @@ __device__ __forceinline__ V3 color_at(const Env& E, bool active, V3 ro, V3 rd, 
                 if (src.exhausted()) break;
                 continue;
             }
-#ifdef RTC_DIAG_LANES
-            k.schlick();                 // diagnostic build: lane-iterations of the ray loop ...
-            if (running) k.pattern();    // ... and how many of them trace a ray
-#endif
             if (!running) continue;
         }
         Hit best{kInfF, -1, 0x7fffffff};

@@ -175,7 +175,7 @@ RTC_HD inline float4 plane_cell_constants(float4 r1, float4 L) {
 constexpr int kTileW = RTC_TILE_W, kTileH = 8;
 constexpr int kBlockThreads = kTileW * kTileH;
 constexpr int kWarpsX = kTileW / 8;
-static_assert(kTileW % 16 == 0 && kBlockThreads <= 1024, "tile width: a multiple of 16 (16-byte rows of the 8-bit canvas)");
+static_assert(kTileW % 8 == 0 && kBlockThreads <= 1024, "tile width: whole 8x4-pixel warps");
 // Dynamic shared memory of the small-scene kernels, in float4 units: [table | light samples | (plane, cell) constants |
 // per-thread shadow-origin cache].  Everything before the cache is the same for every block of a scene: the commit lays
 // it out once (Flattened::small_image -> DevScene::small_image) and a block's staging is a plain coalesced copy.
