@@ -427,9 +427,18 @@ static int camera_render(sg_ctx* c, int cam, int w, int depth, int shard, int n_
     int rc = 0;
     try {
         auto t0 = std::chrono::steady_clock::now();
+        const bool timing = getenv("RTC_TIMING") != nullptr;  // tuning aid: where a one-shot render spends its time
+        auto mark = [&, last = t0](const char* what) mutable {
+            if (!timing) return;
+            const auto now = std::chrono::steady_clock::now();
+            fprintf(stderr, "[rtc one-shot] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(now - last).count());
+            last = now;
+        };
         FlatScene flat;
         fill_scene(scene, c->graph, c->worlds[w], c->cameras[cam], flat);
+        mark("fill_scene");
         rc = commit(c, scene, true, flat.prims.size());
+        mark("commit (host half + upload)");
         if (!rc) {
             if (n_shards > 1)
                 rc = rtc_render_shard(scene, depth, shard, n_shards, out_rgb, out_u8, &c->last_stats);
@@ -437,13 +446,18 @@ static int camera_render(sg_ctx* c, int cam, int w, int depth, int shard, int n_
                 rc = c->options.detailed ? rtc_render_detailed(scene, depth, out_rgb, out_u8, &c->last_stats)
                                          : rtc_render(scene, depth, out_rgb, out_u8, &c->last_stats);
             if (rc) fail(rtc_last_error());
+            mark("render + copies");
         }
         c->last_stats.total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
         to_sg_stats(c->last_stats, stats);
     } catch (const std::exception& e) {
         rc = fail(e.what());
     }
+    const auto t1 = std::chrono::steady_clock::now();
     rtc_scene_destroy(scene);
+    if (getenv("RTC_TIMING"))
+        fprintf(stderr, "[rtc one-shot] %-28s %8.3f ms\n", "scene destroy",
+                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t1).count());
     return rc ? -1 : 0;
 }
 int sg_camera_render(sg_ctx* c, int cam, int w, int depth, float* out_rgb, uint8_t* out_u8, sg_stats* stats) {
