@@ -72,10 +72,11 @@ def build(force: bool = False, verbose: bool = False) -> None:
     if force or jobs or _newer(LIB_DEVICE, list(objs)):
         _run([NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB_DEVICE, *objs, "-cudart", "shared"])
     host_src = os.path.join(CSRC, "host", "rtc_host.cpp")
-    host_deps = [host_src, os.path.join(CSRC, "host", "rtc_host.hpp"), os.path.join(ROOT, "include", "rtc_b200.h"),
-                 os.path.join(ROOT, "include", "rtc_scene.h"), LIB_DEVICE]
+    host_deps = [host_src, os.path.join(CSRC, "host", "rtc_host.hpp"), os.path.join(CSRC, "rtc_parallel.h"),
+                 os.path.join(ROOT, "include", "rtc_b200.h"), os.path.join(ROOT, "include", "rtc_scene.h"), LIB_DEVICE]
     if force or _newer(LIB_HOST, host_deps):
         _run(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-shared", "-Wall",
+              "-pthread",
               "-o", LIB_HOST, host_src, "-L" + PKG, "-lrtc_b200", "-Wl,-rpath,$ORIGIN"])
 
 

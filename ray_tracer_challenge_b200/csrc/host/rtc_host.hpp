@@ -12,17 +12,18 @@
 // reference's Box<dyn Shape> tree — the flattener wants arrays, not pointers.
 #pragma once
 #include <chrono>
-#include <thread>
 #include <cmath>
 #include <cstdint>
 #include <cstring>
 #include <limits>
 #include <map>
+#include <memory>
 #include <stdexcept>
 #include <string>
 #include <vector>
 
 #include "../../../include/rtc_b200.h"
+#include "../rtc_parallel.h"
 
 namespace rtch {
 
@@ -592,8 +593,8 @@ inline CanvasRec canvas_from_ppm(const char* text, size_t n) {
 }
 
 struct FlatScene {
-    std::vector<RtcPrim> prims;
-    std::vector<RtcNode> nodes;
+    rtc::RawVector<RtcPrim> prims;  // resized once, every record written by the walk that owns it
+    rtc::RawVector<RtcNode> nodes;
     std::vector<int32_t> refs;
     std::vector<RtcMaterial> materials;
     std::vector<RtcPattern> patterns;
@@ -602,31 +603,211 @@ struct FlatScene {
     std::vector<int> prim_shape;  // primitive index -> shape handle
 };
 
+// World -> the arrays of include/rtc_b200.h, in the reference's depth-first order (world.rs:18-21, group.rs:16-20,
+// csg.rs:18-24): primitive i is the i-th leaf a depth-first walk meets, node j the j-th group / CSG it enters, and a
+// node's child references follow those of all its descendants.
+//
+// A walk over 100 k shapes is bound by cache misses (the arena's records are visited in tree order, not in memory
+// order), so a large world is flattened by several threads: the top of the tree is opened level by level until a few
+// hundred subtrees are in hand, their sizes are counted in parallel, which fixes where every subtree's records go,
+// and each thread then walks its subtrees writing at those offsets — the same arrays, index for index, as one
+// sequential walk.  Materials are de-duplicated per thread and merged in subtree order (first-use numbering, as a
+// sequential walk would assign).
 class Flattener {
    public:
     Flattener(SceneGraph& g, FlatScene& out) : g_(g), out_(out) {}
     void run(const World& w) {
-        out_.prims.reserve(g_.shapes.size());  // every shape is emitted at most once: no regrowth of the 160 B records
-        out_.prim_shape.reserve(g_.shapes.size());
-        for (int id : w.objects) visit(id, -1);  // depth-first: order, parents, materials (sequential, light)
-        // the heavy part of every leaf record — inverse, parameters, the transformed bounding box — reads the scene
-        // graph only, so a large scene (a 100 k-triangle mesh) is filled by several threads
-        const size_t n = out_.prims.size();
-        const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
-        const size_t n_threads = n < 8192 ? 1 : std::min<size_t>(hw, 16);
-        auto fill = [&](size_t b, size_t e) {
-            for (size_t i = b; i < e; i++) fill_leaf(out_.prims[i], out_.prim_shape[i]);
+        const bool timing = getenv("RTC_TIMING") != nullptr;
+        auto t_last = std::chrono::steady_clock::now();
+        auto lap = [&](const char* what) {
+            if (!timing) return;
+            const auto now = std::chrono::steady_clock::now();
+            fprintf(stderr, "[rtc flatten] %-27s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(now - t_last).count());
+            t_last = now;
         };
-        if (n_threads == 1) {
-            fill(0, n);
-        } else {
-            std::vector<std::thread> pool;
-            for (size_t t = 0; t < n_threads; t++) pool.emplace_back(fill, n * t / n_threads, n * (t + 1) / n_threads);
-            for (std::thread& t : pool) t.join();
+        const size_t n_shapes = g_.shapes.size();
+        const bool threaded = n_shapes >= 8192 && world_has_at_least(w, 4096) && rtc::WorkerPool::instance().threads() > 1;
+        // ---- 1. the subtrees to hand out: the world's objects, with the top levels of a large world's groups opened
+        std::vector<int> frontier(w.objects.begin(), w.objects.end());
+        std::vector<char> opened;
+        const int n_threads = threaded ? rtc::WorkerPool::instance().threads() : 1;
+        if (threaded) {
+            opened.assign(n_shapes, 0);
+            bool any = true;
+            for (int level = 0; level < 10 && any; level++) {
+                any = false;
+                std::vector<int> next;
+                next.reserve(2 * frontier.size());
+                for (int id : frontier) {
+                    g_.check(id);
+                    const ShapeRec& s = g_.shapes[id];
+                    if ((s.kind == GROUP || s.kind == CSG) && !s.children.empty() && !opened[id]) {
+                        opened[id] = 1, any = true;
+                        next.insert(next.end(), s.children.begin(), s.children.end());
+                    } else {
+                        next.push_back(id);
+                    }
+                }
+                frontier.swap(next);
+            }
         }
+        // ---- 2. their sizes
+        std::vector<Counts> counts(frontier.size());
+        {
+            const size_t n_jobs = threaded ? std::min<size_t>(frontier.size(), 16 * (size_t)n_threads) : 1;
+            auto count_range = [&](size_t b, size_t e) {
+                for (size_t k = b; k < e; k++) counts[k] = count(frontier[k]);
+            };
+            if (n_jobs <= 1)
+                count_range(0, frontier.size());
+            else
+                rtc::WorkerPool::instance().run((int)n_jobs, [&](int j) {
+                    count_range(frontier.size() * (size_t)j / n_jobs, frontier.size() * (size_t)(j + 1) / n_jobs);
+                });
+        }
+        lap("frontier + subtree sizes");
+        // ---- 3. where everything goes: a walk of the opened top of the tree
+        struct Entry {
+            int id, parent_node;
+            Cursor at;
+        };
+        struct TopNode {
+            int id, node, parent_node, child_begin;
+            std::vector<int32_t> child_refs;
+        };
+        std::vector<Entry> entries;
+        std::vector<TopNode> tops;
+        entries.reserve(frontier.size());
+        Cursor cur;
+        struct Placer {
+            Flattener& f;
+            const std::vector<char>& opened;
+            const std::vector<Counts>& counts;
+            std::vector<Entry>& entries;
+            std::vector<TopNode>& tops;
+            Cursor& cur;
+            int place(int id, int parent_node) {
+                const ShapeRec& s = f.g_.shapes[id];
+                if (!opened.empty() && opened[id]) {
+                    const size_t me = tops.size();
+                    const int node = cur.node++;
+                    tops.push_back(TopNode{id, node, parent_node, 0, {}});
+                    std::vector<int32_t> refs;
+                    refs.reserve(s.children.size());
+                    for (int c : s.children) refs.push_back(place(c, node));
+                    tops[me].child_begin = cur.ref;
+                    cur.ref += (int)refs.size();
+                    tops[me].child_refs = std::move(refs);
+                    return ~node;
+                }
+                const Counts& n = counts[entries.size()];
+                entries.push_back(Entry{id, parent_node, cur});
+                const int ref = (s.kind == GROUP || s.kind == CSG) ? ~cur.node : cur.prim;
+                cur.prim += n.prims, cur.node += n.nodes, cur.ref += n.refs;
+                return ref;
+            }
+        } placer{*this, opened, counts, entries, tops, cur};
+        for (int id : w.objects) {
+            g_.check(id);
+            placer.place(id, -1);
+        }
+        lap("placement");
+        // ---- 4. the records
+        out_.prims.resize(cur.prim);
+        out_.prim_shape.resize(cur.prim);
+        out_.nodes.resize(cur.node);
+        out_.refs.resize(cur.ref);
+        // contiguous runs of subtrees of about equal weight, a few per thread
+        std::vector<size_t> chunk_begin{0};
+        if (threaded) {
+            const long long total = (long long)cur.prim + cur.node;
+            const long long target = std::max<long long>(1024, total / (4 * n_threads));
+            long long acc = 0;
+            for (size_t k = 0; k < entries.size(); k++) {
+                if (acc >= target) chunk_begin.push_back(k), acc = 0;
+                acc += counts[k].prims + counts[k].nodes;
+            }
+        }
+        chunk_begin.push_back(entries.size());
+        const int n_chunks = (int)chunk_begin.size() - 1;
+        std::vector<LocalMaterials> locals(n_chunks);
+        std::vector<std::pair<int, int>> prim_range(n_chunks, {0, 0});
+        auto emit_chunk = [&](int chunk) {
+            const size_t b = chunk_begin[chunk], e = chunk_begin[chunk + 1];
+            if (b == e) return;
+            LocalMaterials& local = locals[chunk];
+            prim_range[chunk].first = entries[b].at.prim;
+            Cursor c = entries[b].at;
+            for (size_t k = b; k < e; k++) {
+                c = entries[k].at;
+                emit(entries[k].id, entries[k].parent_node, c, local);
+            }
+            prim_range[chunk].second = c.prim;
+        };
+        if (n_chunks == 1)
+            emit_chunk(0);
+        else
+            rtc::WorkerPool::instance().run(n_chunks, emit_chunk);
+        lap("records");
+        if (timing) {
+            fprintf(stderr, "[rtc flatten] %zu shapes, %zu subtrees, %zu opened, %d chunks:", n_shapes, entries.size(), tops.size(), n_chunks);
+            for (auto& r : prim_range) fprintf(stderr, " %d", r.second - r.first);
+            fprintf(stderr, "\n");
+        }
+        // ---- 5. one material table (first-use order), the opened nodes' own records
+        bool identity = true;
+        std::vector<std::vector<int>> remap(n_chunks);
+        for (int chunk = 0; chunk < n_chunks; chunk++) {
+            for (RtcMaterial r : locals[chunk].list) {
+                r.pattern = pattern_index(r.pattern);  // until here: the scene graph's pattern handle
+                const int id = material_index(r);
+                identity = identity && id == (int)remap[chunk].size();
+                remap[chunk].push_back(id);
+            }
+        }
+        if (!identity)
+            rtc::WorkerPool::instance().run(n_chunks, [&](int chunk) {
+                for (int i = prim_range[chunk].first; i < prim_range[chunk].second; i++)
+                    out_.prims[i].material = remap[chunk][out_.prims[i].material];
+            });
+        for (const TopNode& t : tops) {
+            std::copy(t.child_refs.begin(), t.child_refs.end(), out_.refs.begin() + t.child_begin);
+            write_node(t.id, t.node, t.parent_node, t.child_begin, (int)t.child_refs.size());
+        }
+        lap("materials + opened nodes");
     }
 
    private:
+    struct Counts {
+        int prims = 0, nodes = 0, refs = 0;
+    };
+    struct Cursor {  // the next free primitive, node and child-reference slot of a walk
+        int prim = 0, node = 0, ref = 0;
+    };
+    // a walk's own material numbering; `pattern` holds the scene graph's pattern handle until the tables are merged
+    struct LocalMaterials {
+        std::vector<RtcMaterial> list;
+        std::map<std::vector<uint32_t>, int> ids;
+        int last = -1;
+        int index(const Material& m) {
+            RtcMaterial r;
+            memcpy(r.color, m.color, sizeof(r.color));
+            r.ambient = m.ambient, r.diffuse = m.diffuse, r.specular = m.specular, r.shininess = m.shininess;
+            r.reflective = m.reflective, r.transparency = m.transparency, r.refractive_index = m.refractive_index;
+            r.pattern = m.pattern < 0 ? -1 : m.pattern;
+            // a mesh's triangles share one material: compare with the previous one, then with the first few, before the map
+            if (last >= 0 && memcmp(&list[last], &r, 11 * sizeof(uint32_t)) == 0) return last;
+            for (size_t i = 0; i < list.size() && i < 16; i++)
+                if (memcmp(&list[i], &r, 11 * sizeof(uint32_t)) == 0) return last = (int)i;
+            std::vector<uint32_t> key(11);
+            memcpy(key.data(), &r, 11 * sizeof(uint32_t));
+            auto it = ids.find(key);
+            if (it != ids.end()) return last = it->second;
+            list.push_back(r);
+            return last = ids[key] = (int)list.size() - 1;
+        }
+    };
+
     SceneGraph& g_;
     FlatScene& out_;
     std::map<std::vector<uint32_t>, int> material_ids_;
@@ -677,13 +858,7 @@ class Flattener {
         out_.patterns.push_back(r);
         return pattern_ids_[h] = (int)out_.patterns.size() - 1;
     }
-    int material_index(const Material& m) {
-        RtcMaterial r;
-        memcpy(r.color, m.color, sizeof(r.color));
-        r.ambient = m.ambient, r.diffuse = m.diffuse, r.specular = m.specular, r.shininess = m.shininess;
-        r.reflective = m.reflective, r.transparency = m.transparency, r.refractive_index = m.refractive_index;
-        r.pattern = pattern_index(m.pattern);
-        // a mesh's triangles share one material: compare with the previous one, then with the first few, before the map
+    int material_index(const RtcMaterial& r) {  // the scene's table: one entry per distinct material
         if (last_material_ >= 0 && memcmp(&out_.materials[last_material_], &r, 11 * sizeof(uint32_t)) == 0) return last_material_;
         for (size_t i = 0; i < out_.materials.size() && i < 16; i++)
             if (memcmp(&out_.materials[i], &r, 11 * sizeof(uint32_t)) == 0) return last_material_ = (int)i;
@@ -697,37 +872,73 @@ class Flattener {
     static void put_box(const Bounds& b, float lo[3], float hi[3]) {
         for (int a = 0; a < 3; a++) lo[a] = b.lo[a], hi[a] = b.hi[a];
     }
-    // returns the child reference of what was emitted
-    int visit(int id, int parent_node) {
+    // is the world worth several threads?  (a walk that stops at `limit` shapes)
+    bool world_has_at_least(const World& w, size_t limit) const {
+        std::vector<int> stack(w.objects.begin(), w.objects.end());
+        size_t seen = 0;
+        while (!stack.empty()) {
+            const int id = stack.back();
+            stack.pop_back();
+            g_.check(id);
+            if (++seen >= limit) return true;
+            const ShapeRec& s = g_.shapes[id];
+            if (s.kind == GROUP || s.kind == CSG) {
+                if (seen + s.children.size() >= limit) return true;
+                stack.insert(stack.end(), s.children.begin(), s.children.end());
+            }
+        }
+        return false;
+    }
+    // records a depth-first walk of `id` emits
+    Counts count(int id) const {
         g_.check(id);
-        const int kind = g_.shapes[id].kind;
-        if (kind == GROUP || kind == CSG) {
-            int node = (int)out_.nodes.size();
-            out_.nodes.emplace_back();
+        const ShapeRec& s = g_.shapes[id];
+        Counts n;
+        if (s.kind != GROUP && s.kind != CSG) {
+            n.prims = 1;
+            return n;
+        }
+        n.nodes = 1, n.refs = (int)s.children.size();
+        for (int c : s.children) {
+            const Counts k = count(c);
+            n.prims += k.prims, n.nodes += k.nodes, n.refs += k.refs;
+        }
+        return n;
+    }
+    void write_node(int id, int node, int parent_node, int child_begin, int child_count) {
+        const ShapeRec& s = g_.shapes[id];
+        RtcNode n;
+        memset(&n, 0, sizeof(n));
+        n.kind = (s.kind == GROUP) ? RTC_NODE_GROUP : RTC_NODE_CSG;
+        n.parent = parent_node;
+        n.op = s.csg_op;
+        n.child_begin = child_begin;
+        n.child_count = child_count;
+        const Mat4 inv = (s.kind == CSG) ? s.t_inv : Mat4();
+        memcpy(n.inv, inv.m, sizeof(n.inv));
+        put_box(g_.bounding_box(id), n.bbox_min, n.bbox_max);  // cached in the shape on first use (group.rs:138-150)
+        put_box(g_.parent_space_box(id), n.world_bbox_min, n.world_bbox_max);
+        out_.nodes[node] = n;
+    }
+    // the walk: writes the subtree of `id` at the cursor and returns the child reference of what it wrote.  Touches
+    // only this subtree's shapes (their cached boxes included), so disjoint subtrees go to different threads.
+    int emit(int id, int parent_node, Cursor& c, LocalMaterials& materials) {
+        g_.check(id);
+        const ShapeRec& s = g_.shapes[id];
+        if (s.kind == GROUP || s.kind == CSG) {
+            const int node = c.node++;
             std::vector<int32_t> child_refs;
-            const std::vector<int> kids = g_.shapes[id].children;  // copy: visit() may grow g_.shapes
-            child_refs.reserve(kids.size());
-            for (int c : kids) child_refs.push_back(visit(c, node));
-            RtcNode n;
-            memset(&n, 0, sizeof(n));
-            n.kind = (kind == GROUP) ? RTC_NODE_GROUP : RTC_NODE_CSG;
-            n.parent = parent_node;
-            n.op = g_.shapes[id].csg_op;
-            n.child_begin = (int)out_.refs.size();
-            n.child_count = (int)child_refs.size();
-            out_.refs.insert(out_.refs.end(), child_refs.begin(), child_refs.end());
-            Mat4 inv = (kind == CSG) ? g_.shapes[id].t_inv : Mat4();
-            memcpy(n.inv, inv.m, sizeof(n.inv));
-            Bounds own = g_.bounding_box(id);
-            put_box(own, n.bbox_min, n.bbox_max);
-            put_box(g_.parent_space_box(id), n.world_bbox_min, n.world_bbox_max);
-            out_.nodes[node] = n;
+            child_refs.reserve(s.children.size());
+            for (int kid : s.children) child_refs.push_back(emit(kid, node, c, materials));
+            std::copy(child_refs.begin(), child_refs.end(), out_.refs.begin() + c.ref);
+            write_node(id, node, parent_node, c.ref, (int)child_refs.size());
+            c.ref += (int)child_refs.size();
             return ~node;
         }
-        const ShapeRec& s = g_.shapes[id];
-        RtcPrim p;
+        const int i = c.prim++;
+        RtcPrim& p = out_.prims[i];
         memset(&p, 0, sizeof(p));
-        switch (kind) {
+        switch (s.kind) {
             case SPHERE: p.type = RTC_SPHERE; break;
             case PLANE: p.type = RTC_PLANE; break;
             case CUBE: p.type = RTC_CUBE; break;
@@ -735,22 +946,18 @@ class Flattener {
             case CONE: p.type = RTC_CONE; break;
             default: p.type = RTC_TRIANGLE; break;  // SmoothTriangle renders as its flat inner triangle (Q5)
         }
-        p.material = material_index(s.material);
+        p.material = materials.index(s.material);
         p.casts_shadow = s.casts_shadow ? 1 : 0;
         p.parent = parent_node;
-        out_.prims.push_back(p);  // inverse, parameters and box: fill_leaf
-        out_.prim_shape.push_back(id);
-        return (int)out_.prims.size() - 1;
-    }
-    void fill_leaf(RtcPrim& p, int id) const {
-        const ShapeRec& s = g_.shapes[id];
         memcpy(p.inv, s.t_inv.m, sizeof(p.inv));
         if (p.type == RTC_TRIANGLE) {
             memcpy(p.params, s.tri, sizeof(p.params));
         } else if (p.type == RTC_CYLINDER || p.type == RTC_CONE) {
             p.params[0] = s.y_min, p.params[1] = s.y_max, p.params[2] = s.closed ? 1.f : 0.f;
         }
-        put_box(g_.parent_space_box(id), p.bbox_min, p.bbox_max);  // leaves: no cached state is touched
+        put_box(g_.parent_space_box(id), p.bbox_min, p.bbox_max);
+        out_.prim_shape[i] = id;
+        return i;
     }
 };
 

@@ -202,8 +202,22 @@ int upload_replica(RtcScene* s, const Flattened& f, Replica& r, int device) {
     size_t o_linear = w.add(f.linear), o_nodes = w.add(f.nodes), o_ops = w.add(f.ops), o_mat = w.add(f.materials);
     size_t o_pat = w.add(f.patterns), o_uv = w.add(f.uvs), o_tex = w.add(f.texels), o_img = w.add(f.small_image);
     if ((rc = ensure_arena(slot, std::max<size_t>(w.bytes, 256)))) return rc;
-    for (const auto& p : w.parts) memcpy(slot->staging + p.off, p.src, p.n);
+    const bool timing = getenv("RTC_TIMING") != nullptr;  // tuning aid (adds a synchronize)
+    auto t0 = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+        if (!timing) return;
+        const auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[rtc upload] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(now - t0).count());
+        t0 = now;
+    };
+    for (const auto& p : w.parts) parallel_stream_copy(slot->staging + p.off, p.src, p.n);
+    lap("arrays -> pinned staging");
     if (w.bytes) CUDA_TRY(cudaMemcpyAsync(slot->arena, slot->staging, w.bytes, cudaMemcpyHostToDevice, slot->stream));
+    if (timing) {
+        CUDA_TRY(cudaStreamSynchronize(slot->stream));
+        fprintf(stderr, "[rtc upload] %zu bytes\n", w.bytes);
+        lap("staging -> device");
+    }
     auto at = [&](size_t off, bool present) -> const void* { return present ? slot->arena + off : nullptr; };
     d.jitter = (const float*)at(o_jitter, !s->jitter.empty());
     d.samples = (const float4*)at(o_samples, !f.samples.empty());
@@ -457,11 +471,16 @@ int render_impl(RtcScene* s, int depth, int shard0, int n_shards_ext, float* rgb
         if (rgb && (rc = copy_bands(c.slot, s, c.shard, n_shards, c.b0, c.b1, c.slot->d_rgb, rgb, 3 * sizeof(float)))) return rc;
         if (u8 && (rc = copy_bands(c.slot, s, c.shard, n_shards, c.b0, c.b1, c.slot->d_u8, u8, 3))) return rc;
     }
+    const bool timing = getenv("RTC_TIMING") != nullptr;  // tuning aid
+    auto since = [&] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); };
+    if (timing) fprintf(stderr, "[rtc render] launches queued at      %8.3f ms\n", since());
     for (int i = 0; i < ndev; i++) {
         DeviceSlot* slot = s->replicas[i].slot;
         CUDA_TRY(cudaSetDevice(slot->device));
         CUDA_TRY(cudaStreamSynchronize(slot->stream));
+        if (timing) fprintf(stderr, "[rtc render] kernels done at          %8.3f ms\n", since());
         CUDA_TRY(cudaStreamSynchronize(slot->copy_stream));
+        if (timing) fprintf(stderr, "[rtc render] copies done at           %8.3f ms\n", since());
         float ms = 0.f;
         CUDA_TRY(cudaEventElapsedTime(&ms, slot->ev0, slot->ev1));
         st.kernel_ms = std::max(st.kernel_ms, (double)ms);
@@ -598,13 +617,15 @@ int rtc_set_camera(RtcScene* s, uint32_t w, uint32_t h, float half_w, float half
 int rtc_set_primitives(RtcScene* s, uint32_t n, const RtcPrim* prims) {
     if (!s || (n && !prims)) return fail(RTC_ERR_INVALID, "null argument");
     if (n >= (1u << 27)) return fail(RTC_ERR_CAPACITY, "too many primitives");
-    s->prims.assign(prims, prims + n);
+    s->prims.resize(n);
+    parallel_copy(s->prims.data(), prims, (size_t)n * sizeof(RtcPrim));
     s->committed = false;
     return 0;
 }
 int rtc_set_nodes(RtcScene* s, uint32_t n_nodes, const RtcNode* nodes, uint32_t n_refs, const int32_t* refs) {
     if (!s || (n_nodes && !nodes) || (n_refs && !refs)) return fail(RTC_ERR_INVALID, "null argument");
-    s->nodes.assign(nodes, nodes + n_nodes);
+    s->nodes.resize(n_nodes);
+    parallel_copy(s->nodes.data(), nodes, (size_t)n_nodes * sizeof(RtcNode));
     s->refs.assign(refs, refs + n_refs);
     s->committed = false;
     return 0;

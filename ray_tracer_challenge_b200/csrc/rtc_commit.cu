@@ -174,17 +174,37 @@ int max_hits(int type) {
     }
 }
 
+// The lowest i in [0, n) with pred(i), or n: a scan by all threads.
+template <class Pred>
+int first_index(int n, Pred pred, size_t grain = 16384) {
+    std::atomic<int> first{n};
+    parallel_for((size_t)n, grain, [&](size_t b, size_t e, int) {
+        for (size_t i = b; i < e && (int)i < first.load(std::memory_order_relaxed); i++)
+            if (pred((int)i)) {
+                int seen = first.load();
+                while ((int)i < seen && !first.compare_exchange_weak(seen, (int)i)) {
+                }
+                break;
+            }
+    });
+    return first.load();
+}
+
 // Every index the flattened scene carries must point inside its table (the reference cannot express a dangling
 // reference; a foreign host can).
 int validate_scene(const RtcScene* s) {
     const int np = (int)s->prims.size(), nn = (int)s->nodes.size();
-    // ---- validate references
-    for (int i = 0; i < np; i++) {
+    // ---- validate references (the primitive passes run on all threads; the lowest failing index is the one reported)
+    auto prim_error = [&](int i) -> const char* {
         const RtcPrim& p = s->prims[i];
-        if (p.type < RTC_SPHERE || p.type > RTC_TRIANGLE) return fail(RTC_ERR_INVALID, "primitive " + std::to_string(i) + ": bad type");
-        if (p.material < 0 || p.material >= (int)s->materials.size())
-            return fail(RTC_ERR_INVALID, "primitive " + std::to_string(i) + ": bad material index");
-        if (p.parent < -1 || p.parent >= nn) return fail(RTC_ERR_INVALID, "primitive " + std::to_string(i) + ": bad parent");
+        if (p.type < RTC_SPHERE || p.type > RTC_TRIANGLE) return "bad type";
+        if (p.material < 0 || p.material >= (int)s->materials.size()) return "bad material index";
+        if (p.parent < -1 || p.parent >= nn) return "bad parent";
+        return nullptr;
+    };
+    {
+        const int bad = first_index(np, [&](int i) { return prim_error(i) != nullptr; });
+        if (bad < np) return fail(RTC_ERR_INVALID, "primitive " + std::to_string(bad) + ": " + prim_error(bad));
     }
     for (int i = 0; i < nn; i++) {
         const RtcNode& n = s->nodes[i];
@@ -203,25 +223,42 @@ int validate_scene(const RtcScene* s) {
     // referring node, no item is referenced twice, every item with a parent is in that parent's list, and parent chains
     // end.  A parent cycle would spin the device's cull-chain walk forever; a reference cycle would recurse the CSG
     // emitter without bound.
-    std::vector<char> prim_seen(np, 0), node_seen(nn, 0);
-    for (int i = 0; i < nn; i++) {
+    // (a node marks only children whose parent field names it, so the marks of different nodes never collide and the
+    // nodes can be checked on all threads)
+    std::vector<unsigned char> prim_seen(np, 0), node_seen(nn, 0);
+    auto link_error = [&](int i) -> const char* {
         const RtcNode& n = s->nodes[i];
         for (int c = 0; c < n.child_count; c++) {
             const int r = s->refs[n.child_begin + c];
-            char& seen = r >= 0 ? prim_seen[r] : node_seen[~r];
-            const int claimed = r >= 0 ? s->prims[r].parent : s->nodes[~r].parent;
-            if (seen) return fail(RTC_ERR_INVALID, "node " + std::to_string(i) + ": a child is referenced twice");
-            if (claimed != i) return fail(RTC_ERR_INVALID, "node " + std::to_string(i) + ": child's parent field does not point back");
+            if ((r >= 0 ? s->prims[r].parent : s->nodes[~r].parent) != i) return "child's parent field does not point back";
+        }
+        for (int c = 0; c < n.child_count; c++) {
+            const int r = s->refs[n.child_begin + c];
+            unsigned char& seen = r >= 0 ? prim_seen[r] : node_seen[~r];
+            if (seen) return "a child is referenced twice";
             seen = 1;
         }
+        return nullptr;
+    };
+    {
+        std::vector<const char*> why(nn, nullptr);
+        const int bad = first_index(nn, [&](int i) { return (why[i] = link_error(i)) != nullptr; }, 512);
+        if (bad < nn) return fail(RTC_ERR_INVALID, "node " + std::to_string(bad) + ": " + why[bad]);
     }
-    for (int i = 0; i < np; i++)
-        if (s->prims[i].parent >= 0 && !prim_seen[i]) return fail(RTC_ERR_INVALID, "primitive " + std::to_string(i) + ": not in its parent's child list");
-    for (int i = 0; i < nn; i++) {
-        if (s->nodes[i].parent >= 0 && !node_seen[i]) return fail(RTC_ERR_INVALID, "node " + std::to_string(i) + ": not in its parent's child list");
-        int steps = 0;
-        for (int a = s->nodes[i].parent; a >= 0; a = s->nodes[a].parent)
-            if (++steps > nn) return fail(RTC_ERR_INVALID, "node parents form a cycle");
+    {
+        const int bad = first_index(np, [&](int i) { return s->prims[i].parent >= 0 && !prim_seen[i]; });
+        if (bad < np) return fail(RTC_ERR_INVALID, "primitive " + std::to_string(bad) + ": not in its parent's child list");
+    }
+    {
+        const int orphan = first_index(nn, [&](int i) { return s->nodes[i].parent >= 0 && !node_seen[i]; }, 4096);
+        const int cyclic = first_index(nn, [&](int i) {
+            int steps = 0;
+            for (int a = s->nodes[i].parent; a >= 0; a = s->nodes[a].parent)
+                if (++steps > nn) return true;
+            return false;
+        }, 512);
+        if (orphan < nn && orphan <= cyclic) return fail(RTC_ERR_INVALID, "node " + std::to_string(orphan) + ": not in its parent's child list");
+        if (cyclic < nn) return fail(RTC_ERR_INVALID, "node parents form a cycle");
     }
     for (const RtcMaterial& m : s->materials)
         if (m.pattern < -1 || m.pattern >= (int)s->patterns.size()) return fail(RTC_ERR_INVALID, "material: bad pattern index");
@@ -502,12 +539,17 @@ int flatten(RtcScene* s, Flattened& f, TreeBuilderFn tree_builder, void* tree_bu
         }
         return top;
     };
-    for (int i = 0; i < nn; i++) {
-        top_csg_of_node[i] = resolve(i);
+    parallel_for((size_t)nn, 512, [&](size_t b, size_t e, int) {
+        for (size_t i = b; i < e; i++) top_csg_of_node[i] = resolve((int)i);
+    });
+    for (int i = 0; i < nn; i++)
         if (top_csg_of_node[i] == -2) return fail(RTC_ERR_INVALID, "node parents form a cycle");
-    }
+    // (the passes over the primitives below run on all threads — rtc_parallel.h — and keep primitive order)
+    constexpr size_t kGrain = 16384;
     std::vector<int> prim_top_csg(np, -1);
-    for (int i = 0; i < np; i++) prim_top_csg[i] = s->prims[i].parent >= 0 ? top_csg_of_node[s->prims[i].parent] : -1;
+    parallel_for((size_t)np, kGrain, [&](size_t b, size_t e, int) {
+        for (size_t i = b; i < e; i++) prim_top_csg[i] = s->prims[i].parent >= 0 ? top_csg_of_node[s->prims[i].parent] : -1;
+    });
 
     // ---- top-level items: free primitives and outermost CSG nodes
     struct Item {
@@ -515,16 +557,36 @@ int flatten(RtcScene* s, Flattened& f, TreeBuilderFn tree_builder, void* tree_bu
         Box box;
     };
     std::vector<Item> bounded, unbounded;
-    auto add_item = [&](int ref, const float* lo, const float* hi) {
+    auto make_item = [](int ref, const float* lo, const float* hi) {
         Item it;
         it.prim = ref;
         for (int a = 0; a < 3; a++) it.box.lo[a] = lo[a], it.box.hi[a] = hi[a];
-        (it.box.finite() ? bounded : unbounded).push_back(it);
+        return it;
     };
-    for (int i = 0; i < np; i++)
-        if (prim_top_csg[i] < 0) add_item(i, s->prims[i].bbox_min, s->prims[i].bbox_max);
+    {
+        const int n_parts = parallel_chunks((size_t)np, kGrain);
+        std::vector<std::vector<Item>> bounded_part(n_parts), unbounded_part(n_parts);
+        parallel_for((size_t)np, kGrain, [&](size_t b, size_t e, int part) {
+            bounded_part[part].reserve(e - b);
+            for (size_t i = b; i < e; i++) {
+                if (prim_top_csg[i] >= 0) continue;
+                const Item it = make_item((int)i, s->prims[i].bbox_min, s->prims[i].bbox_max);
+                (it.box.finite() ? bounded_part[part] : unbounded_part[part]).push_back(it);
+            }
+        });
+        size_t n_bounded = 0;
+        for (const auto& part : bounded_part) n_bounded += part.size();
+        bounded.reserve(n_bounded + 64);
+        for (int part = 0; part < n_parts; part++) {
+            bounded.insert(bounded.end(), bounded_part[part].begin(), bounded_part[part].end());
+            unbounded.insert(unbounded.end(), unbounded_part[part].begin(), unbounded_part[part].end());
+        }
+    }
     for (int i = 0; i < nn; i++)
-        if (s->nodes[i].kind == RTC_NODE_CSG && top_csg_of_node[i] == i) add_item(~i, s->nodes[i].world_bbox_min, s->nodes[i].world_bbox_max);
+        if (s->nodes[i].kind == RTC_NODE_CSG && top_csg_of_node[i] == i) {
+            const Item it = make_item(~i, s->nodes[i].world_bbox_min, s->nodes[i].world_bbox_max);
+            (it.box.finite() ? bounded : unbounded).push_back(it);
+        }
     if ((int)bounded.size() < s->bvh_min_prims) {  // tiny scene: test everything for every ray, no tree
         unbounded.insert(unbounded.end(), bounded.begin(), bounded.end());
         bounded.clear();
@@ -546,8 +608,16 @@ int flatten(RtcScene* s, Flattened& f, TreeBuilderFn tree_builder, void* tree_bu
     // ---- BVH
     // the largest coordinate a ray of this scene starts from or aims at: the bounded items, the camera, the light
     float extent = 0.f;
-    for (const Item& it : bounded)
-        for (int a = 0; a < 3; a++) extent = std::max(extent, std::max(std::fabs(it.box.lo[a]), std::fabs(it.box.hi[a])));
+    {
+        std::vector<float> part_extent(parallel_chunks(bounded.size(), kGrain), 0.f);
+        parallel_for(bounded.size(), kGrain, [&](size_t b, size_t e, int part) {
+            float m = 0.f;
+            for (size_t i = b; i < e; i++)
+                for (int a = 0; a < 3; a++) m = std::max(m, std::max(std::fabs(bounded[i].box.lo[a]), std::fabs(bounded[i].box.hi[a])));
+            part_extent[part] = m;
+        });
+        for (float m : part_extent) extent = std::max(extent, m);
+    }
     {
         float m[16], cam[3] = {0.f, 0.f, 0.f};
         memcpy(m, s->cam_inv, sizeof(m));  // the camera's origin = inverse * (0, 0, 0): the translation column
@@ -561,45 +631,59 @@ int flatten(RtcScene* s, Flattened& f, TreeBuilderFn tree_builder, void* tree_bu
         }
     }
     std::vector<BuildItem> build_items(bounded.size());
-    for (size_t i = 0; i < bounded.size(); i++) {
-        BuildItem& b = build_items[i];
-        b.box = bounded[i].box;
-        b.item = (int)i;
-        b.closed = bounded[i].prim >= 0 && (s->prims[bounded[i].prim].type == RTC_SPHERE || s->prims[bounded[i].prim].type == RTC_CUBE);
-        for (int a = 0; a < 3; a++) {
-            // pad: the tree must never reject a hit the reference would report (it is only an accelerator).  The last
-            // term covers the traversal's own arithmetic: slab distances are formed as fma(plane, 1/d, -(o * 1/d)), two
-            // roundings of products as large as the ray origin's coordinate, and 1/d is rounded once — together below 2^-21 of
-            // the scene's extent in length; 2^-20 is added
-            float ext = b.box.hi[a] - b.box.lo[a];
-            float pad = 1e-4f * ext + 1e-5f * std::max(std::fabs(b.box.lo[a]), std::fabs(b.box.hi[a])) + 1e-6f + 9.54e-7f * extent;
-            b.box.lo[a] -= pad;
-            b.box.hi[a] += pad;
-            b.centroid[a] = 0.5f * (b.box.lo[a] + b.box.hi[a]);
+    parallel_for(bounded.size(), kGrain, [&](size_t begin, size_t end, int) {
+        for (size_t i = begin; i < end; i++) {
+            BuildItem& b = build_items[i];
+            b.box = bounded[i].box;
+            b.item = (int)i;
+            b.closed = bounded[i].prim >= 0 && (s->prims[bounded[i].prim].type == RTC_SPHERE || s->prims[bounded[i].prim].type == RTC_CUBE);
+            for (int a = 0; a < 3; a++) {
+                // pad: the tree must never reject a hit the reference would report (it is only an accelerator).  The last
+                // term covers the traversal's own arithmetic: slab distances are formed as fma(plane, 1/d, -(o * 1/d)), two
+                // roundings of products as large as the ray origin's coordinate, and 1/d is rounded once — together below 2^-21 of
+                // the scene's extent in length; 2^-20 is added
+                float ext = b.box.hi[a] - b.box.lo[a];
+                float pad = 1e-4f * ext + 1e-5f * std::max(std::fabs(b.box.lo[a]), std::fabs(b.box.hi[a])) + 1e-6f + 9.54e-7f * extent;
+                b.box.lo[a] -= pad;
+                b.box.hi[a] += pad;
+                b.centroid[a] = 0.5f * (b.box.lo[a] + b.box.hi[a]);
+            }
         }
-    }
+    });
     if (!build_items.empty()) {
         // Leaf size: a mesh's triangles share one transform (the object-space ray is cached), so a few per leaf cost
         // less than the extra boxes; every other primitive pays its own ray transform, and one per leaf wins
         // (measured on B200: 102 k triangles 0.50 ms at 4 vs 0.58 at 1; 100 k spheres 38.7 ms at 1 vs 51.7 at 4).
         size_t n_triangles = 0;
-        for (const Item& it : bounded) n_triangles += it.prim >= 0 && s->prims[it.prim].type == RTC_TRIANGLE;
+        {
+            std::vector<size_t> part_triangles(parallel_chunks(bounded.size(), kGrain), 0);
+            parallel_for(bounded.size(), kGrain, [&](size_t b, size_t e, int part) {
+                size_t n = 0;
+                for (size_t i = b; i < e; i++) n += bounded[i].prim >= 0 && s->prims[bounded[i].prim].type == RTC_TRIANGLE;
+                part_triangles[part] = n;
+            });
+            for (size_t n : part_triangles) n_triangles += n;
+        }
         int leaf = s->leaf_size > 0 ? s->leaf_size : (2 * n_triangles > bounded.size() ? 4 : 1);
         if (const char* env = getenv("RTC_BVH_LEAF")) leaf = atoi(env);  // tuning aid
         f.leaf_size = std::min(std::max(leaf, 1), 16);
         int root = 0;
         s->built_on_device = 0;
         if (tree_builder && build_items.size() >= 1024) {  // the device builder: the same padded boxes, Morton order
-            std::vector<float> boxes(6 * build_items.size());
-            std::vector<unsigned char> closed(build_items.size());
-            for (size_t i = 0; i < build_items.size(); i++) {
-                for (int a = 0; a < 3; a++) boxes[6 * i + a] = build_items[i].box.lo[a], boxes[6 * i + 3 + a] = build_items[i].box.hi[a];
-                closed[i] = build_items[i].closed;
-            }
+            RawVector<float> boxes(6 * build_items.size());
+            RawVector<unsigned char> closed(build_items.size());
+            parallel_for(build_items.size(), kGrain, [&](size_t b, size_t e, int) {
+                for (size_t i = b; i < e; i++) {
+                    for (int a = 0; a < 3; a++) boxes[6 * i + a] = build_items[i].box.lo[a], boxes[6 * i + 3 + a] = build_items[i].box.hi[a];
+                    closed[i] = build_items[i].closed;
+                }
+            });
             TreeBuildOutput out;
             if (tree_builder(tree_builder_ctx, TreeBuildInput{boxes.data(), closed.data(), (int)build_items.size(), f.leaf_size}, out) == 0) {
                 std::vector<BuildItem> sorted(build_items.size());
-                for (size_t i = 0; i < sorted.size(); i++) sorted[i] = build_items[out.order[i]];
+                parallel_for(sorted.size(), kGrain, [&](size_t b, size_t e, int) {
+                    for (size_t i = b; i < e; i++) sorted[i] = build_items[out.order[i]];
+                });
                 build_items.swap(sorted);
                 f.bvh.swap(out.nodes);
                 root = out.root;
@@ -635,25 +719,33 @@ int flatten(RtcScene* s, Flattened& f, TreeBuilderFn tree_builder, void* tree_bu
 
     lap("bvh build");
     // ---- device positions: BVH order, then the linear list, then CSG-internal primitives
-    std::vector<int> item_refs;
-    for (const BuildItem& b : build_items) item_refs.push_back(bounded[b.item].prim);
-    const int n_tree = (int)item_refs.size();
-    for (const Item& it : unbounded) item_refs.push_back(it.prim);
-    const int n_items = (int)item_refs.size();
+    const int n_tree = (int)build_items.size();
+    const int n_items = n_tree + (int)unbounded.size();
+    std::vector<int> item_refs(n_items);
+    parallel_for((size_t)n_tree, kGrain, [&](size_t b, size_t e, int) {
+        for (size_t i = b; i < e; i++) item_refs[i] = bounded[build_items[i].item].prim;
+    });
+    for (size_t i = 0; i < unbounded.size(); i++) item_refs[n_tree + i] = unbounded[i].prim;
     std::vector<int> prim_pos(np, -1), csg_pos(nn, -1);
-    for (int i = 0; i < n_items; i++) {
-        if (item_refs[i] >= 0)
-            prim_pos[item_refs[i]] = i;
-        else
-            csg_pos[~item_refs[i]] = i;
-    }
+    parallel_for((size_t)n_items, kGrain, [&](size_t b, size_t e, int) {
+        for (size_t i = b; i < e; i++) {
+            if (item_refs[i] >= 0)
+                prim_pos[item_refs[i]] = (int)i;
+            else
+                csg_pos[~item_refs[i]] = (int)i;
+        }
+    });
     int next = n_items;
     for (int i = 0; i < np; i++)
         if (prim_top_csg[i] >= 0) prim_pos[i] = next++;
     f.n_pos = next;
     for (int i = n_tree; i < n_items; i++) f.linear.push_back(i);
 
-    // ---- transforms (deduplicated bitwise), triangle and bound tables, heads
+    // ---- transforms, triangle and bound tables, heads.  Transform table: one slot per non-triangle primitive in
+    // primitive order, then the triangles' transforms de-duplicated bitwise in first-use order (only a mesh's triangles
+    // share transforms in practice, and only they profit: the object-space ray is cached by transform id).  Two passes
+    // over the primitives on all threads — count, then write at the offsets the counts fix — with the same result
+    // for any number of threads.
     struct XfKey {
         uint32_t w[12];
         bool operator==(const XfKey& o) const { return memcmp(w, o.w, sizeof(w)) == 0; }
@@ -665,58 +757,108 @@ int flatten(RtcScene* s, Flattened& f, TreeBuilderFn tree_builder, void* tree_bu
             return (size_t)h;
         }
     };
-    std::unordered_map<XfKey, int, XfHash> xf_ids;
-    f.xform.reserve(3 * (size_t)np);
-    XfKey last_key{};
-    int last_id = -1;
-    // only a mesh's triangles share transforms in practice (and only they profit: the object-space ray is cached by
-    // transform id), so every other primitive gets its own slot without a lookup
-    auto xform_id = [&](const float m[16], bool dedup) {
-        if (!dedup) {
-            float4 r[3];
-            rows3(m, r);
-            f.xform.insert(f.xform.end(), r, r + 3);
-            return (int)f.xform.size() / 3 - 1;
-        }
-        XfKey key;
-        memcpy(key.w, m, sizeof(key.w));
-        if (last_id >= 0 && key == last_key) return last_id;  // a mesh's triangles share one transform
-        last_key = key;
-        auto it = xf_ids.find(key);
-        if (it != xf_ids.end()) return last_id = it->second;
-        int id = (int)f.xform.size() / 3;
-        float4 r[3];
-        rows3(m, r);
-        f.xform.insert(f.xform.end(), r, r + 3);
-        xf_ids.emplace(key, id);
-        return last_id = id;
+    struct Part {
+        int plain = 0, tris = 0, bounds = 0;  // non-triangle primitives, triangles, cylinders + cones of the chunk
+        bool all_cast = true;
+        std::vector<XfKey> keys;     // the chunk's distinct triangle transforms, first use first
+        std::vector<int> tri_key;    // per triangle of the chunk: index into `keys`, later the global transform id
     };
-    f.head.assign(2 * (size_t)f.n_pos, make_int4(0, 0, 0, 0));
-    s->pos_to_prim.assign(f.n_pos, -1);
-    f.tri.reserve(3 * (size_t)np);
-    for (int i = 0; i < np; i++) {
-        const RtcPrim& p = s->prims[i];
-        int pos = prim_pos[i];
-        int aux = 0;
-        if (p.type == RTC_TRIANGLE) {
-            aux = (int)f.tri.size() / 3;
-            const float* q = p.params;  // p1, e1, e2, normal
-            f.tri.push_back(make_float4(q[0], q[1], q[2], q[3]));
-            f.tri.push_back(make_float4(q[4], q[5], q[6], q[7]));
-            f.tri.push_back(make_float4(q[8], q[9], q[10], q[11]));
-        } else if (p.type == RTC_CYLINDER || p.type == RTC_CONE) {
-            aux = (int)f.bound.size();
-            f.bound.push_back(make_float4(p.params[0], p.params[1], p.params[2] != 0.f ? 1.f : 0.f, 0.f));
+    const int n_parts = parallel_chunks((size_t)np, kGrain);
+    std::vector<Part> parts(n_parts);
+    parallel_for((size_t)np, kGrain, [&](size_t b, size_t e, int c) {
+        Part& part = parts[c];
+        std::unordered_map<XfKey, int, XfHash> ids;
+        XfKey last_key{};
+        int last_id = -1;
+        for (size_t i = b; i < e; i++) {
+            const RtcPrim& p = s->prims[i];
+            part.all_cast = part.all_cast && p.casts_shadow;
+            if (p.type != RTC_TRIANGLE) {
+                part.plain++;
+                part.bounds += p.type == RTC_CYLINDER || p.type == RTC_CONE;
+                continue;
+            }
+            part.tris++;
+            XfKey key;
+            memcpy(key.w, p.inv, sizeof(key.w));
+            if (last_id < 0 || !(key == last_key)) {  // a mesh's triangles share one transform
+                last_key = key;
+                auto it = ids.find(key);
+                if (it == ids.end()) {
+                    it = ids.emplace(key, (int)part.keys.size()).first;
+                    part.keys.push_back(key);
+                }
+                last_id = it->second;
+            }
+            part.tri_key.push_back(last_id);
         }
-        int flags = p.casts_shadow ? kFlagCastsShadow : 0;
-        if (!p.casts_shadow) f.all_cast_shadow = 0;
-        bool in_linear = pos >= n_tree && pos < n_items;
-        if (in_linear && p.parent >= 0) flags |= kFlagHasParent;
-        f.head[pos] = make_int4(p.type | (flags << 4) | (p.material << 8), xform_id(p.inv, p.type == RTC_TRIANGLE), aux, i);
-        f.head[f.n_pos + pos] = make_int4(prim_top_csg[i] < 0 ? p.parent : -1, i, 0, 0);
-        s->pos_to_prim[pos] = i;
+    });
+    std::vector<int> plain_base(n_parts + 1, 0), tri_base(n_parts + 1, 0), bound_base(n_parts + 1, 0);
+    for (int c = 0; c < n_parts; c++) {
+        plain_base[c + 1] = plain_base[c] + parts[c].plain, tri_base[c + 1] = tri_base[c] + parts[c].tris;
+        bound_base[c + 1] = bound_base[c] + parts[c].bounds;
+        if (!parts[c].all_cast) f.all_cast_shadow = 0;
     }
-
+    const int n_plain = plain_base[n_parts];
+    {
+        std::unordered_map<XfKey, int, XfHash> ids;
+        std::vector<XfKey> distinct;
+        std::vector<std::vector<int>> global(n_parts);
+        for (int c = 0; c < n_parts; c++)
+            for (const XfKey& key : parts[c].keys) {
+                auto it = ids.find(key);
+                if (it == ids.end()) {
+                    it = ids.emplace(key, (int)distinct.size()).first;
+                    distinct.push_back(key);
+                }
+                global[c].push_back(n_plain + it->second);
+            }
+        f.xform.resize(3 * ((size_t)n_plain + distinct.size()));
+        for (size_t k = 0; k < distinct.size(); k++) {
+            float m[16] = {0};
+            memcpy(m, distinct[k].w, sizeof(distinct[k].w));
+            rows3(m, &f.xform[3 * ((size_t)n_plain + k)]);
+        }
+        parallel_for((size_t)n_parts, 1, [&](size_t b, size_t e, int) {
+            for (size_t c = b; c < e; c++)
+                for (int& k : parts[c].tri_key) k = global[c][k];
+        });
+    }
+    f.head.resize(2 * (size_t)f.n_pos);
+    s->pos_to_prim.assign(f.n_pos, -1);
+    f.tri.resize(3 * (size_t)tri_base[n_parts]);
+    f.bound.resize(bound_base[n_parts]);
+    parallel_for((size_t)np, kGrain, [&](size_t b, size_t e, int c) {
+        int plain = plain_base[c], tri = tri_base[c], bound = bound_base[c], k = 0;
+        for (size_t i = b; i < e; i++) {
+            const RtcPrim& p = s->prims[i];
+            const int pos = prim_pos[i];
+            int aux = 0, xf;
+            if (p.type == RTC_TRIANGLE) {
+                aux = tri;
+                const float* q = p.params;  // p1, e1, e2, normal
+                f.tri[3 * (size_t)tri] = make_float4(q[0], q[1], q[2], q[3]);
+                f.tri[3 * (size_t)tri + 1] = make_float4(q[4], q[5], q[6], q[7]);
+                f.tri[3 * (size_t)tri + 2] = make_float4(q[8], q[9], q[10], q[11]);
+                tri++;
+                xf = parts[c].tri_key[k++];
+            } else {
+                if (p.type == RTC_CYLINDER || p.type == RTC_CONE) {
+                    aux = bound;
+                    f.bound[bound++] = make_float4(p.params[0], p.params[1], p.params[2] != 0.f ? 1.f : 0.f, 0.f);
+                }
+                xf = plain;
+                rows3(p.inv, &f.xform[3 * (size_t)plain]);
+                plain++;
+            }
+            int flags = p.casts_shadow ? kFlagCastsShadow : 0;
+            const bool in_linear = pos >= n_tree && pos < n_items;
+            if (in_linear && p.parent >= 0) flags |= kFlagHasParent;
+            f.head[pos] = make_int4(p.type | (flags << 4) | (p.material << 8), xf, aux, (int)i);
+            f.head[f.n_pos + pos] = make_int4(prim_top_csg[i] < 0 ? p.parent : -1, (int)i, 0, 0);
+            s->pos_to_prim[pos] = (int)i;
+        }
+    });
     lap("positions, transforms, heads");
     // ---- reference shape-tree nodes
     f.nodes.resize(nn);
@@ -781,15 +923,17 @@ int flatten(RtcScene* s, Flattened& f, TreeBuilderFn tree_builder, void* tree_bu
 
     lap("nodes + csg programs");
     // ---- traversal records: head + the rows the intersection test needs, one 64 B fetch per primitive
-    f.rec.assign(4 * (size_t)f.n_pos, make_float4(0.f, 0.f, 0.f, 0.f));
-    for (int pos = 0; pos < f.n_pos; pos++) {
-        int4 h = f.head[pos];
-        memcpy(&f.rec[4 * (size_t)pos], &h, sizeof(h));
-        int type = h.x & 15;
-        if (type == T_CSG) continue;
-        const float4* src = (type == T_TRIANGLE) ? &f.tri[3 * (size_t)h.z] : &f.xform[3 * (size_t)h.y];
-        for (int r = 0; r < 3; r++) f.rec[4 * (size_t)pos + 1 + r] = src[r];
-    }
+    f.rec.resize(4 * (size_t)f.n_pos);
+    parallel_for((size_t)f.n_pos, kGrain, [&](size_t b, size_t e, int) {
+        for (size_t pos = b; pos < e; pos++) {
+            int4 h = f.head[pos];
+            memcpy(&f.rec[4 * pos], &h, sizeof(h));
+            int type = h.x & 15;
+            if (type == T_CSG) continue;  // (resize zeroed the rows)
+            const float4* src = (type == T_TRIANGLE) ? &f.tri[3 * (size_t)h.z] : &f.xform[3 * (size_t)h.y];
+            for (int r = 0; r < 3; r++) f.rec[4 * pos + 1 + r] = src[r];
+        }
+    });
 
     if (int rc = build_shading_tables(s, f)) return rc;
     plan_small_scene(s, f, n_items);

@@ -9,6 +9,7 @@
 #include <cuda_runtime.h>
 
 #include "../../include/rtc_b200.h"
+#include "rtc_parallel.h"
 #include "rtc_types.h"
 
 namespace rtc {
@@ -124,8 +125,8 @@ struct RtcScene {
     uint32_t width = 0, height = 0;
     float half_w = 0, half_h = 0, pixel_size = 0;
     float cam_inv[16];
-    std::vector<RtcPrim> prims;
-    std::vector<RtcNode> nodes;
+    rtc::RawVector<RtcPrim> prims;  // copied in by all threads (rtc_set_primitives)
+    rtc::RawVector<RtcNode> nodes;
     std::vector<int32_t> refs;
     std::vector<RtcMaterial> materials;
     std::vector<RtcPattern> patterns;

@@ -22,6 +22,9 @@
 // there when the build is the frame.  Group boxes and divide() of the reference (group.rs:48-77, 115-133) play no part
 // in either: primitives arrive here already flattened in depth-first order.
 #include <cfloat>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstdint>
 #include <cstring>
 #include <vector>
@@ -214,16 +217,36 @@ int lbvh_build(void* ctx_, const TreeBuildInput& in, TreeBuildOutput& out) {
     if (n < 2) return 1;
     LbvhContext& ctx = *static_cast<LbvhContext*>(ctx_);
     cudaStream_t stream = ctx.stream;
+    const bool timing = getenv("RTC_TIMING") != nullptr;  // tuning aid
+    auto t_last = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+        if (!timing) return;
+        const auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[rtc lbvh]   %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(now - t_last).count());
+        t_last = now;
+    };
     int padded = 1, log2n = 0;
     while (padded < n) padded <<= 1, log2n++;
     // depth <= 3 * bits (code bits) + log2n (position bits among equal codes): keep it inside the traversal stack
     const int bits = std::max(1, std::min(21, (kBvhStack - 4 - log2n) / 3));
     float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
-    for (int i = 0; i < n; i++)
-        for (int a = 0; a < 3; a++) {
-            const float c = 0.5f * (in.boxes[6 * (size_t)i + a] + in.boxes[6 * (size_t)i + 3 + a]);
-            lo[a] = std::min(lo[a], c), hi[a] = std::max(hi[a], c);
-        }
+    {
+        struct Range {
+            float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+        };
+        std::vector<Range> part(parallel_chunks((size_t)n, 16384));
+        parallel_for((size_t)n, 16384, [&](size_t b, size_t e, int k) {
+            Range r;
+            for (size_t i = b; i < e; i++)
+                for (int a = 0; a < 3; a++) {
+                    const float c = 0.5f * (in.boxes[6 * i + a] + in.boxes[6 * i + 3 + a]);
+                    r.lo[a] = std::min(r.lo[a], c), r.hi[a] = std::max(r.hi[a], c);
+                }
+            part[k] = r;
+        });
+        for (const Range& r : part)
+            for (int a = 0; a < 3; a++) lo[a] = std::min(lo[a], r.lo[a]), hi[a] = std::max(hi[a], r.hi[a]);
+    }
     const float cells = (float)(1u << bits);
     float scale[3];
     for (int a = 0; a < 3; a++) scale[a] = hi[a] > lo[a] ? cells / (hi[a] - lo[a]) : 0.0f;
@@ -264,8 +287,9 @@ int lbvh_build(void* ctx_, const TreeBuildInput& in, TreeBuildOutput& out) {
     }
     char* h_up = *ctx.pinned;
     char* h_down = *ctx.pinned + up_bytes;
-    memcpy(h_up, in.boxes, (size_t)n * sizeof(LbvhBox));
-    memcpy(h_up + (size_t)n * sizeof(LbvhBox), in.closed, n);
+    parallel_stream_copy(h_up, in.boxes, (size_t)n * sizeof(LbvhBox));
+    parallel_stream_copy(h_up + (size_t)n * sizeof(LbvhBox), in.closed, n);
+    lap("centroid bounds + staging");
     LBVH_TRY(cudaMemcpyAsync(d_boxes, h_up, (size_t)n * sizeof(LbvhBox), cudaMemcpyHostToDevice, stream));
     LBVH_TRY(cudaMemcpyAsync(d_closed, h_up + (size_t)n * sizeof(LbvhBox), (size_t)n, cudaMemcpyHostToDevice, stream));
     LBVH_TRY(cudaMemsetAsync(d_arrivals, 0, (size_t)n * sizeof(int), stream));
@@ -282,6 +306,7 @@ int lbvh_build(void* ctx_, const TreeBuildInput& in, TreeBuildOutput& out) {
                                                                    d_bounds, d_arrivals, d_out);
     lbvh_depth<<<(n + threads - 1) / threads, threads, 0, stream>>>(d_nodes, d_leaf_parent, n, in.leaf_size, d_depth);
     LBVH_TRY(cudaGetLastError());
+    lap("launches queued");
     int* h_order = reinterpret_cast<int*>(h_down);
     DevBvhNode* h_nodes = reinterpret_cast<DevBvhNode*>(h_down + (((size_t)n * sizeof(int) + 63) & ~size_t(63)));
     int* h_depth = reinterpret_cast<int*>(reinterpret_cast<char*>(h_nodes) + (size_t)n * sizeof(DevBvhNode));
@@ -289,12 +314,16 @@ int lbvh_build(void* ctx_, const TreeBuildInput& in, TreeBuildOutput& out) {
     LBVH_TRY(cudaMemcpyAsync(h_order, d_items, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, stream));
     LBVH_TRY(cudaMemcpyAsync(h_nodes, d_out, (size_t)(n - 1) * sizeof(DevBvhNode), cudaMemcpyDeviceToHost, stream));
     LBVH_TRY(cudaStreamSynchronize(stream));
+    lap("device done, tree on the host");
     if (*h_depth > kBvhStack - 2) return 1;  // cannot happen (the bit budget above); refused rather than truncated if it does
     out.depth = *h_depth;
-    out.order.assign(h_order, h_order + n);
-    out.nodes.assign(h_nodes, h_nodes + (n - 1));
+    out.order.resize(n);
+    out.nodes.resize(n - 1);
+    parallel_copy(out.order.data(), h_order, (size_t)n * sizeof(int));
+    parallel_copy(out.nodes.data(), h_nodes, (size_t)(n - 1) * sizeof(DevBvhNode));
     // the whole tree fits one leaf: the caller wraps it (as it does for the host builder)
     out.root = n <= in.leaf_size ? ~((0 << 4) | (n - 1)) : 0;
+    lap("copies out of staging");
     return 0;
 }
 
