@@ -166,8 +166,8 @@ struct ArenaWriter {
         size_t n, off;
     };
     std::vector<Part> parts;
-    template <class T>
-    size_t add(const std::vector<T>& v) {
+    template <class T, class A>
+    size_t add(const std::vector<T, A>& v) {
         size_t off = bytes;
         if (!v.empty()) {
             parts.push_back({v.data(), v.size() * sizeof(T), off});

@@ -27,8 +27,8 @@ struct BuildItem {
     bool closed;  // sphere or cube: it has an odd number of hits behind a ray origin only if the origin is inside it
 };
 struct Builder {
-    std::vector<BuildItem>& items;
-    std::vector<DevBvhNode>& nodes;
+    RawVector<BuildItem>& items;
+    RawVector<DevBvhNode>& nodes;
     int leaf_size;
     // returns the link for the range [b, e): >= 0 inner node, < 0 leaf code
     // The traversal stack holds one deferred child per level (kBvhStack entries, dev_bvh.cuh) and a full stack must
@@ -119,7 +119,7 @@ struct Builder {
     // Subtrees of the top `par_depth` levels are built by separate threads into their own node arrays (the ranges of
     // `items` they partition are disjoint) and appended afterwards with their inner links shifted.
     int par_depth = 0;
-    static void append(std::vector<DevBvhNode>& dst, std::vector<DevBvhNode>& sub, int& link) {
+    static void append(RawVector<DevBvhNode>& dst, RawVector<DevBvhNode>& sub, int& link) {
         const int off = (int)dst.size();
         for (DevBvhNode& n : sub) {
             if (n.d.x >= 0) n.d.x += off;
@@ -136,7 +136,7 @@ struct Builder {
         for (int i = mid; i < e; i++) b1.grow(items[i].box);
         int c0, c1;
         if (depth < par_depth && e - b > 4096) {
-            std::vector<DevBvhNode> left_nodes, right_nodes;
+            RawVector<DevBvhNode> left_nodes, right_nodes;
             Builder left{items, left_nodes, leaf_size}, right{items, right_nodes, leaf_size};
             left.par_depth = right.par_depth = par_depth;
             auto task = std::async(std::launch::async, [&] { return left.build(b, mid, depth + 1); });
@@ -528,6 +528,7 @@ int flatten(RtcScene* s, Flattened& f, TreeBuilderFn tree_builder, void* tree_bu
         t_last = now;
     };
     if (int rc = validate_scene(s)) return rc;
+    lap("  validate");
 
     // ---- which CSG (if any) is the outermost CSG ancestor of each node / primitive
     std::vector<int> top_csg_of_node(nn, -1);
@@ -551,42 +552,80 @@ int flatten(RtcScene* s, Flattened& f, TreeBuilderFn tree_builder, void* tree_bu
         for (size_t i = b; i < e; i++) prim_top_csg[i] = s->prims[i].parent >= 0 ? top_csg_of_node[s->prims[i].parent] : -1;
     });
 
-    // ---- top-level items: free primitives and outermost CSG nodes
+    lap("  csg ancestors");
+    // ---- top-level items: free primitives and outermost CSG nodes.  Two passes over the primitives: tally (how many
+    // bounded and unbounded items each chunk holds, the scene's extent, the triangles), then write at the offsets.
     struct Item {
         int prim;  // >= 0 primitive, else ~csg node
-        Box box;
+        float lo[3], hi[3];
+        Box box() const {
+            Box b;
+            for (int a = 0; a < 3; a++) b.lo[a] = lo[a], b.hi[a] = hi[a];
+            return b;
+        }
     };
-    std::vector<Item> bounded, unbounded;
     auto make_item = [](int ref, const float* lo, const float* hi) {
         Item it;
         it.prim = ref;
-        for (int a = 0; a < 3; a++) it.box.lo[a] = lo[a], it.box.hi[a] = hi[a];
+        for (int a = 0; a < 3; a++) it.lo[a] = lo[a], it.hi[a] = hi[a];
         return it;
     };
+    auto reach = [](const Item& it) {  // the largest coordinate of a bounded item
+        float m = 0.f;
+        for (int a = 0; a < 3; a++) m = std::max(m, std::max(std::fabs(it.lo[a]), std::fabs(it.hi[a])));
+        return m;
+    };
+    RawVector<Item> bounded;
+    std::vector<Item> unbounded;
+    float extent = 0.f;  // the largest coordinate a ray of this scene starts from or aims at (bounded items; camera and light below)
+    size_t n_triangles = 0;
     {
+        struct Tally {
+            int bounded = 0;
+            size_t triangles = 0;
+            float extent = 0.f;
+            std::vector<Item> unbounded;
+        };
         const int n_parts = parallel_chunks((size_t)np, kGrain);
-        std::vector<std::vector<Item>> bounded_part(n_parts), unbounded_part(n_parts);
+        std::vector<Tally> tally(n_parts);
         parallel_for((size_t)np, kGrain, [&](size_t b, size_t e, int part) {
-            bounded_part[part].reserve(e - b);
+            Tally t;
             for (size_t i = b; i < e; i++) {
                 if (prim_top_csg[i] >= 0) continue;
                 const Item it = make_item((int)i, s->prims[i].bbox_min, s->prims[i].bbox_max);
-                (it.box.finite() ? bounded_part[part] : unbounded_part[part]).push_back(it);
+                if (it.box().finite())
+                    t.bounded++, t.triangles += s->prims[i].type == RTC_TRIANGLE, t.extent = std::max(t.extent, reach(it));
+                else
+                    t.unbounded.push_back(it);
+            }
+            tally[part] = std::move(t);
+        });
+        std::vector<Item> csg_bounded;
+        for (int i = 0; i < nn; i++)
+            if (s->nodes[i].kind == RTC_NODE_CSG && top_csg_of_node[i] == i) {
+                const Item it = make_item(~i, s->nodes[i].world_bbox_min, s->nodes[i].world_bbox_max);
+                if (it.box().finite())
+                    csg_bounded.push_back(it), extent = std::max(extent, reach(it));
+                else
+                    tally.back().unbounded.push_back(it);  // after every primitive, as a sequential walk lists them
+            }
+        std::vector<int> base(n_parts + 1, 0);
+        for (int part = 0; part < n_parts; part++) {
+            base[part + 1] = base[part] + tally[part].bounded;
+            n_triangles += tally[part].triangles, extent = std::max(extent, tally[part].extent);
+            unbounded.insert(unbounded.end(), tally[part].unbounded.begin(), tally[part].unbounded.end());
+        }
+        bounded.resize((size_t)base[n_parts] + csg_bounded.size());
+        parallel_for((size_t)np, kGrain, [&](size_t b, size_t e, int part) {
+            Item* out = bounded.data() + base[part];
+            for (size_t i = b; i < e; i++) {
+                if (prim_top_csg[i] >= 0) continue;
+                const Item it = make_item((int)i, s->prims[i].bbox_min, s->prims[i].bbox_max);
+                if (it.box().finite()) *out++ = it;
             }
         });
-        size_t n_bounded = 0;
-        for (const auto& part : bounded_part) n_bounded += part.size();
-        bounded.reserve(n_bounded + 64);
-        for (int part = 0; part < n_parts; part++) {
-            bounded.insert(bounded.end(), bounded_part[part].begin(), bounded_part[part].end());
-            unbounded.insert(unbounded.end(), unbounded_part[part].begin(), unbounded_part[part].end());
-        }
+        std::copy(csg_bounded.begin(), csg_bounded.end(), bounded.begin() + base[n_parts]);
     }
-    for (int i = 0; i < nn; i++)
-        if (s->nodes[i].kind == RTC_NODE_CSG && top_csg_of_node[i] == i) {
-            const Item it = make_item(~i, s->nodes[i].world_bbox_min, s->nodes[i].world_bbox_max);
-            (it.box.finite() ? bounded : unbounded).push_back(it);
-        }
     if ((int)bounded.size() < s->bvh_min_prims) {  // tiny scene: test everything for every ray, no tree
         unbounded.insert(unbounded.end(), bounded.begin(), bounded.end());
         bounded.clear();
@@ -604,20 +643,9 @@ int flatten(RtcScene* s, Flattened& f, TreeBuilderFn tree_builder, void* tree_bu
         });
     }
 
-    lap("validate + item lists");
+    lap("  item lists");
     // ---- BVH
-    // the largest coordinate a ray of this scene starts from or aims at: the bounded items, the camera, the light
-    float extent = 0.f;
-    {
-        std::vector<float> part_extent(parallel_chunks(bounded.size(), kGrain), 0.f);
-        parallel_for(bounded.size(), kGrain, [&](size_t b, size_t e, int part) {
-            float m = 0.f;
-            for (size_t i = b; i < e; i++)
-                for (int a = 0; a < 3; a++) m = std::max(m, std::max(std::fabs(bounded[i].box.lo[a]), std::fabs(bounded[i].box.hi[a])));
-            part_extent[part] = m;
-        });
-        for (float m : part_extent) extent = std::max(extent, m);
-    }
+    // the scene's extent also covers the camera and the light
     {
         float m[16], cam[3] = {0.f, 0.f, 0.f};
         memcpy(m, s->cam_inv, sizeof(m));  // the camera's origin = inverse * (0, 0, 0): the translation column
@@ -630,11 +658,11 @@ int flatten(RtcScene* s, Flattened& f, TreeBuilderFn tree_builder, void* tree_bu
             if (std::isfinite(l)) extent = std::max(extent, l);
         }
     }
-    std::vector<BuildItem> build_items(bounded.size());
+    RawVector<BuildItem> build_items(bounded.size());
     parallel_for(bounded.size(), kGrain, [&](size_t begin, size_t end, int) {
         for (size_t i = begin; i < end; i++) {
             BuildItem& b = build_items[i];
-            b.box = bounded[i].box;
+            b.box = bounded[i].box();
             b.item = (int)i;
             b.closed = bounded[i].prim >= 0 && (s->prims[bounded[i].prim].type == RTC_SPHERE || s->prims[bounded[i].prim].type == RTC_CUBE);
             for (int a = 0; a < 3; a++) {
@@ -650,20 +678,11 @@ int flatten(RtcScene* s, Flattened& f, TreeBuilderFn tree_builder, void* tree_bu
             }
         }
     });
+    lap("  padded boxes");
     if (!build_items.empty()) {
         // Leaf size: a mesh's triangles share one transform (the object-space ray is cached), so a few per leaf cost
         // less than the extra boxes; every other primitive pays its own ray transform, and one per leaf wins
         // (measured on B200: 102 k triangles 0.50 ms at 4 vs 0.58 at 1; 100 k spheres 38.7 ms at 1 vs 51.7 at 4).
-        size_t n_triangles = 0;
-        {
-            std::vector<size_t> part_triangles(parallel_chunks(bounded.size(), kGrain), 0);
-            parallel_for(bounded.size(), kGrain, [&](size_t b, size_t e, int part) {
-                size_t n = 0;
-                for (size_t i = b; i < e; i++) n += bounded[i].prim >= 0 && s->prims[bounded[i].prim].type == RTC_TRIANGLE;
-                part_triangles[part] = n;
-            });
-            for (size_t n : part_triangles) n_triangles += n;
-        }
         int leaf = s->leaf_size > 0 ? s->leaf_size : (2 * n_triangles > bounded.size() ? 4 : 1);
         if (const char* env = getenv("RTC_BVH_LEAF")) leaf = atoi(env);  // tuning aid
         f.leaf_size = std::min(std::max(leaf, 1), 16);
@@ -679,12 +698,14 @@ int flatten(RtcScene* s, Flattened& f, TreeBuilderFn tree_builder, void* tree_bu
                 }
             });
             TreeBuildOutput out;
+            lap("  builder input");
             if (tree_builder(tree_builder_ctx, TreeBuildInput{boxes.data(), closed.data(), (int)build_items.size(), f.leaf_size}, out) == 0) {
-                std::vector<BuildItem> sorted(build_items.size());
+                RawVector<BuildItem> sorted(build_items.size());
                 parallel_for(sorted.size(), kGrain, [&](size_t b, size_t e, int) {
                     for (size_t i = b; i < e; i++) sorted[i] = build_items[out.order[i]];
                 });
                 build_items.swap(sorted);
+                lap("  device builder + reorder");
                 f.bvh.swap(out.nodes);
                 root = out.root;
                 f.bvh_depth = out.depth;

@@ -100,7 +100,7 @@ struct Replica {
 struct Flattened {
     std::vector<int4> head;  // 2 * n_pos entries: [pos] main, [n_pos + pos] {cull-chain parent node, api prim, 0, 0}
     std::vector<float4> xform, tri, bound, rec;
-    std::vector<DevBvhNode> bvh;
+    RawVector<DevBvhNode> bvh;
     std::vector<int> linear;
     std::vector<DevNode> nodes;
     std::vector<DevCsgOp> ops;
@@ -172,8 +172,8 @@ struct TreeBuildInput {
     int n, leaf_size;
 };
 struct TreeBuildOutput {
-    std::vector<int> order;
-    std::vector<DevBvhNode> nodes;
+    RawVector<int> order;
+    RawVector<DevBvhNode> nodes;
     int root = -1, depth = 0;
 };
 using TreeBuilderFn = int (*)(void* ctx, const TreeBuildInput&, TreeBuildOutput&);

@@ -84,6 +84,36 @@ __global__ void lbvh_sort(unsigned long long* keys, int* items, int padded, int 
     }
 }
 
+// The passes whose partner distance j stays inside a block's 2048 elements, in shared memory: for every k in
+// [k_first, k_last] (doubling), the steps j = min(k / 2, 1024) .. 1.  With k_first = 2 it sorts every 2048-element
+// block outright (66 passes of lbvh_sort in one launch); with k_first = k_last = k > 2048 it finishes the merge of
+// size k after lbvh_sort has done its steps j >= 2048.  Same comparisons, same total order, as lbvh_sort.
+constexpr int kSortBlock = 2048;
+__global__ void __launch_bounds__(kSortBlock / 2) lbvh_sort_shared(unsigned long long* keys, int* items, int k_first, int k_last) {
+    __shared__ unsigned long long s_key[kSortBlock];
+    __shared__ int s_item[kSortBlock];
+    const int base = blockIdx.x * kSortBlock;
+    for (int t = threadIdx.x; t < kSortBlock; t += blockDim.x) s_key[t] = keys[base + t], s_item[t] = items[base + t];
+    __syncthreads();
+    for (int k = k_first; k <= k_last; k <<= 1)
+        for (int j = min(k >> 1, kSortBlock / 2); j > 0; j >>= 1) {
+            // thread t owns the pair (i, i ^ j) with bit j of i clear
+            const int t = threadIdx.x;
+            const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+            const int p = i | j;
+            const unsigned long long ka = s_key[i], kb = s_key[p];
+            const int ia = s_item[i], ib = s_item[p];
+            const bool a_after_b = ka > kb || (ka == kb && (unsigned)ia > (unsigned)ib);
+            const bool ascending = ((base + i) & k) == 0;
+            if (a_after_b == ascending) {
+                s_key[i] = kb, s_key[p] = ka;
+                s_item[i] = ib, s_item[p] = ia;
+            }
+            __syncthreads();
+        }
+    for (int t = threadIdx.x; t < kSortBlock; t += blockDim.x) keys[base + t] = s_key[t], items[base + t] = s_item[t];
+}
+
 // length of the common prefix of the keys at sorted positions i and j (-1 outside the array); equal keys: 64 + the
 // common prefix of the positions (Karras 2012, section 4)
 __device__ __forceinline__ int prefix(const unsigned long long* keys, int n, int i, int j) {
@@ -299,8 +329,17 @@ int lbvh_build(void* ctx_, const TreeBuildInput& in, TreeBuildOutput& out) {
     lbvh_codes<<<(padded + threads - 1) / threads, threads, 0, stream>>>(d_boxes, n, padded, make_float3(lo[0], lo[1], lo[2]),
                                                                          make_float3(scale[0], scale[1], scale[2]), cells - 1.0f, d_keys,
                                                                          d_items);
-    for (int k = 2; k <= padded; k <<= 1)
-        for (int j = k >> 1; j > 0; j >>= 1) lbvh_sort<<<(padded + threads - 1) / threads, threads, 0, stream>>>(d_keys, d_items, padded, j, k);
+    if (padded >= kSortBlock) {  // 2^17 items: 28 launches instead of 153
+        lbvh_sort_shared<<<padded / kSortBlock, kSortBlock / 2, 0, stream>>>(d_keys, d_items, 2, kSortBlock);
+        for (int k = 2 * kSortBlock; k <= padded; k <<= 1) {
+            for (int j = k >> 1; j >= kSortBlock; j >>= 1)
+                lbvh_sort<<<(padded + threads - 1) / threads, threads, 0, stream>>>(d_keys, d_items, padded, j, k);
+            lbvh_sort_shared<<<padded / kSortBlock, kSortBlock / 2, 0, stream>>>(d_keys, d_items, k, k);
+        }
+    } else {
+        for (int k = 2; k <= padded; k <<= 1)
+            for (int j = k >> 1; j > 0; j >>= 1) lbvh_sort<<<(padded + threads - 1) / threads, threads, 0, stream>>>(d_keys, d_items, padded, j, k);
+    }
     lbvh_topology<<<(n + threads - 1) / threads, threads, 0, stream>>>(d_keys, n, d_nodes, d_leaf_parent);
     lbvh_refit<<<(n + threads - 1) / threads, threads, 0, stream>>>(d_boxes, d_closed, d_items, n, d_nodes, d_leaf_parent, in.leaf_size,
                                                                    d_bounds, d_arrivals, d_out);
