@@ -148,6 +148,12 @@ int rtc_set_camera(RtcScene*, uint32_t width, uint32_t height, float half_width,
                    const float transform_inverse[16]);
 int rtc_set_primitives(RtcScene*, uint32_t n, const RtcPrim* prims);
 int rtc_set_nodes(RtcScene*, uint32_t n_nodes, const RtcNode* nodes, uint32_t n_refs, const int32_t* child_refs);
+/* The same without the copy: the scene allocates the arrays and the host writes its records in place (a
+ * 100 000-primitive array is 14 MB; a one-shot Camera::render_b200 would otherwise write it twice).  The storage is
+ * uninitialised: every record must be written before rtc_scene_commit.  The pointers stay valid until the next
+ * rtc_set_* / rtc_map_* call for the same array, or rtc_scene_destroy. */
+int rtc_map_primitives(RtcScene*, uint32_t n, RtcPrim** prims);
+int rtc_map_nodes(RtcScene*, uint32_t n_nodes, uint32_t n_refs, RtcNode** nodes, int32_t** child_refs);
 int rtc_set_materials(RtcScene*, uint32_t n, const RtcMaterial* materials);
 int rtc_set_patterns(RtcScene*, uint32_t n, const RtcPattern* patterns, uint32_t n_uv, const RtcUvPattern* uv);
 /* Image textures referenced by RTC_UV_IMAGE patterns.  UVImage::color_at (uv.rs:366-377): x = round(u * (width - 1)),

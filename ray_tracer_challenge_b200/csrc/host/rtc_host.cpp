@@ -437,7 +437,7 @@ static int camera_render(sg_ctx* c, int cam, int w, int depth, int shard, int n_
         FlatScene flat;
         fill_scene(scene, c->graph, c->worlds[w], c->cameras[cam], flat);
         mark("fill_scene");
-        rc = commit(c, scene, true, flat.prims.size());
+        rc = commit(c, scene, true, flat.n_prims);
         mark("commit (host half + upload)");
         if (!rc) {
             if (n_shards > 1)
@@ -522,7 +522,7 @@ int sg_prepare(sg_ctx* c, int cam, int w) {
         rtc_scene_destroy(p->scene);
         return fail(e.what());
     }
-    if (commit(c, p->scene, false, p->flat.prims.size())) {
+    if (commit(c, p->scene, false, p->flat.n_prims)) {
         rtc_scene_destroy(p->scene);
         return -1;
     }

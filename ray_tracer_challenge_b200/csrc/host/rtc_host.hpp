@@ -593,9 +593,13 @@ inline CanvasRec canvas_from_ppm(const char* text, size_t n) {
 }
 
 struct FlatScene {
+    // With `target` set the geometry arrays are written straight into that scene's storage (rtc_map_primitives /
+    // rtc_map_nodes: no second copy of a 14 MB array) and the three vectors stay empty.
+    RtcScene* target = nullptr;
+    size_t n_prims = 0, n_nodes = 0, n_refs = 0;
     rtc::RawVector<RtcPrim> prims;  // resized once, every record written by the walk that owns it
     rtc::RawVector<RtcNode> nodes;
-    std::vector<int32_t> refs;
+    rtc::RawVector<int32_t> refs;
     std::vector<RtcMaterial> materials;
     std::vector<RtcPattern> patterns;
     std::vector<RtcUvPattern> uvs;
@@ -713,10 +717,16 @@ class Flattener {
         }
         lap("placement");
         // ---- 4. the records
-        out_.prims.resize(cur.prim);
+        out_.n_prims = cur.prim, out_.n_nodes = cur.node, out_.n_refs = cur.ref;
         out_.prim_shape.resize(cur.prim);
-        out_.nodes.resize(cur.node);
-        out_.refs.resize(cur.ref);
+        if (out_.target) {
+            if (rtc_map_primitives(out_.target, (uint32_t)cur.prim, &prims_) ||
+                rtc_map_nodes(out_.target, (uint32_t)cur.node, (uint32_t)cur.ref, &nodes_, &refs_))
+                throw Error(rtc_last_error());
+        } else {
+            out_.prims.resize(cur.prim), out_.nodes.resize(cur.node), out_.refs.resize(cur.ref);
+            prims_ = out_.prims.data(), nodes_ = out_.nodes.data(), refs_ = out_.refs.data();
+        }
         // contiguous runs of subtrees of about equal weight, a few per thread
         std::vector<size_t> chunk_begin{0};
         if (threaded) {
@@ -768,10 +778,10 @@ class Flattener {
         if (!identity)
             rtc::WorkerPool::instance().run(n_chunks, [&](int chunk) {
                 for (int i = prim_range[chunk].first; i < prim_range[chunk].second; i++)
-                    out_.prims[i].material = remap[chunk][out_.prims[i].material];
+                    prims_[i].material = remap[chunk][prims_[i].material];
             });
         for (const TopNode& t : tops) {
-            std::copy(t.child_refs.begin(), t.child_refs.end(), out_.refs.begin() + t.child_begin);
+            std::copy(t.child_refs.begin(), t.child_refs.end(), refs_ + t.child_begin);
             write_node(t.id, t.node, t.parent_node, t.child_begin, (int)t.child_refs.size());
         }
         lap("materials + opened nodes");
@@ -810,6 +820,9 @@ class Flattener {
 
     SceneGraph& g_;
     FlatScene& out_;
+    RtcPrim* prims_ = nullptr;  // where the walks write: out_'s vectors, or the target scene's mapped arrays
+    RtcNode* nodes_ = nullptr;
+    int32_t* refs_ = nullptr;
     std::map<std::vector<uint32_t>, int> material_ids_;
     std::map<int, int> pattern_ids_, uv_ids_, texture_ids_;
     int last_material_ = -1;
@@ -918,7 +931,7 @@ class Flattener {
         memcpy(n.inv, inv.m, sizeof(n.inv));
         put_box(g_.bounding_box(id), n.bbox_min, n.bbox_max);  // cached in the shape on first use (group.rs:138-150)
         put_box(g_.parent_space_box(id), n.world_bbox_min, n.world_bbox_max);
-        out_.nodes[node] = n;
+        nodes_[node] = n;
     }
     // the walk: writes the subtree of `id` at the cursor and returns the child reference of what it wrote.  Touches
     // only this subtree's shapes (their cached boxes included), so disjoint subtrees go to different threads.
@@ -930,13 +943,13 @@ class Flattener {
             std::vector<int32_t> child_refs;
             child_refs.reserve(s.children.size());
             for (int kid : s.children) child_refs.push_back(emit(kid, node, c, materials));
-            std::copy(child_refs.begin(), child_refs.end(), out_.refs.begin() + c.ref);
+            std::copy(child_refs.begin(), child_refs.end(), refs_ + c.ref);
             write_node(id, node, parent_node, c.ref, (int)child_refs.size());
             c.ref += (int)child_refs.size();
             return ~node;
         }
         const int i = c.prim++;
-        RtcPrim& p = out_.prims[i];
+        RtcPrim& p = prims_[i];
         memset(&p, 0, sizeof(p));
         switch (s.kind) {
             case SPHERE: p.type = RTC_SPHERE; break;
@@ -978,13 +991,12 @@ inline void fill_scene(RtcScene* scene, SceneGraph& g, const World& w, const Cam
     if (!w.light.set) throw Error("World light should be set");  // world.rs:66
     const bool timing = getenv("RTC_TIMING") != nullptr;
     const auto t0 = std::chrono::steady_clock::now();
+    flat.target = scene;  // primitives, nodes and child references are written in place
     Flattener(g, flat).run(w);
     if (timing)
         fprintf(stderr, "[rtc host]   %-28s %8.3f ms\n", "scene graph -> flat arrays",
                 std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
     ck(rtc_set_camera(scene, cam.width, cam.height, cam.half_width, cam.half_height, cam.pixel_size, cam.transform_inverse.m));
-    ck(rtc_set_primitives(scene, (uint32_t)flat.prims.size(), flat.prims.data()));
-    ck(rtc_set_nodes(scene, (uint32_t)flat.nodes.size(), flat.nodes.data(), (uint32_t)flat.refs.size(), flat.refs.data()));
     ck(rtc_set_materials(scene, (uint32_t)flat.materials.size(), flat.materials.data()));
     ck(rtc_set_patterns(scene, (uint32_t)flat.patterns.size(), flat.patterns.data(), (uint32_t)flat.uvs.size(), flat.uvs.data()));
     ck(rtc_set_textures(scene, (uint32_t)flat.textures.size(), flat.textures.data()));

@@ -630,6 +630,22 @@ int rtc_set_nodes(RtcScene* s, uint32_t n_nodes, const RtcNode* nodes, uint32_t 
     s->committed = false;
     return 0;
 }
+int rtc_map_primitives(RtcScene* s, uint32_t n, RtcPrim** prims) {
+    if (!s || !prims) return fail(RTC_ERR_INVALID, "null argument");
+    if (n >= (1u << 27)) return fail(RTC_ERR_CAPACITY, "too many primitives");
+    s->prims.resize(n);
+    *prims = s->prims.data();
+    s->committed = false;
+    return 0;
+}
+int rtc_map_nodes(RtcScene* s, uint32_t n_nodes, uint32_t n_refs, RtcNode** nodes, int32_t** refs) {
+    if (!s || !nodes || !refs) return fail(RTC_ERR_INVALID, "null argument");
+    s->nodes.resize(n_nodes);
+    s->refs.resize(n_refs);
+    *nodes = s->nodes.data(), *refs = s->refs.data();
+    s->committed = false;
+    return 0;
+}
 int rtc_set_materials(RtcScene* s, uint32_t n, const RtcMaterial* m) {
     if (!s || (n && !m)) return fail(RTC_ERR_INVALID, "null argument");
     if (n >= (1u << 23)) return fail(RTC_ERR_CAPACITY, "too many materials");

@@ -846,7 +846,9 @@ int flatten(RtcScene* s, Flattened& f, TreeBuilderFn tree_builder, void* tree_bu
         });
     }
     f.head.resize(2 * (size_t)f.n_pos);
-    s->pos_to_prim.assign(f.n_pos, -1);
+    s->pos_to_prim.resize(f.n_pos);
+    for (int i = 0; i < nn; i++)
+        if (csg_pos[i] >= 0) s->pos_to_prim[csg_pos[i]] = -1;  // a CSG's own position is no primitive
     f.tri.resize(3 * (size_t)tri_base[n_parts]);
     f.bound.resize(bound_base[n_parts]);
     parallel_for((size_t)np, kGrain, [&](size_t b, size_t e, int c) {
@@ -950,7 +952,10 @@ int flatten(RtcScene* s, Flattened& f, TreeBuilderFn tree_builder, void* tree_bu
             int4 h = f.head[pos];
             memcpy(&f.rec[4 * pos], &h, sizeof(h));
             int type = h.x & 15;
-            if (type == T_CSG) continue;  // (resize zeroed the rows)
+            if (type == T_CSG) {
+                for (int r = 0; r < 3; r++) f.rec[4 * pos + 1 + r] = make_float4(0.f, 0.f, 0.f, 0.f);
+                continue;
+            }
             const float4* src = (type == T_TRIANGLE) ? &f.tri[3 * (size_t)h.z] : &f.xform[3 * (size_t)h.y];
             for (int r = 0; r < 3; r++) f.rec[4 * pos + 1 + r] = src[r];
         }

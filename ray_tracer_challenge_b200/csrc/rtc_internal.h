@@ -98,8 +98,8 @@ struct Replica {
 
 // Everything rtc_scene_commit derives from the scene on the host, ready for upload (rtc_commit.cu: flatten).
 struct Flattened {
-    std::vector<int4> head;  // 2 * n_pos entries: [pos] main, [n_pos + pos] {cull-chain parent node, api prim, 0, 0}
-    std::vector<float4> xform, tri, bound, rec;
+    RawVector<int4> head;  // 2 * n_pos entries: [pos] main, [n_pos + pos] {cull-chain parent node, api prim, 0, 0}
+    RawVector<float4> xform, tri, bound, rec;  // (raw: sized once, every element written by the pass that owns it)
     RawVector<DevBvhNode> bvh;
     std::vector<int> linear;
     std::vector<DevNode> nodes;
@@ -156,7 +156,7 @@ struct RtcScene {
     int order_max_waves = 128;  // the longest-first order is not even tried for launches longer than this many waves
     std::vector<rtc::Replica> replicas;
     std::vector<int> replica_devices;
-    std::vector<int> pos_to_prim;  // device position -> API primitive index (-1 for CSG pseudo-primitives)
+    rtc::RawVector<int> pos_to_prim;  // device position -> API primitive index (-1 for CSG pseudo-primitives)
     // commit statistics
     int n_bvh_nodes = 0, n_linear = 0, n_xforms = 0;
 };

@@ -3,7 +3,9 @@
 // A one-shot Camera::render_b200 of a 100 k-primitive scene spends more time flattening and committing the scene on
 // the host than rendering it on the device, and that work is a handful of passes over arrays of
 // 100 k+ records whose cost is memory latency: it splits over threads cleanly.  One lazily started pool per process
-// (per library: the header is shared by librtc_b200.so and librtc_host.so), workers asleep between jobs.
+// (per library: the header is shared by librtc_b200.so and librtc_host.so), workers asleep between jobs.  Size: the
+// host's cores (at most 16), divided by LOCAL_WORLD_SIZE when torchrun runs one process per GPU; RTC_HOST_THREADS
+// overrides it.
 //
 //   rtc::parallel_for(n, grain, [&](size_t begin, size_t end, int chunk) { ... });
 //
@@ -80,7 +82,10 @@ class WorkerPool {
 #endif
     }
     WorkerPool() : pid_(getpid()) {
-        unsigned n = std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
+        unsigned n = std::max(1u, std::thread::hardware_concurrency());
+        // one process per GPU (torchrun): the ranks of a node share its cores
+        if (const char* ranks = getenv("LOCAL_WORLD_SIZE")) n = std::max(1u, n / (unsigned)std::max(1, atoi(ranks)));
+        n = std::min(16u, n);
         if (const char* env = getenv("RTC_HOST_THREADS")) n = (unsigned)std::max(1, atoi(env));
         for (unsigned i = 1; i < n; i++) {
             workers_.emplace_back([this] { worker(); });

@@ -178,6 +178,9 @@ extern "C" {
                           pixel_size: f32, transform_inverse: *const f32) -> c_int;
     pub fn rtc_set_primitives(scene: *mut RtcScene, n: u32, prims: *const RtcPrim) -> c_int;
     pub fn rtc_set_nodes(scene: *mut RtcScene, n_nodes: u32, nodes: *const RtcNode, n_refs: u32, refs: *const i32) -> c_int;
+    /// Zero-copy variants: the scene allocates (uninitialised) and the host writes the records in place.
+    pub fn rtc_map_primitives(scene: *mut RtcScene, n: u32, prims: *mut *mut RtcPrim) -> c_int;
+    pub fn rtc_map_nodes(scene: *mut RtcScene, n_nodes: u32, n_refs: u32, nodes: *mut *mut RtcNode, refs: *mut *mut i32) -> c_int;
     pub fn rtc_set_materials(scene: *mut RtcScene, n: u32, materials: *const RtcMaterial) -> c_int;
     pub fn rtc_set_patterns(scene: *mut RtcScene, n: u32, patterns: *const RtcPattern, n_uv: u32, uv: *const RtcUvPattern) -> c_int;
     pub fn rtc_set_textures(scene: *mut RtcScene, n: u32, textures: *const RtcTexture) -> c_int;

@@ -407,3 +407,48 @@ def test_rust_glue_covers_every_implementer_and_only_uses_what_the_sys_crate_dec
             if name in ("if", "else", "sys", "self", "unsafe"):
                 continue
             assert name in fields or not name.islower() or name in ("w", "h", "px"), (struct, name, fields)
+
+
+def test_mapped_arrays_commit_like_copied_ones():
+    """rtc_map_primitives / rtc_map_nodes hand out the scene's own storage: records written in place give the commit
+    plan (digest included) that rtc_set_primitives / rtc_set_nodes give for the same records."""
+    import ray_tracer_challenge_b200 as rt
+
+    lib = C.CDLL(rt.LIB_DEVICE)
+    lib.rtc_set_primitives.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(rt.RtcPrim)]
+    lib.rtc_set_nodes.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(rt.RtcNode), C.c_uint32, C.POINTER(C.c_int32)]
+    lib.rtc_map_primitives.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.POINTER(rt.RtcPrim))]
+    lib.rtc_map_nodes.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(C.POINTER(rt.RtcNode)), C.POINTER(C.POINTER(C.c_int32))]
+
+    def records(ident):
+        prims = [_sphere(rt, ident, centre=(3.0 * i, 0.0, 5.0), parent=0 if i < 3 else -1) for i in range(40)]
+        node = rt.RtcNode()
+        node.kind, node.parent, node.op, node.child_begin, node.child_count = 0, -1, 0, 0, 3
+        node.inv[:] = list(ident)
+        node.bbox_min[:], node.bbox_max[:] = [-1, -1, 4], [7, 1, 6]
+        node.world_bbox_min[:], node.world_bbox_max[:] = [-1, -1, 4], [7, 1, 6]
+        return prims, [node], [0, 1, 2]
+
+    digests = []
+    for mapped in (False, True):
+        scene, ident = _raw_scene(lib, rt)
+        prims, nodes, refs = records(ident)
+        if mapped:
+            pp, pn, pr = C.POINTER(rt.RtcPrim)(), C.POINTER(rt.RtcNode)(), C.POINTER(C.c_int32)()
+            assert lib.rtc_map_primitives(scene, len(prims), C.byref(pp)) == 0
+            assert lib.rtc_map_nodes(scene, len(nodes), len(refs), C.byref(pn), C.byref(pr)) == 0
+            for i, p in enumerate(prims):
+                pp[i] = p
+            for i, n in enumerate(nodes):
+                pn[i] = n
+            for i, r in enumerate(refs):
+                pr[i] = r
+        else:
+            assert lib.rtc_set_primitives(scene, len(prims), (rt.RtcPrim * len(prims))(*prims)) == 0
+            assert lib.rtc_set_nodes(scene, len(nodes), (rt.RtcNode * len(nodes))(*nodes), len(refs), (C.c_int32 * len(refs))(*refs)) == 0
+        info = rt.RtcCommitInfo()
+        assert lib.rtc_scene_inspect(scene, C.byref(info)) == 0, lib.rtc_last_error()
+        digests.append((info.digest, info.n_positions, info.n_bvh_nodes))
+        lib.rtc_scene_destroy(scene)
+    assert digests[0] == digests[1] and digests[0][1] == 40
+    assert lib.rtc_map_primitives(None, 1, None) != 0
