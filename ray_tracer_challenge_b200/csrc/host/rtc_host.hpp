@@ -637,22 +637,29 @@ class Flattener {
         const int n_threads = threaded ? rtc::WorkerPool::instance().threads() : 1;
         if (threaded) {
             opened.assign(n_shapes, 0);
+            std::vector<char> is_leaf(frontier.size(), 0);  // examined before and found to be a leaf: not looked at again
             bool any = true;
             for (int level = 0; level < 10 && any; level++) {
                 any = false;
                 std::vector<int> next;
-                next.reserve(2 * frontier.size());
-                for (int id : frontier) {
-                    g_.check(id);
-                    const ShapeRec& s = g_.shapes[id];
-                    if ((s.kind == GROUP || s.kind == CSG) && !s.children.empty() && !opened[id]) {
-                        opened[id] = 1, any = true;
-                        next.insert(next.end(), s.children.begin(), s.children.end());
-                    } else {
-                        next.push_back(id);
+                std::vector<char> next_leaf;
+                next.reserve(2 * frontier.size()), next_leaf.reserve(2 * frontier.size());
+                for (size_t k = 0; k < frontier.size(); k++) {
+                    const int id = frontier[k];
+                    if (!is_leaf[k]) {
+                        g_.check(id);
+                        const ShapeRec& s = g_.shapes[id];
+                        if ((s.kind == GROUP || s.kind == CSG) && !s.children.empty() && !opened[id]) {
+                            opened[id] = 1, any = true;
+                            for (int c : s.children) prefetch_kind(c);
+                            next.insert(next.end(), s.children.begin(), s.children.end());
+                            next_leaf.insert(next_leaf.end(), s.children.size(), 0);
+                            continue;
+                        }
                     }
+                    next.push_back(id), next_leaf.push_back(1);  // a leaf, an empty group, or a group met twice
                 }
-                frontier.swap(next);
+                frontier.swap(next), is_leaf.swap(next_leaf);
             }
         }
         // ---- 2. their sizes
@@ -691,8 +698,8 @@ class Flattener {
             std::vector<TopNode>& tops;
             Cursor& cur;
             int place(int id, int parent_node) {
-                const ShapeRec& s = f.g_.shapes[id];
                 if (!opened.empty() && opened[id]) {
+                    const ShapeRec& s = f.g_.shapes[id];
                     const size_t me = tops.size();
                     const int node = cur.node++;
                     tops.push_back(TopNode{id, node, parent_node, 0, {}});
@@ -706,7 +713,7 @@ class Flattener {
                 }
                 const Counts& n = counts[entries.size()];
                 entries.push_back(Entry{id, parent_node, cur});
-                const int ref = (s.kind == GROUP || s.kind == CSG) ? ~cur.node : cur.prim;
+                const int ref = n.nodes > 0 ? ~cur.node : cur.prim;  // a group or CSG counts itself as a node
                 cur.prim += n.prims, cur.node += n.nodes, cur.ref += n.refs;
                 return ref;
             }
@@ -902,6 +909,17 @@ class Flattener {
         }
         return false;
     }
+    // The walks visit the arena in tree order, not in memory order: every shape record is a cache miss (five lines).
+    // A group's children are known before they are visited, so their records are requested a few children ahead.
+    static constexpr size_t kAhead = 4;
+    void prefetch_kind(int id) const {
+        if (id >= 0 && id < (int)g_.shapes.size()) __builtin_prefetch(&g_.shapes[id].kind);
+    }
+    void prefetch_record(int id) const {
+        if (id < 0 || id >= (int)g_.shapes.size()) return;
+        const char* p = reinterpret_cast<const char*>(&g_.shapes[id]);
+        for (size_t off = 0; off < sizeof(ShapeRec); off += 64) __builtin_prefetch(p + off);
+    }
     // records a depth-first walk of `id` emits
     Counts count(int id) const {
         g_.check(id);
@@ -912,8 +930,11 @@ class Flattener {
             return n;
         }
         n.nodes = 1, n.refs = (int)s.children.size();
-        for (int c : s.children) {
-            const Counts k = count(c);
+        const size_t kids = s.children.size();
+        for (size_t i = 0; i < kids && i < kAhead; i++) prefetch_kind(s.children[i]);
+        for (size_t i = 0; i < kids; i++) {
+            if (i + kAhead < kids) prefetch_kind(s.children[i + kAhead]);
+            const Counts k = count(s.children[i]);
             n.prims += k.prims, n.nodes += k.nodes, n.refs += k.refs;
         }
         return n;
@@ -942,7 +963,12 @@ class Flattener {
             const int node = c.node++;
             std::vector<int32_t> child_refs;
             child_refs.reserve(s.children.size());
-            for (int kid : s.children) child_refs.push_back(emit(kid, node, c, materials));
+            const size_t kids = s.children.size();
+            for (size_t i = 0; i < kids && i < kAhead; i++) prefetch_record(s.children[i]);
+            for (size_t i = 0; i < kids; i++) {
+                if (i + kAhead < kids) prefetch_record(s.children[i + kAhead]);
+                child_refs.push_back(emit(s.children[i], node, c, materials));
+            }
             std::copy(child_refs.begin(), child_refs.end(), refs_ + c.ref);
             write_node(id, node, parent_node, c.ref, (int)child_refs.size());
             c.ref += (int)child_refs.size();
