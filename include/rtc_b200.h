@@ -186,8 +186,9 @@ enum {
     RTC_OPT_BVH_LEAF_SIZE = 2, /* primitives per BVH leaf, 1..16; 0 (default) = 4 for triangle meshes, 1 otherwise */
     RTC_OPT_BVH_MIN_PRIMS = 3,
     RTC_OPT_RENDER_SLICES = 4, /* at most this many kernel launches a frame is cut into when it is copied to host memory, so
-                                  the copy of one slice overlaps the kernel of the next (default 6; never more than one
-                                  slice per 4 MiB copied: a slice costs ~45 us of launches and copy set-up) */
+                                  the copy of one slice overlaps the kernels of the next (default 24, 1..64; never more than
+                                  one slice per MiB copied).  The slices rotate over three streams: the blocks of a slice
+                                  fill the SMs as the previous one drains */
     RTC_OPT_ADAPTIVE_ORDER = 5, /* default 1: a repeated render of the same shard launches its 16x8-pixel tiles
                                   most-expensive-first (clock cycles per tile recorded by an earlier render) when a
                                   timed trial render shows that order to be faster; changes no pixel */

@@ -81,6 +81,7 @@ int lease_slot(int device, DeviceSlot** out) {
     d->device = device;
     CUDA_TRY(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaStreamCreateWithFlags(&d->copy_stream, cudaStreamNonBlocking));
+    for (cudaStream_t& st : d->slice_stream) CUDA_TRY(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
     CUDA_TRY(cudaEventCreate(&d->ev0));
     CUDA_TRY(cudaEventCreate(&d->ev1));
     CUDA_TRY(cudaMalloc(&d->d_counters, sizeof(DevCounters)));
@@ -377,12 +378,17 @@ int render_impl(RtcScene* s, int depth, int shard0, int n_shards_ext, float* rgb
         // persistent launch pays its tail once per launch and such frames take far longer than their copy, so they
         // are not sliced
         const bool stream_scene = r.small.n == 0 && (s->stream < 0 ? s->has_branching_materials : s->stream != 0);
-        // a slice costs ~45 us of launches, events and copy set-up, so a frame is cut only as finely as its copy is long:
-        // one slice per 4 MiB that leave the device (c3's 24.9 MB 8-bit canvas: 6 slices, 0.74 ms against 1.10 in one piece;
-        // c1's 1.2 MB: 1 slice, 0.22 ms against 0.43 in six)
+        // a frame is cut only as finely as its copy is long: one slice per MiB that leaves the device, at most
+        // `render_slices` (c3's 24.9 MB 8-bit canvas: 23 slices, 0.67 ms end to end against 1.10 in one piece; c1's 1.2 MB:
+        // 1 slice, 0.22 ms against 0.43 in six).  Slices on one stream cost ~15 us each of launch ramp and tail (6 slices
+        // of 4 MiB: 0.74 ms); rotated over three streams (below) they cost next to nothing and can be small
         const size_t copy_bytes = (size_t)s->width * kBandRows * nb * ((rgb ? 12 : 0) + (u8 ? 3 : 0));
+        static const int slice_shift = [] {
+            const char* env = getenv("RTC_SLICE_BYTES_LOG2");  // tuning aid
+            return env ? std::max(16, std::min(30, atoi(env))) : 20;
+        }();
         const int n_slices = copy_out && !stream_scene
-                                 ? std::max(1, std::min(std::min(s->render_slices, nb), (int)(copy_bytes >> 22)))
+                                 ? std::max(1, std::min(std::min(s->render_slices, nb), (int)(copy_bytes >> slice_shift)))
                                  : 1;
         const bool use_wave = stream_scene && !detailed && !s->light_is_rect && s->wavefront != 0 && nb > 0;
         const int tiles_x = ((int)s->width + kTileW - 1) / kTileW;
@@ -440,9 +446,22 @@ int render_impl(RtcScene* s, int depth, int shard0, int n_shards_ext, float* rgb
                 }
             }
         }
+        // The slices of a frame are independent launches, so they rotate over three streams: the blocks of slice k + 1
+        // fill the SMs as slice k drains instead of waiting for its last block (per slice that tail and the next launch's
+        // ramp were ~15 us of mostly idle SMs).  Every stream starts behind ev0 (the counters are reset), the frame ends
+        // at ev1 on the first stream behind the others' last slices, each slice's copy waits for its own event.
+        static const bool rotate = [] {
+            const char* env = getenv("RTC_SLICE_STREAMS");  // tuning aid: 0 = all slices on one stream
+            return !env || atoi(env) != 0;
+        }();
+        cudaStream_t lanes[3] = {slot->stream, slot->slice_stream[0], slot->slice_stream[1]};
+        const int n_lanes = rotate && n_slices > 1 && !use_wave ? std::min(3, n_slices) : 1;
+        for (int l = 1; l < n_lanes; l++) CUDA_TRY(cudaStreamWaitEvent(lanes[l], slot->ev0, 0));
+        int last_on_lane[3] = {-1, -1, -1};
         for (int k = 0; k < n_slices && !use_wave; k++) {
             const int b0 = (int)((int64_t)nb * k / n_slices), b1 = (int)((int64_t)nb * (k + 1) / n_slices);
             if (b1 <= b0) continue;
+            cudaStream_t lane = lanes[k % n_lanes];
             DevFrame F{slot->d_rgb, slot->d_u8, shard, n_shards, depth, b1 - b0, b0, use_order ? slot->d_tile_order : nullptr,
                        r.learning ? slot->d_tile_cost : nullptr, s->converge < 0 ? (int)s->has_branching_materials : s->converge,
                        nullptr, 0};
@@ -452,17 +471,20 @@ int render_impl(RtcScene* s, int depth, int shard0, int n_shards_ext, float* rgb
                 F.tile_order = nullptr, F.tile_cost = nullptr;
             }
             if (s->strict_fp)
-                strict::launch_render(r.scene, r.small, F, slot->d_counters, detailed, slot->stream);
+                strict::launch_render(r.scene, r.small, F, slot->d_counters, detailed, lane);
             else
-                fast::launch_render(r.scene, r.small, F, slot->d_counters, detailed, slot->stream);
+                fast::launch_render(r.scene, r.small, F, slot->d_counters, detailed, lane);
             CUDA_TRY(cudaGetLastError());
             st.launches++;
             if (copy_out) {
-                CUDA_TRY(cudaEventRecord(slot->slice_done[k], slot->stream));
+                CUDA_TRY(cudaEventRecord(slot->slice_done[k], lane));
                 CUDA_TRY(cudaStreamWaitEvent(slot->copy_stream, slot->slice_done[k], 0));
                 if (int rc = queue_copy(slot, shard, b0, b1)) return rc;
+                last_on_lane[k % n_lanes] = k;
             }
         }
+        for (int l = 1; l < n_lanes; l++)
+            if (last_on_lane[l] >= 0) CUDA_TRY(cudaStreamWaitEvent(slot->stream, slot->slice_done[last_on_lane[l]], 0));
         CUDA_TRY(cudaEventRecord(slot->ev1, slot->stream));
     }
     for (const PendingCopy& c : pending) {  // the copy stream of each device already waits for the slice's event

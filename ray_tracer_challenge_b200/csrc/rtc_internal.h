@@ -49,6 +49,7 @@ struct DeviceSlot {
     cudaStream_t copy_stream = nullptr;  // device-to-host copies, overlapped with the kernels of later slices
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::vector<cudaEvent_t> slice_done;
+    cudaStream_t slice_stream[2] = {nullptr, nullptr};  // with `stream`: the slices of a frame rotate over three streams
     float* d_rgb = nullptr;
     unsigned char* d_u8 = nullptr;
     size_t frame_px = 0;
@@ -144,7 +145,7 @@ struct RtcScene {
     int strict_fp = 1, leaf_size = 0 /* automatic */, bvh_min_prims = rtc::kSmallCap + 1;
     int bvh_builder = 0;       // RTC_OPT_BVH_BUILDER: 0 host binned SAH, 1 device LBVH (scenes of >= kLbvhMinItems bounded items)
     int built_on_device = 0;   // the last commit's tree came from the device builder
-    int render_slices = 6;  // kernel / copy pipeline depth when rendering into host memory
+    int render_slices = 24;  // kernel / copy pipeline depth when rendering into host memory
     int adaptive_order = 1;  // launch a shard's bands longest-first, learnt from the previous render
     int shadow_filter = 1;   // RTC_OPT_SHADOW_FILTER
     int wavefront = 0;         // RTC_OPT_WAVEFRONT: tree scenes with branching ray trees and a point light go through the

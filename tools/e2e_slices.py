@@ -33,4 +33,5 @@ t0 = time.perf_counter()
 n = 20
 for _ in range(n):
     api.check(api.lib.sg_camera_render_shard(api.ctx, cam.handle, world.handle, depth, 0, 1, None, u8.ctypes.data_as(U8P), C.byref(stats)))
-print(f"{sys.argv[1]} slices={os.environ.get('RTC_RENDER_SLICES', 'default')}: one-shot e2e {(time.perf_counter() - t0) / n * 1e3:.3f} ms", flush=True)
+print(f"{sys.argv[1]} slices={os.environ.get('RTC_RENDER_SLICES', 'default')}: one-shot e2e {(time.perf_counter() - t0) / n * 1e3:.3f} ms "
+      f"(kernel span {api.last_rtc_stats().kernel_ms:.3f} ms, {api.last_rtc_stats().launches} launches)", flush=True)
