@@ -85,6 +85,7 @@ int lease_slot(int device, DeviceSlot** out) {
     CUDA_TRY(cudaEventCreate(&d->ev0));
     CUDA_TRY(cudaEventCreate(&d->ev1));
     CUDA_TRY(cudaMalloc(&d->d_counters, sizeof(DevCounters)));
+    CUDA_TRY(cudaHostAlloc(&d->h_counters, sizeof(DevCounters), cudaHostAllocDefault));
     CUDA_TRY(cudaMalloc(&d->d_stream_counter, 64 * sizeof(unsigned)));  // RTC_OPT_RENDER_SLICES <= 64
     CUDA_TRY(cudaDeviceGetAttribute(&d->sm_count, cudaDevAttrMultiProcessorCount, device));
     // the kernels keep their bounce and traversal stacks in local memory
@@ -486,6 +487,7 @@ int render_impl(RtcScene* s, int depth, int shard0, int n_shards_ext, float* rgb
         for (int l = 1; l < n_lanes; l++)
             if (last_on_lane[l] >= 0) CUDA_TRY(cudaStreamWaitEvent(slot->stream, slot->slice_done[last_on_lane[l]], 0));
         CUDA_TRY(cudaEventRecord(slot->ev1, slot->stream));
+        CUDA_TRY(cudaMemcpyAsync(slot->h_counters, slot->d_counters, sizeof(DevCounters), cudaMemcpyDeviceToHost, slot->stream));
     }
     for (const PendingCopy& c : pending) {  // the copy stream of each device already waits for the slice's event
         CUDA_TRY(cudaSetDevice(c.slot->device));
@@ -543,12 +545,12 @@ int render_impl(RtcScene* s, int depth, int shard0, int n_shards_ext, float* rgb
             if (again) {
                 CUDA_TRY(cudaStreamSynchronize(slot->copy_stream));
                 slot->wave_rays_per_pixel = std::min(64, slot->wave_rays_per_pixel * 2);  // a bigger pool next time
+                CUDA_TRY(cudaMemcpy(slot->h_counters, slot->d_counters, sizeof(DevCounters), cudaMemcpyDeviceToHost));  // the re-rendered chunks counted too
             }
             st.secondary_rays += extra.secondary, st.shades += extra.shades;
             st.shadow_rays += extra.shades * (s->light_is_rect ? (uint64_t)s->u_steps * s->v_steps : 1);
         }
-        DevCounters c;
-        CUDA_TRY(cudaMemcpy(&c, slot->d_counters, sizeof(c), cudaMemcpyDeviceToHost));
+        const DevCounters c = *slot->h_counters;  // copied behind ev1 on the render stream (synchronized above)
         {
             // camera.rs:80-81: rows y < h - 1 and columns x < w - 1 of this shard's bands
             const int shard = external ? shard0 : i;

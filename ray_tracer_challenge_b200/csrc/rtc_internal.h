@@ -49,6 +49,7 @@ struct DeviceSlot {
     cudaStream_t copy_stream = nullptr;  // device-to-host copies, overlapped with the kernels of later slices
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::vector<cudaEvent_t> slice_done;
+    DevCounters* h_counters = nullptr;  // pinned: the frame's counters arrive behind its last kernel, no extra round trip
     cudaStream_t slice_stream[2] = {nullptr, nullptr};  // with `stream`: the slices of a frame rotate over three streams
     float* d_rgb = nullptr;
     unsigned char* d_u8 = nullptr;
