@@ -296,6 +296,43 @@ int copy_bands(DeviceSlot* slot, const RtcScene* s, int shard, int n_shards, int
     return 0;
 }
 
+// The same rows from a pinned staging frame into the caller's pageable canvas, by the host's threads.
+void host_copy_bands(const RtcScene* s, int shard, int n_shards, int b0, int b1, const char* src, char* dst, size_t px_bytes) {
+    const size_t row = (size_t)s->width * px_bytes;
+    const size_t band = row * kBandRows;
+    if (b1 <= b0) return;
+    if (n_shards == 1) {
+        const int last_rows = std::min<int>(kBandRows, (int)s->height - (b1 - 1) * kBandRows);
+        const size_t off = (size_t)b0 * band, bytes = (size_t)(b1 - b0 - 1) * band + row * last_rows;
+        parallel_copy(dst + off, src + off, bytes, (size_t)96 << 10);  // a slice is ~1 MiB: all threads take a piece of it
+        return;
+    }
+    parallel_for((size_t)(b1 - b0), 1, [&](size_t jb, size_t je, int) {
+        for (size_t j = jb; j < je; j++) {
+            const int frame_band = shard + (b0 + (int)j) * n_shards;
+            const int rows = std::min<int>(kBandRows, (int)s->height - frame_band * kBandRows);
+            memcpy(dst + (size_t)frame_band * band, src + (size_t)frame_band * band, row * rows);
+        }
+    });
+}
+bool is_pageable(const void* p) {
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;  // let the copy itself report what is wrong with the pointer
+    }
+    return attr.type == cudaMemoryTypeUnregistered;
+}
+int ensure_stage(DeviceSlot* d, char** stage, size_t* have, size_t bytes) {
+    if (bytes <= *have) return 0;
+    CUDA_TRY(cudaSetDevice(d->device));
+    if (*stage) cudaFreeHost(*stage);
+    *stage = nullptr, *have = 0;
+    CUDA_TRY(cudaHostAlloc(stage, bytes, cudaHostAllocPortable));
+    *have = bytes;
+    return 0;
+}
+
 // The wavefront renderer's chunking: about a million pixels of the shard at a time (whole bands).
 int wave_chunk_bands(int width, int nb) {
     const int per_band = std::max(1, width) * kBandRows;
@@ -345,15 +382,65 @@ int render_impl(RtcScene* s, int depth, int shard0, int n_shards_ext, float* rgb
         int shard, b0, b1;
     };
     std::vector<PendingCopy> pending;
+    // A pageable destination (the reference's Canvas is a Vec): cudaMemcpyAsync into it would block the calling thread
+    // slice after slice at the driver's single-threaded staging rate (~10 GB/s).  Instead the slices land in a pinned
+    // frame kept with the device slot, and the host's threads move each one on as soon as its copy event has fired,
+    // while the device renders and copies the next (c3's 24.9 MB 8-bit canvas into a heap array: 0.71 ms end to end instead of
+    // 3.07; into pinned memory 0.66).
+    // (small planes are left to the driver: waking the worker threads costs more than its pageable path loses — c1's 1.2 MB:
+    // 0.28 ms through the driver, 0.40 ms staged)
+    const size_t frame_px = (size_t)s->width * s->height;
+    const bool stage_rgb = rgb && frame_px * 12 >= ((size_t)4 << 20) && is_pageable(rgb);
+    const bool stage_u8 = u8 && frame_px * 3 >= ((size_t)4 << 20) && is_pageable(u8);
+    struct Unstage {
+        cudaEvent_t done;
+        DeviceSlot* slot;
+        int shard, b0, b1;
+    };
+    std::vector<Unstage> unstage;
+    std::vector<int> events_used(ndev, 0);
+    auto slot_index = [&](DeviceSlot* slot) {
+        for (int i = 0; i < ndev; i++)
+            if (s->replicas[i].slot == slot) return i;
+        return 0;
+    };
+    auto copy_out_bands = [&](DeviceSlot* slot, int shard, int b0, int b1) -> int {  // device frame -> canvas or staging frame
+        int rc;
+        const size_t px = (size_t)s->width * s->height;
+        if (stage_rgb && (rc = ensure_stage(slot, &slot->h_stage_rgb, &slot->h_stage_rgb_bytes, px * 12))) return rc;
+        if (stage_u8 && (rc = ensure_stage(slot, &slot->h_stage_u8, &slot->h_stage_u8_bytes, px * 3))) return rc;
+        if (rgb && (rc = copy_bands(slot, s, shard, n_shards, b0, b1, slot->d_rgb, stage_rgb ? (void*)slot->h_stage_rgb : (void*)rgb, 12))) return rc;
+        if (u8 && (rc = copy_bands(slot, s, shard, n_shards, b0, b1, slot->d_u8, stage_u8 ? (void*)slot->h_stage_u8 : (void*)u8, 3))) return rc;
+        if (stage_rgb || stage_u8) {
+            int& used = events_used[slot_index(slot)];
+            while ((int)slot->copy_done.size() <= used) {
+                cudaEvent_t e;
+                CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+                slot->copy_done.push_back(e);
+            }
+            CUDA_TRY(cudaEventRecord(slot->copy_done[used], slot->copy_stream));
+            unstage.push_back({slot->copy_done[used], slot, shard, b0, b1});
+            used++;
+        }
+        return 0;
+    };
+    size_t unstaged = 0;
+    auto drain_unstage = [&]() -> int {  // the host half of the staged copies queued so far
+        for (; unstaged < unstage.size(); unstaged++) {
+            const Unstage& u = unstage[unstaged];
+            CUDA_TRY(cudaSetDevice(u.slot->device));
+            CUDA_TRY(cudaEventSynchronize(u.done));
+            if (stage_rgb) host_copy_bands(s, u.shard, n_shards, u.b0, u.b1, u.slot->h_stage_rgb, (char*)rgb, 12);
+            if (stage_u8) host_copy_bands(s, u.shard, n_shards, u.b0, u.b1, u.slot->h_stage_u8, (char*)u8, 3);
+        }
+        return 0;
+    };
     auto queue_copy = [&](DeviceSlot* slot, int shard, int b0, int b1) -> int {
         if (ndev > 1) {
             pending.push_back({slot, shard, b0, b1});
             return 0;
         }
-        int rc;
-        if (rgb && (rc = copy_bands(slot, s, shard, n_shards, b0, b1, slot->d_rgb, rgb, 3 * sizeof(float)))) return rc;
-        if (u8 && (rc = copy_bands(slot, s, shard, n_shards, b0, b1, slot->d_u8, u8, 3))) return rc;
-        return 0;
+        return copy_out_bands(slot, shard, b0, b1);
     };
     for (int i = 0; i < ndev; i++) {
         Replica& r = s->replicas[i];
@@ -491,10 +578,9 @@ int render_impl(RtcScene* s, int depth, int shard0, int n_shards_ext, float* rgb
     }
     for (const PendingCopy& c : pending) {  // the copy stream of each device already waits for the slice's event
         CUDA_TRY(cudaSetDevice(c.slot->device));
-        int rc;
-        if (rgb && (rc = copy_bands(c.slot, s, c.shard, n_shards, c.b0, c.b1, c.slot->d_rgb, rgb, 3 * sizeof(float)))) return rc;
-        if (u8 && (rc = copy_bands(c.slot, s, c.shard, n_shards, c.b0, c.b1, c.slot->d_u8, u8, 3))) return rc;
+        if (int rc = copy_out_bands(c.slot, c.shard, c.b0, c.b1)) return rc;
     }
+    if (int rc = drain_unstage()) return rc;
     const bool timing = getenv("RTC_TIMING") != nullptr;  // tuning aid
     auto since = [&] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); };
     if (timing) fprintf(stderr, "[rtc render] launches queued at      %8.3f ms\n", since());
@@ -538,12 +624,11 @@ int render_impl(RtcScene* s, int depth, int shard0, int n_shards_ext, float* rgb
                 CUDA_TRY(cudaGetLastError());
                 st.launches++;
                 CUDA_TRY(cudaStreamSynchronize(slot->stream));  // one chunk at a time: they may share a counter slot
-                int rc;
-                if (rgb && (rc = copy_bands(slot, s, shard, n_shards, b0, b1, slot->d_rgb, rgb, 3 * sizeof(float)))) return rc;
-                if (u8 && (rc = copy_bands(slot, s, shard, n_shards, b0, b1, slot->d_u8, u8, 3))) return rc;
+                if (int rc = copy_out_bands(slot, shard, b0, b1)) return rc;
             }
             if (again) {
                 CUDA_TRY(cudaStreamSynchronize(slot->copy_stream));
+                if (int rc = drain_unstage()) return rc;
                 slot->wave_rays_per_pixel = std::min(64, slot->wave_rays_per_pixel * 2);  // a bigger pool next time
                 CUDA_TRY(cudaMemcpy(slot->h_counters, slot->d_counters, sizeof(DevCounters), cudaMemcpyDeviceToHost));  // the re-rendered chunks counted too
             }

@@ -49,6 +49,12 @@ struct DeviceSlot {
     cudaStream_t copy_stream = nullptr;  // device-to-host copies, overlapped with the kernels of later slices
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::vector<cudaEvent_t> slice_done;
+    // a caller's pageable canvas: the frame lands here (pinned, full frame, grown on demand) slice by slice and the
+    // host's threads move each slice on while the device renders the next ones (rtc_api.cu: render_impl)
+    char* h_stage_rgb = nullptr;
+    char* h_stage_u8 = nullptr;
+    size_t h_stage_rgb_bytes = 0, h_stage_u8_bytes = 0;
+    std::vector<cudaEvent_t> copy_done;
     DevCounters* h_counters = nullptr;  // pinned: the frame's counters arrive behind its last kernel, no extra round trip
     cudaStream_t slice_stream[2] = {nullptr, nullptr};  // with `stream`: the slices of a frame rotate over three streams
     float* d_rgb = nullptr;

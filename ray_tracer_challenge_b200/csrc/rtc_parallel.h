@@ -167,8 +167,8 @@ inline int parallel_chunks(size_t n, size_t grain) {
 }
 
 // memcpy of a large block by all threads (a 14 MB primitive array is a millisecond of one core's time)
-inline void parallel_copy(void* dst, const void* src, size_t bytes) {
-    parallel_for(bytes, (size_t)1 << 20, [&](size_t b, size_t e, int) { memcpy((char*)dst + b, (const char*)src + b, e - b); });
+inline void parallel_copy(void* dst, const void* src, size_t bytes, size_t grain = (size_t)1 << 20) {
+    parallel_for(bytes, grain, [&](size_t b, size_t e, int) { memcpy((char*)dst + b, (const char*)src + b, e - b); });
 }
 
 // The same into a buffer the device is about to read over PCIe: non-temporal stores, so that no line of it is left

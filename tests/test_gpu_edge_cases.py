@@ -92,3 +92,41 @@ def test_deepest_recursion(gpu, oracle):
     got, want, st, ost = both(gpu, oracle, build, depth=23)
     rep = compare_frames(got.to_u8(), want.to_u8(), got.data, want.data)
     assert rep["exact_u8"] >= 0.999 and st.rays == ost.rays and st.secondary_rays > 5 * st.primary_rays, rep
+
+
+def test_pageable_and_pinned_destinations_receive_the_same_frame(gpu):
+    """A caller's heap array (the reference's Canvas is a Vec) is filled through a pinned staging frame by the host's
+    threads, slice by slice; pinned memory is written by the copy engine directly.  Same bytes either way, for the whole
+    frame and for the interleaved bands of a 3-way shard split."""
+    import ctypes as C
+
+    import ray_tracer_challenge_b200 as rt
+
+    cam, world = scenes.soft_shadows(gpu, width=2048, height=1025, u_steps=2, v_steps=2)  # 6.3 MB / 25 MB planes, ragged last band
+    w, h = cam.width_pixels, cam.height_pixels
+    p = cam.prepare(world)
+    lib = rt.device_library()
+    lib.rtc_host_alloc.restype = C.c_void_p
+    lib.rtc_host_alloc.argtypes = [C.c_size_t]
+    lib.rtc_host_free.argtypes = [C.c_void_p]
+    a_rgb, a_u8 = lib.rtc_host_alloc(w * h * 12), lib.rtc_host_alloc(w * h * 3)
+    pin_rgb = np.ctypeslib.as_array(C.cast(a_rgb, C.POINTER(C.c_float)), shape=(h, w, 3))
+    pin_u8 = np.ctypeslib.as_array(C.cast(a_u8, C.POINTER(C.c_uint8)), shape=(h, w, 3))
+    pin_rgb[:], pin_u8[:] = -1.0, 7
+    p.render(3, out_rgb=pin_rgb, out_u8=pin_u8)
+    heap_rgb, heap_u8 = np.full((h, w, 3), -1.0, np.float32), np.full((h, w, 3), 7, np.uint8)
+    p.render(3, out_rgb=heap_rgb, out_u8=heap_u8)
+    assert np.array_equal(heap_u8, pin_u8) and np.array_equal(heap_rgb.view(np.uint32), pin_rgb.view(np.uint32))
+    assert heap_u8.max() > 7  # something was rendered
+    # three shards into one heap canvas: every band arrives exactly once
+    shard_rgb, shard_u8 = np.full((h, w, 3), -1.0, np.float32), np.full((h, w, 3), 7, np.uint8)
+    for k in range(3):
+        p.render(3, out_rgb=shard_rgb, out_u8=shard_u8, shard=k, n_shards=3)
+    assert np.array_equal(shard_u8, pin_u8) and np.array_equal(shard_rgb.view(np.uint32), pin_rgb.view(np.uint32))
+    # the 8-bit plane alone (render_b200_u8's path)
+    only_u8 = np.full((h, w, 3), 7, np.uint8)
+    p.render(3, out_u8=only_u8, want_rgb=False)
+    assert np.array_equal(only_u8, pin_u8)
+    p.release()
+    del pin_rgb, pin_u8
+    lib.rtc_host_free(a_rgb), lib.rtc_host_free(a_u8)

@@ -25,7 +25,10 @@ lib.rtc_host_alloc.restype = C.c_void_p
 lib.rtc_host_alloc.argtypes = [C.c_size_t]
 cam, world, depth, _ = build_scene(api, sys.argv[1])
 w, h = cam.width_pixels, cam.height_pixels
-u8 = np.ctypeslib.as_array(C.cast(lib.rtc_host_alloc(w * h * 3), C.POINTER(C.c_uint8)), shape=(h, w, 3))
+if os.environ.get("PAGEABLE"):  # what the reference-shaped API hands over: a plain heap array (Canvas is a Vec)
+    u8 = np.zeros((h, w, 3), np.uint8)
+else:
+    u8 = np.ctypeslib.as_array(C.cast(lib.rtc_host_alloc(w * h * 3), C.POINTER(C.c_uint8)), shape=(h, w, 3))
 stats = rt.SgStats()
 for _ in range(5):
     api.check(api.lib.sg_camera_render_shard(api.ctx, cam.handle, world.handle, depth, 0, 1, None, u8.ctypes.data_as(U8P), C.byref(stats)))
