@@ -293,17 +293,17 @@ def measure_e2e(ctx: Ctx, workload: str, cam, world, depth: int, rays_per_frame:
         registered = lib.rtc_host_register(canvas.address, canvas.nbytes) == 0
     stats = ctx.rt.SgStats()
 
-    def one_shot(with_f32: bool):
+    def one_shot(with_f32: bool, into=None):
         api.check(api.lib.sg_camera_render_shard(api.ctx, cam.handle, world.handle, depth, rank, n_sh, fptr(rgb) if with_f32 else None,
-                                                 u8.ctypes.data_as(U8P), C.byref(stats)))
+                                                 (u8 if into is None else into).ctypes.data_as(U8P), C.byref(stats)))
 
-    def timed(with_f32: bool) -> float:
+    def timed(with_f32: bool, into=None) -> float:
         for _ in range(2):
-            one_shot(with_f32)
+            one_shot(with_f32, into)
         ctx.barrier()
         t0 = time.perf_counter()
         for _ in range(e_steps):
-            one_shot(with_f32)
+            one_shot(with_f32, into)
         ctx.barrier()
         return ctx.reduce(time.perf_counter() - t0, "max") / e_steps
 
@@ -319,6 +319,13 @@ def measure_e2e(ctx: Ctx, workload: str, cam, world, depth: int, rays_per_frame:
         out["f32_canvas"] = {"value": round(rays_per_frame / dt_f32 / 1e6, 3), "ms_per_frame": round(dt_f32 * 1e3, 3),
                              "d2h_bytes_per_step": int(w * h * 15),
                              "path": "the same with the f32 Canvas (canvas.rs:6-10) copied to the host as well"}
+        if ctx.world_size == 1:
+            heap = np.zeros((h, w, 3), np.uint8)  # what the glue's CanvasU8 owns, like the reference's Vec: pageable memory
+            dt_heap = timed(False, heap)
+            out["heap_canvas"] = {"value": round(rays_per_frame / dt_heap / 1e6, 3), "ms_per_frame": round(dt_heap * 1e3, 3),
+                                  "d2h_bytes_per_step": int(w * h * 3),
+                                  "path": "the 8-bit canvas into a plain heap array instead of pinned memory (staged through a "
+                                          "pinned frame by the host's threads)"}
     if ctx.world_size == 1:
         lib.rtc_host_free(p_rgb)
         lib.rtc_host_free(p_u8)
