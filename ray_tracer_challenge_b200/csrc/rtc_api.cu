@@ -490,6 +490,7 @@ int render_impl(RtcScene* s, int depth, int shard0, int n_shards_ext, float* rgb
         r.learning = order_wanted && !learnt && r.renders_done > 0;
         // undecided: stage 1 = natural order again, stages 2 and 3 = the learnt order; decided: by the verdict
         r.order_timed = order_wanted && learnt && r.order_verdict == 0 && !detailed;
+        r.order_lost_here = order_wanted && learnt && r.order_verdict < 0 && !detailed;
         const bool use_order = order_wanted && learnt && (r.order_verdict > 0 || (r.order_verdict == 0 && r.order_stage >= 2));
         if (r.learning) CUDA_TRY(cudaMemsetAsync(slot->d_tile_cost, 0, (size_t)total_bands * tiles_x * sizeof(unsigned), slot->stream));
         // With a host destination the frame is rendered in a few slices so that the device-to-host copy of one
@@ -647,11 +648,17 @@ int render_impl(RtcScene* s, int depth, int shard0, int n_shards_ext, float* rgb
         Replica& r = s->replicas[i];
         r.renders_done++;
         if (r.order_timed) {
-            if (r.order_stage == 1) r.natural_ms = std::min(r.natural_ms, ms);
+            if (r.order_stage <= 1) r.natural_ms = std::min(r.natural_ms, ms);
             if (r.order_stage == 2) r.ordered_ms = ms;
-            if (r.order_stage == 3) r.order_verdict = std::min(r.ordered_ms, ms) < 0.98f * r.natural_ms ? 1 : -1;
+            if (r.order_stage == 3) {
+                r.order_verdict = std::min(r.ordered_ms, ms) < 0.98f * r.natural_ms ? 1 : -1;
+                r.renders_since_loss = 0;
+            }
             r.order_stage++;
             r.order_timed = false;
+        } else if (r.order_lost_here && r.order_retrials < 3 && ++r.renders_since_loss >= 32) {
+            r.order_retrials++;
+            r.order_verdict = 0, r.order_stage = 0, r.natural_ms = 3.4e38f;  // stages 0, 1: natural order; 2, 3: the learnt one
         }
         if (r.learning) {  // sort this shard's tiles by the cycles their blocks took: the launch order from now on
             const int shard = external ? shard0 : i;
@@ -670,7 +677,7 @@ int render_impl(RtcScene* s, int depth, int shard0, int n_shards_ext, float* rgb
             }
             CUDA_TRY(cudaMemcpy(slot->d_tile_order, order.data(), order.size() * sizeof(int), cudaMemcpyHostToDevice));
             r.order_shard = shard, r.order_n_shards = n_shards, r.order_depth = depth, r.order_filter = s->shadow_filter;
-            r.order_verdict = 0, r.order_stage = 1, r.natural_ms = ms;
+            r.order_verdict = 0, r.order_stage = 1, r.natural_ms = ms, r.order_retrials = 0, r.renders_since_loss = 0;
             r.learning = false;
         }
     }

@@ -96,7 +96,12 @@ struct Replica {
     // The learnt order is kept only if it wins a timed trial: after the render that records the costs, one more in
     // natural order and two in the learnt order are timed (stages 1..3) and the minima compared.
     // order_verdict: 0 undecided, 1 the learnt order won and is used, -1 it lost (natural order is kept)
+    // A lost trial is repeated (two natural-order and two learnt-order renders again) after 32 more renders of the same
+    // shard, at most three times: one noisy sample must not pin a shard to the slower order for the life of the scene
+    // (with eight ranks the frame is as slow as the unluckiest one).
     int order_verdict = 0, order_stage = 0;
+    int order_retrials = 0, renders_since_loss = 0;
+    bool order_lost_here = false;  // this render uses natural order because the trial was lost
     bool order_timed = false;  // this render is one of the timed trial renders
     float natural_ms = 0.f, ordered_ms = 0.f;
     int renders_done = 0;  // the first render of a replica is cold (module load, caches): its time is not compared
