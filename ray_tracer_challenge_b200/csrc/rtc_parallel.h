@@ -194,6 +194,55 @@ inline void parallel_stream_copy(void* dst, const void* src, size_t bytes) {
     parallel_for(bytes, (size_t)1 << 20, [&](size_t b, size_t e, int) { stream_copy_range((char*)dst + b, (const char*)src + b, e - b); });
 }
 
+// Big blocks are kept between uses.  A one-shot render of a 100 k-primitive scene allocates ~100 MB of arrays and frees
+// them a few milliseconds later; whether malloc hands such blocks back to the kernel (munmap, then page faults on every
+// page of the next frame: + 4 ms per c4 frame) depends on the history of the process's heap — here it does not.
+class BlockCache {
+   public:
+    static constexpr size_t kMinBytes = (size_t)1 << 20, kHeader = 64, kMaxHeld = (size_t)768 << 20;
+    static BlockCache& instance() {
+        static BlockCache* cache = new BlockCache();  // never destroyed: blocks may be returned during static destruction
+        return *cache;
+    }
+    void* allocate(size_t bytes) {  // bytes >= kMinBytes
+        const size_t want = (bytes + kMinBytes - 1) & ~(kMinBytes - 1);
+        {
+            std::lock_guard<std::mutex> lock(m_);
+            size_t best = free_.size();
+            for (size_t i = 0; i < free_.size(); i++)
+                if (free_[i].first >= want && free_[i].first <= 2 * want && (best == free_.size() || free_[i].first < free_[best].first)) best = i;
+            if (best < free_.size()) {
+                char* block = free_[best].second;
+                held_ -= free_[best].first;
+                free_[best] = free_.back();
+                free_.pop_back();
+                return block + kHeader;
+            }
+        }
+        char* block = static_cast<char*>(::operator new(want + kHeader));
+        *reinterpret_cast<size_t*>(block) = want;
+        return block + kHeader;
+    }
+    void deallocate(void* p) {
+        char* block = static_cast<char*>(p) - kHeader;
+        const size_t capacity = *reinterpret_cast<size_t*>(block);
+        {
+            std::lock_guard<std::mutex> lock(m_);
+            if (held_ + capacity <= kMaxHeld) {
+                free_.emplace_back(capacity, block);
+                held_ += capacity;
+                return;
+            }
+        }
+        ::operator delete(block);
+    }
+
+   private:
+    std::mutex m_;
+    std::vector<std::pair<size_t, char*>> free_;
+    size_t held_ = 0;
+};
+
 // std::allocator that leaves what a resize adds untouched (not even default member initialisers run): for arrays of
 // plain records that the threads fill right after — a sequential fill of 14 MB first would cost what the threads save.
 template <class T>
@@ -211,6 +260,18 @@ struct NoInit : std::allocator<T> {
     template <class U, class... A>
     void construct(U* p, A&&... a) {
         ::new (static_cast<void*>(p)) U(std::forward<A>(a)...);
+    }
+    // blocks of a MiB and more come from, and go back to, the process-wide cache above
+    T* allocate(size_t n) {
+        const size_t bytes = n * sizeof(T);
+        if (bytes >= BlockCache::kMinBytes) return static_cast<T*>(BlockCache::instance().allocate(bytes));
+        return static_cast<T*>(::operator new(bytes));
+    }
+    void deallocate(T* p, size_t n) noexcept {
+        if (n * sizeof(T) >= BlockCache::kMinBytes)
+            BlockCache::instance().deallocate(p);
+        else
+            ::operator delete(p);
     }
 };
 template <class T>
