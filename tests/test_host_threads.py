@@ -167,6 +167,31 @@ print("child", os.WEXITSTATUS(status))
     assert res.stdout.strip().splitlines()[-1] == "child 0"
 
 
+def test_flattener_stays_inside_its_arrays_under_address_sanitizer(tmp_path):
+    """The threads write their subtrees' records at offsets computed from the subtree sizes, into arrays that are sized
+    once and not initialised: the same driver built with -fsanitize=address,undefined must run clean."""
+    import shutil
+
+    import ray_tracer_challenge_b200 as rt
+
+    if shutil.which("g++") is None:
+        pytest.skip("no g++")
+    exe = tmp_path / "flatten_asan"
+    pkg = os.path.dirname(rt.LIB_DEVICE)
+    cmd = ["g++", "-std=c++17", "-O1", "-g", "-fsanitize=address,undefined", "-fno-sanitize-recover=undefined", "-fPIC", "-pthread",
+           "-o", str(exe), os.path.join(ROOT, "tests", "tsan", "flatten_tsan.cpp"), os.path.join(pkg, "csrc", "host", "rtc_host.cpp"),
+           "-L" + pkg, "-lrtc_b200", "-Wl,-rpath," + pkg]
+    build = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    if build.returncode != 0 and "asan" in (build.stderr + build.stdout).lower():
+        pytest.skip("AddressSanitizer runtime not available: " + build.stderr[-300:])
+    assert build.returncode == 0, build.stderr[-2000:]
+    env = dict(os.environ, RTC_HOST_THREADS="6", ASAN_OPTIONS="detect_leaks=0:abort_on_error=0:exitcode=67")
+    run = subprocess.run([str(exe)], capture_output=True, text=True, env=env, timeout=600)
+    assert run.returncode == 0, (run.stdout + run.stderr)[-3000:]
+    assert "ERROR: AddressSanitizer" not in run.stderr and "runtime error" not in run.stderr
+    assert "flattened: 26000 prims" in run.stdout
+
+
 def test_flattener_is_race_free_under_thread_sanitizer(tmp_path):
     """The threaded flattener (subtree walks writing disjoint ranges, per-thread material tables, the worker pool's
     hand-off) compiled with -fsanitize=thread and run on a 26 000-primitive world: TSan must stay silent."""
